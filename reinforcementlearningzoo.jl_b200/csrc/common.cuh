@@ -1,0 +1,119 @@
+// Shared declarations of libzoo_sm100 (sm_100a only; no other architecture is compiled).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/zoo_sm100.h"
+
+namespace zoo {
+
+typedef __nv_bfloat16 bf16;
+
+void set_err(const char *fmt, ...);
+extern thread_local int g_launches;  // kernels enqueued since the counter was last reset
+
+#define ZOO_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            zoo::set_err("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return ZOO_CUDA_ERROR;                                                            \
+        }                                                                                     \
+    } while (0)
+
+#define ZOO_TRY(call)                    \
+    do {                                 \
+        zoo_status s__ = (call);         \
+        if (s__ != ZOO_OK) return s__;   \
+    } while (0)
+
+#define ZOO_REQUIRE(cond, ...)           \
+    do {                                 \
+        if (!(cond)) {                   \
+            zoo::set_err(__VA_ARGS__);   \
+            return ZOO_BAD_ARG;          \
+        }                                \
+    } while (0)
+
+#define ZOO_LAUNCH_CHECK()                                                                   \
+    do {                                                                                     \
+        zoo::g_launches++;                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess) {                                                            \
+            zoo::set_err("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return ZOO_CUDA_ERROR;                                                           \
+        }                                                                                    \
+    } while (0)
+
+zoo_status require_sm100();
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------- GEMM engines ------------
+// D(m,n) = sum_k A(m,k) * B(n,k)
+struct Operand {
+    const void *p;
+    int is_bf16;   // element type: 1 = bf16, 0 = fp32
+    long long ld;  // leading dimension in elements
+    int kmajor;    // 1: (i,k) at p[i*ld + k];  0: (i,k) at p[k*ld + i]
+};
+
+struct Epilogue {
+    void *out = nullptr;
+    int out_bf16 = 0;
+    long long sm = 0, sn = 1;  // D(m,n) stored at out[m*sm + n*sn]
+    const float *bias = nullptr;
+    int bias_mode = 0;  // 0 none, 1 per-n, 2 per-m
+    int relu = 0;
+    const void *mask = nullptr;  // multiply by (mask(m,n) > 0): relu' of the layer this gradient enters
+    int mask_bf16 = 0;
+    long long mask_sm = 0, mask_sn = 1;
+    const void *rowmul = nullptr;  // multiply by rowmul[(m / rowmul_div)][n] (IQN Hadamard merge), same dtype as out
+    int rowmul_div = 1;
+    long long rowmul_ld = 0;
+    int accumulate = 0;  // 1: atomically add into fp32 out (out must be fp32; bias/relu/mask not allowed)
+};
+
+// fp32 CUDA-core engine (any shapes, fp32 or bf16 inputs, fp32 accumulate)
+zoo_status simt_gemm(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, int split_k,
+                     float *ws, size_t ws_elems, cudaStream_t st);
+// tcgen05 engine (bf16 inputs).  tc_gemm_supported tells whether the shapes/alignments qualify.
+bool tc_gemm_supported(const Operand &A, const Operand &B, int M, int N, int K);
+zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, int split_k,
+                   float *ws, size_t ws_elems, cudaStream_t st);
+// dispatch: tcgen05 when both inputs are bf16 and supported, otherwise SIMT
+zoo_status gemm(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, int split_k, float *ws,
+                size_t ws_elems, cudaStream_t st);
+
+__device__ __forceinline__ float ld_elem(const void *p, int is_bf16, long long i) {
+    return is_bf16 ? __bfloat162float(((const bf16 *)p)[i]) : ((const float *)p)[i];
+}
+__device__ __forceinline__ void st_elem(void *p, int is_bf16, long long i, float v) {
+    if (is_bf16) ((bf16 *)p)[i] = __float2bfloat16_rn(v);
+    else ((float *)p)[i] = v;
+}
+
+// applies everything of the epilogue except the store decision; shared by both engines + finish kernel
+__device__ __forceinline__ float epi_apply(const Epilogue &e, float v, int m, int n) {
+    if (e.bias_mode == 1) v += e.bias[n];
+    else if (e.bias_mode == 2) v += e.bias[m];
+    if (e.relu) v = fmaxf(v, 0.f);
+    if (e.mask) v = ld_elem(e.mask, e.mask_bf16, (long long)m * e.mask_sm + (long long)n * e.mask_sn) > 0.f ? v : 0.f;
+    if (e.rowmul) v *= ld_elem(e.rowmul, e.out_bf16, (long long)(m / e.rowmul_div) * e.rowmul_ld + n);
+    return v;
+}
+__device__ __forceinline__ void epi_store(const Epilogue &e, float v, int m, int n) {
+    long long o = (long long)m * e.sm + (long long)n * e.sn;
+    if (e.accumulate) atomicAdd((float *)e.out + o, v);
+    else st_elem(e.out, e.out_bf16, o, epi_apply(e, v, m, n));
+}
+
+}  // namespace zoo

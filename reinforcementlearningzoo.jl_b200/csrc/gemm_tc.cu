@@ -1,0 +1,355 @@
+// tcgen05 GEMM engine for sm_100a (ZOO_PREC_BF16 path).
+//   D(m,n) = sum_k A(m,k) B(n,k), bf16 operands, fp32 accumulation in TMEM.
+// One 128 x BN output tile (x one K-split) per CTA:
+//   warp 0      TMA producer  (cp.async.bulk.tensor 2D, SWIZZLE_128B, 4-stage mbarrier ring)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, kind::f16, M=128, N=BN, K=16)
+//   warps 2..5  epilogue: tcgen05.ld 32x32b -> bias / relu / relu' mask / Hadamard -> global (fp32 | bf16 | atomic add)
+// Operands may be K-major ([rows][K]) or MN-major ([K][rows]); the latter is what dgrad (W as [N'][K']) and
+// wgrad (dY and X as [batch rows][features]) need, so no operand is ever transposed in memory.
+// Contractions served: CrossCor-as-GEMM and Dense forward / dgrad / wgrad of the Nature-CNN and the IQN net
+// (reference layers: src/experiments/atari/Dopamine_DQN_Atari.jl:26-35, Dopamine_IQN_Atari.jl:30-44).
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace zoo {
+
+static constexpr int BM = 128;      // UMMA M (cta_group::1)
+static constexpr int BK = 64;       // K elements per stage = one 128-byte swizzle span of bf16
+static constexpr int UMMA_K = 16;   // K per tcgen05.mma for 16-bit inputs
+static constexpr int TC_THREADS = 192;
+
+// ---------------------------------------------------------------- PTX wrappers ------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in [0,14),
+// leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version = 1 in [46,48),
+// layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 at [4,6), a/b format BF16 = 1 at [7,10)/[10,13),
+// a_major at 15, b_major at 16 (0 = K-major, 1 = MN-major), N >> 3 at [17,23), M >> 4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct TcParams {
+    int M, N, K;
+    int kb_per_split;  // K blocks (of 64) per grid.z slice
+    Epilogue epi;
+    float *ws;  // split-K workspace [M][N] (atomic accumulate) or nullptr
+};
+
+// smem per stage: A tile 128 x 64 bf16 (16 KB) + B tile BN x 64 bf16
+template <int BN>
+struct TcCfg {
+    static constexpr int STAGES = BN >= 128 ? 3 : 4;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN, bool A_K, bool B_K>
+__global__ void __launch_bounds__(TC_THREADS)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
+    using C = TcCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = (uint64_t *)(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + C::STAGES;
+    uint64_t *tmem_full_bar = empty_bar + C::STAGES;
+    uint32_t *tmem_slot = (uint32_t *)(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int total_kb = (P.K + BK - 1) / BK;
+    const int kb0 = blockIdx.z * P.kb_per_split;
+    const int kb1 = min(total_kb, kb0 + P.kb_per_split);
+    const int nkb = kb1 - kb0;  // host guarantees >= 1
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % C::STAGES;
+                const uint32_t ph = (i / C::STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t *sa = smem + s * C::STAGE_BYTES;
+                uint8_t *sb = sa + C::A_BYTES;
+                mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+                const int k0 = (kb0 + i) * BK;
+                if (A_K) {
+                    tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box {64 k, 128 rows}
+                } else {
+                    tma_load_2d(sa, &tmA, &full_bar[s], m0, k0);  // box {64 m, 64 k}, two MN halves
+                    tma_load_2d(sa + 8192, &tmA, &full_bar[s], m0 + 64, k0);
+                }
+                if (B_K) {
+                    tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box {64 k, BN rows}
+                } else {
+#pragma unroll
+                    for (int h = 0; h < BN / 64; ++h) tma_load_2d(sb + h * 8192, &tmB, &full_bar[s], n0 + h * 64, k0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, !A_K, !B_K);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % C::STAGES;
+                const uint32_t ph = (i / C::STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+                const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // K-major SW128: 8-row groups 1024 B apart (SBO), 16 K-elements = 32 B inside the swizzle span.
+                    // MN-major SW128: 64-element MN blocks BK*128 B apart (LBO), 8-k groups 1024 B apart (SBO),
+                    //                 16 K-elements = two 8-k groups = 2048 B.
+                    const uint64_t ad = A_K ? make_smem_desc(sa + k * 32, 16, 1024) : make_smem_desc(sa + k * 2048, BK * 128, 1024);
+                    const uint64_t bd = B_K ? make_smem_desc(sb + k * 32, 16, 1024) : make_smem_desc(sb + k * 2048, BK * 128, 1024);
+                    umma_bf16(tmem_base, ad, bd, idesc, (i | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);  // accumulator complete
+        }
+    } else {
+        // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+        const int q = warp & 3;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int m = m0 + q * 32 + lane;
+        const Epilogue &e = P.epi;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+            if (m < P.M) {
+                if (P.ws) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        int n = n0 + c + j;
+                        if (n < P.N) atomicAdd(P.ws + (long long)m * P.N + n, __uint_as_float(r[j]));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        int n = n0 + c + j;
+                        if (n < P.N) epi_store(e, __uint_as_float(r[j]), m, n);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------- host side ---------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static EncodeTiledFn get_encode() {
+    std::call_once(g_encode_once, [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            g_encode = (EncodeTiledFn)fn;
+    });
+    return g_encode;
+}
+
+// 2D bf16 tensor map: inner (contiguous) extent d0, outer extent d1, row pitch ld elements, box {b0, b1}, SWIZZLE_128B
+static zoo_status make_map(CUtensorMap *tm, const void *p, long long d0, long long d1, long long ld, int b0, int b1) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_err("cuTensorMapEncodeTiled not available from the driver");
+        return ZOO_CUDA_ERROR;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)b0, (cuuint32_t)b1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(p), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_err("cuTensorMapEncodeTiled failed (%d): dims %lld x %lld ld %lld box %d x %d ptr %p", (int)r, d0, d1, ld, b0, b1, p);
+        return ZOO_CUDA_ERROR;
+    }
+    return ZOO_OK;
+}
+
+bool tc_gemm_supported(const Operand &A, const Operand &B, int M, int N, int K) {
+    if (!A.is_bf16 || !B.is_bf16) return false;
+    if (M < 1 || N < 8 || K < 8) return false;
+    if (A.ld % 8 || B.ld % 8) return false;                                    // 16-byte global strides
+    if (((uintptr_t)A.p & 15) || ((uintptr_t)B.p & 15)) return false;        // 16-byte base alignment
+    return true;
+}
+
+zoo_status splitk_finish(const float *ws, int M, int N, const Epilogue &epi, cudaStream_t st);
+
+template <int BN, bool A_K, bool B_K>
+static zoo_status launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid, cudaStream_t st) {
+    using C = TcCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, A_K, B_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    tc_gemm_kernel<BN, A_K, B_K><<<grid, TC_THREADS, C::SMEM, st>>>(tmA, tmB, P);
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+
+zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, int split_k, float *ws,
+                   size_t ws_elems, cudaStream_t st) {
+    ZOO_REQUIRE(tc_gemm_supported(A, B, M, N, K), "tc_gemm: unsupported operands (M=%d N=%d K=%d)", M, N, K);
+    // MN-major B tiles are loaded in 64-wide boxes -> BN must be a multiple of 64 there
+    int BN = (N <= 32 && B.kmajor) ? 32 : (N <= 64 ? 64 : 128);
+    dim3 grid(cdiv(M, BM), cdiv(N, BN), 1);
+    const int total_kb = cdiv(K, BK);
+    if (split_k <= 0) {
+        long long tiles = (long long)grid.x * grid.y;
+        split_k = 1;
+        if (tiles < 148 && total_kb >= 4) split_k = (int)std::min<long long>(total_kb / 2, (296 + tiles - 1) / tiles);
+        if (split_k < 1) split_k = 1;
+    }
+    split_k = std::min(split_k, total_kb);
+    int kbps = cdiv(total_kb, split_k);
+    split_k = cdiv(total_kb, kbps);
+    grid.z = split_k;
+
+    TcParams P;
+    P.M = M; P.N = N; P.K = K; P.kb_per_split = kbps; P.epi = epi; P.ws = nullptr;
+    bool direct_acc = epi.accumulate && !epi.out_bf16;
+    if (split_k > 1 && !direct_acc) {
+        ZOO_REQUIRE(ws && ws_elems >= (size_t)M * N, "tc_gemm: split-K workspace too small (%zu < %lld)", ws_elems, (long long)M * N);
+        ZOO_CUDA(cudaMemsetAsync(ws, 0, (size_t)M * N * sizeof(float), st));
+        P.ws = ws;
+    }
+    CUtensorMap tmA, tmB;
+    if (A.kmajor) ZOO_TRY(make_map(&tmA, A.p, K, M, A.ld, BK, BM));
+    else ZOO_TRY(make_map(&tmA, A.p, M, K, A.ld, 64, BK));
+    if (B.kmajor) ZOO_TRY(make_map(&tmB, B.p, K, N, B.ld, BK, BN));
+    else ZOO_TRY(make_map(&tmB, B.p, N, K, B.ld, 64, BK));
+
+#define GO(BNv)                                                                             \
+    do {                                                                                    \
+        if (A.kmajor && B.kmajor) ZOO_TRY((launch_tc<BNv, true, true>(tmA, tmB, P, grid, st)));      \
+        else if (A.kmajor && !B.kmajor) ZOO_TRY((launch_tc<BNv, true, false>(tmA, tmB, P, grid, st))); \
+        else if (!A.kmajor && B.kmajor) ZOO_TRY((launch_tc<BNv, false, true>(tmA, tmB, P, grid, st))); \
+        else ZOO_TRY((launch_tc<BNv, false, false>(tmA, tmB, P, grid, st)));                         \
+    } while (0)
+    if (BN == 32) {
+        if (A.kmajor) ZOO_TRY((launch_tc<32, true, true>(tmA, tmB, P, grid, st)));
+        else ZOO_TRY((launch_tc<32, false, true>(tmA, tmB, P, grid, st)));
+    } else if (BN == 64) GO(64);
+    else GO(128);
+#undef GO
+    if (P.ws) ZOO_TRY(splitk_finish(P.ws, M, N, epi, st));
+    return ZOO_OK;
+}
+
+}  // namespace zoo

@@ -1,0 +1,84 @@
+// Q-network engine: Flux Chain / ImplicitQuantileNet / DuelingNetwork forward + backward on the device.
+// Reference: model definitions src/experiments/atari/Dopamine_{DQN,Rainbow,IQN}_Atari.jl:26-44,
+//            ImplicitQuantileNet src/algorithms/dqns/iqn.jl:17-33, DuelingNetwork src/algorithms/dqns/common.jl:44-56.
+#pragma once
+#include "common.cuh"
+
+namespace zoo {
+
+// How a Flux parameter tensor (ABI layout = Julia bytes) maps to the internal, GEMM-friendly layout.
+//   dense W : ABI [in][out]            -> internal [out][in]   (K-major B operand of the forward GEMM)
+//   conv  W : ABI [O][C][kh][kw]       -> internal [O][kh][kw][C] for convs that read internal NHWC activations,
+//                                         unchanged for a first conv that reads the NCHW observation
+//   "flat"  : a feature axis that is the flatten of a conv output is stored (h,w,c) internally (NHWC) but is
+//             (c,h,w) in the reference (reshape(x,:,B) of a (W,H,C,B) array) -> that axis is permuted.
+struct TensorInfo {
+    int kind;      // 0 dense W, 1 conv W, 2 bias
+    int n_out, n_in, ksize;
+    int conv_nhwc;           // conv W stored [O][kh][kw][C]
+    int perm_in, perm_out;   // axis lives in the flatten space (fc, fh, fw)
+    int fc, fh, fw;
+    long long offset, count; // into the flat parameter / gradient / optimiser-state buffers
+};
+
+struct LayerExec {
+    int kind;  // ZOO_LAYER_CONV or ZOO_LAYER_DENSE
+    int cin, cout, ksize, stride, pad, relu;
+    int ih, iw, oh, ow;  // conv geometry
+    int first_raw;       // reads the raw observation (u8/f32 NCHW or f32 vector)
+    int scale255;        // fold x ./ 255 into the first layer's load
+    int out_fp32;        // network output layer: fp32 result, fp32 incoming gradient
+    int wt, bt;          // tensor ids
+    long long K;         // GEMM reduction length (conv: k*k*cin, dense: in)
+    long long opr;       // outputs rows per sample (conv: oh*ow, dense: 1)
+    void *cols = nullptr, *out = nullptr, *dout = nullptr, *dcols = nullptr;
+};
+
+struct Chain {
+    std::vector<LayerExec> layers;
+    long long rows_cap = 0;        // sample rows this chain's buffers hold
+    long long in_feat = 0, out_feat = 0;
+    void *out() const { return layers.empty() ? nullptr : layers.back().out; }
+};
+
+}  // namespace zoo
+
+struct zoo_net {
+    zoo_net_desc desc;
+    int prec;      // ZOO_PREC_*
+    int esz;       // bytes per internal activation element (4 | 2)
+    std::vector<zoo::TensorInfo> tensors;
+    long long n_flat = 0;      // padded element count of the flat buffers
+    long long n_params = 0;    // true parameter count
+    float *params = nullptr;   // fp32 master, internal layout
+    zoo::bf16 *shadow = nullptr;  // bf16 copy (BF16 precision only), same layout
+    float *grads = nullptr;    // allocated when a learner/optimiser attaches
+    zoo::Chain a, b, c;
+    int fc = 0, fh = 0, fw = 0;  // flatten space
+    int n_out = 0;
+    long long max_batch = 0, max_q = 0;
+    // fp32 network output / its gradient
+    float *out_final = nullptr, *dout_final = nullptr;
+    // IQN extras
+    void *emb = nullptr, *merged = nullptr, *dmerged = nullptr;
+    float *tau_dev = nullptr;
+    // dueling extras
+    void *dh1 = nullptr, *dh2 = nullptr;
+    float *ws = nullptr;  // split-K workspace
+    size_t ws_elems = 0;
+    void *obs = nullptr;  // staged observation for zoo_net_forward
+    float *stage = nullptr; size_t stage_elems = 0;  // param up/download staging
+    cudaStream_t st = nullptr;
+    bool bwd_ready = false;
+};
+
+namespace zoo {
+zoo_status net_alloc_backward(zoo_net *net);
+// obs: device pointer, raw observation rows [rows][C][H][W] (u8|f32).  tau: device [rows][n_tau] (IQN).
+// Result: net->out_final fp32 [rows (* n_tau)][n_out].
+zoo_status net_forward(zoo_net *net, const void *obs, int obs_dtype, int rows, const float *tau, int n_tau, cudaStream_t st);
+// consumes net->dout_final (fp32, same shape as out_final, for the first `rows` samples) and accumulates into net->grads
+zoo_status net_backward(zoo_net *net, int obs_dtype, const void *obs, int rows, int n_tau, cudaStream_t st);
+zoo_status net_refresh_shadow(zoo_net *net, cudaStream_t st);
+long long obs_elems(const zoo_net *net);
+}  // namespace zoo
