@@ -74,8 +74,11 @@ enum { ZOO_NET_CHAIN = 0,   /* Flux Chain                                       
        ZOO_NET_IQN = 1,     /* ImplicitQuantileNet(psi, phi, header)  iqn.jl:17-33 */
        ZOO_NET_DUELING = 2  /* DuelingNetwork(base, val, adv)     common.jl:44-56 */ };
 
-enum { ZOO_PREC_FP32 = 0, /* fp32 CUDA-core contractions; parity <= 1e-4 rel            */
-       ZOO_PREC_BF16 = 1  /* bf16 operands on tcgen05, fp32 TMEM accumulate; <= 2e-2 rel */ };
+enum { ZOO_PREC_FP32 = 0,      /* fp32 storage; contractions on tcgen05 as 3xTF32 (error-compensated hi/lo split,
+                                   fp32-grade) with CUDA-core fallback for tiny/misaligned shapes; parity <= 1e-4 rel */
+       ZOO_PREC_BF16 = 1,      /* bf16 operands on tcgen05 (kind::f16), fp32 TMEM accumulate; fastest, see DESIGN.md */
+       ZOO_PREC_TF32 = 2,      /* fp32 storage, single-pass tcgen05 kind::tf32                                       */
+       ZOO_PREC_FP32_SIMT = 3  /* fp32 storage, CUDA-core FFMA contractions only (second, independent fp32 path)      */ };
 
 #define ZOO_MAX_LAYERS 12
 typedef struct {
@@ -234,7 +237,7 @@ ZOO_API zoo_status zoo_dp_destroy(zoo_dp *dp);
 /* ------------------------------------------------------------------ test hooks ---------- */
 /* Stand-alone GEMM of the two contraction engines, for parity tests of the kernels themselves:
  * D[M][N] = sum_k A(m,k) B(n,k).  a_kmajor: A stored [M][K] (1) or [K][M] (0); same for B ([N][K] / [K][N]).
- * engine: ZOO_PREC_FP32 (SIMT) or ZOO_PREC_BF16 (tcgen05; inputs rounded to bf16).  Host pointers. */
+ * engine: 0 = CUDA-core fp32, 1 = tcgen05 bf16 (inputs rounded to bf16), 2 = tcgen05 tf32, 3 = tcgen05 3xTF32.  Host pointers. */
 ZOO_API zoo_status zoo_test_gemm(int32_t engine, int32_t M, int32_t N, int32_t K, const float *A, int32_t a_kmajor,
                                  const float *B, int32_t b_kmajor, float *D, int32_t split_k);
 

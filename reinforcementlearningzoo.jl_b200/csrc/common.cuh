@@ -80,6 +80,7 @@ struct Epilogue {
     int rowmul_div = 1;
     long long rowmul_ld = 0;
     int accumulate = 0;  // 1: atomically add into fp32 out (out must be fp32; bias/relu/mask not allowed)
+    int tf32_passes = 0; // fp32 operands on tcgen05: 0 = never (CUDA cores), 1 = plain tf32, 3 = 3xTF32 (fp32-grade)
 };
 
 // fp32 CUDA-core engine (any shapes, fp32 or bf16 inputs, fp32 accumulate)
@@ -89,7 +90,7 @@ zoo_status simt_gemm(const Operand &A, const Operand &B, int M, int N, int K, co
 bool tc_gemm_supported(const Operand &A, const Operand &B, int M, int N, int K);
 zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, int split_k,
                    float *ws, size_t ws_elems, cudaStream_t st);
-// dispatch: tcgen05 when both inputs are bf16 and supported, otherwise SIMT
+// dispatch: tcgen05 when supported (bf16 x bf16, or fp32 x fp32 with epi.tf32_passes > 0), otherwise SIMT
 zoo_status gemm(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, int split_k, float *ws,
                 size_t ws_elems, cudaStream_t st);
 

@@ -132,7 +132,8 @@ zoo_status simt_gemm(const Operand &A, const Operand &B, int M, int N, int K, co
 
 zoo_status gemm(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, int split_k, float *ws,
                 size_t ws_elems, cudaStream_t st) {
-    if (A.is_bf16 && B.is_bf16 && tc_gemm_supported(A, B, M, N, K)) return tc_gemm(A, B, M, N, K, epi, split_k, ws, ws_elems, st);
+    const bool want_tc = (A.is_bf16 && B.is_bf16) || (!A.is_bf16 && !B.is_bf16 && epi.tf32_passes > 0);
+    if (want_tc && tc_gemm_supported(A, B, M, N, K)) return tc_gemm(A, B, M, N, K, epi, split_k, ws, ws_elems, st);
     return simt_gemm(A, B, M, N, K, epi, split_k, ws, ws_elems, st);
 }
 

@@ -1,5 +1,10 @@
-// tcgen05 GEMM engine for sm_100a (ZOO_PREC_BF16 path).
-//   D(m,n) = sum_k A(m,k) B(n,k), bf16 operands, fp32 accumulation in TMEM.
+// tcgen05 GEMM engine for sm_100a.
+//   D(m,n) = sum_k A(m,k) B(n,k), fp32 accumulation in TMEM, three operand modes:
+//     bf16    (EB = 2)        kind::f16  on bf16 operands                          -- ZOO_PREC_BF16
+//     tf32    (EB = 4)        kind::tf32 on fp32 operands, one pass                -- ZOO_PREC_TF32
+//     3xtf32  (EB = 4, X3)    error-compensated: every fp32 operand tile is split in shared memory into
+//                             hi = x & 0xffffe000 and lo = x - hi by the (otherwise idle) epilogue warps and
+//                             the MMA warp issues hi*hi + hi*lo + lo*hi: fp32-grade results -- ZOO_PREC_FP32
 // One 128 x BN output tile (x one K-split) per CTA:
 //   warp 0      TMA producer  (cp.async.bulk.tensor 2D, SWIZZLE_128B, 4-stage mbarrier ring)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, kind::f16, M=128, N=BN, K=16)
@@ -16,8 +21,7 @@
 namespace zoo {
 
 static constexpr int BM = 128;      // UMMA M (cta_group::1)
-static constexpr int BK = 64;       // K elements per stage = one 128-byte swizzle span of bf16
-static constexpr int UMMA_K = 16;   // K per tcgen05.mma for 16-bit inputs
+// per stage: one 128-byte swizzle span of K per row -> BK = 128 / EB elements, 4 MMAs of K = 32 / EB each
 static constexpr int TC_THREADS = 192;
 
 // ---------------------------------------------------------------- PTX wrappers ------------
@@ -69,6 +73,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -92,55 +108,74 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in [0,14),
 // leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version = 1 in [46,48),
 // layout type SWIZZLE_128B = 2 in [61,64).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// 32-bit MN-major operands must use SWIZZLE_128B_BASE32B = 1 (32-byte swizzle atoms, pattern period 4 rows).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 at [4,6), a/b format BF16 = 1 at [7,10)/[10,13),
 // a_major at 15, b_major at 16 (0 = K-major, 1 = MN-major), N >> 3 at [17,23), M >> 4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, uint32_t fmt /*1 = BF16, 2 = TF32*/) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 struct TcParams {
     int M, N, K;
-    int kb_per_split;  // K blocks (of 64) per grid.z slice
+    int kb_per_split;  // K blocks (of 128 bytes of K) per grid.z slice
     Epilogue epi;
     float *ws;  // split-K workspace [M][N] (atomic accumulate) or nullptr
 };
 
-// smem per stage: A tile 128 x 64 bf16 (16 KB) + B tile BN x 64 bf16
-template <int BN>
+// EB: operand element bytes (2 = bf16, 4 = fp32 consumed as tf32).  X3: 3xTF32 split (EB = 4 only).
+// smem per stage: A tile 128 rows x 128 B (16 KB) + B tile BN rows x 128 B; X3 doubles it for the lo tiles.
+template <int EB, int BN, bool X3>
 struct TcCfg {
-    static constexpr int STAGES = BN >= 128 ? 3 : 4;
-    static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BK = 128 / EB;          // K elements per stage
+    static constexpr int UMMA_K = 32 / EB;       // K elements per tcgen05.mma
+    static constexpr int MN_BOX = 128 / EB;      // MN elements per 128-byte row of an MN-major box
+    static constexpr int BOX_BYTES = BK * 128;   // one MN-major box: BK k-rows x 128 B
+    static constexpr int KSTEP_MN = UMMA_K * 128;  // MN-major: one 128-byte row per k
+    // MN-major swizzle atoms: bf16 -> 8 k-rows (SWIZZLE_128B); fp32 -> 4 k-rows (SWIZZLE_128B_BASE32B, the only
+    // MN-major layout tcgen05 accepts for 32-bit operands)
+    static constexpr int MN_SBO = EB == 2 ? 1024 : 512;
+    static constexpr int MN_LAYOUT = EB == 2 ? 2 : 1;
+    static constexpr int A_BYTES = BM * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = RAW_BYTES * (X3 ? 2 : 1);
+    static constexpr int STAGES = X3 ? (BN >= 128 ? 3 : 4) : (BN >= 128 ? 3 : 4);
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
-template <int BN, bool A_K, bool B_K>
+template <int EB>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+    if (EB == 2) umma_bf16(tmem_d, ad, bd, idesc, acc);
+    else umma_tf32(tmem_d, ad, bd, idesc, acc);
+}
+
+template <int EB, int BN, bool A_K, bool B_K, bool X3>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
-    using C = TcCfg<BN>;
+    using C = TcCfg<EB, BN, X3>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = (uint64_t *)(smem + C::STAGES * C::STAGE_BYTES);
     uint64_t *empty_bar = full_bar + C::STAGES;
-    uint64_t *tmem_full_bar = empty_bar + C::STAGES;
+    uint64_t *conv_bar = empty_bar + C::STAGES;  // X3: lo tiles written (128 converter threads arrive)
+    uint64_t *tmem_full_bar = conv_bar + C::STAGES;
     uint32_t *tmem_slot = (uint32_t *)(tmem_full_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    const int total_kb = (P.K + BK - 1) / BK;
+    const int total_kb = (P.K + C::BK - 1) / C::BK;
     const int kb0 = blockIdx.z * P.kb_per_split;
     const int kb1 = min(total_kb, kb0 + P.kb_per_split);
     const int nkb = kb1 - kb0;  // host guarantees >= 1
@@ -149,6 +184,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+            mbar_init(&conv_bar[s], 128);
         }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -169,47 +205,84 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t *sa = smem + s * C::STAGE_BYTES;
                 uint8_t *sb = sa + C::A_BYTES;
-                mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
-                const int k0 = (kb0 + i) * BK;
+                mbar_expect_tx(&full_bar[s], C::RAW_BYTES);
+                const int k0 = (kb0 + i) * C::BK;
                 if (A_K) {
-                    tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box {64 k, 128 rows}
-                } else {
-                    tma_load_2d(sa, &tmA, &full_bar[s], m0, k0);  // box {64 m, 64 k}, two MN halves
-                    tma_load_2d(sa + 8192, &tmA, &full_bar[s], m0 + 64, k0);
-                }
-                if (B_K) {
-                    tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box {64 k, BN rows}
+                    tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box {BK k, 128 rows}
                 } else {
 #pragma unroll
-                    for (int h = 0; h < BN / 64; ++h) tma_load_2d(sb + h * 8192, &tmB, &full_bar[s], n0 + h * 64, k0);
+                    for (int h = 0; h < BM / C::MN_BOX; ++h)  // boxes {MN_BOX m, BK k}
+                        tma_load_2d(sa + h * C::BOX_BYTES, &tmA, &full_bar[s], m0 + h * C::MN_BOX, k0);
+                }
+                if (B_K) {
+                    tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box {BK k, BN rows}
+                } else {
+#pragma unroll
+                    for (int h = 0; h < BN / C::MN_BOX; ++h)
+                        tma_load_2d(sb + h * C::BOX_BYTES, &tmB, &full_bar[s], n0 + h * C::MN_BOX, k0);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN, !A_K, !B_K);
+            constexpr uint32_t idesc = make_idesc(BN, !A_K, !B_K, EB == 2 ? 1u : 2u);
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % C::STAGES;
                 const uint32_t ph = (i / C::STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+                if (X3) mbar_wait(&conv_bar[s], ph);
+                else mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
                 const uint32_t sb = sa + C::A_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    // K-major SW128: 8-row groups 1024 B apart (SBO), 16 K-elements = 32 B inside the swizzle span.
-                    // MN-major SW128: 64-element MN blocks BK*128 B apart (LBO), 8-k groups 1024 B apart (SBO),
-                    //                 16 K-elements = two 8-k groups = 2048 B.
-                    const uint64_t ad = A_K ? make_smem_desc(sa + k * 32, 16, 1024) : make_smem_desc(sa + k * 2048, BK * 128, 1024);
-                    const uint64_t bd = B_K ? make_smem_desc(sb + k * 32, 16, 1024) : make_smem_desc(sb + k * 2048, BK * 128, 1024);
-                    umma_bf16(tmem_base, ad, bd, idesc, (i | k) != 0);
+                for (int k = 0; k < 4; ++k) {
+                    // K-major SW128: 8-row groups 1024 B apart (SBO); one MMA's K slice = 32 B inside the swizzle span.
+                    // MN-major SW128: MN blocks of 128 B BOX_BYTES apart (LBO), 8-k groups 1024 B apart (SBO).
+                    const uint32_t ao = A_K ? k * 32 : k * C::KSTEP_MN;
+                    const uint32_t bo = B_K ? k * 32 : k * C::KSTEP_MN;
+                    const uint64_t ad = A_K ? make_smem_desc(sa + ao, 16, 1024) : make_smem_desc(sa + ao, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
+                    const uint64_t bd = B_K ? make_smem_desc(sb + bo, 16, 1024) : make_smem_desc(sb + bo, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
+                    umma<EB>(tmem_base, ad, bd, idesc, (i | k) != 0);
+                    if (X3) {
+                        // lo tiles live RAW_BYTES above the (in-place truncated) hi tiles, same layout
+                        const uint64_t adl = A_K ? make_smem_desc(sa + C::RAW_BYTES + ao, 16, 1024)
+                                                 : make_smem_desc(sa + C::RAW_BYTES + ao, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
+                        const uint64_t bdl = B_K ? make_smem_desc(sb + C::RAW_BYTES + bo, 16, 1024)
+                                                 : make_smem_desc(sb + C::RAW_BYTES + bo, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
+                        umma<EB>(tmem_base, ad, bdl, idesc, 1);
+                        umma<EB>(tmem_base, adl, bd, idesc, 1);
+                    }
                 }
                 umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
             }
             umma_commit(tmem_full_bar);  // accumulator complete
         }
     } else {
-        // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+        // warps 2..5.  X3: first split every landed fp32 tile into hi (in place) and lo (second half of the stage).
+        if (X3) {
+            const int t = threadIdx.x - 64;  // 0..127
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % C::STAGES;
+                const uint32_t ph = (i / C::STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                uint4 *raw = reinterpret_cast<uint4 *>(smem + s * C::STAGE_BYTES);
+                uint4 *lo = reinterpret_cast<uint4 *>(smem + s * C::STAGE_BYTES + C::RAW_BYTES);
+#pragma unroll 4
+                for (int j = t; j < C::RAW_BYTES / 16; j += 128) {
+                    uint4 v = raw[j], h, l;
+                    h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+                    l.x = __float_as_uint(__fsub_rn(__uint_as_float(v.x), __uint_as_float(h.x)));
+                    l.y = __float_as_uint(__fsub_rn(__uint_as_float(v.y), __uint_as_float(h.y)));
+                    l.z = __float_as_uint(__fsub_rn(__uint_as_float(v.z), __uint_as_float(h.z)));
+                    l.w = __float_as_uint(__fsub_rn(__uint_as_float(v.w), __uint_as_float(h.w)));
+                    raw[j] = h;
+                    lo[j] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
+                mbar_arrive(&conv_bar[s]);
+            }
+        }
+        // epilogue: TMEM lane quadrant = warp % 4
         const int q = warp & 3;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
@@ -259,20 +332,21 @@ static EncodeTiledFn get_encode() {
     return g_encode;
 }
 
-// 2D bf16 tensor map: inner (contiguous) extent d0, outer extent d1, row pitch ld elements, box {b0, b1}, SWIZZLE_128B
-static zoo_status make_map(CUtensorMap *tm, const void *p, long long d0, long long d1, long long ld, int b0, int b1) {
+// 2D tensor map: inner (contiguous) extent d0, outer extent d1, row pitch ld elements, box {b0, b1}, SWIZZLE_128B
+static zoo_status make_map(CUtensorMap *tm, const void *p, int eb, long long d0, long long d1, long long ld, int b0, int b1, bool mn_major) {
     EncodeTiledFn enc = get_encode();
     if (!enc) {
         set_err("cuTensorMapEncodeTiled not available from the driver");
         return ZOO_CUDA_ERROR;
     }
     cuuint64_t dims[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * eb};
     cuuint32_t box[2] = {(cuuint32_t)b0, (cuuint32_t)b1};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(p), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(tm, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(p), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     (eb == 4 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_err("cuTensorMapEncodeTiled failed (%d): dims %lld x %lld ld %lld box %d x %d ptr %p", (int)r, d0, d1, ld, b0, b1, p);
         return ZOO_CUDA_ERROR;
@@ -281,41 +355,72 @@ static zoo_status make_map(CUtensorMap *tm, const void *p, long long d0, long lo
 }
 
 bool tc_gemm_supported(const Operand &A, const Operand &B, int M, int N, int K) {
-    if (!A.is_bf16 || !B.is_bf16) return false;
-    if (M < 1 || N < 8 || K < 8) return false;
-    if (A.ld % 8 || B.ld % 8) return false;                                    // 16-byte global strides
+    if (A.is_bf16 != B.is_bf16) return false;
+    const int al = A.is_bf16 ? 8 : 4;  // elements per 16 bytes
+    if (M < 1 || N < 8 || K < al) return false;
+    if (A.ld % al || B.ld % al) return false;                                  // 16-byte global strides
     if (((uintptr_t)A.p & 15) || ((uintptr_t)B.p & 15)) return false;        // 16-byte base alignment
     return true;
 }
 
 zoo_status splitk_finish(const float *ws, int M, int N, const Epilogue &epi, cudaStream_t st);
 
-template <int BN, bool A_K, bool B_K>
+template <int EB, int BN, bool A_K, bool B_K, bool X3>
 static zoo_status launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid, cudaStream_t st) {
-    using C = TcCfg<BN>;
+    using C = TcCfg<EB, BN, X3>;
     static bool attr_set = false;
     if (!attr_set) {
-        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, A_K, B_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, A_K, B_K, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    tc_gemm_kernel<BN, A_K, B_K><<<grid, TC_THREADS, C::SMEM, st>>>(tmA, tmB, P);
+    tc_gemm_kernel<EB, BN, A_K, B_K, X3><<<grid, TC_THREADS, C::SMEM, st>>>(tmA, tmB, P);
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
 
+template <int EB, int BN, bool X3>
+static zoo_status launch_tc_major(bool ak, bool bk, const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid,
+                                  cudaStream_t st) {
+    if (ak && bk) return launch_tc<EB, BN, true, true, X3>(tmA, tmB, P, grid, st);
+    if (ak && !bk) return launch_tc<EB, BN, true, false, X3>(tmA, tmB, P, grid, st);
+    if (!ak && bk) return launch_tc<EB, BN, false, true, X3>(tmA, tmB, P, grid, st);
+    return launch_tc<EB, BN, false, false, X3>(tmA, tmB, P, grid, st);
+}
+
+template <int EB, bool X3>
+static zoo_status launch_tc_bn(int BN, bool ak, bool bk, const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid,
+                               cudaStream_t st) {
+    if (BN == 32) {
+        if (EB == 2) {  // bf16 MN-major boxes are 64 wide: BN = 32 only with a K-major B
+            if (ak) return launch_tc<EB, 32, true, true, X3>(tmA, tmB, P, grid, st);
+            return launch_tc<EB, 32, false, true, X3>(tmA, tmB, P, grid, st);
+        }
+        return launch_tc_major<EB, 32, X3>(ak, bk, tmA, tmB, P, grid, st);
+    }
+    if (BN == 64) return launch_tc_major<EB, 64, X3>(ak, bk, tmA, tmB, P, grid, st);
+    return launch_tc_major<EB, 128, X3>(ak, bk, tmA, tmB, P, grid, st);
+}
+
+// tf32_passes: for fp32 operands 1 (plain tf32) or 3 (3xTF32); ignored for bf16 operands
 zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, int split_k, float *ws,
                    size_t ws_elems, cudaStream_t st) {
     ZOO_REQUIRE(tc_gemm_supported(A, B, M, N, K), "tc_gemm: unsupported operands (M=%d N=%d K=%d)", M, N, K);
-    // MN-major B tiles are loaded in 64-wide boxes -> BN must be a multiple of 64 there
-    int BN = (N <= 32 && B.kmajor) ? 32 : (N <= 64 ? 64 : 128);
+    const int eb = A.is_bf16 ? 2 : 4;
+    const int bk = 128 / eb, mn_box = 128 / eb;
+    const bool x3 = eb == 4 && epi.tf32_passes == 3;
+    int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+    if (eb == 2 && BN == 32 && !B.kmajor) BN = 64;
     dim3 grid(cdiv(M, BM), cdiv(N, BN), 1);
-    const int total_kb = cdiv(K, BK);
+    const int total_kb = cdiv(K, bk);
     if (split_k <= 0) {
         long long tiles = (long long)grid.x * grid.y;
         split_k = 1;
         if (tiles < 148 && total_kb >= 4) split_k = (int)std::min<long long>(total_kb / 2, (296 + tiles - 1) / tiles);
         if (split_k < 1) split_k = 1;
     }
+    // TMEM accumulation truncates (measured: 5.8e-5 rel after K = 7744 in one chain vs 1.4e-6 split): in the
+    // fp32-grade mode cap one accumulation chain at 32 K-blocks (1024 elements)
+    if (x3 && cdiv(total_kb, split_k) > 32) split_k = cdiv(total_kb, 32);
     split_k = std::min(split_k, total_kb);
     int kbps = cdiv(total_kb, split_k);
     split_k = cdiv(total_kb, kbps);
@@ -330,24 +435,14 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
         P.ws = ws;
     }
     CUtensorMap tmA, tmB;
-    if (A.kmajor) ZOO_TRY(make_map(&tmA, A.p, K, M, A.ld, BK, BM));
-    else ZOO_TRY(make_map(&tmA, A.p, M, K, A.ld, 64, BK));
-    if (B.kmajor) ZOO_TRY(make_map(&tmB, B.p, K, N, B.ld, BK, BN));
-    else ZOO_TRY(make_map(&tmB, B.p, N, K, B.ld, 64, BK));
+    if (A.kmajor) ZOO_TRY(make_map(&tmA, A.p, eb, K, M, A.ld, bk, BM, false));
+    else ZOO_TRY(make_map(&tmA, A.p, eb, M, K, A.ld, mn_box, bk, true));
+    if (B.kmajor) ZOO_TRY(make_map(&tmB, B.p, eb, K, N, B.ld, bk, BN, false));
+    else ZOO_TRY(make_map(&tmB, B.p, eb, N, K, B.ld, mn_box, bk, true));
 
-#define GO(BNv)                                                                             \
-    do {                                                                                    \
-        if (A.kmajor && B.kmajor) ZOO_TRY((launch_tc<BNv, true, true>(tmA, tmB, P, grid, st)));      \
-        else if (A.kmajor && !B.kmajor) ZOO_TRY((launch_tc<BNv, true, false>(tmA, tmB, P, grid, st))); \
-        else if (!A.kmajor && B.kmajor) ZOO_TRY((launch_tc<BNv, false, true>(tmA, tmB, P, grid, st))); \
-        else ZOO_TRY((launch_tc<BNv, false, false>(tmA, tmB, P, grid, st)));                         \
-    } while (0)
-    if (BN == 32) {
-        if (A.kmajor) ZOO_TRY((launch_tc<32, true, true>(tmA, tmB, P, grid, st)));
-        else ZOO_TRY((launch_tc<32, false, true>(tmA, tmB, P, grid, st)));
-    } else if (BN == 64) GO(64);
-    else GO(128);
-#undef GO
+    if (eb == 2) ZOO_TRY((launch_tc_bn<2, false>(BN, A.kmajor, B.kmajor, tmA, tmB, P, grid, st)));
+    else if (x3) ZOO_TRY((launch_tc_bn<4, true>(BN, A.kmajor, B.kmajor, tmA, tmB, P, grid, st)));
+    else ZOO_TRY((launch_tc_bn<4, false>(BN, A.kmajor, B.kmajor, tmA, tmB, P, grid, st)));
     if (P.ws) ZOO_TRY(splitk_finish(P.ws, M, N, epi, st));
     return ZOO_OK;
 }

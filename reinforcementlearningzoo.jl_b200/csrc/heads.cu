@@ -1,0 +1,292 @@
+// Loss heads (see heads.cuh).  Reference lines restated per kernel.
+#include <curand_kernel.h>
+
+#include "heads.cuh"
+
+namespace zoo {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide reductions (blockDim.x multiple of 32, <= 1024); result identical in every thread
+__device__ float block_sum(float v, float *red) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[w] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int i = 0; i < nw; ++i) s += red[i];
+    return s;
+}
+__device__ float block_max(float v, float *red) {
+    v = warp_max(v);
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[w] = v;
+    __syncthreads();
+    float s = red[0];
+    for (int i = 1; i < nw; ++i) s = fmaxf(s, red[i]);
+    return s;
+}
+
+__device__ __forceinline__ float sample_scale(const HeadArgs &h, int b) {
+    // dot(w, l) * 1//B with w ./= maximum(w)  (prioritized_dqn.jl:126,141) or mean (dqn.jl:137)
+    if (h.w_raw) return __fmul_rn(__fdiv_rn(h.w_raw[b], h.w_max[0]), h.inv_B);
+    return h.inv_B;
+}
+// Julia argmax/findmax order: NaN counts as the maximum, ties go to the lowest index (q8)
+__device__ __forceinline__ bool better(float v, float best) { return v > best || (isnan(v) && !isnan(best)); }
+
+// w = 1f0 ./ ((priority .+ 1f-10) .^ beta)  -- prioritized_dqn.jl:125, rainbow.jl:171, iqn.jl:197
+__global__ void __launch_bounds__(1024) per_weights_kernel(const float *__restrict__ priority, float beta, int B,
+                                                           float *__restrict__ w_raw, float *__restrict__ w_max) {
+    __shared__ float red[32];
+    float mx = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float w = __fdiv_rn(1.0f, powf(__fadd_rn(priority[b], 1e-10f), beta));
+        w_raw[b] = w;
+        mx = fmaxf(mx, w);
+    }
+    mx = block_max(mx, red);
+    if (threadIdx.x == 0) w_max[0] = mx;
+}
+
+// dqn.jl:115-142, prioritized_dqn.jl:129-146, basic_dqn.jl:78-87
+__global__ void dqn_head_kernel(int kind, int double_dqn, HeadArgs h, const float *__restrict__ q_on, const float *__restrict__ q_t,
+                                float gamma_n, float *__restrict__ dout) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= h.B) return;
+    const int A = h.A;
+    const uint8_t *mk = h.mask ? h.mask + (size_t)b * A : nullptr;
+    float q2;
+    int amax = 0;
+    if (kind == ZOO_LEARNER_BASIC_DQN) {
+        const float *qn = q_on + (size_t)(h.B + b) * A;  // Q(s') of the same network
+        float best = qn[0];
+        for (int a = 1; a < A; ++a) if (better(qn[a], best)) { best = qn[a]; amax = a; }
+        q2 = best;
+    } else if (double_dqn) {
+        const float *qn = q_on + (size_t)(h.B + b) * A;  // online Q(s') selects, target evaluates
+        float best = qn[0] + ((mk && !mk[0]) ? -INFINITY : 0.f);
+        for (int a = 1; a < A; ++a) {
+            float v = qn[a] + ((mk && !mk[a]) ? -INFINITY : 0.f);
+            if (better(v, best)) { best = v; amax = a; }
+        }
+        q2 = q_t[(size_t)b * A + amax];
+    } else {
+        const float *qn = q_t + (size_t)b * A;
+        float best = qn[0] + ((mk && !mk[0]) ? -INFINITY : 0.f);
+        for (int a = 1; a < A; ++a) {
+            float v = qn[a] + ((mk && !mk[a]) ? -INFINITY : 0.f);
+            if (better(v, best)) { best = v; amax = a; }
+        }
+        q2 = best;
+    }
+    // G = r .+ gamma^n .* (1 .- t) .* q'
+    const float disc = __fmul_rn(gamma_n, h.terminal[b] ? 0.f : 1.f);
+    const float G = __fadd_rn(h.reward[b], __fmul_rn(disc, q2));
+    const int a_b = h.action[b];
+    const float q = q_on[(size_t)b * A + a_b];
+    // huber_loss(G, q; delta = 1): strict < mask (q4)
+    const float e = __fsub_rn(G, q), ae = fabsf(e);
+    const bool quad = ae < 1.0f;
+    h.per_sample[b] = quad ? __fmul_rn(__fmul_rn(ae, ae), 0.5f) : __fsub_rn(ae, 0.5f);
+    const float dG = quad ? e : (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f));
+    const float sc = sample_scale(h, b);
+    for (int a = 0; a < A; ++a) dout[(size_t)b * A + a] = a == a_b ? -dG * sc : 0.f;
+    if (kind == ZOO_LEARNER_BASIC_DQN)  // gradient also flows through the target (q3)
+        for (int a = 0; a < A; ++a) dout[(size_t)(h.B + b) * A + a] = a == amax ? dG * disc * sc : 0.f;
+}
+
+// rainbow.jl:146-191 + project_distribution rainbow.jl:204-221 + logitcrossentropy (Dopamine_Rainbow_Atari.jl:54)
+// one CTA of 64 threads per sample; thread j owns atom j
+__global__ void __launch_bounds__(64) c51_head_kernel(HeadArgs h, int n, const float *__restrict__ tlogits, const float *__restrict__ logits,
+                                                      const float *__restrict__ support, float delta_z, float vmin, float vmax,
+                                                      float gamma_n, float *__restrict__ dout, float *__restrict__ target_dist) {
+    __shared__ float red[2];
+    __shared__ float p_sel[64], cl[64], dsl[64];
+    const int b = blockIdx.x, j = threadIdx.x, A = h.A;
+    const bool valid = j < n;
+    const float zj = valid ? support[j] : 0.f;
+    // next_probs = softmax over atoms; next_q = sum(support .* next_probs); mask; first-max action
+    float best = 0.f, p_keep = 0.f;
+    for (int a = 0; a < A; ++a) {
+        const float x = valid ? tlogits[((size_t)b * A + a) * n + j] : -INFINITY;
+        const float mx = block_max(x, red);
+        const float ex = valid ? expf(x - mx) : 0.f;
+        const float sm = block_sum(ex, red);
+        const float p = ex / sm;
+        float q = block_sum(valid ? __fmul_rn(zj, p) : 0.f, red);
+        if (h.mask && !h.mask[(size_t)b * A + a]) q += -INFINITY;
+        if (a == 0 || better(q, best)) { best = q; p_keep = p; }
+    }
+    // target_support = r .+ support * (gamma^n .* (1 .- t)); clamp to [Vmin, Vmax]
+    const float disc = __fmul_rn(gamma_n, h.terminal[b] ? 0.f : 1.f);
+    const float Tz = __fadd_rn(h.reward[b], __fmul_rn(zj, disc));
+    p_sel[j] = valid ? p_keep : 0.f;
+    cl[j] = fminf(fmaxf(Tz, vmin), vmax);
+    __syncthreads();
+    // out[j] = sum_i p[i] * clamp(1 - |clamp(Tz[i]) - z[j]| / dz, 0, 1)   (dense triangular kernel)
+    float m = 0.f;
+    if (valid) {
+        for (int i = 0; i < n; ++i) {
+            float k = __fsub_rn(1.0f, __fdiv_rn(fabsf(__fsub_rn(cl[i], zj)), delta_z));
+            k = fminf(fmaxf(k, 0.f), 1.f);
+            m = __fadd_rn(m, __fmul_rn(k, p_sel[i]));
+        }
+        if (target_dist) target_dist[(size_t)b * n + j] = m;
+    }
+    // batch_losses = -sum(target .* logsoftmax(select_logits)); d/dlogits = softmax * sum(target) - target
+    const int a_b = h.action[b];
+    const float x = valid ? logits[((size_t)b * A + a_b) * n + j] : -INFINITY;
+    const float mx = block_max(x, red);
+    const float zc = x - mx;
+    const float lse = logf(block_sum(valid ? expf(zc) : 0.f, red));
+    const float lsm = zc - lse;
+    const float per = -block_sum(valid ? m * lsm : 0.f, red);
+    const float msum = block_sum(m, red);
+    const float sc = sample_scale(h, b);
+    dsl[j] = valid ? (expf(lsm) * msum - m) * sc : 0.f;
+    if (j == 0) h.per_sample[b] = per;
+    __syncthreads();
+    for (int idx = j; idx < A * n; idx += 64) {
+        const int a = idx / n, jj = idx - a * n;
+        dout[(size_t)b * A * n + idx] = a == a_b ? dsl[jj] : 0.f;
+    }
+}
+
+// iqn.jl:175-189: mean over N' quantiles, (mask), first-max action, target = r + gamma * (1 - t) * z_t[a*]  (gamma^1: q1)
+__global__ void iqn_target_kernel(HeadArgs h, int Np, const float *__restrict__ zt, float gamma, float *__restrict__ target) {
+    __shared__ float red[32];
+    const int b = blockIdx.x, i = threadIdx.x, A = h.A;
+    const bool valid = i < Np;
+    float best = 0.f;
+    int sel = 0;
+    for (int a = 0; a < A; ++a) {
+        float s = block_sum(valid ? zt[((size_t)b * Np + i) * A + a] : 0.f, red);
+        float avg = __fdiv_rn(s, (float)Np);
+        if (h.mask && !h.mask[(size_t)b * A + a]) avg += -INFINITY;
+        if (a == 0 || better(avg, best)) { best = avg; sel = a; }
+    }
+    if (valid) {
+        const float disc = __fmul_rn(gamma, h.terminal[b] ? 0.f : 1.f);
+        target[(size_t)b * Np + i] = __fadd_rn(h.reward[b], __fmul_rn(disc, zt[((size_t)b * Np + i) * A + sel]));
+    }
+}
+
+// iqn.jl:203-222: TD[i,j] = target[i] - q[j]; raw = |tau[j] - 1{TD<0}| * huber_kappa(TD) / kappa;
+// per-sample = mean_j sum_i raw (sum over N', mean over N: q2)
+__global__ void iqn_loss_kernel(HeadArgs h, int N, int Np, const float *__restrict__ z, const float *__restrict__ target,
+                                const float *__restrict__ tau, float kappa, float *__restrict__ dout) {
+    extern __shared__ float tgt[];  // Np
+    __shared__ float red[32];
+    const int b = blockIdx.x, j = threadIdx.x, A = h.A;
+    for (int i = j; i < Np; i += blockDim.x) tgt[i] = target[(size_t)b * Np + i];
+    __syncthreads();
+    const bool valid = j < N;
+    const int a_b = h.action[b];
+    float acc = 0.f, dacc = 0.f;
+    if (valid) {
+        const float q = z[((size_t)b * N + j) * A + a_b];
+        const float tj = tau[(size_t)b * N + j];
+        for (int i = 0; i < Np; ++i) {
+            const float TD = __fsub_rn(tgt[i], q);
+            const float ae = fabsf(TD);
+            const float quad = fminf(ae, kappa);
+            const float lin = __fsub_rn(ae, quad);
+            const float hub = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, quad), quad), __fmul_rn(kappa, lin));
+            const float wgt = fabsf(__fsub_rn(tj, TD < 0.f ? 1.f : 0.f));
+            acc = __fadd_rn(acc, __fdiv_rn(__fmul_rn(wgt, hub), kappa));
+            dacc += wgt * fminf(fmaxf(TD, -kappa), kappa) / kappa;
+        }
+    }
+    const float tot = block_sum(acc, red);
+    if (j == 0) h.per_sample[b] = __fdiv_rn(tot, (float)N);
+    if (valid) {
+        const float dq = -dacc / (float)N * sample_scale(h, b);
+        for (int a = 0; a < A; ++a) dout[((size_t)b * N + j) * A + a] = a == a_b ? dq : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(1024) loss_reduce_kernel(HeadArgs h, float beta, float *__restrict__ loss, float *__restrict__ prio_out) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int b = threadIdx.x; b < h.B; b += blockDim.x) {
+        const float l = h.per_sample[b];
+        acc += l * sample_scale(h, b);
+        // (batch_losses .+ 1f-10) .^ beta  -- prioritized_dqn.jl:143
+        if (prio_out) prio_out[b] = powf(__fadd_rn(l, 1e-10f), beta);
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) loss[0] = acc;
+}
+
+// tau ~ U[0,1) on the device (iqn.jl:173,191) when the batch carries none: Philox4x32-10, one counter tick per update
+__global__ void tau_kernel(float *__restrict__ tau, long long n, unsigned long long seed, const unsigned long long *__restrict__ counter,
+                           int stream_id) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    curandStatePhilox4_32_10_t s;
+    curand_init(seed, (unsigned long long)(i / 4), (counter[0] * 2 + stream_id) * 4ull, &s);
+    float4 r = curand_uniform4(&s);  // (0,1]
+    float v[4] = {1.0f - r.x, 1.0f - r.y, 1.0f - r.z, 1.0f - r.w};  // -> [0,1)
+    for (int k = 0; k < 4 && i + k < n; ++k) tau[i + k] = v[k];
+}
+
+// ---------------------------------------------------------------- launchers ---------------
+zoo_status launch_per_weights(const float *priority, float beta, int B, float *w_raw, float *w_max, cudaStream_t st) {
+    per_weights_kernel<<<1, 1024, 0, st>>>(priority, beta, B, w_raw, w_max);
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+zoo_status launch_dqn_head(int kind, int double_dqn, const HeadArgs &h, const float *q_on, const float *q_t, float gamma_n,
+                           float *dout, cudaStream_t st) {
+    dqn_head_kernel<<<cdiv(h.B, 128), 128, 0, st>>>(kind, double_dqn, h, q_on, q_t, gamma_n, dout);
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+zoo_status launch_c51_head(const HeadArgs &h, int n_atoms, const float *tlogits, const float *logits, const float *support,
+                           float delta_z, float vmin, float vmax, float gamma_n, float *dout, float *target_dist, cudaStream_t st) {
+    ZOO_REQUIRE(n_atoms >= 2 && n_atoms <= 64, "C51 head supports 2..64 atoms, got %d", n_atoms);
+    c51_head_kernel<<<h.B, 64, 0, st>>>(h, n_atoms, tlogits, logits, support, delta_z, vmin, vmax, gamma_n, dout, target_dist);
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+static int pow2_threads(int n) {
+    int t = 32;
+    while (t < n) t <<= 1;
+    return t;
+}
+zoo_status launch_iqn_target(const HeadArgs &h, int Np, const float *zt, float gamma, float *target, cudaStream_t st) {
+    ZOO_REQUIRE(Np >= 1 && Np <= 1024, "IQN: N' must be in 1..1024");
+    iqn_target_kernel<<<h.B, pow2_threads(Np), 0, st>>>(h, Np, zt, gamma, target);
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+zoo_status launch_iqn_loss(const HeadArgs &h, int N, int Np, const float *z, const float *target, const float *tau, float kappa,
+                           float *dout, cudaStream_t st) {
+    ZOO_REQUIRE(N >= 1 && N <= 1024 && Np >= 1 && Np <= 1024, "IQN: N and N' must be in 1..1024");
+    iqn_loss_kernel<<<h.B, pow2_threads(N), Np * sizeof(float), st>>>(h, N, Np, z, target, tau, kappa, dout);
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+zoo_status launch_loss_reduce(const HeadArgs &h, float beta, float *loss, float *prio_out, cudaStream_t st) {
+    loss_reduce_kernel<<<1, 1024, 0, st>>>(h, beta, loss, prio_out);
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+zoo_status launch_tau(float *tau, long long n, unsigned long long seed, const unsigned long long *counter, int stream_id, cudaStream_t st) {
+    tau_kernel<<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(tau, n, seed, counter, stream_id);
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+
+}  // namespace zoo

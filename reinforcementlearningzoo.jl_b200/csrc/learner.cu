@@ -1,0 +1,430 @@
+// Optimisers (Flux RMSProp / ADAM) and the learner update orchestration.
+// Reference: update!(learner, batch) basic_dqn.jl:69-90, dqn.jl:102-145, prioritized_dqn.jl:111-151,
+//            rainbow.jl:126-196, iqn.jl:159-237; update!(Q, gs) -> Flux.Optimise.update!.
+#include <cmath>
+
+#include "heads.cuh"
+#include "net.cuh"
+
+extern "C" zoo_status zoo_internal_tensor_io(zoo_net *net, float *flat, int32_t id, float *host, int64_t n, int to_device);
+
+namespace zoo {
+zoo_status dp_allreduce_sum(zoo_dp *dp, float *buf, long long n, cudaStream_t st);
+zoo_status dp_allreduce_max(zoo_dp *dp, float *buf, long long n, cudaStream_t st);
+int dp_world(const zoo_dp *dp);
+
+struct OptScalars {
+    double b1p, b2p;        // beta^t carried like Flux's per-array state (starts at beta)
+    float c1, c2;           // 1/(1-b1p), 1/(1-b2p) for the step being applied
+    unsigned long long t;   // optimiser steps applied so far
+    unsigned long long rng; // tau stream counter (one tick per learner update)
+};
+
+// one thread: latch this step's bias corrections, then advance beta^t (ADAM) and the counters
+__global__ void opt_tick_kernel(OptScalars *s, double b1, double b2) {
+    s->c1 = (float)(1.0 / (1.0 - s->b1p));
+    s->c2 = (float)(1.0 / (1.0 - s->b2p));
+    s->b1p *= b1;
+    s->b2p *= b2;
+    s->t += 1;
+}
+__global__ void rng_tick_kernel(OptScalars *s) { s->rng += 1; }
+
+// RMSProp: acc = rho*acc + (1-rho)*g^2;  p -= g * eta / (sqrt(acc) + eps).  fp32 arithmetic with fp64-derived scalars.
+__global__ void rmsprop_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ acc, bf16 *__restrict__ shadow,
+                               long long n4, float rho, float omr, float eta, float eps) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 pv = reinterpret_cast<float4 *>(p)[i];
+    const float4 gv = reinterpret_cast<const float4 *>(g)[i];
+    float4 av = reinterpret_cast<float4 *>(acc)[i];
+    float *pp = &pv.x; const float *gp = &gv.x; float *ap = &av.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float gg = gp[k];
+        const float a = rho * ap[k] + omr * (gg * gg);
+        ap[k] = a;
+        pp[k] -= gg * (eta / (sqrtf(a) + eps));
+    }
+    reinterpret_cast<float4 *>(p)[i] = pv;
+    reinterpret_cast<float4 *>(acc)[i] = av;
+    if (shadow) {
+        reinterpret_cast<__nv_bfloat162 *>(shadow)[2 * i] = __floats2bfloat162_rn(pv.x, pv.y);
+        reinterpret_cast<__nv_bfloat162 *>(shadow)[2 * i + 1] = __floats2bfloat162_rn(pv.z, pv.w);
+    }
+}
+
+// ADAM: m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g^2; p -= m/(1-b1^t) / (sqrt(v/(1-b2^t)) + eps) * eta
+__global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+                            bf16 *__restrict__ shadow, long long n4, float b1, float omb1, float b2, float omb2, float eta, float eps,
+                            const OptScalars *__restrict__ sc) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float c1 = sc->c1, c2 = sc->c2;
+    float4 pv = reinterpret_cast<float4 *>(p)[i];
+    const float4 gv = reinterpret_cast<const float4 *>(g)[i];
+    float4 mv = reinterpret_cast<float4 *>(m)[i];
+    float4 vv = reinterpret_cast<float4 *>(v)[i];
+    float *pp = &pv.x; const float *gp = &gv.x; float *mp = &mv.x; float *vp = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float gg = gp[k];
+        const float mm = b1 * mp[k] + omb1 * gg;
+        const float vn = b2 * vp[k] + omb2 * (gg * gg);
+        mp[k] = mm; vp[k] = vn;
+        pp[k] -= (mm * c1) / (sqrtf(vn * c2) + eps) * eta;
+    }
+    reinterpret_cast<float4 *>(p)[i] = pv;
+    reinterpret_cast<float4 *>(m)[i] = mv;
+    reinterpret_cast<float4 *>(v)[i] = vv;
+    if (shadow) {
+        reinterpret_cast<__nv_bfloat162 *>(shadow)[2 * i] = __floats2bfloat162_rn(pv.x, pv.y);
+        reinterpret_cast<__nv_bfloat162 *>(shadow)[2 * i + 1] = __floats2bfloat162_rn(pv.z, pv.w);
+    }
+}
+
+}  // namespace zoo
+
+using namespace zoo;
+
+struct zoo_opt {
+    zoo_net *net;
+    int kind;
+    double eta, a, b, eps;
+    float *s0 = nullptr, *s1 = nullptr;  // acc | m, v  (flat, internal layout)
+    OptScalars *sc = nullptr;            // device
+    long long host_t = 0;
+};
+
+struct zoo_learner {
+    zoo_learner_cfg cfg;
+    zoo_net *online, *target;
+    zoo_opt *opt;
+    zoo_dp *dp;
+    cudaStream_t st;
+    int B;
+    int obs_dtype = -1;
+    // device staging of the batch
+    void *d_obs = nullptr;  // [2B][obs] : state rows 0..B-1, next_state rows B..2B-1
+    int *d_action = nullptr; float *d_reward = nullptr; uint8_t *d_terminal = nullptr; float *d_priority = nullptr;
+    uint8_t *d_mask = nullptr; float *d_tau = nullptr, *d_taup = nullptr;
+    float *d_support = nullptr, *d_target = nullptr, *d_tdist = nullptr;
+    float *d_per = nullptr, *d_prio = nullptr, *d_wraw = nullptr, *d_wmax = nullptr;
+    float *d_loss = nullptr;  // lives at grads[n_flat] so one all-reduce covers gradients and loss
+    float gamma_n;
+    int last_launches = 0;
+    // CUDA graph of the device part of compute_grads + apply
+    int use_graph = 0;
+    cudaGraphExec_t gexec = nullptr;
+    int graph_key = -1;  // encodes (has_priority, has_mask, has_tau, obs_dtype, full)
+    int graph_launches = 0;
+    int warm = 0;
+};
+
+static zoo_status opt_step(zoo_opt *o, cudaStream_t st) {
+    zoo_net *net = o->net;
+    const long long n4 = net->n_flat / 4;
+    opt_tick_kernel<<<1, 1, 0, st>>>(o->sc, o->a, o->b);
+    ZOO_LAUNCH_CHECK();
+    if (o->kind == ZOO_OPT_RMSPROP)
+        rmsprop_kernel<<<cdiv(n4, 256), 256, 0, st>>>(net->params, net->grads, o->s0, net->shadow, n4, (float)o->a, (float)(1.0 - o->a),
+                                                      (float)o->eta, (float)o->eps);
+    else
+        adam_kernel<<<cdiv(n4, 256), 256, 0, st>>>(net->params, net->grads, o->s0, o->s1, net->shadow, n4, (float)o->a, (float)(1.0 - o->a),
+                                                   (float)o->b, (float)(1.0 - o->b), (float)o->eta, (float)o->eps, o->sc);
+    ZOO_LAUNCH_CHECK();
+    o->host_t += 1;
+    return ZOO_OK;
+}
+
+// everything between "batch is on the device" and "results are on the device"
+static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bool has_tau) {
+    const zoo_learner_cfg &c = L->cfg;
+    zoo_net *on = L->online, *tg = L->target;
+    cudaStream_t st = L->st;
+    const int B = L->B;
+    const size_t obs_row = (size_t)obs_elems(on) * (L->obs_dtype == ZOO_OBS_U8 ? 1 : 4);
+    const void *s_ptr = L->d_obs;
+    const void *s2_ptr = (const uint8_t *)L->d_obs + (size_t)B * obs_row;
+    const int world = L->dp ? dp_world(L->dp) : 1;
+    ZOO_CUDA(cudaMemsetAsync(on->grads, 0, (on->n_flat + 64) * sizeof(float), st));
+    HeadArgs h;
+    h.B = B; h.A = c.n_actions; h.action = L->d_action; h.reward = L->d_reward; h.terminal = L->d_terminal;
+    h.mask = has_mask ? L->d_mask : nullptr; h.w_raw = nullptr; h.w_max = nullptr;
+    h.inv_B = 1.0f / (float)((long long)B * world); h.per_sample = L->d_per;
+    const bool per_kind = c.kind == ZOO_LEARNER_PRIORITIZED_DQN || ((c.kind == ZOO_LEARNER_RAINBOW || c.kind == ZOO_LEARNER_IQN) && has_prio);
+    if (per_kind) {
+        ZOO_TRY(launch_per_weights(L->d_priority, c.beta_priority, B, L->d_wraw, L->d_wmax, st));
+        if (L->dp) ZOO_TRY(dp_allreduce_max(L->dp, L->d_wmax, 1, st));
+        h.w_raw = L->d_wraw; h.w_max = L->d_wmax;
+    }
+    int bwd_rows = B, n_tau = 0;
+    if (c.kind == ZOO_LEARNER_BASIC_DQN) {
+        ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, 2 * B, nullptr, 0, st));  // Q([s; s'])
+        ZOO_TRY(launch_dqn_head(c.kind, 0, h, on->out_final, nullptr, c.gamma, on->dout_final, st));
+        bwd_rows = 2 * B;
+    } else if (c.kind == ZOO_LEARNER_DQN || c.kind == ZOO_LEARNER_PRIORITIZED_DQN) {
+        const int dbl = c.kind == ZOO_LEARNER_DQN && c.double_dqn;
+        ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, dbl ? 2 * B : B, nullptr, 0, st));
+        ZOO_TRY(net_forward(tg, s2_ptr, L->obs_dtype, B, nullptr, 0, st));
+        ZOO_TRY(launch_dqn_head(c.kind, dbl, h, on->out_final, tg->out_final, L->gamma_n, on->dout_final, st));
+    } else if (c.kind == ZOO_LEARNER_RAINBOW) {
+        ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, B, nullptr, 0, st));
+        ZOO_TRY(net_forward(tg, s2_ptr, L->obs_dtype, B, nullptr, 0, st));
+        ZOO_TRY(launch_c51_head(h, c.n_atoms, tg->out_final, on->out_final, L->d_support, c.delta_z, c.v_min, c.v_max, L->gamma_n,
+                                on->dout_final, L->d_tdist, st));
+    } else {  // IQN
+        if (!has_tau) {
+            ZOO_TRY(launch_tau(L->d_taup, (long long)B * c.N_prime, c.seed, &L->opt->sc->rng, 0, st));
+            ZOO_TRY(launch_tau(L->d_tau, (long long)B * c.N, c.seed, &L->opt->sc->rng, 1, st));
+            rng_tick_kernel<<<1, 1, 0, st>>>(L->opt->sc);
+            ZOO_LAUNCH_CHECK();
+        }
+        ZOO_TRY(net_forward(tg, s2_ptr, L->obs_dtype, B, L->d_taup, c.N_prime, st));
+        ZOO_TRY(launch_iqn_target(h, c.N_prime, tg->out_final, c.gamma, L->d_target, st));
+        ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, B, L->d_tau, c.N, st));
+        ZOO_TRY(launch_iqn_loss(h, c.N, c.N_prime, on->out_final, L->d_target, L->d_tau, c.kappa, on->dout_final, st));
+        n_tau = c.N;
+    }
+    ZOO_TRY(launch_loss_reduce(h, c.beta_priority, L->d_loss, L->d_prio, st));
+    ZOO_TRY(net_backward(on, L->obs_dtype, s_ptr, bwd_rows, n_tau, st));
+    if (L->dp) ZOO_TRY(dp_allreduce_sum(L->dp, on->grads, on->n_flat + 64, st));  // gradients + loss in one collective
+    return ZOO_OK;
+}
+
+static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b) {
+    const zoo_learner_cfg &c = L->cfg;
+    cudaStream_t st = L->st;
+    const int B = L->B;
+    ZOO_REQUIRE(b && b->B == B, "update: batch size %d != learner batch_size %d", b ? b->B : -1, B);
+    ZOO_REQUIRE(b->obs_dtype == ZOO_OBS_U8 || b->obs_dtype == ZOO_OBS_F32, "update: bad obs dtype");
+    ZOO_REQUIRE(b->state && b->next_state && b->action && b->reward && b->terminal, "update: state/next_state/action/reward/terminal are required");
+    if (c.kind == ZOO_LEARNER_PRIORITIZED_DQN) ZOO_REQUIRE(b->priority, "update: PrioritizedDQNLearner needs batch.priority");
+    L->obs_dtype = b->obs_dtype;
+    const size_t obs_bytes = (size_t)B * obs_elems(L->online) * (b->obs_dtype == ZOO_OBS_U8 ? 1 : 4);
+    const cudaMemcpyKind k = b->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    ZOO_CUDA(cudaMemcpyAsync(L->d_obs, b->state, obs_bytes, k, st));
+    ZOO_CUDA(cudaMemcpyAsync((uint8_t *)L->d_obs + obs_bytes, b->next_state, obs_bytes, k, st));
+    ZOO_CUDA(cudaMemcpyAsync(L->d_action, b->action, B * sizeof(int), k, st));
+    ZOO_CUDA(cudaMemcpyAsync(L->d_reward, b->reward, B * sizeof(float), k, st));
+    ZOO_CUDA(cudaMemcpyAsync(L->d_terminal, b->terminal, B, k, st));
+    if (b->priority) ZOO_CUDA(cudaMemcpyAsync(L->d_priority, b->priority, B * sizeof(float), k, st));
+    if (b->next_mask) ZOO_CUDA(cudaMemcpyAsync(L->d_mask, b->next_mask, (size_t)B * c.n_actions, k, st));
+    if (c.kind == ZOO_LEARNER_IQN) {
+        ZOO_REQUIRE((b->tau != nullptr) == (b->tau_prime != nullptr), "update: pass both tau and tau_prime or neither");
+        if (b->tau) {
+            ZOO_CUDA(cudaMemcpyAsync(L->d_tau, b->tau, (size_t)B * c.N * sizeof(float), k, st));
+            ZOO_CUDA(cudaMemcpyAsync(L->d_taup, b->tau_prime, (size_t)B * c.N_prime * sizeof(float), k, st));
+        }
+    }
+    return ZOO_OK;
+}
+
+static zoo_status run_update(zoo_learner *L, const zoo_batch *b, float *loss_out, float *prio_out, bool full) {
+    ZOO_REQUIRE(L, "update: null learner");
+    ZOO_TRY(stage_batch(L, b));
+    const bool has_prio = b->priority != nullptr, has_mask = b->next_mask != nullptr, has_tau = b->tau != nullptr;
+    const int key = (has_prio ? 1 : 0) | (has_mask ? 2 : 0) | (has_tau ? 4 : 0) | (L->obs_dtype << 3) | (full ? 16 : 0);
+    g_launches = 0;
+    if (L->use_graph && L->warm) {
+        if (!L->gexec || L->graph_key != key) {
+            if (L->gexec) { cudaGraphExecDestroy(L->gexec); L->gexec = nullptr; }
+            cudaGraph_t graph;
+            ZOO_CUDA(cudaStreamBeginCapture(L->st, cudaStreamCaptureModeThreadLocal));
+            zoo_status s = enqueue_grads(L, has_prio, has_mask, has_tau);
+            if (s == ZOO_OK && full) s = opt_step(L->opt, L->st);
+            cudaError_t ce = cudaStreamEndCapture(L->st, &graph);
+            if (s != ZOO_OK) { if (ce == cudaSuccess) cudaGraphDestroy(graph); return s; }
+            ZOO_CUDA(ce);
+            ZOO_CUDA(cudaGraphInstantiate(&L->gexec, graph, 0));
+            cudaGraphDestroy(graph);
+            L->graph_key = key;
+            L->graph_launches = g_launches;
+            if (full) L->opt->host_t -= 1;  // the capture pass did not execute
+        }
+        ZOO_CUDA(cudaGraphLaunch(L->gexec, L->st));
+        if (full) L->opt->host_t += 1;
+        L->last_launches = L->graph_launches;
+    } else {
+        ZOO_TRY(enqueue_grads(L, has_prio, has_mask, has_tau));
+        if (full) ZOO_TRY(opt_step(L->opt, L->st));
+        L->last_launches = g_launches;
+        L->warm = 1;
+    }
+    if (prio_out) ZOO_CUDA(cudaMemcpyAsync(prio_out, L->d_prio, L->B * sizeof(float), cudaMemcpyDeviceToHost, L->st));
+    if (loss_out) ZOO_CUDA(cudaMemcpyAsync(loss_out, L->d_loss, sizeof(float), cudaMemcpyDeviceToHost, L->st));
+    if (prio_out || loss_out) ZOO_CUDA(cudaStreamSynchronize(L->st));
+    return ZOO_OK;
+}
+
+extern "C" {
+
+zoo_status zoo_opt_create(zoo_net *net, int32_t kind, double eta, double a, double b, double eps, zoo_opt **out) {
+    ZOO_REQUIRE(net && out, "zoo_opt_create: null argument");
+    ZOO_REQUIRE(kind == ZOO_OPT_RMSPROP || kind == ZOO_OPT_ADAM, "zoo_opt_create: unknown optimiser %d", kind);
+    ZOO_TRY(net_alloc_backward(net));
+    zoo_opt *o = new zoo_opt();
+    o->net = net; o->kind = kind; o->eta = eta; o->a = a; o->b = kind == ZOO_OPT_ADAM ? b : 0.0; o->eps = eps;
+    ZOO_CUDA(cudaMalloc(&o->s0, net->n_flat * sizeof(float)));
+    ZOO_CUDA(cudaMemset(o->s0, 0, net->n_flat * sizeof(float)));
+    if (kind == ZOO_OPT_ADAM) {
+        ZOO_CUDA(cudaMalloc(&o->s1, net->n_flat * sizeof(float)));
+        ZOO_CUDA(cudaMemset(o->s1, 0, net->n_flat * sizeof(float)));
+    }
+    ZOO_CUDA(cudaMalloc(&o->sc, sizeof(OptScalars)));
+    OptScalars h{};
+    h.b1p = o->a; h.b2p = o->b; h.t = 0; h.rng = 0;
+    ZOO_CUDA(cudaMemcpy(o->sc, &h, sizeof(h), cudaMemcpyHostToDevice));
+    *out = o;
+    return ZOO_OK;
+}
+
+zoo_status zoo_opt_destroy(zoo_opt *o) {
+    if (!o) return ZOO_OK;
+    cudaDeviceSynchronize();
+    cudaFree(o->s0); if (o->s1) cudaFree(o->s1); cudaFree(o->sc);
+    delete o;
+    return ZOO_OK;
+}
+
+static float *opt_slot(const zoo_opt *o, int slot) { return slot == 0 ? o->s0 : (slot == 1 ? o->s1 : nullptr); }
+
+zoo_status zoo_opt_get_state(const zoo_opt *o, int32_t slot, int32_t id, float *host, int64_t n) {
+    ZOO_REQUIRE(o && opt_slot(o, slot), "zoo_opt_get_state: bad optimiser/slot");
+    return zoo_internal_tensor_io(o->net, opt_slot(o, slot), id, host, n, 0);
+}
+zoo_status zoo_opt_set_state(zoo_opt *o, int32_t slot, int32_t id, const float *host, int64_t n) {
+    ZOO_REQUIRE(o && opt_slot(o, slot), "zoo_opt_set_state: bad optimiser/slot");
+    return zoo_internal_tensor_io(o->net, opt_slot(o, slot), id, const_cast<float *>(host), n, 1);
+}
+zoo_status zoo_opt_get_step(const zoo_opt *o, int64_t *t) {
+    ZOO_REQUIRE(o && t, "zoo_opt_get_step: null argument");
+    *t = o->host_t;
+    return ZOO_OK;
+}
+zoo_status zoo_opt_set_step(zoo_opt *o, int64_t t) {
+    ZOO_REQUIRE(o && t >= 0, "zoo_opt_set_step: bad argument");
+    OptScalars h{};
+    ZOO_CUDA(cudaDeviceSynchronize());
+    ZOO_CUDA(cudaMemcpy(&h, o->sc, sizeof(h), cudaMemcpyDeviceToHost));
+    h.b1p = std::pow(o->a, (double)(t + 1)); h.b2p = std::pow(o->b, (double)(t + 1)); h.t = (unsigned long long)t;
+    ZOO_CUDA(cudaMemcpy(o->sc, &h, sizeof(h), cudaMemcpyHostToDevice));
+    o->host_t = t;
+    return ZOO_OK;
+}
+
+zoo_status zoo_learner_create(const zoo_learner_cfg *cfg, zoo_net *online, zoo_net *target, zoo_opt *opt, zoo_dp *dp, zoo_learner **out) {
+    ZOO_REQUIRE(cfg && online && opt && out, "zoo_learner_create: null argument");
+    ZOO_REQUIRE(cfg->kind >= ZOO_LEARNER_BASIC_DQN && cfg->kind <= ZOO_LEARNER_IQN, "zoo_learner_create: unknown learner kind %d", cfg->kind);
+    ZOO_REQUIRE(cfg->kind == ZOO_LEARNER_BASIC_DQN || target, "zoo_learner_create: this learner needs a target network");
+    ZOO_REQUIRE(opt->net == online, "zoo_learner_create: the optimiser must belong to the online network");
+    ZOO_REQUIRE(cfg->batch_size > 0 && cfg->batch_size <= online->max_batch, "zoo_learner_create: batch_size %d exceeds the net's max_batch %lld",
+                cfg->batch_size, online->max_batch);
+    ZOO_REQUIRE(cfg->n_actions > 0 && cfg->update_horizon >= 1, "zoo_learner_create: bad n_actions / update_horizon");
+    if (target) ZOO_REQUIRE(target->n_flat == online->n_flat && target->max_batch >= cfg->batch_size, "zoo_learner_create: target net does not match");
+    const bool iqn = cfg->kind == ZOO_LEARNER_IQN;
+    ZOO_REQUIRE(iqn == (online->desc.kind == ZOO_NET_IQN), "zoo_learner_create: IQNLearner <-> ImplicitQuantileNet mismatch");
+    if (cfg->kind == ZOO_LEARNER_RAINBOW) {
+        ZOO_REQUIRE(cfg->n_atoms >= 2 && cfg->support && online->n_out == cfg->n_atoms * cfg->n_actions,
+                    "zoo_learner_create: Rainbow net must output n_atoms*n_actions = %d logits (has %d)", cfg->n_atoms * cfg->n_actions, online->n_out);
+    } else {
+        ZOO_REQUIRE(online->n_out == cfg->n_actions, "zoo_learner_create: net outputs %d values, n_actions is %d", online->n_out, cfg->n_actions);
+    }
+    if (iqn) ZOO_REQUIRE(cfg->N > 0 && cfg->N_prime > 0 && cfg->N <= online->max_q && cfg->N_prime <= target->max_q && cfg->N_em == online->b.in_feat,
+                         "zoo_learner_create: IQN N/N'/N_em do not fit the networks");
+    zoo_learner *L = new zoo_learner();
+    L->cfg = *cfg; L->cfg.support = nullptr;
+    L->online = online; L->target = target; L->opt = opt; L->dp = dp; L->B = cfg->batch_size;
+    L->gamma_n = (float)std::pow((double)cfg->gamma, (double)cfg->update_horizon);  // gamma^n, gamma::Float32 (dqn.jl:133)
+    ZOO_CUDA(cudaStreamCreateWithFlags(&L->st, cudaStreamNonBlocking));
+    const int B = L->B, A = cfg->n_actions;
+    L->d_loss = online->grads + online->n_flat;  // tail of the gradient buffer (see net_alloc_backward)
+    ZOO_CUDA(cudaMalloc(&L->d_obs, (size_t)2 * B * obs_elems(online) * sizeof(float)));
+    ZOO_CUDA(cudaMalloc(&L->d_action, B * sizeof(int)));
+    ZOO_CUDA(cudaMalloc(&L->d_reward, B * sizeof(float)));
+    ZOO_CUDA(cudaMalloc(&L->d_terminal, B));
+    ZOO_CUDA(cudaMalloc(&L->d_priority, B * sizeof(float)));
+    ZOO_CUDA(cudaMalloc(&L->d_mask, (size_t)B * A));
+    ZOO_CUDA(cudaMalloc(&L->d_per, B * sizeof(float)));
+    ZOO_CUDA(cudaMalloc(&L->d_prio, B * sizeof(float)));
+    ZOO_CUDA(cudaMalloc(&L->d_wraw, B * sizeof(float)));
+    ZOO_CUDA(cudaMalloc(&L->d_wmax, sizeof(float)));
+    if (cfg->kind == ZOO_LEARNER_RAINBOW) {
+        ZOO_CUDA(cudaMalloc(&L->d_support, cfg->n_atoms * sizeof(float)));
+        ZOO_CUDA(cudaMemcpy(L->d_support, cfg->support, cfg->n_atoms * sizeof(float), cudaMemcpyHostToDevice));
+        ZOO_CUDA(cudaMalloc(&L->d_tdist, (size_t)B * cfg->n_atoms * sizeof(float)));
+    }
+    if (iqn) {
+        ZOO_CUDA(cudaMalloc(&L->d_tau, (size_t)B * cfg->N * sizeof(float)));
+        ZOO_CUDA(cudaMalloc(&L->d_taup, (size_t)B * cfg->N_prime * sizeof(float)));
+        ZOO_CUDA(cudaMalloc(&L->d_target, (size_t)B * cfg->N_prime * sizeof(float)));
+    }
+    *out = L;
+    return ZOO_OK;
+}
+
+zoo_status zoo_learner_destroy(zoo_learner *L) {
+    if (!L) return ZOO_OK;
+    cudaStreamSynchronize(L->st);
+    if (L->gexec) cudaGraphExecDestroy(L->gexec);
+    void *ptrs[] = {L->d_obs, L->d_action, L->d_reward, L->d_terminal, L->d_priority, L->d_mask, L->d_tau, L->d_taup, L->d_support,
+                    L->d_target, L->d_tdist, L->d_per, L->d_prio, L->d_wraw, L->d_wmax};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    cudaStreamDestroy(L->st);
+    delete L;
+    return ZOO_OK;
+}
+
+zoo_status zoo_learner_update(zoo_learner *L, const zoo_batch *b, float *loss_out, float *prio_out) { return run_update(L, b, loss_out, prio_out, true); }
+zoo_status zoo_learner_compute_grads(zoo_learner *L, const zoo_batch *b, float *loss_out, float *prio_out) { return run_update(L, b, loss_out, prio_out, false); }
+
+zoo_status zoo_learner_apply(zoo_learner *L) {
+    ZOO_REQUIRE(L, "zoo_learner_apply: null learner");
+    g_launches = 0;
+    ZOO_TRY(opt_step(L->opt, L->st));
+    ZOO_CUDA(cudaStreamSynchronize(L->st));
+    return ZOO_OK;
+}
+
+zoo_status zoo_learner_get_grad(const zoo_learner *L, int32_t id, float *host, int64_t n) {
+    ZOO_REQUIRE(L, "zoo_learner_get_grad: null learner");
+    ZOO_CUDA(cudaStreamSynchronize(L->st));
+    return zoo_internal_tensor_io(L->online, L->online->grads, id, host, n, 0);
+}
+
+zoo_status zoo_learner_grad_buffer(zoo_learner *L, void **dev_ptr, int64_t *n) {
+    ZOO_REQUIRE(L && dev_ptr && n, "zoo_learner_grad_buffer: null argument");
+    *dev_ptr = L->online->grads;
+    *n = L->online->n_flat;
+    return ZOO_OK;
+}
+
+zoo_status zoo_learner_get_per_sample_loss(const zoo_learner *L, float *host, int32_t n) {
+    ZOO_REQUIRE(L && host && n == L->B, "zoo_learner_get_per_sample_loss: expected %d floats", L ? L->B : 0);
+    ZOO_CUDA(cudaMemcpyAsync(host, L->d_per, n * sizeof(float), cudaMemcpyDeviceToHost, L->st));
+    ZOO_CUDA(cudaStreamSynchronize(L->st));
+    return ZOO_OK;
+}
+
+zoo_status zoo_learner_stream(zoo_learner *L, void **stream) {
+    ZOO_REQUIRE(L && stream, "zoo_learner_stream: null argument");
+    *stream = (void *)L->st;
+    return ZOO_OK;
+}
+zoo_status zoo_learner_sync(zoo_learner *L) {
+    ZOO_REQUIRE(L, "zoo_learner_sync: null learner");
+    ZOO_CUDA(cudaStreamSynchronize(L->st));
+    return ZOO_OK;
+}
+zoo_status zoo_learner_last_launches(const zoo_learner *L, int32_t *n) {
+    ZOO_REQUIRE(L && n, "zoo_learner_last_launches: null argument");
+    *n = L->last_launches;
+    return ZOO_OK;
+}
+zoo_status zoo_learner_use_graph(zoo_learner *L, int32_t enable) {
+    ZOO_REQUIRE(L, "zoo_learner_use_graph: null learner");
+    L->use_graph = enable;
+    return ZOO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,789 @@
+// Q-network engine (see net.cuh).  Activations are NHWC internally ([rows*OH*OW][C]), which makes every conv a
+// GEMM over an im2col matrix and makes reshape(x,:,B) before the first Dense a no-op; the feature permutation this
+// implies relative to the reference's (c,h,w) flatten order is applied once, when parameters cross the C ABI.
+#include "net.cuh"
+
+namespace zoo {
+
+// ---------------------------------------------------------------- kernels -----------------
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f(uint8_t v) { return (float)v; }
+
+// first conv: raw NCHW observation -> cols[M][C*k*k] with k index (c,ky,kx); folds `x ./ 255` (IEEE divide,
+// Dopamine_DQN_Atari.jl:28) into the load.  One thread per (m, c, ky) writes k contiguous outputs.
+template <typename Tin, typename T>
+__global__ void im2col_first_kernel(const Tin *__restrict__ x, T *__restrict__ cols, long long total, int C, int H, int W,
+                                    int k, int s, int p, int OH, int OW, int scale255) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int ky = (int)(idx % k);
+    long long t = idx / k;
+    int c = (int)(t % C);
+    long long m = t / C;
+    int ow = (int)(m % OW);
+    long long t2 = m / OW;
+    int oh = (int)(t2 % OH);
+    long long b = t2 / OH;
+    int iy = oh * s - p + ky;
+    T *dst = cols + idx * k;
+    const Tin *src = x + ((b * C + c) * H + iy) * (long long)W;
+    bool rowok = iy >= 0 && iy < H;
+    for (int kx = 0; kx < k; ++kx) {
+        int ix = ow * s - p + kx;
+        float v = 0.f;
+        if (rowok && ix >= 0 && ix < W) {
+            v = to_f(src[ix]);
+            if (scale255) v = __fdiv_rn(v, 255.f);
+        }
+        dst[kx] = from_f<T>(v);
+    }
+}
+
+template <typename T, int VEC> struct alignas(sizeof(T) * VEC) VecT { T v[VEC]; };
+
+// conv reading internal NHWC activations: cols[M][k*k*C] with k index (ky,kx,c); VEC channels per thread
+template <typename T, int VEC>
+__global__ void im2col_nhwc_kernel(const T *__restrict__ x, T *__restrict__ cols, long long total, int C, int H, int W, int k,
+                                   int s, int p, int OH, int OW) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = C / VEC;
+    int cc = (int)(idx % cv);
+    long long t = idx / cv;
+    int kx = (int)(t % k); t /= k;
+    int ky = (int)(t % k);
+    long long m = t / k;
+    int ow = (int)(m % OW);
+    long long t2 = m / OW;
+    int oh = (int)(t2 % OH);
+    long long b = t2 / OH;
+    int iy = oh * s - p + ky, ix = ow * s - p + kx;
+    VecT<T, VEC> v;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        v = *reinterpret_cast<const VecT<T, VEC> *>(x + (((b * H + iy) * W + ix) * (long long)C + cc * VEC));
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v.v[i] = from_f<T>(0.f);
+    }
+    *reinterpret_cast<VecT<T, VEC> *>(cols + idx * VEC) = v;
+}
+
+// gather-form col2im (no atomics): dx[b,h,w,c] = sum over (ky,kx) of dcols[(b,oh,ow)][(ky,kx,c)], then relu' mask
+template <typename T, int VEC>
+__global__ void col2im_nhwc_kernel(const T *__restrict__ dcols, T *__restrict__ dx, const T *__restrict__ act, long long total,
+                                   int C, int H, int W, int k, int s, int p, int OH, int OW) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = C / VEC;
+    int cc = (int)(idx % cv);
+    long long t = idx / cv;
+    int w = (int)(t % W); t /= W;
+    int h = (int)(t % H);
+    long long b = t / H;
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+    const long long KK = (long long)k * k * C;
+    for (int ky = 0; ky < k; ++ky) {
+        int ty = h + p - ky;
+        if (ty < 0 || ty % s) continue;
+        int oh = ty / s;
+        if (oh >= OH) continue;
+        for (int kx = 0; kx < k; ++kx) {
+            int tx = w + p - kx;
+            if (tx < 0 || tx % s) continue;
+            int ow = tx / s;
+            if (ow >= OW) continue;
+            long long m = (b * OH + oh) * OW + ow;
+            VecT<T, VEC> v = *reinterpret_cast<const VecT<T, VEC> *>(dcols + m * KK + (long long)(ky * k + kx) * C + cc * VEC);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] += to_f(v.v[i]);
+        }
+    }
+    VecT<T, VEC> o;
+    if (act) {
+        VecT<T, VEC> a = *reinterpret_cast<const VecT<T, VEC> *>(act + idx * VEC);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o.v[i] = from_f<T>(to_f(a.v[i]) > 0.f ? acc[i] : 0.f);
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o.v[i] = from_f<T>(acc[i]);
+    }
+    *reinterpret_cast<VecT<T, VEC> *>(dx + idx * VEC) = o;
+}
+
+// bias gradient: db[n] += sum_m dy[m][n]
+template <typename T>
+__global__ void colsum_kernel(const T *__restrict__ dy, long long M, int N, float *__restrict__ db) {
+    __shared__ float red[8][33];
+    int n = blockIdx.x * 32 + threadIdx.x;
+    float acc = 0.f;
+    if (n < N)
+        for (long long m = (long long)blockIdx.y * 8 + threadIdx.y; m < M; m += (long long)gridDim.y * 8) acc += to_f(dy[m * N + n]);
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+        atomicAdd(db + n, s);
+    }
+}
+
+// embed(tau, N_em) = cos.(Float32(pi) .* (1:N_em) .* tau)  -- iqn.jl:157
+template <typename T>
+__global__ void embed_kernel(const float *__restrict__ tau, T *__restrict__ emb, long long rows, int nem) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * nem) return;
+    int i = (int)(idx % nem);
+    long long r = idx / nem;
+    float a = __fmul_rn(__fmul_rn(3.14159274101257324f, (float)(i + 1)), tau[r]);
+    emb[idx] = from_f<T>(cosf(a));
+}
+
+// merged[r][f] = feat[r / N][f] * ea[r][f]  -- iqn.jl:28-30
+template <typename T>
+__global__ void iqn_merge_kernel(const T *__restrict__ feat, const T *__restrict__ ea, T *__restrict__ merged, long long rows,
+                                 int F, int N) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * F) return;
+    int f = (int)(idx % F);
+    long long r = idx / F;
+    merged[idx] = from_f<T>(to_f(feat[(r / N) * F + f]) * to_f(ea[idx]));
+}
+
+// adjoint of the merge: dea = dm * feat * relu'(ea);  dfeat[b] = relu'(feat) * sum_n dm * ea
+template <typename T>
+__global__ void iqn_merge_bwd_kernel(const T *__restrict__ dm, const T *__restrict__ feat, const T *__restrict__ ea,
+                                     T *__restrict__ dea, T *__restrict__ dfeat, int B, int F, int N, int phi_relu, int psi_relu) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * F) return;
+    int f = (int)(idx % F);
+    long long b = idx / F;
+    float ft = to_f(feat[idx]);
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) {
+        long long o = (b * N + n) * F + f;
+        float d = to_f(dm[o]), e = to_f(ea[o]);
+        dea[o] = from_f<T>((!phi_relu || e > 0.f) ? d * ft : 0.f);
+        acc += d * e;
+    }
+    dfeat[idx] = from_f<T>((!psi_relu || ft > 0.f) ? acc : 0.f);
+}
+
+// DuelingNetwork: q = val .+ adv .- mean(adv, dims=1)  -- common.jl:51-56
+__global__ void dueling_combine_kernel(const float *__restrict__ val, const float *__restrict__ adv, float *__restrict__ q, int B, int A) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float s = 0.f;
+    for (int a = 0; a < A; ++a) s += adv[b * A + a];
+    float mean = s / (float)A;
+    for (int a = 0; a < A; ++a) q[b * A + a] = val[b] + adv[b * A + a] - mean;
+}
+__global__ void dueling_combine_bwd_kernel(const float *__restrict__ dq, float *__restrict__ dval, float *__restrict__ dadv, int B, int A) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float s = 0.f;
+    for (int a = 0; a < A; ++a) s += dq[b * A + a];
+    dval[b] = s;
+    float mean = s / (float)A;
+    for (int a = 0; a < A; ++a) dadv[b * A + a] = dq[b * A + a] - mean;
+}
+template <typename T>
+__global__ void add_mask_kernel(const T *__restrict__ a, const T *__restrict__ b, const T *__restrict__ act, T *__restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = to_f(a[i]) + to_f(b[i]);
+    if (act && !(to_f(act[i]) > 0.f)) v = 0.f;
+    out[i] = from_f<T>(v);
+}
+
+__global__ void cast_bf16_kernel(const float *__restrict__ in, bf16 *__restrict__ out, long long n) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        float4 v = *reinterpret_cast<const float4 *>(in + i);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<__nv_bfloat162 *>(out + i) = lo;
+        *reinterpret_cast<__nv_bfloat162 *>(out + i + 2) = hi;
+    } else {
+        for (; i < n; ++i) out[i] = __float2bfloat16_rn(in[i]);
+    }
+}
+
+// ABI (Julia bytes) <-> internal layout.  dir 0: abi -> internal, 1: internal -> abi.
+__global__ void permute_param_kernel(float *__restrict__ internal, float *__restrict__ abi, TensorInfo ti, int dir) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // internal linear index
+    if (i >= ti.count) return;
+    long long src;
+    const int hw = ti.fh * ti.fw;
+    if (ti.kind == 2) {  // bias
+        long long o = i;
+        if (ti.perm_out) { int c = (int)(o % ti.fc); long long p = o / ti.fc; o = (long long)c * hw + p; }
+        src = o;
+    } else if (ti.kind == 0) {  // dense: internal [out][in] <- abi [in][out]
+        long long o = i / ti.n_in, in = i % ti.n_in;
+        if (ti.perm_out) { int c = (int)(o % ti.fc); long long p = o / ti.fc; o = (long long)c * hw + p; }
+        if (ti.perm_in) { int c = (int)(in % ti.fc); long long p = in / ti.fc; in = (long long)c * hw + p; }
+        src = in * ti.n_out + o;
+    } else {  // conv
+        if (ti.conv_nhwc) {  // internal [O][ky][kx][C] <- abi [O][C][ky][kx]
+            int c = (int)(i % ti.n_in);
+            long long t = i / ti.n_in;
+            int kx = (int)(t % ti.ksize); t /= ti.ksize;
+            int ky = (int)(t % ti.ksize);
+            long long o = t / ti.ksize;
+            src = ((o * ti.n_in + c) * ti.ksize + ky) * ti.ksize + kx;
+        } else src = i;
+    }
+    if (dir == 0) internal[i] = abi[src];
+    else abi[src] = internal[i];
+}
+
+// ---------------------------------------------------------------- helpers -----------------
+static inline bool is_bf(const zoo_net *n) { return n->prec == ZOO_PREC_BF16; }
+
+template <typename T>
+static zoo_status launch_im2col_nhwc(const void *x, void *cols, long long M, const LayerExec &L, cudaStream_t st) {
+    constexpr int V = 16 / sizeof(T);
+    if (L.cin % V == 0) {
+        long long total = M * L.ksize * L.ksize * (L.cin / V);
+        im2col_nhwc_kernel<T, V><<<cdiv(total, 256), 256, 0, st>>>((const T *)x, (T *)cols, total, L.cin, L.ih, L.iw, L.ksize,
+                                                                   L.stride, L.pad, L.oh, L.ow);
+    } else {
+        long long total = M * L.ksize * L.ksize * L.cin;
+        im2col_nhwc_kernel<T, 1><<<cdiv(total, 256), 256, 0, st>>>((const T *)x, (T *)cols, total, L.cin, L.ih, L.iw, L.ksize,
+                                                                   L.stride, L.pad, L.oh, L.ow);
+    }
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+
+template <typename T>
+static zoo_status launch_col2im_nhwc(const void *dcols, void *dx, const void *act, long long rows, const LayerExec &L, cudaStream_t st) {
+    constexpr int V = 16 / sizeof(T);
+    if (L.cin % V == 0) {
+        long long total = rows * L.ih * L.iw * (L.cin / V);
+        col2im_nhwc_kernel<T, V><<<cdiv(total, 256), 256, 0, st>>>((const T *)dcols, (T *)dx, (const T *)act, total, L.cin, L.ih,
+                                                                   L.iw, L.ksize, L.stride, L.pad, L.oh, L.ow);
+    } else {
+        long long total = rows * L.ih * L.iw * L.cin;
+        col2im_nhwc_kernel<T, 1><<<cdiv(total, 256), 256, 0, st>>>((const T *)dcols, (T *)dx, (const T *)act, total, L.cin, L.ih,
+                                                                   L.iw, L.ksize, L.stride, L.pad, L.oh, L.ow);
+    }
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+
+static zoo_status launch_colsum(const void *dy, int dy_bf16, long long M, int N, float *db, cudaStream_t st) {
+    dim3 grid(cdiv(N, 32), (unsigned)std::max<long long>(1, std::min<long long>(64, M / 64)));
+    dim3 block(32, 8);
+    if (dy_bf16) colsum_kernel<bf16><<<grid, block, 0, st>>>((const bf16 *)dy, M, N, db);
+    else colsum_kernel<float><<<grid, block, 0, st>>>((const float *)dy, M, N, db);
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+
+// weight as the B operand; bf16 shadow only when the tcgen05 engine will take the GEMM, fp32 master otherwise
+static Operand weight_operand(const zoo_net *net, const TensorInfo &W, const Operand &A, int M, int N, int K, long long ld, int kmajor) {
+    Operand B{net->params + W.offset, 0, ld, kmajor};
+    if (is_bf(net) && A.is_bf16) {
+        Operand Bs{net->shadow + W.offset, 1, ld, kmajor};
+        if (tc_gemm_supported(A, Bs, M, N, K)) return Bs;
+    }
+    return B;
+}
+
+// in_kind: 0 raw u8, 1 raw f32, 2 internal T
+static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_kind, long long rows, cudaStream_t st) {
+    ZOO_REQUIRE(rows <= ch.rows_cap, "forward: %lld rows exceed the capacity %lld this net was created with", rows, ch.rows_cap);
+    const int bf = is_bf(net);
+    const void *cur = in;
+    int cur_kind = in_kind;
+    for (auto &L : ch.layers) {
+        const long long M = rows * L.opr;
+        const TensorInfo &W = net->tensors[L.wt];
+        const TensorInfo &Bt = net->tensors[L.bt];
+        Operand A;
+        if (L.kind == ZOO_LAYER_CONV) {
+            if (L.first_raw) {
+                long long total = M * L.cin * L.ksize;
+                int blocks = cdiv(total, 256);
+#define IM2COL_FIRST(Tin, T)                                                                                              \
+    im2col_first_kernel<Tin, T><<<blocks, 256, 0, st>>>((const Tin *)cur, (T *)L.cols, total, L.cin, L.ih, L.iw, L.ksize, \
+                                                        L.stride, L.pad, L.oh, L.ow, L.scale255)
+                if (cur_kind == 0) { if (bf) IM2COL_FIRST(uint8_t, bf16); else IM2COL_FIRST(uint8_t, float); }
+                else if (cur_kind == 1) { if (bf) IM2COL_FIRST(float, bf16); else IM2COL_FIRST(float, float); }
+                else { set_err("conv: first layer expects a raw observation"); return ZOO_BAD_ARG; }
+#undef IM2COL_FIRST
+                ZOO_LAUNCH_CHECK();
+            } else {
+                if (bf) ZOO_TRY(launch_im2col_nhwc<bf16>(cur, L.cols, M, L, st));
+                else ZOO_TRY(launch_im2col_nhwc<float>(cur, L.cols, M, L, st));
+            }
+            A = Operand{L.cols, bf, L.K, 1};
+        } else {
+            ZOO_REQUIRE(cur_kind != 0, "dense: uint8 observations need a conv or scale layer first");
+            A = Operand{cur, cur_kind == 2 ? bf : 0, L.K, 1};
+        }
+        Operand B = weight_operand(net, W, A, (int)M, L.cout, (int)L.K, L.K, 1);
+        Epilogue e;
+        e.out = L.out; e.out_bf16 = L.out_fp32 ? 0 : bf; e.sm = L.cout; e.sn = 1;
+        e.bias = net->params + Bt.offset; e.bias_mode = 1; e.relu = L.relu; e.tf32_passes = net->tf32_passes;
+        ZOO_TRY(gemm(A, B, (int)M, L.cout, (int)L.K, e, 0, net->ws, net->ws_elems, st));
+        cur = L.out;
+        cur_kind = 2;
+    }
+    return ZOO_OK;
+}
+
+// Each layer's dout must already hold d(loss)/d(out) with the layer's own relu' applied.
+// dx (optional): gradient w.r.t. the chain input, internal T [rows][in_feat]; dx_mask: relu' source for it.
+static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in_kind, long long rows, void *dx, const void *dx_mask,
+                                 cudaStream_t st) {
+    const int bf = is_bf(net);
+    for (int li = (int)ch.layers.size() - 1; li >= 0; --li) {
+        LayerExec &L = ch.layers[li];
+        const long long M = rows * L.opr;
+        const TensorInfo &W = net->tensors[L.wt];
+        const TensorInfo &Bt = net->tensors[L.bt];
+        const int dy_bf = L.out_fp32 ? 0 : bf;
+        ZOO_TRY(launch_colsum(L.dout, dy_bf, M, L.cout, net->grads + Bt.offset, st));
+        // wgrad: dW[cout][K] += dY^T X   (both operands MN-major: stored [rows][features])
+        Operand X;
+        if (L.kind == ZOO_LAYER_CONV) X = Operand{L.cols, bf, L.K, 0};
+        else if (li == 0) X = Operand{in, in_kind == 2 ? bf : 0, L.K, 0};
+        else X = Operand{ch.layers[li - 1].out, bf, L.K, 0};
+        Operand dYt{L.dout, dy_bf, L.cout, 0};
+        Epilogue ew;
+        ew.out = net->grads + W.offset; ew.sm = L.K; ew.sn = 1; ew.accumulate = 1; ew.tf32_passes = net->tf32_passes;
+        ZOO_TRY(gemm(dYt, X, L.cout, (int)L.K, (int)M, ew, 0, net->ws, net->ws_elems, st));
+        // dgrad
+        if (li == 0 && !dx) continue;
+        Operand dY{L.dout, dy_bf, L.cout, 1};
+        Operand Wn = weight_operand(net, W, dY, (int)M, (int)L.K, L.cout, L.K, 0);
+        Epilogue ed;
+        ed.sm = L.K; ed.sn = 1; ed.out_bf16 = bf; ed.tf32_passes = net->tf32_passes;
+        if (L.kind == ZOO_LAYER_CONV) {
+            ZOO_REQUIRE(li > 0, "backward: gradient w.r.t. the observation is not supported");
+            LayerExec &P = ch.layers[li - 1];
+            ed.out = L.dcols;
+            ZOO_TRY(gemm(dY, Wn, (int)M, (int)L.K, L.cout, ed, 0, net->ws, net->ws_elems, st));
+            if (bf) ZOO_TRY(launch_col2im_nhwc<bf16>(L.dcols, P.dout, P.relu ? P.out : nullptr, rows, L, st));
+            else ZOO_TRY(launch_col2im_nhwc<float>(L.dcols, P.dout, P.relu ? P.out : nullptr, rows, L, st));
+        } else {
+            if (li > 0) {
+                LayerExec &P = ch.layers[li - 1];
+                ed.out = P.dout;
+                if (P.relu) { ed.mask = P.out; ed.mask_bf16 = bf; ed.mask_sm = L.K; ed.mask_sn = 1; }
+            } else {
+                ed.out = dx;
+                if (dx_mask) { ed.mask = dx_mask; ed.mask_bf16 = bf; ed.mask_sm = L.K; ed.mask_sn = 1; }
+            }
+            ZOO_TRY(gemm(dY, Wn, (int)M, (int)L.K, L.cout, ed, 0, net->ws, net->ws_elems, st));
+        }
+    }
+    return ZOO_OK;
+}
+
+long long obs_elems(const zoo_net *net) { return (long long)net->desc.in_c * net->desc.in_h * net->desc.in_w; }
+
+zoo_status net_refresh_shadow(zoo_net *net, cudaStream_t st) {
+    if (!net->shadow) return ZOO_OK;
+    cast_bf16_kernel<<<cdiv(net->n_flat / 4 + 1, 256), 256, 0, st>>>(net->params, net->shadow, net->n_flat);
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+
+zoo_status net_forward(zoo_net *net, const void *obs, int obs_dtype, int rows, const float *tau, int n_tau, cudaStream_t st) {
+    const int bf = is_bf(net);
+    const int in_kind = obs_dtype == ZOO_OBS_U8 ? 0 : 1;
+    if (net->desc.kind == ZOO_NET_CHAIN) return chain_forward(net, net->a, obs, in_kind, rows, st);
+    if (net->desc.kind == ZOO_NET_DUELING) {
+        ZOO_TRY(chain_forward(net, net->a, obs, in_kind, rows, st));
+        ZOO_TRY(chain_forward(net, net->b, net->a.out(), 2, rows, st));
+        ZOO_TRY(chain_forward(net, net->c, net->a.out(), 2, rows, st));
+        dueling_combine_kernel<<<cdiv(rows, 128), 128, 0, st>>>((const float *)net->b.out(), (const float *)net->c.out(),
+                                                                net->out_final, rows, net->n_out);
+        ZOO_LAUNCH_CHECK();
+        return ZOO_OK;
+    }
+    // IQN -- iqn.jl:25-33
+    ZOO_REQUIRE(tau && n_tau > 0 && n_tau <= net->max_q, "IQN forward: tau missing or n_tau %d > max_quantiles %lld", n_tau, net->max_q);
+    const long long R = (long long)rows * n_tau;
+    const int nem = (int)net->b.in_feat, F = (int)net->a.out_feat;
+    ZOO_TRY(chain_forward(net, net->a, obs, in_kind, rows, st));
+    if (bf) embed_kernel<bf16><<<cdiv(R * nem, 256), 256, 0, st>>>(tau, (bf16 *)net->emb, R, nem);
+    else embed_kernel<float><<<cdiv(R * nem, 256), 256, 0, st>>>(tau, (float *)net->emb, R, nem);
+    ZOO_LAUNCH_CHECK();
+    ZOO_TRY(chain_forward(net, net->b, net->emb, 2, R, st));
+    if (bf) iqn_merge_kernel<bf16><<<cdiv(R * F, 256), 256, 0, st>>>((const bf16 *)net->a.out(), (const bf16 *)net->b.out(), (bf16 *)net->merged, R, F, n_tau);
+    else iqn_merge_kernel<float><<<cdiv(R * F, 256), 256, 0, st>>>((const float *)net->a.out(), (const float *)net->b.out(), (float *)net->merged, R, F, n_tau);
+    ZOO_LAUNCH_CHECK();
+    return chain_forward(net, net->c, net->merged, 2, R, st);
+}
+
+zoo_status net_backward(zoo_net *net, int obs_dtype, const void *obs, int rows, int n_tau, cudaStream_t st) {
+    ZOO_REQUIRE(net->bwd_ready && net->grads, "backward: net has no gradient buffers (attach an optimiser/learner first)");
+    const int bf = is_bf(net);
+    const int in_kind = obs_dtype == ZOO_OBS_U8 ? 0 : 1;
+    if (net->desc.kind == ZOO_NET_CHAIN) return chain_backward(net, net->a, obs, in_kind, rows, nullptr, nullptr, st);
+    if (net->desc.kind == ZOO_NET_DUELING) {
+        dueling_combine_bwd_kernel<<<cdiv(rows, 128), 128, 0, st>>>(net->dout_final, (float *)net->b.layers.back().dout,
+                                                                    (float *)net->c.layers.back().dout, rows, net->n_out);
+        ZOO_LAUNCH_CHECK();
+        ZOO_TRY(chain_backward(net, net->b, net->a.out(), 2, rows, net->dh1, nullptr, st));
+        ZOO_TRY(chain_backward(net, net->c, net->a.out(), 2, rows, net->dh2, nullptr, st));
+        LayerExec &P = net->a.layers.back();
+        long long n = (long long)rows * net->a.out_feat;
+        if (bf) add_mask_kernel<bf16><<<cdiv(n, 256), 256, 0, st>>>((const bf16 *)net->dh1, (const bf16 *)net->dh2, P.relu ? (const bf16 *)P.out : nullptr, (bf16 *)P.dout, n);
+        else add_mask_kernel<float><<<cdiv(n, 256), 256, 0, st>>>((const float *)net->dh1, (const float *)net->dh2, P.relu ? (const float *)P.out : nullptr, (float *)P.dout, n);
+        ZOO_LAUNCH_CHECK();
+        return chain_backward(net, net->a, obs, in_kind, rows, nullptr, nullptr, st);
+    }
+    const long long R = (long long)rows * n_tau;
+    const int F = (int)net->a.out_feat;
+    ZOO_TRY(chain_backward(net, net->c, net->merged, 2, R, net->dmerged, nullptr, st));
+    LayerExec &Pphi = net->b.layers.back();
+    LayerExec &Ppsi = net->a.layers.back();
+    long long n = (long long)rows * F;
+    if (bf) iqn_merge_bwd_kernel<bf16><<<cdiv(n, 256), 256, 0, st>>>((const bf16 *)net->dmerged, (const bf16 *)Ppsi.out, (const bf16 *)Pphi.out, (bf16 *)Pphi.dout, (bf16 *)Ppsi.dout, rows, F, n_tau, Pphi.relu, Ppsi.relu);
+    else iqn_merge_bwd_kernel<float><<<cdiv(n, 256), 256, 0, st>>>((const float *)net->dmerged, (const float *)Ppsi.out, (const float *)Pphi.out, (float *)Pphi.dout, (float *)Ppsi.dout, rows, F, n_tau, Pphi.relu, Ppsi.relu);
+    ZOO_LAUNCH_CHECK();
+    ZOO_TRY(chain_backward(net, net->b, net->emb, 2, R, nullptr, nullptr, st));
+    return chain_backward(net, net->a, obs, in_kind, rows, nullptr, nullptr, st);
+}
+
+// ---------------------------------------------------------------- construction ------------
+struct ParseState {
+    int c, h, w;        // spatial dims while spatial
+    bool spatial;
+    long long feat;     // feature count once flat
+    bool flat_pending;  // the current feature axis is a flattened conv output (needs the (c,h,w)->(h,w,c) permutation)
+    bool raw;           // next layer reads the raw observation
+    bool scale;         // pending x ./ 255
+};
+
+static long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
+
+static zoo_status parse_chain(zoo_net *net, const zoo_layer *Ls, int n, ParseState &S, Chain &ch, bool is_output_chain, const char *name) {
+    ch.in_feat = S.spatial ? (long long)S.c * S.h * S.w : S.feat;
+    for (int i = 0; i < n; ++i) {
+        const zoo_layer &l = Ls[i];
+        if (l.kind == ZOO_LAYER_SCALE255) {
+            ZOO_REQUIRE(S.raw && i == 0, "%s: the x./255 layer must be the first layer of the first chain", name);
+            S.scale = true;
+        } else if (l.kind == ZOO_LAYER_CONV) {
+            ZOO_REQUIRE(S.spatial, "%s[%d]: conv after flatten", name, i);
+            ZOO_REQUIRE(l.n_in == S.c, "%s[%d]: conv expects %d input channels, got %d", name, i, l.n_in, S.c);
+            ZOO_REQUIRE(l.ksize > 0 && l.stride > 0 && l.pad >= 0 && l.n_out > 0, "%s[%d]: bad conv geometry", name, i);
+            LayerExec L{};
+            L.kind = ZOO_LAYER_CONV; L.cin = l.n_in; L.cout = l.n_out; L.ksize = l.ksize; L.stride = l.stride; L.pad = l.pad;
+            L.relu = l.relu; L.ih = S.h; L.iw = S.w;
+            L.oh = (S.h + 2 * l.pad - l.ksize) / l.stride + 1;
+            L.ow = (S.w + 2 * l.pad - l.ksize) / l.stride + 1;
+            ZOO_REQUIRE(L.oh > 0 && L.ow > 0, "%s[%d]: conv output is empty", name, i);
+            L.first_raw = S.raw; L.scale255 = S.scale; L.K = (long long)l.ksize * l.ksize * l.n_in; L.opr = (long long)L.oh * L.ow;
+            TensorInfo w{}; w.kind = 1; w.n_out = l.n_out; w.n_in = l.n_in; w.ksize = l.ksize; w.conv_nhwc = !S.raw;
+            w.count = (long long)l.n_out * L.K;
+            TensorInfo b{}; b.kind = 2; b.n_out = l.n_out; b.count = l.n_out;
+            L.wt = (int)net->tensors.size(); net->tensors.push_back(w);
+            L.bt = (int)net->tensors.size(); net->tensors.push_back(b);
+            ch.layers.push_back(L);
+            S.c = l.n_out; S.h = L.oh; S.w = L.ow; S.raw = false; S.scale = false;
+        } else if (l.kind == ZOO_LAYER_FLATTEN) {
+            if (S.spatial) {
+                ZOO_REQUIRE(!S.raw, "%s[%d]: flatten of the raw observation is not supported (use in_h = in_w = 1)", name, i);
+                S.spatial = false; S.feat = (long long)S.c * S.h * S.w; S.flat_pending = (S.h * S.w > 1);
+                net->fc = S.c; net->fh = S.h; net->fw = S.w;
+            }
+        } else if (l.kind == ZOO_LAYER_DENSE) {
+            ZOO_REQUIRE(!S.spatial, "%s[%d]: dense needs a flatten after the convs", name, i);
+            ZOO_REQUIRE(l.n_in == S.feat, "%s[%d]: dense expects %lld inputs, got %d", name, i, S.feat, l.n_in);
+            ZOO_REQUIRE(l.n_out > 0, "%s[%d]: bad dense size", name, i);
+            LayerExec L{};
+            L.kind = ZOO_LAYER_DENSE; L.cin = l.n_in; L.cout = l.n_out; L.relu = l.relu; L.first_raw = S.raw; L.scale255 = 0;
+            ZOO_REQUIRE(!S.scale, "%s[%d]: x./255 directly before a dense layer is not supported", name, i);
+            L.K = l.n_in; L.opr = 1;
+            TensorInfo w{}; w.kind = 0; w.n_out = l.n_out; w.n_in = l.n_in; w.perm_in = S.flat_pending; w.fc = net->fc; w.fh = net->fh; w.fw = net->fw;
+            w.count = (long long)l.n_out * l.n_in;
+            TensorInfo b{}; b.kind = 2; b.n_out = l.n_out; b.count = l.n_out; b.fc = net->fc; b.fh = net->fh; b.fw = net->fw;
+            L.wt = (int)net->tensors.size(); net->tensors.push_back(w);
+            L.bt = (int)net->tensors.size(); net->tensors.push_back(b);
+            ch.layers.push_back(L);
+            S.feat = l.n_out; S.flat_pending = false; S.raw = false;
+        } else {
+            set_err("%s[%d]: unknown layer kind %d", name, i, l.kind);
+            return ZOO_BAD_ARG;
+        }
+    }
+    ZOO_REQUIRE(!ch.layers.empty(), "%s: chain has no parameter layers", name);
+    ch.out_feat = S.spatial ? (long long)S.c * S.h * S.w : S.feat;
+    if (is_output_chain) {
+        ZOO_REQUIRE(ch.layers.back().kind == ZOO_LAYER_DENSE, "%s: the output layer must be dense", name);
+        ch.layers.back().out_fp32 = 1;
+    }
+    return ZOO_OK;
+}
+
+static zoo_status alloc_chain(zoo_net *net, Chain &ch, long long rows_cap, float *final_out) {
+    ch.rows_cap = rows_cap;
+    for (auto &L : ch.layers) {
+        long long M = rows_cap * L.opr;
+        if (L.kind == ZOO_LAYER_CONV) ZOO_CUDA(cudaMalloc(&L.cols, (size_t)M * L.K * net->esz));
+        if (L.out_fp32 && final_out) L.out = final_out;
+        else ZOO_CUDA(cudaMalloc(&L.out, (size_t)M * L.cout * (L.out_fp32 ? 4 : net->esz)));
+    }
+    return ZOO_OK;
+}
+
+static zoo_status alloc_chain_bwd(zoo_net *net, Chain &ch, float *final_dout) {
+    for (size_t i = 0; i < ch.layers.size(); ++i) {
+        auto &L = ch.layers[i];
+        long long M = ch.rows_cap * L.opr;
+        if (L.out_fp32 && final_dout) L.dout = final_dout;
+        else ZOO_CUDA(cudaMalloc(&L.dout, (size_t)M * L.cout * (L.out_fp32 ? 4 : net->esz)));
+        if (L.kind == ZOO_LAYER_CONV && i > 0) ZOO_CUDA(cudaMalloc(&L.dcols, (size_t)M * L.K * net->esz));
+    }
+    return ZOO_OK;
+}
+
+zoo_status net_alloc_backward(zoo_net *net) {
+    if (net->bwd_ready) return ZOO_OK;
+    // 64 extra floats: grads[n_flat] carries the loss so data-parallel needs one all-reduce for both
+    ZOO_CUDA(cudaMalloc(&net->grads, (net->n_flat + 64) * sizeof(float)));
+    ZOO_CUDA(cudaMemset(net->grads, 0, (net->n_flat + 64) * sizeof(float)));
+    const long long rq = net->max_batch * std::max<long long>(1, net->max_q);
+    const long long out_rows = net->desc.kind == ZOO_NET_IQN ? rq : net->a.rows_cap;
+    ZOO_CUDA(cudaMalloc(&net->dout_final, (size_t)out_rows * net->n_out * sizeof(float)));
+    ZOO_CUDA(cudaMemset(net->dout_final, 0, (size_t)out_rows * net->n_out * sizeof(float)));
+    if (net->desc.kind == ZOO_NET_CHAIN) ZOO_TRY(alloc_chain_bwd(net, net->a, net->dout_final));
+    else if (net->desc.kind == ZOO_NET_IQN) {
+        ZOO_TRY(alloc_chain_bwd(net, net->a, nullptr));
+        ZOO_TRY(alloc_chain_bwd(net, net->b, nullptr));
+        ZOO_TRY(alloc_chain_bwd(net, net->c, net->dout_final));
+        ZOO_CUDA(cudaMalloc(&net->dmerged, (size_t)rq * net->a.out_feat * net->esz));
+    } else {
+        ZOO_TRY(alloc_chain_bwd(net, net->a, nullptr));
+        ZOO_TRY(alloc_chain_bwd(net, net->b, nullptr));
+        ZOO_TRY(alloc_chain_bwd(net, net->c, nullptr));
+        ZOO_CUDA(cudaMalloc(&net->dh1, (size_t)net->a.rows_cap * net->a.out_feat * net->esz));
+        ZOO_CUDA(cudaMalloc(&net->dh2, (size_t)net->a.rows_cap * net->a.out_feat * net->esz));
+    }
+    net->bwd_ready = true;
+    return ZOO_OK;
+}
+
+}  // namespace zoo
+
+using namespace zoo;
+
+static zoo_status ensure_stage(zoo_net *net, size_t n) {
+    if (net->stage_elems >= n) return ZOO_OK;
+    if (net->stage) cudaFree(net->stage);
+    ZOO_CUDA(cudaMalloc(&net->stage, n * sizeof(float)));
+    net->stage_elems = n;
+    return ZOO_OK;
+}
+
+extern "C" {
+
+zoo_status zoo_net_create(const zoo_net_desc *d, zoo_net **out) {
+    ZOO_REQUIRE(d && out, "zoo_net_create: null argument");
+    ZOO_TRY(require_sm100());
+    ZOO_REQUIRE(d->precision >= ZOO_PREC_FP32 && d->precision <= ZOO_PREC_FP32_SIMT, "zoo_net_create: bad precision %d", d->precision);
+    ZOO_REQUIRE(d->max_batch > 0 && d->in_c > 0 && d->in_h > 0 && d->in_w > 0, "zoo_net_create: bad observation shape / max_batch");
+    ZOO_REQUIRE(d->n_a >= 1 && d->n_a <= ZOO_MAX_LAYERS && d->n_b >= 0 && d->n_b <= ZOO_MAX_LAYERS && d->n_c >= 0 && d->n_c <= ZOO_MAX_LAYERS,
+                "zoo_net_create: bad layer counts");
+    zoo_net *net = new zoo_net();
+    net->desc = *d;
+    net->prec = d->precision;
+    net->esz = d->precision == ZOO_PREC_BF16 ? 2 : 4;
+    net->tf32_passes = d->precision == ZOO_PREC_FP32 ? 3 : (d->precision == ZOO_PREC_TF32 ? 1 : 0);
+    net->max_batch = d->max_batch;
+    net->max_q = d->kind == ZOO_NET_IQN ? d->max_quantiles : 0;
+    ParseState S{d->in_c, d->in_h, d->in_w, !(d->in_h == 1 && d->in_w == 1), (long long)d->in_c, false, true, false};
+    zoo_status s = ZOO_OK;
+    if (d->kind == ZOO_NET_CHAIN) {
+        s = parse_chain(net, d->a, d->n_a, S, net->a, true, "chain");
+        if (s == ZOO_OK) net->n_out = (int)net->a.out_feat;
+    } else if (d->kind == ZOO_NET_IQN) {
+        if (d->max_quantiles <= 0 || d->n_b < 1 || d->n_c < 1) { set_err("zoo_net_create: IQN needs psi, phi, header and max_quantiles"); s = ZOO_BAD_ARG; }
+        if (s == ZOO_OK) s = parse_chain(net, d->a, d->n_a, S, net->a, false, "psi");
+        if (s == ZOO_OK) {
+            if (S.spatial) {  // psi ending without an explicit flatten: flatten implicitly
+                S.spatial = false; S.feat = (long long)S.c * S.h * S.w; S.flat_pending = S.h * S.w > 1;
+                net->fc = S.c; net->fh = S.h; net->fw = S.w;
+            }
+            const bool pend = S.flat_pending;
+            const long long F = S.feat;
+            ParseState Sb{0, 1, 1, false, (long long)d->b[0].n_in, false, false, false};
+            s = parse_chain(net, d->b, d->n_b, Sb, net->b, false, "phi");
+            if (s == ZOO_OK && net->b.out_feat != F) { set_err("IQN: phi output %lld != psi output %lld", net->b.out_feat, F); s = ZOO_BAD_ARG; }
+            if (s == ZOO_OK && pend) {  // phi's output axis lives in the flatten space
+                net->tensors[net->b.layers.back().wt].perm_out = 1;
+                TensorInfo &wb = net->tensors[net->b.layers.back().wt]; wb.fc = net->fc; wb.fh = net->fh; wb.fw = net->fw;
+                TensorInfo &bb = net->tensors[net->b.layers.back().bt]; bb.perm_out = 1; bb.fc = net->fc; bb.fh = net->fh; bb.fw = net->fw;
+            }
+            ParseState Sc{0, 1, 1, false, F, pend, false, false};
+            if (s == ZOO_OK) s = parse_chain(net, d->c, d->n_c, Sc, net->c, true, "header");
+            if (s == ZOO_OK) net->n_out = (int)net->c.out_feat;
+        }
+    } else if (d->kind == ZOO_NET_DUELING) {
+        if (d->n_b < 1 || d->n_c < 1) { set_err("zoo_net_create: dueling needs base, val, adv"); s = ZOO_BAD_ARG; }
+        if (s == ZOO_OK) s = parse_chain(net, d->a, d->n_a, S, net->a, false, "base");
+        if (s == ZOO_OK) {
+            if (S.spatial) { S.spatial = false; S.feat = (long long)S.c * S.h * S.w; S.flat_pending = S.h * S.w > 1; net->fc = S.c; net->fh = S.h; net->fw = S.w; }
+            ParseState Sb = S, Sc = S;
+            s = parse_chain(net, d->b, d->n_b, Sb, net->b, true, "val");
+            if (s == ZOO_OK) s = parse_chain(net, d->c, d->n_c, Sc, net->c, true, "adv");
+            if (s == ZOO_OK && net->b.out_feat != 1) { set_err("dueling: val must have one output"); s = ZOO_BAD_ARG; }
+            if (s == ZOO_OK) net->n_out = (int)net->c.out_feat;
+        }
+    } else {
+        set_err("zoo_net_create: unknown net kind %d", d->kind);
+        s = ZOO_BAD_ARG;
+    }
+    if (s != ZOO_OK) { delete net; return s; }
+
+    long long off = 0;
+    for (auto &t : net->tensors) { t.offset = off; off = align_up(off + t.count, 64); net->n_params += t.count; }
+    net->n_flat = align_up(off, 64);
+    ZOO_CUDA(cudaStreamCreateWithFlags(&net->st, cudaStreamNonBlocking));
+    ZOO_CUDA(cudaMalloc(&net->params, net->n_flat * sizeof(float)));
+    ZOO_CUDA(cudaMemset(net->params, 0, net->n_flat * sizeof(float)));
+    if (net->prec == ZOO_PREC_BF16) {
+        ZOO_CUDA(cudaMalloc(&net->shadow, net->n_flat * sizeof(bf16)));
+        ZOO_CUDA(cudaMemset(net->shadow, 0, net->n_flat * sizeof(bf16)));
+    }
+    const long long rq = net->max_batch * std::max<long long>(1, net->max_q);
+    const long long rows_a = d->kind == ZOO_NET_IQN ? net->max_batch : 2 * net->max_batch;  // online nets evaluate [s; s'] in one pass
+    const long long out_rows = d->kind == ZOO_NET_IQN ? rq : rows_a;
+    ZOO_CUDA(cudaMalloc(&net->out_final, (size_t)out_rows * net->n_out * sizeof(float)));
+    if (d->kind == ZOO_NET_CHAIN) ZOO_TRY(alloc_chain(net, net->a, rows_a, net->out_final));
+    else if (d->kind == ZOO_NET_IQN) {
+        ZOO_TRY(alloc_chain(net, net->a, rows_a, nullptr));
+        ZOO_TRY(alloc_chain(net, net->b, rq, nullptr));
+        ZOO_TRY(alloc_chain(net, net->c, rq, net->out_final));
+        ZOO_CUDA(cudaMalloc(&net->emb, (size_t)rq * net->b.in_feat * net->esz));
+        ZOO_CUDA(cudaMalloc(&net->merged, (size_t)rq * net->a.out_feat * net->esz));
+        ZOO_CUDA(cudaMalloc(&net->tau_dev, (size_t)rq * sizeof(float)));
+    } else {
+        ZOO_TRY(alloc_chain(net, net->a, rows_a, nullptr));
+        ZOO_TRY(alloc_chain(net, net->b, rows_a, nullptr));
+        ZOO_TRY(alloc_chain(net, net->c, rows_a, nullptr));
+    }
+    net->ws_elems = (size_t)6 << 20;  // 24 MB split-K workspace (largest split-K output: 148 tiles of 128 x 128 fp32)
+    ZOO_CUDA(cudaMalloc(&net->ws, net->ws_elems * sizeof(float)));
+    ZOO_CUDA(cudaMalloc(&net->obs, (size_t)rows_a * obs_elems(net) * sizeof(float)));
+    *out = net;
+    return ZOO_OK;
+}
+
+static void free_chain(Chain &ch, float *fo, float *fd) {
+    for (auto &L : ch.layers) {
+        if (L.cols) cudaFree(L.cols);
+        if (L.out && L.out != fo) cudaFree(L.out);
+        if (L.dout && L.dout != fd) cudaFree(L.dout);
+        if (L.dcols) cudaFree(L.dcols);
+    }
+}
+
+zoo_status zoo_net_destroy(zoo_net *net) {
+    if (!net) return ZOO_OK;
+    cudaStreamSynchronize(net->st);
+    free_chain(net->a, net->out_final, net->dout_final);
+    free_chain(net->b, net->out_final, net->dout_final);
+    free_chain(net->c, net->out_final, net->dout_final);
+    void *ptrs[] = {net->params, net->shadow, net->grads, net->out_final, net->dout_final, net->emb, net->merged, net->dmerged,
+                    net->tau_dev, net->dh1, net->dh2, net->ws, net->obs, net->stage};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    cudaStreamDestroy(net->st);
+    delete net;
+    return ZOO_OK;
+}
+
+zoo_status zoo_net_num_tensors(const zoo_net *net, int32_t *n) {
+    ZOO_REQUIRE(net && n, "zoo_net_num_tensors: null argument");
+    *n = (int32_t)net->tensors.size();
+    return ZOO_OK;
+}
+zoo_status zoo_net_tensor_size(const zoo_net *net, int32_t id, int64_t *n) {
+    ZOO_REQUIRE(net && n && id >= 0 && id < (int)net->tensors.size(), "zoo_net_tensor_size: bad tensor id %d", id);
+    *n = net->tensors[id].count;
+    return ZOO_OK;
+}
+zoo_status zoo_net_num_params(const zoo_net *net, int64_t *n) {
+    ZOO_REQUIRE(net && n, "zoo_net_num_params: null argument");
+    *n = net->n_params;
+    return ZOO_OK;
+}
+zoo_status zoo_net_out_dim(const zoo_net *net, int32_t *n) {
+    ZOO_REQUIRE(net && n, "zoo_net_out_dim: null argument");
+    *n = net->n_out;
+    return ZOO_OK;
+}
+
+// shared by params / grads / optimiser state: flat = device buffer in the internal layout
+zoo_status zoo_internal_tensor_io(zoo_net *net, float *flat, int32_t id, float *host, int64_t n, int to_device) {
+    ZOO_REQUIRE(net && flat && host && id >= 0 && id < (int)net->tensors.size(), "tensor io: bad tensor id %d", id);
+    const TensorInfo &t = net->tensors[id];
+    ZOO_REQUIRE(n == t.count, "tensor io: tensor %d has %lld elements, caller passed %lld", id, t.count, (long long)n);
+    ZOO_TRY(ensure_stage(net, (size_t)t.count));
+    if (to_device) {
+        ZOO_CUDA(cudaMemcpyAsync(net->stage, host, t.count * sizeof(float), cudaMemcpyHostToDevice, net->st));
+        permute_param_kernel<<<cdiv(t.count, 256), 256, 0, net->st>>>(flat + t.offset, net->stage, t, 0);
+        ZOO_LAUNCH_CHECK();
+    } else {
+        permute_param_kernel<<<cdiv(t.count, 256), 256, 0, net->st>>>(flat + t.offset, net->stage, t, 1);
+        ZOO_LAUNCH_CHECK();
+        ZOO_CUDA(cudaMemcpyAsync(host, net->stage, t.count * sizeof(float), cudaMemcpyDeviceToHost, net->st));
+    }
+    ZOO_CUDA(cudaStreamSynchronize(net->st));
+    return ZOO_OK;
+}
+
+zoo_status zoo_net_set_params(zoo_net *net, int32_t id, const float *host, int64_t n) {
+    ZOO_REQUIRE(net, "zoo_net_set_params: null net");
+    ZOO_TRY(zoo_internal_tensor_io(net, net->params, id, const_cast<float *>(host), n, 1));
+    ZOO_TRY(net_refresh_shadow(net, net->st));
+    ZOO_CUDA(cudaStreamSynchronize(net->st));
+    return ZOO_OK;
+}
+zoo_status zoo_net_get_params(const zoo_net *net, int32_t id, float *host, int64_t n) {
+    ZOO_REQUIRE(net, "zoo_net_get_params: null net");
+    zoo_net *m = const_cast<zoo_net *>(net);
+    return zoo_internal_tensor_io(m, m->params, id, host, n, 0);
+}
+
+zoo_status zoo_net_copy(zoo_net *dst, const zoo_net *src) {
+    ZOO_REQUIRE(dst && src, "zoo_net_copy: null argument");
+    ZOO_REQUIRE(dst->n_flat == src->n_flat && dst->tensors.size() == src->tensors.size(), "zoo_net_copy: nets have different structure");
+    ZOO_CUDA(cudaMemcpyAsync(dst->params, src->params, src->n_flat * sizeof(float), cudaMemcpyDeviceToDevice, dst->st));
+    ZOO_TRY(net_refresh_shadow(dst, dst->st));
+    ZOO_CUDA(cudaStreamSynchronize(dst->st));
+    return ZOO_OK;
+}
+
+zoo_status zoo_net_forward(zoo_net *net, const void *obs_host, int32_t obs_dtype, int32_t B, const float *tau_host, int32_t n_tau, float *out_host) {
+    ZOO_REQUIRE(net && obs_host && out_host && B > 0, "zoo_net_forward: bad argument");
+    ZOO_REQUIRE(obs_dtype == ZOO_OBS_U8 || obs_dtype == ZOO_OBS_F32, "zoo_net_forward: bad obs dtype");
+    ZOO_REQUIRE(B <= net->a.rows_cap, "zoo_net_forward: B %d exceeds capacity %lld", B, net->a.rows_cap);
+    size_t ob = (size_t)B * obs_elems(net) * (obs_dtype == ZOO_OBS_U8 ? 1 : 4);
+    ZOO_CUDA(cudaMemcpyAsync(net->obs, obs_host, ob, cudaMemcpyHostToDevice, net->st));
+    long long R = B;
+    if (net->desc.kind == ZOO_NET_IQN) {
+        ZOO_REQUIRE(tau_host && n_tau > 0 && n_tau <= net->max_q && B <= net->max_batch, "zoo_net_forward: IQN needs tau [B][n_tau], n_tau <= max_quantiles");
+        R = (long long)B * n_tau;
+        ZOO_CUDA(cudaMemcpyAsync(net->tau_dev, tau_host, R * sizeof(float), cudaMemcpyHostToDevice, net->st));
+    }
+    ZOO_TRY(net_forward(net, net->obs, obs_dtype, B, net->tau_dev, n_tau, net->st));
+    ZOO_CUDA(cudaMemcpyAsync(out_host, net->out_final, (size_t)R * net->n_out * sizeof(float), cudaMemcpyDeviceToHost, net->st));
+    ZOO_CUDA(cudaStreamSynchronize(net->st));
+    return ZOO_OK;
+}
+
+}  // extern "C"

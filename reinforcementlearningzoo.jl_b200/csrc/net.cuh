@@ -47,6 +47,7 @@ struct zoo_net {
     zoo_net_desc desc;
     int prec;      // ZOO_PREC_*
     int esz;       // bytes per internal activation element (4 | 2)
+    int tf32_passes = 0;  // fp32 operands on tcgen05: 3 (FP32), 1 (TF32), 0 (FP32_SIMT)
     std::vector<zoo::TensorInfo> tensors;
     long long n_flat = 0;      // padded element count of the flat buffers
     long long n_params = 0;    // true parameter count
