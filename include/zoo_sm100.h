@@ -234,6 +234,14 @@ ZOO_API zoo_status zoo_dp_unique_id(uint8_t id_out[128]);
 ZOO_API zoo_status zoo_dp_init(const uint8_t id[128], int32_t rank, int32_t world, zoo_dp **out);
 ZOO_API zoo_status zoo_dp_destroy(zoo_dp *dp);
 
+/* ------------------------------------------------------------------ profiling ----------- */
+/* In-situ launch profiler: between begin and end an event is recorded on `stream` after every kernel this
+ * thread enqueues through the library (eager mode only, not graph replay); zoo_prof_get returns launch i's
+ * label ("<phase>:<layer>|<launcher>:<line>") and its device time in ms (time since the previous launch ended). */
+ZOO_API zoo_status zoo_prof_begin(void *stream);
+ZOO_API zoo_status zoo_prof_end(int32_t *n_launches);
+ZOO_API zoo_status zoo_prof_get(int32_t i, char *name, int32_t name_cap, float *ms);
+
 /* ------------------------------------------------------------------ test hooks ---------- */
 /* Stand-alone GEMM of the two contraction engines, for parity tests of the kernels themselves:
  * D[M][N] = sum_k A(m,k) B(n,k).  a_kmajor: A stored [M][K] (1) or [K][M] (0); same for B ([N][K] / [K][N]).

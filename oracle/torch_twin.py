@@ -77,6 +77,9 @@ def _t(x, dtype):
 
 
 def _leaf(params, dtype):
+    # already-leaf tensors (the CPU timing arm keeps its parameters as torch leaves) are used in place
+    if all(isinstance(p, torch.Tensor) and p.requires_grad for p in params):
+        return list(params)
     return [_t(p, dtype).clone().requires_grad_(True) for p in params]
 
 
@@ -101,8 +104,13 @@ def _per_w(batch, beta, dtype):
     return (w / w.max()).to(dtype)
 
 
+KEEP_TORCH_GRADS = False  # the CPU timing arm sets this: leave gradients in p.grad, skip the numpy copies
+
+
 def _finish(loss, ps, extra):
     loss.backward()
+    if KEEP_TORCH_GRADS:
+        return {"loss": loss.detach()}
     out = {"loss": loss.detach().numpy().copy(), "grads": [p.grad.numpy().copy() if p.grad is not None else np.zeros(p.shape, np.float32) for p in ps]}
     out.update(extra)
     return out
@@ -245,3 +253,31 @@ class Adam:
             v.mul_(b2).addcmul_(g, g, value=1 - b2)
             p.sub_(m / (1 - self.bp[0]) / ((v / (1 - self.bp[1])).sqrt() + 1e-8) * self.eta)
         self.bp = [self.bp[0] * b1, self.bp[1] * b2]
+
+
+class CpuLearner:
+    """The reference's update!(learner, batch) executed on the host cores with torch (MKL/oneDNN, fp32): the CPU arm
+    bench.py times (cpu_baseline / --impl reference).  kind in {"dqn", "rainbow", "iqn"}."""
+
+    def __init__(self, kind, net, params, tparams, opt, **cfg):
+        self.kind, self.net, self.cfg = kind, net, cfg
+        self.ps = [torch.from_numpy(np.ascontiguousarray(p)).clone().requires_grad_(True) for p in params]
+        self.tps = [torch.from_numpy(np.ascontiguousarray(p)).clone() for p in tparams]
+        self.opt = RMSProp(self.ps, *opt[1:]) if opt[0] == "rmsprop" else Adam(self.ps, *opt[1:])
+
+    def update(self, batch, tau=None, tau_prime=None):
+        global KEEP_TORCH_GRADS
+        KEEP_TORCH_GRADS = True
+        try:
+            for p in self.ps:
+                p.grad = None
+            if self.kind == "dqn":
+                r = dqn_grads(self.net, self.ps, self.tps, batch, **self.cfg)
+            elif self.kind == "rainbow":
+                r = rainbow_grads(self.net, self.ps, self.tps, batch, **self.cfg)
+            else:
+                r = iqn_grads(self.net, self.ps, self.tps, batch, tau, tau_prime, **self.cfg)
+            self.opt.step(self.ps, [p.grad for p in self.ps])
+            return float(r["loss"])
+        finally:
+            KEEP_TORCH_GRADS = False

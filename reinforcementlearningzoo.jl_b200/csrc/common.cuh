@@ -43,9 +43,16 @@ extern thread_local int g_launches;  // kernels enqueued since the counter was l
         }                                \
     } while (0)
 
+// Built-in launch profiler (zoo_prof_*): when armed, an event is recorded after every kernel launch on the profiled
+// stream, so consecutive differences give warm, in-situ per-kernel durations (bench.py's roofline leg).
+extern thread_local bool g_prof_on;
+void prof_mark(const char *func, int line);
+void prof_label(const char *fmt, ...);
+
 #define ZOO_LAUNCH_CHECK()                                                                   \
     do {                                                                                     \
         zoo::g_launches++;                                                                   \
+        if (zoo::g_prof_on) zoo::prof_mark(__func__, __LINE__);                              \
         cudaError_t e__ = cudaGetLastError();                                                \
         if (e__ != cudaSuccess) {                                                            \
             zoo::set_err("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \

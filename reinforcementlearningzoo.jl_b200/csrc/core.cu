@@ -15,6 +15,31 @@ void set_err(const char *fmt, ...) {
     g_err = buf;
 }
 
+thread_local bool g_prof_on = false;
+static thread_local cudaStream_t g_prof_stream = nullptr;
+static thread_local std::vector<cudaEvent_t> g_prof_events;
+static thread_local std::vector<std::string> g_prof_names;
+static thread_local std::vector<float> g_prof_ms;
+static thread_local char g_prof_lbl[96] = "";
+
+void prof_label(const char *fmt, ...) {
+    if (!g_prof_on) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_prof_lbl, sizeof(g_prof_lbl), fmt, ap);
+    va_end(ap);
+}
+
+void prof_mark(const char *func, int line) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, g_prof_stream);
+    g_prof_events.push_back(e);
+    char buf[192];
+    snprintf(buf, sizeof(buf), "%s%s%s:%d", g_prof_lbl, g_prof_lbl[0] ? "|" : "", func, line);
+    g_prof_names.push_back(buf);
+}
+
 // No CPU fallback and no other architecture: everything here is sm_100a SASS.
 zoo_status require_sm100() {
     static int cached = -1;
@@ -61,6 +86,33 @@ int32_t zoo_device_arch(void) {
 
 zoo_status zoo_set_device(int32_t device) {
     ZOO_CUDA(cudaSetDevice(device));
+    return ZOO_OK;
+}
+
+zoo_status zoo_prof_begin(void *stream) {
+    for (cudaEvent_t e : g_prof_events) cudaEventDestroy(e);
+    g_prof_events.clear(); g_prof_names.clear(); g_prof_ms.clear();
+    g_prof_stream = (cudaStream_t)stream;
+    g_prof_lbl[0] = 0;
+    g_prof_on = true;
+    prof_mark("begin", 0);
+    return ZOO_OK;
+}
+
+zoo_status zoo_prof_end(int32_t *n) {
+    ZOO_REQUIRE(n, "zoo_prof_end: null argument");
+    g_prof_on = false;
+    ZOO_CUDA(cudaStreamSynchronize(g_prof_stream));
+    g_prof_ms.assign(g_prof_events.size(), 0.f);
+    for (size_t i = 1; i < g_prof_events.size(); ++i) cudaEventElapsedTime(&g_prof_ms[i], g_prof_events[i - 1], g_prof_events[i]);
+    *n = (int32_t)g_prof_events.size() - 1;
+    return ZOO_OK;
+}
+
+zoo_status zoo_prof_get(int32_t i, char *name, int32_t cap, float *ms) {
+    ZOO_REQUIRE(name && ms && i >= 0 && i + 1 < (int)g_prof_events.size() && cap > 0, "zoo_prof_get: bad index");
+    snprintf(name, cap, "%s", g_prof_names[i + 1].c_str());
+    *ms = g_prof_ms[i + 1];
     return ZOO_OK;
 }
 

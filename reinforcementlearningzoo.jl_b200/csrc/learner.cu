@@ -124,6 +124,7 @@ struct zoo_learner {
 static zoo_status opt_step(zoo_opt *o, cudaStream_t st) {
     zoo_net *net = o->net;
     const long long n4 = net->n_flat / 4;
+    prof_label("opt");
     opt_tick_kernel<<<1, 1, 0, st>>>(o->sc, o->a, o->b);
     ZOO_LAUNCH_CHECK();
     if (o->kind == ZOO_OPT_RMSPROP)
@@ -148,45 +149,46 @@ static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bo
     const void *s2_ptr = (const uint8_t *)L->d_obs + (size_t)B * obs_row;
     const int world = L->dp ? dp_world(L->dp) : 1;
     ZOO_CUDA(cudaMemsetAsync(on->grads, 0, (on->n_flat + 64) * sizeof(float), st));
+    prof_label("head");
     HeadArgs h;
     h.B = B; h.A = c.n_actions; h.action = L->d_action; h.reward = L->d_reward; h.terminal = L->d_terminal;
     h.mask = has_mask ? L->d_mask : nullptr; h.w_raw = nullptr; h.w_max = nullptr;
     h.inv_B = 1.0f / (float)((long long)B * world); h.per_sample = L->d_per;
     const bool per_kind = c.kind == ZOO_LEARNER_PRIORITIZED_DQN || ((c.kind == ZOO_LEARNER_RAINBOW || c.kind == ZOO_LEARNER_IQN) && has_prio);
     if (per_kind) {
-        ZOO_TRY(launch_per_weights(L->d_priority, c.beta_priority, B, L->d_wraw, L->d_wmax, st));
+        prof_label("head"); ZOO_TRY(launch_per_weights(L->d_priority, c.beta_priority, B, L->d_wraw, L->d_wmax, st));
         if (L->dp) ZOO_TRY(dp_allreduce_max(L->dp, L->d_wmax, 1, st));
         h.w_raw = L->d_wraw; h.w_max = L->d_wmax;
     }
     int bwd_rows = B, n_tau = 0;
     if (c.kind == ZOO_LEARNER_BASIC_DQN) {
         ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, 2 * B, nullptr, 0, st));  // Q([s; s'])
-        ZOO_TRY(launch_dqn_head(c.kind, 0, h, on->out_final, nullptr, c.gamma, on->dout_final, st));
+        prof_label("head"); ZOO_TRY(launch_dqn_head(c.kind, 0, h, on->out_final, nullptr, c.gamma, on->dout_final, st));
         bwd_rows = 2 * B;
     } else if (c.kind == ZOO_LEARNER_DQN || c.kind == ZOO_LEARNER_PRIORITIZED_DQN) {
         const int dbl = c.kind == ZOO_LEARNER_DQN && c.double_dqn;
         ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, dbl ? 2 * B : B, nullptr, 0, st));
         ZOO_TRY(net_forward(tg, s2_ptr, L->obs_dtype, B, nullptr, 0, st));
-        ZOO_TRY(launch_dqn_head(c.kind, dbl, h, on->out_final, tg->out_final, L->gamma_n, on->dout_final, st));
+        prof_label("head"); ZOO_TRY(launch_dqn_head(c.kind, dbl, h, on->out_final, tg->out_final, L->gamma_n, on->dout_final, st));
     } else if (c.kind == ZOO_LEARNER_RAINBOW) {
         ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, B, nullptr, 0, st));
         ZOO_TRY(net_forward(tg, s2_ptr, L->obs_dtype, B, nullptr, 0, st));
-        ZOO_TRY(launch_c51_head(h, c.n_atoms, tg->out_final, on->out_final, L->d_support, c.delta_z, c.v_min, c.v_max, L->gamma_n,
+        prof_label("head"); ZOO_TRY(launch_c51_head(h, c.n_atoms, tg->out_final, on->out_final, L->d_support, c.delta_z, c.v_min, c.v_max, L->gamma_n,
                                 on->dout_final, L->d_tdist, st));
     } else {  // IQN
         if (!has_tau) {
-            ZOO_TRY(launch_tau(L->d_taup, (long long)B * c.N_prime, c.seed, &L->opt->sc->rng, 0, st));
+            prof_label("head"); ZOO_TRY(launch_tau(L->d_taup, (long long)B * c.N_prime, c.seed, &L->opt->sc->rng, 0, st));
             ZOO_TRY(launch_tau(L->d_tau, (long long)B * c.N, c.seed, &L->opt->sc->rng, 1, st));
             rng_tick_kernel<<<1, 1, 0, st>>>(L->opt->sc);
             ZOO_LAUNCH_CHECK();
         }
         ZOO_TRY(net_forward(tg, s2_ptr, L->obs_dtype, B, L->d_taup, c.N_prime, st));
-        ZOO_TRY(launch_iqn_target(h, c.N_prime, tg->out_final, c.gamma, L->d_target, st));
+        prof_label("head"); ZOO_TRY(launch_iqn_target(h, c.N_prime, tg->out_final, c.gamma, L->d_target, st));
         ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, B, L->d_tau, c.N, st));
-        ZOO_TRY(launch_iqn_loss(h, c.N, c.N_prime, on->out_final, L->d_target, L->d_tau, c.kappa, on->dout_final, st));
+        prof_label("head"); ZOO_TRY(launch_iqn_loss(h, c.N, c.N_prime, on->out_final, L->d_target, L->d_tau, c.kappa, on->dout_final, st));
         n_tau = c.N;
     }
-    ZOO_TRY(launch_loss_reduce(h, c.beta_priority, L->d_loss, L->d_prio, st));
+    prof_label("head"); ZOO_TRY(launch_loss_reduce(h, c.beta_priority, L->d_loss, L->d_prio, st));
     ZOO_TRY(net_backward(on, L->obs_dtype, s_ptr, bwd_rows, n_tau, st));
     if (L->dp) ZOO_TRY(dp_allreduce_sum(L->dp, on->grads, on->n_flat + 64, st));  // gradients + loss in one collective
     return ZOO_OK;

@@ -307,6 +307,7 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
         const long long M = rows * L.opr;
         const TensorInfo &W = net->tensors[L.wt];
         const TensorInfo &Bt = net->tensors[L.bt];
+        prof_label("fwd:t%d[%lldx%dx%lld]", L.wt, M, L.cout, L.K);
         Operand A;
         if (L.kind == ZOO_LAYER_CONV) {
             if (L.first_raw) {
@@ -351,6 +352,7 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
         const TensorInfo &W = net->tensors[L.wt];
         const TensorInfo &Bt = net->tensors[L.bt];
         const int dy_bf = L.out_fp32 ? 0 : bf;
+        prof_label("bgrad:t%d", L.bt);
         ZOO_TRY(launch_colsum(L.dout, dy_bf, M, L.cout, net->grads + Bt.offset, st));
         // wgrad: dW[cout][K] += dY^T X   (both operands MN-major: stored [rows][features])
         Operand X;
@@ -358,12 +360,14 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
         else if (li == 0) X = Operand{in, in_kind == 2 ? bf : 0, L.K, 0};
         else X = Operand{ch.layers[li - 1].out, bf, L.K, 0};
         Operand dYt{L.dout, dy_bf, L.cout, 0};
+        prof_label("wgrad:t%d[%dx%lldx%lld]", L.wt, L.cout, L.K, M);
         Epilogue ew;
         ew.out = net->grads + W.offset; ew.sm = L.K; ew.sn = 1; ew.accumulate = 1; ew.tf32_passes = net->tf32_passes;
         ZOO_TRY(gemm(dYt, X, L.cout, (int)L.K, (int)M, ew, 0, net->ws, net->ws_elems, st));
         // dgrad
         if (li == 0 && !dx) continue;
         Operand dY{L.dout, dy_bf, L.cout, 1};
+        prof_label("dgrad:t%d[%lldx%lldx%d]", L.wt, M, L.K, L.cout);
         Operand Wn = weight_operand(net, W, dY, (int)M, (int)L.K, L.cout, L.K, 0);
         Epilogue ed;
         ed.sm = L.K; ed.sn = 1; ed.out_bf16 = bf; ed.tf32_passes = net->tf32_passes;
