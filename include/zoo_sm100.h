@@ -236,9 +236,11 @@ ZOO_API zoo_status zoo_dp_destroy(zoo_dp *dp);
 
 /* ------------------------------------------------------------------ profiling ----------- */
 /* In-situ launch profiler: between begin and end an event is recorded on `stream` after every kernel this
- * thread enqueues through the library (eager mode only, not graph replay); zoo_prof_get returns launch i's
+ * thread enqueues through the library (eager mode only, not graph replay).  delay_us > 0 first parks a sleeping
+ * kernel on the stream so the launches queue up behind it and the gaps are device time, not host launch rate.
+ * zoo_prof_get returns launch i's
  * label ("<phase>:<layer>|<launcher>:<line>") and its device time in ms (time since the previous launch ended). */
-ZOO_API zoo_status zoo_prof_begin(void *stream);
+ZOO_API zoo_status zoo_prof_begin(void *stream, int32_t delay_us);
 ZOO_API zoo_status zoo_prof_end(int32_t *n_launches);
 ZOO_API zoo_status zoo_prof_get(int32_t i, char *name, int32_t name_cap, float *ms);
 

@@ -104,7 +104,7 @@ SIGNATURES = {
     "zoo_dp_unique_id": [V],
     "zoo_dp_init": [V, I32, I32, PV],
     "zoo_dp_destroy": [V],
-    "zoo_prof_begin": [V],
+    "zoo_prof_begin": [V, I32],
     "zoo_prof_end": [C.POINTER(I32)],
     "zoo_prof_get": [I32, C.c_char_p, I32, C.POINTER(F32)],
     "zoo_test_gemm": [I32, I32, I32, I32, V, I32, V, I32, V, I32],

@@ -40,6 +40,15 @@ void prof_mark(const char *func, int line) {
     g_prof_names.push_back(buf);
 }
 
+__global__ void prof_delay_kernel(unsigned long long ns) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(1000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while (t - t0 < ns);
+}
+
 // No CPU fallback and no other architecture: everything here is sm_100a SASS.
 zoo_status require_sm100() {
     static int cached = -1;
@@ -89,11 +98,13 @@ zoo_status zoo_set_device(int32_t device) {
     return ZOO_OK;
 }
 
-zoo_status zoo_prof_begin(void *stream) {
+zoo_status zoo_prof_begin(void *stream, int32_t delay_us) {
     for (cudaEvent_t e : g_prof_events) cudaEventDestroy(e);
     g_prof_events.clear(); g_prof_names.clear(); g_prof_ms.clear();
     g_prof_stream = (cudaStream_t)stream;
     g_prof_lbl[0] = 0;
+    // hold the stream busy while the host enqueues, so event differences are device time, not launch-rate gaps
+    if (delay_us > 0) prof_delay_kernel<<<1, 1, 0, g_prof_stream>>>((unsigned long long)delay_us * 1000ull);
     g_prof_on = true;
     prof_mark("begin", 0);
     return ZOO_OK;

@@ -149,6 +149,7 @@ static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bo
     const void *s2_ptr = (const uint8_t *)L->d_obs + (size_t)B * obs_row;
     const int world = L->dp ? dp_world(L->dp) : 1;
     ZOO_CUDA(cudaMemsetAsync(on->grads, 0, (on->n_flat + 64) * sizeof(float), st));
+    if (g_prof_on) { prof_label("stage+zero_grads"); prof_mark("memcpy/memset", __LINE__); }
     prof_label("head");
     HeadArgs h;
     h.B = B; h.A = c.n_actions; h.action = L->d_action; h.reward = L->d_reward; h.terminal = L->d_terminal;

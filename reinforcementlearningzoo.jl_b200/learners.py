@@ -41,11 +41,27 @@ class _Learner:
             pass
 
     def _batch(self, batch, tau=None, tau_prime=None):
+        """dict of host numpy arrays, or of device tensors (anything with ``data_ptr()``, e.g. torch CUDA tensors on the
+        library's device with the ABI dtypes: u8|f32 frames, int32 actions, f32 rewards, u8 terminals) -> zoo_batch."""
+        b = L.Batch()
+        if hasattr(batch["state"], "data_ptr"):
+            s = batch["state"]
+            keep = [s, batch["next_state"], batch["action"], batch["reward"], batch["terminal"], batch.get("priority"),
+                    batch.get("next_legal_actions_mask"), tau, tau_prime]
+            want = [None, None, 4, 4, 1, 4, 1, 4, 4]
+            for x, w in zip(keep, want):
+                if x is not None and not (x.is_cuda and x.is_contiguous() and (w is None or x.element_size() == w)):
+                    raise ValueError("device batches must be contiguous CUDA tensors with the ABI dtypes")
+            b.B = int(s.shape[0])
+            b.obs_dtype = L.OBS_U8 if s.element_size() == 1 else L.OBS_F32
+            (b.state, b.next_state, b.action, b.reward, b.terminal, b.priority, b.next_mask, b.tau, b.tau_prime) = (
+                None if x is None else x.data_ptr() for x in keep)
+            b.on_device = 1
+            return b, keep
         s = np.ascontiguousarray(batch["state"])
         s2 = np.ascontiguousarray(batch["next_state"])
         if s.dtype != np.uint8:
             s, s2 = s.astype(np.float32, copy=False), s2.astype(np.float32, copy=False)
-        b = L.Batch()
         keep = [s, s2, _c(batch["action"], np.int32), _c(batch["reward"], np.float32), _c(batch["terminal"], np.uint8),
                 _c(batch.get("priority"), np.float32), _c(batch.get("next_legal_actions_mask"), np.uint8),
                 _c(tau, np.float32), _c(tau_prime, np.float32)]
@@ -55,14 +71,14 @@ class _Learner:
         b.on_device = 0
         return b, keep
 
-    def update(self, batch, tau=None, tau_prime=None, want_loss=True, apply=True):
+    def update(self, batch, tau=None, tau_prime=None, want_loss=True, apply=True, want_priorities=True):
         """``RLBase.update!(learner, batch::NamedTuple)``.  0-based actions.  IQN: tau/tau_prime [B,N]/[B,N′]
         override the on-device RNG (used for parity)."""
         lib = L.lib()
         b, keep = self._batch(batch, tau, tau_prime)
         per = batch.get("priority") is not None
         loss = C.c_float(0)
-        prio = np.empty(b.B, np.float32) if per else None
+        prio = np.empty(b.B, np.float32) if (per and want_priorities) else None
         fn = lib.zoo_learner_update if apply else lib.zoo_learner_compute_grads
         L.check(fn(self.h, C.byref(b), C.byref(loss) if want_loss else None, L.ptr(prio)))
         if want_loss:
@@ -97,6 +113,24 @@ class _Learner:
         s = C.c_void_p()
         L.check(L.lib().zoo_learner_stream(self.h, C.byref(s)))
         return s.value
+
+    def profile(self, batch, delay_us=3000, **kw):
+        """One eager (non-graph) update under the built-in launch profiler: [(label, ms), ...] per kernel launch."""
+        lib = L.lib()
+        b, keep = self._batch(batch, kw.get("tau"), kw.get("tau_prime"))
+        L.check(lib.zoo_learner_use_graph(self.h, 0))
+        L.check(lib.zoo_prof_begin(self.stream(), int(delay_us)))
+        try:
+            L.check(lib.zoo_learner_update(self.h, C.byref(b), None, None))
+        finally:
+            n = C.c_int32()
+            L.check(lib.zoo_prof_end(C.byref(n)))
+        out = []
+        name, ms = C.create_string_buffer(256), C.c_float()
+        for i in range(n.value):
+            L.check(lib.zoo_prof_get(i, name, 256, C.byref(ms)))
+            out.append((name.value.decode(), ms.value))
+        return out
 
     def last_launches(self):
         n = C.c_int32()
