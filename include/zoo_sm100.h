@@ -251,6 +251,15 @@ ZOO_API zoo_status zoo_prof_get(int32_t i, char *name, int32_t name_cap, float *
 ZOO_API zoo_status zoo_test_gemm(int32_t engine, int32_t M, int32_t N, int32_t K, const float *A, int32_t a_kmajor,
                                  const float *B, int32_t b_kmajor, float *D, int32_t split_k);
 
+/* device-time benchmark of one GEMM shape: mean microseconds over `iters` back-to-back GEMMs (operands resident, zeros).
+ * mode: 0 plain store, 1 atomic accumulate (wgrad), 2 bias + relu (forward). */
+ZOO_API zoo_status zoo_test_gemm_bench(int32_t engine, int32_t M, int32_t N, int32_t K, int32_t a_kmajor, int32_t b_kmajor,
+                                       int32_t split_k, int32_t mode, int32_t iters, float *us_out);
+
+/* %globaltimer stamps (ns) of CTA (0,0,0) of one tcgen05 GEMM launch at its phase boundaries (see core.cu) */
+ZOO_API zoo_status zoo_test_gemm_trace(int32_t engine, int32_t M, int32_t N, int32_t K, int32_t a_kmajor, int32_t b_kmajor,
+                                       int32_t split_k, uint64_t *stamps9);
+
 #ifdef __cplusplus
 }
 #endif

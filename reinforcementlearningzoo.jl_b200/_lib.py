@@ -108,6 +108,8 @@ SIGNATURES = {
     "zoo_prof_end": [C.POINTER(I32)],
     "zoo_prof_get": [I32, C.c_char_p, I32, C.POINTER(F32)],
     "zoo_test_gemm": [I32, I32, I32, I32, V, I32, V, I32, V, I32],
+    "zoo_test_gemm_trace": [I32, I32, I32, I32, I32, I32, I32, V],
+    "zoo_test_gemm_bench": [I32, I32, I32, I32, I32, I32, I32, I32, I32, C.POINTER(F32)],
 }
 _OTHER_RESTYPE = {"zoo_last_error": ([], C.c_char_p), "zoo_version": ([], I32), "zoo_device_arch": ([], I32)}
 

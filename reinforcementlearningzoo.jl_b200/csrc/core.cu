@@ -50,6 +50,8 @@ __global__ void prof_delay_kernel(unsigned long long ns) {
 }
 
 // No CPU fallback and no other architecture: everything here is sm_100a SASS.
+extern unsigned long long *g_tc_dbg;
+
 zoo_status require_sm100() {
     static int cached = -1;
     if (cached < 0) {
@@ -138,7 +140,8 @@ zoo_status zoo_test_gemm(int32_t engine, int32_t M, int32_t N, int32_t K, const 
     ZOO_CUDA(cudaMalloc(&dA, na * 4));
     ZOO_CUDA(cudaMalloc(&dB, nb * 4));
     ZOO_CUDA(cudaMalloc(&dD, nd * 4));
-    ZOO_CUDA(cudaMalloc(&ws, nd * 4));
+    ZOO_CUDA(cudaMalloc(&ws, (nd + 4096) * 4));
+    ZOO_CUDA(cudaMemsetAsync(ws, 0, (nd + 4096) * 4, st));
     ZOO_CUDA(cudaMemcpyAsync(dA, A, na * 4, cudaMemcpyHostToDevice, st));
     ZOO_CUDA(cudaMemcpyAsync(dB, B, nb * 4, cudaMemcpyHostToDevice, st));
     Operand oa{dA, 0, a_kmajor ? K : M, a_kmajor}, ob{dB, 0, b_kmajor ? K : N, b_kmajor};
@@ -153,13 +156,13 @@ zoo_status zoo_test_gemm(int32_t engine, int32_t M, int32_t N, int32_t K, const 
         f32_to_bf16_kernel<<<cdiv(nb, 256), 256, 0, st>>>(dB, hB, nb);
         oa.p = hA; oa.is_bf16 = 1; ob.p = hB; ob.is_bf16 = 1;
         ZOO_REQUIRE(tc_gemm_supported(oa, ob, M, N, K), "zoo_test_gemm: shape not supported by the tcgen05 engine");
-        s = tc_gemm(oa, ob, M, N, K, e, split_k, ws, nd, st);
+        s = tc_gemm(oa, ob, M, N, K, e, split_k, ws, nd + 4096, st);
     } else if (engine == 2 || engine == 3) {
         e.tf32_passes = engine == 2 ? 1 : 3;
         ZOO_REQUIRE(tc_gemm_supported(oa, ob, M, N, K), "zoo_test_gemm: shape not supported by the tcgen05 engine");
-        s = tc_gemm(oa, ob, M, N, K, e, split_k, ws, nd, st);
+        s = tc_gemm(oa, ob, M, N, K, e, split_k, ws, nd + 4096, st);
     } else {
-        s = simt_gemm(oa, ob, M, N, K, e, split_k, ws, nd, st);
+        s = simt_gemm(oa, ob, M, N, K, e, split_k, ws, nd + 4096, st);
     }
     if (s != ZOO_OK) return s;
     ZOO_CUDA(cudaMemcpyAsync(D, dD, nd * 4, cudaMemcpyDeviceToHost, st));
@@ -167,6 +170,79 @@ zoo_status zoo_test_gemm(int32_t engine, int32_t M, int32_t N, int32_t K, const 
     cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(ws);
     if (hA) cudaFree(hA);
     if (hB) cudaFree(hB);
+    cudaStreamDestroy(st);
+    return ZOO_OK;
+}
+
+// Phase timestamps (ns, %globaltimer) of CTA (0,0,0) of one tcgen05 GEMM launch: 0 entry, 1 setup done, 2 first TMA issued,
+// 3 first stage landed, 4 last MMA committed, 5 accumulator ready (epilogue), 6 epilogue done, 7 CTA joined, 8 TMEM freed.
+zoo_status zoo_test_gemm_trace(int32_t engine, int32_t M, int32_t N, int32_t K, int32_t a_kmajor, int32_t b_kmajor, int32_t split_k,
+                               uint64_t *stamps9) {
+    ZOO_REQUIRE(stamps9, "zoo_test_gemm_trace: null argument");
+    unsigned long long *d;
+    ZOO_CUDA(cudaMalloc(&d, 16 * 8));
+    ZOO_CUDA(cudaMemset(d, 0, 16 * 8));
+    float us;
+    zoo_status s = zoo_test_gemm_bench(engine, M, N, K, a_kmajor, b_kmajor, split_k, 0, 3, &us);  // warm
+    g_tc_dbg = d;
+    if (s == ZOO_OK) s = zoo_test_gemm_bench(engine, M, N, K, a_kmajor, b_kmajor, split_k, 0, 1, &us);
+    g_tc_dbg = nullptr;
+    ZOO_CUDA(cudaMemcpy(stamps9, d, 12 * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return s;
+}
+
+// Device-time benchmark of one GEMM shape (test hook): random-free (zeros) operands resident on the device, `iters`
+// back-to-back launches between two events; returns the mean microseconds per GEMM (all its launches).
+zoo_status zoo_test_gemm_bench(int32_t engine, int32_t M, int32_t N, int32_t K, int32_t a_kmajor, int32_t b_kmajor, int32_t split_k,
+                               int32_t mode, int32_t iters, float *us_out) {
+    ZOO_REQUIRE(us_out && M > 0 && N > 0 && K > 0 && iters > 0, "zoo_test_gemm_bench: bad argument");
+    ZOO_TRY(require_sm100());
+    cudaStream_t st;
+    ZOO_CUDA(cudaStreamCreate(&st));
+    const int eb = engine == 1 ? 2 : 4;
+    void *dA, *dB; float *dD, *ws;
+    size_t na = (size_t)M * K, nb = (size_t)N * K, nd = (size_t)M * N;
+    ZOO_CUDA(cudaMalloc(&dA, na * eb));
+    ZOO_CUDA(cudaMalloc(&dB, nb * eb));
+    ZOO_CUDA(cudaMalloc(&dD, nd * 4));
+    ZOO_CUDA(cudaMalloc(&ws, (nd + 4096) * 4));
+    ZOO_CUDA(cudaMemsetAsync(dA, 0, na * eb, st));
+    ZOO_CUDA(cudaMemsetAsync(dB, 0, nb * eb, st));
+    ZOO_CUDA(cudaMemsetAsync(dD, 0, nd * 4, st));
+    ZOO_CUDA(cudaMemsetAsync(ws, 0, (nd + 4096) * 4, st));
+    Operand oa{dA, eb == 2, a_kmajor ? K : M, a_kmajor}, ob{dB, eb == 2, b_kmajor ? K : N, b_kmajor};
+    Epilogue e;
+    e.out = dD; e.sm = N; e.sn = 1;
+    if (mode == 1) e.accumulate = 1;            // wgrad-style atomic accumulate
+    if (mode == 2) { e.relu = 1; e.bias = dD; e.bias_mode = 1; }  // forward-style
+    e.tf32_passes = engine == 2 ? 1 : (engine == 3 ? 3 : 0);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    auto one = [&]() { return engine == 0 ? simt_gemm(oa, ob, M, N, K, e, split_k, ws, nd + 4096, st) : tc_gemm(oa, ob, M, N, K, e, split_k, ws, nd + 4096, st); };
+    for (int it = 0; it < 3; ++it) ZOO_TRY(one());
+    // the timed launches are replayed from a CUDA graph so the number is device time, not host launch rate
+    cudaGraph_t graph;
+    cudaGraphExec_t gexec;
+    ZOO_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    for (int it = 0; it < iters; ++it) {
+        zoo_status s = one();
+        if (s != ZOO_OK) { cudaStreamEndCapture(st, &graph); return s; }
+    }
+    ZOO_CUDA(cudaStreamEndCapture(st, &graph));
+    ZOO_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+    ZOO_CUDA(cudaGraphLaunch(gexec, st));
+    cudaEventRecord(e0, st);
+    ZOO_CUDA(cudaGraphLaunch(gexec, st));
+    cudaEventRecord(e1, st);
+    ZOO_CUDA(cudaStreamSynchronize(st));
+    cudaGraphExecDestroy(gexec);
+    cudaGraphDestroy(graph);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *us_out = ms * 1e3f / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(ws);
     cudaStreamDestroy(st);
     return ZOO_OK;
 }

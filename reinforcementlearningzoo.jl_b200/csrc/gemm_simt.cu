@@ -76,14 +76,17 @@ simt_gemm_kernel(Operand A, Operand B, int M, int N, int K, Epilogue epi, int k_
 }
 
 // finishes a split-K GEMM whose partial sums were atomically accumulated in ws[M][N]
-__global__ void splitk_finish_kernel(const float *ws, int M, int N, Epilogue epi) {
+// (and re-zeroes ws: the split-K workspace is all-zero between launches, shared with the tcgen05 engine)
+__global__ void splitk_finish_kernel(float *ws, int M, int N, Epilogue epi) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)M * N) return;
     int m = (int)(i / N), n = (int)(i % N);
-    epi_store(epi, ws[i], m, n);
+    const float v = ws[i];
+    ws[i] = 0.f;
+    epi_store(epi, v, m, n);
 }
 
-zoo_status splitk_finish(const float *ws, int M, int N, const Epilogue &epi, cudaStream_t st) {
+zoo_status splitk_finish(float *ws, int M, int N, const Epilogue &epi, cudaStream_t st) {
     long long tot = (long long)M * N;
     splitk_finish_kernel<<<cdiv(tot, 256), 256, 0, st>>>(ws, M, N, epi);
     ZOO_LAUNCH_CHECK();
@@ -108,6 +111,7 @@ zoo_status simt_gemm(const Operand &A, const Operand &B, int M, int N, int K, co
     float *wsp = nullptr;
     bool direct_acc = epi.accumulate && !epi.out_bf16;
     Epilogue e = epi;
+    if (split_k == 1 && e.accumulate == 2) e.accumulate = 0;  // "overwrite or accumulate": nothing to sum
     if (split_k > 1) {
         if (direct_acc) {
             // accumulate straight into the (fp32) destination: every split adds its partial sum
@@ -115,8 +119,7 @@ zoo_status simt_gemm(const Operand &A, const Operand &B, int M, int N, int K, co
         } else {
             ZOO_REQUIRE(ws && ws_elems >= (size_t)M * N, "simt_gemm: split-K workspace too small (%zu < %lld)", ws_elems,
                         (long long)M * N);
-            ZOO_CUDA(cudaMemsetAsync(ws, 0, (size_t)M * N * sizeof(float), st));
-            wsp = ws;
+            wsp = ws;  // all-zero on entry (invariant), re-zeroed by splitk_finish
         }
     }
 #define LAUNCH(AKv, BKv) simt_gemm_kernel<AKv, BKv><<<grid, 256, 0, st>>>(A, B, M, N, K, e, kps, wsp)

@@ -23,6 +23,8 @@ namespace zoo {
 static constexpr int BM = 128;      // UMMA M (cta_group::1)
 // per stage: one 128-byte swizzle span of K per row -> BK = 128 / EB elements, 4 MMAs of K = 32 / EB each
 static constexpr int TC_THREADS = 192;
+static constexpr int X3_CHAIN_KB = 4;         // 3xTF32: K-blocks (of 32 floats) per TMEM accumulation chain (see the kernel)
+static constexpr int TC_WS_COUNTERS = 4096;  // tail of the split-K workspace: per-tile arrival counters
 
 // ---------------------------------------------------------------- PTX wrappers ------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,6 +90,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -130,8 +138,20 @@ struct TcParams {
     int M, N, K;
     int kb_per_split;  // K blocks (of 128 bytes of K) per grid.z slice
     Epilogue epi;
-    float *ws;  // split-K workspace [M][N] (atomic accumulate) or nullptr
+    float *ws;      // split-K workspace [M][N] (atomic accumulate, kept all-zero between launches) or nullptr
+    unsigned *ctr;  // split-K per-tile arrival counters (kept all-zero between launches)
+    unsigned long long *dbg;  // test hook: CTA 0 writes %globaltimer at its phase boundaries (nullptr = off)
 };
+
+unsigned long long *g_tc_dbg = nullptr;  // set by zoo_test_gemm_trace
+
+__device__ __forceinline__ void dbg_stamp(const TcParams &P, int slot) {
+    if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.dbg[slot] = t;
+    }
+}
 
 // EB: operand element bytes (2 = bf16, 4 = fp32 consumed as tf32).  X3: 3xTF32 split (EB = 4 only).
 // smem per stage: A tile 128 rows x 128 B (16 KB) + B tile BN rows x 128 B; X3 doubles it for the lo tiles.
@@ -150,9 +170,10 @@ struct TcCfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGE_BYTES = RAW_BYTES * (X3 ? 2 : 1);
+    // bf16 / tf32: two CTAs per SM (<= ~97 KB each); 3xTF32 owns an SM (TMA -> split -> MMA needs the deeper ring)
     static constexpr int STAGES = X3 ? (BN >= 128 ? 3 : 4) : (BN >= 128 ? 3 : 4);
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = X3 ? 2 * BN : (BN < 32 ? 32 : BN);  // 3xTF32: two accumulators (chains alternate)
 };
 
 template <int EB>
@@ -165,20 +186,29 @@ template <int EB, int BN, bool A_K, bool B_K, bool X3>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
     using C = TcCfg<EB, BN, X3>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // SWIZZLE_128B tiles need 1024-byte alignment; declaring it on the array (instead of rounding the pointer up) keeps
+    // the shared address space visible to the compiler, so the epilogue staging below compiles to LDS/STS
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
     uint64_t *full_bar = (uint64_t *)(smem + C::STAGES * C::STAGE_BYTES);
     uint64_t *empty_bar = full_bar + C::STAGES;
     uint64_t *conv_bar = empty_bar + C::STAGES;  // X3: lo tiles written (128 converter threads arrive)
-    uint64_t *tmem_full_bar = conv_bar + C::STAGES;
-    uint32_t *tmem_slot = (uint32_t *)(tmem_full_bar + 1);
+    uint64_t *acc_full = conv_bar + C::STAGES;   // [2] accumulator buffer b holds a finished chain (tcgen05.commit)
+    uint64_t *acc_empty = acc_full + 2;          // [2] buffer b has been drained to registers (128 threads arrive)
+    uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    if (threadIdx.x == 0) dbg_stamp(P, 0);
     const int total_kb = (P.K + C::BK - 1) / C::BK;
     const int kb0 = blockIdx.z * P.kb_per_split;
     const int kb1 = min(total_kb, kb0 + P.kb_per_split);
     const int nkb = kb1 - kb0;  // host guarantees >= 1
+    // 3xTF32: the K loop is cut into chains of CHAIN K-blocks that alternate between two TMEM accumulators; the
+    // converter warps sum finished chains in registers with round-to-nearest fp32 adds, because a TMEM accumulator
+    // truncates on every add and that bias grows with the chain length.  Other modes: one chain, one accumulator.
+    constexpr int CHAIN = X3 ? X3_CHAIN_KB : (1 << 30);
+    const int nchains = (nkb + CHAIN - 1) / CHAIN;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -186,7 +216,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&empty_bar[s], 1);
             mbar_init(&conv_bar[s], 128);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 128);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -194,6 +227,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) dbg_stamp(P, 1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -221,6 +255,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int h = 0; h < BN / C::MN_BOX; ++h)
                         tma_load_2d(sb + h * C::BOX_BYTES, &tmB, &full_bar[s], n0 + h * C::MN_BOX, k0);
                 }
+                if (i == 0) dbg_stamp(P, 2);
             }
         }
     } else if (warp == 1) {
@@ -229,11 +264,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % C::STAGES;
                 const uint32_t ph = (i / C::STAGES) & 1;
+                const int chain = i / CHAIN, cb = chain & 1;
+                const bool chain_start = (i % CHAIN) == 0;
+                if (X3 && chain_start && chain >= 2) {  // the buffer's previous chain must have been drained
+                    mbar_wait(&acc_empty[cb], ((chain >> 1) - 1) & 1);
+                    tc_fence_after();
+                }
                 if (X3) mbar_wait(&conv_bar[s], ph);
                 else mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
+                if (i == 0) dbg_stamp(P, 3);
                 const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
                 const uint32_t sb = sa + C::A_BYTES;
+                const uint32_t td = tmem_base + (uint32_t)(cb * BN);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     // K-major SW128: 8-row groups 1024 B apart (SBO); one MMA's K slice = 32 B inside the swizzle span.
@@ -242,25 +285,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t bo = B_K ? k * 32 : k * C::KSTEP_MN;
                     const uint64_t ad = A_K ? make_smem_desc(sa + ao, 16, 1024) : make_smem_desc(sa + ao, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
                     const uint64_t bd = B_K ? make_smem_desc(sb + bo, 16, 1024) : make_smem_desc(sb + bo, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
-                    umma<EB>(tmem_base, ad, bd, idesc, (i | k) != 0);
                     if (X3) {
-                        // lo tiles live RAW_BYTES above the (in-place truncated) hi tiles, same layout
+                        // lo tiles live RAW_BYTES above the (in-place truncated) hi tiles, same layout; small terms first
                         const uint64_t adl = A_K ? make_smem_desc(sa + C::RAW_BYTES + ao, 16, 1024)
                                                  : make_smem_desc(sa + C::RAW_BYTES + ao, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
                         const uint64_t bdl = B_K ? make_smem_desc(sb + C::RAW_BYTES + bo, 16, 1024)
                                                  : make_smem_desc(sb + C::RAW_BYTES + bo, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
-                        umma<EB>(tmem_base, ad, bdl, idesc, 1);
-                        umma<EB>(tmem_base, adl, bd, idesc, 1);
+                        umma<EB>(td, ad, bdl, idesc, !(chain_start && k == 0));
+                        umma<EB>(td, adl, bd, idesc, 1);
+                        umma<EB>(td, ad, bd, idesc, 1);
+                    } else {
+                        umma<EB>(td, ad, bd, idesc, (i | k) != 0);
                     }
                 }
                 umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+                if ((i % CHAIN) == CHAIN - 1 || i == nkb - 1) umma_commit(&acc_full[cb]);  // chain complete
             }
-            umma_commit(tmem_full_bar);  // accumulator complete
+            dbg_stamp(P, 4);
         }
     } else {
-        // warps 2..5.  X3: first split every landed fp32 tile into hi (in place) and lo (second half of the stage).
+        // warps 2..5: TMEM lane quadrant = warp % 4, thread = accumulator row.
+        const int q = warp & 3;
+        const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+        float acc[X3 ? BN : 1];  // running fp32 sum of the drained chains (3xTF32 only)
         if (X3) {
+#pragma unroll
+            for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+            // split every landed fp32 tile into hi (in place) and lo (second half of the stage); one chain behind the
+            // MMA warp, fold finished chains into acc
             const int t = threadIdx.x - 64;  // 0..127
+            int drained = 0;
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % C::STAGES;
                 const uint32_t ph = (i / C::STAGES) & 1;
@@ -280,38 +334,154 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
                 mbar_arrive(&conv_bar[s]);
+                // chain `drained` ended at K-block (drained+1)*CHAIN - 1; by the time two more blocks have been converted
+                // its MMAs have retired, so the wait below does not stall the conversion pipeline
+                if (drained < nchains - 1 && i + 1 >= (drained + 1) * CHAIN + 2) {
+                    const int cb = drained & 1;
+                    mbar_wait(&acc_full[cb], (drained >> 1) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < BN; c += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(tq + (uint32_t)(cb * BN + c), r);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c + j] = __fadd_rn(acc[c + j], __uint_as_float(r[j]));
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[cb]);
+                    ++drained;
+                }
+            }
+            for (; drained < nchains - 1; ++drained) {  // chains whose delayed drain slot never came (short tail)
+                const int cb = drained & 1;
+                mbar_wait(&acc_full[cb], (drained >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tq + (uint32_t)(cb * BN + c), r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c + j] = __fadd_rn(acc[c + j], __uint_as_float(r[j]));
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[cb]);
             }
         }
-        // epilogue: TMEM lane quadrant = warp % 4
-        const int q = warp & 3;
-        mbar_wait(tmem_full_bar, 0);
+        // epilogue.  Each warp pulls 32 x 32 chunks of the last chain's accumulator, adds the register sums, transposes
+        // the chunk through shared memory (the pipeline stages are idle once the last chain has been committed) and then
+        // walks the rows with lane = column, so every global access below is one coalesced 128-byte row segment.
+        const int lastc = nchains - 1, lb = lastc & 1;
+        mbar_wait(&acc_full[lb], (lastc >> 1) & 1);
         tc_fence_after();
-        const int m = m0 + q * 32 + lane;
-        const Epilogue &e = P.epi;
-#pragma unroll 1
+        if (threadIdx.x == 64) dbg_stamp(P, 5);
+        float(*stg)[33] = reinterpret_cast<float(*)[33]>(smem) + q * 32;  // 32 x 33 floats per warp, in pipeline stage 0
+        const int row0 = m0 + q * 32;
+        const int rows = min(32, P.M - row0);
+        // the epilogue description is copied out of the parameter bank once: re-reading it per row costs a chain of
+        // uniform constant loads per store (measured 100 ns per row)
+        const Epilogue e = P.epi;
+        const bool split = P.ws != nullptr;
+        float *const ws = P.ws;
+        const int Nn = P.N;
+        const int bias_mode = e.bias_mode, relu = e.relu, out_bf16 = e.out_bf16;
+        const long long sm = e.sm, sn = e.sn;
+        const bool simple = !e.rowmul && bias_mode != 2;
+        const void *const maskp = e.mask;
+        const int mask_bf16 = e.mask_bf16;
+        const long long msm = e.mask_sm, msn = e.mask_sn;
+#pragma unroll
         for (int c = 0; c < BN; c += 32) {
             uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-            if (m < P.M) {
-                if (P.ws) {
+            tmem_ld32(tq + (uint32_t)(lb * BN + c), r);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        int n = n0 + c + j;
-                        if (n < P.N) atomicAdd(P.ws + (long long)m * P.N + n, __uint_as_float(r[j]));
+            for (int j = 0; j < 32; ++j) {
+                float v = __uint_as_float(r[j]);
+                if (X3) v = __fadd_rn(v, acc[c + j]);
+                stg[lane][j] = v;
+            }
+            __syncwarp();
+            const int n = n0 + c + lane;
+            if (n < Nn) {
+                if (split) {
+                    float *wp = ws + (long long)row0 * Nn + n;
+#pragma unroll 8
+                    for (int rr = 0; rr < rows; ++rr) atomicAdd(wp + (long long)rr * Nn, stg[rr][lane]);
+                } else if (e.accumulate) {
+                    float *op = (float *)e.out + (long long)row0 * sm + (long long)n * sn;
+#pragma unroll 8
+                    for (int rr = 0; rr < rows; ++rr) atomicAdd(op + (long long)rr * sm, stg[rr][lane]);
+                } else if (simple) {
+                    const float bv = bias_mode == 1 ? __ldg(e.bias + n) : 0.f;
+                    if (out_bf16) {
+                        bf16 *op = (bf16 *)e.out + (long long)row0 * sm + (long long)n * sn;
+#pragma unroll 8
+                        for (int rr = 0; rr < rows; ++rr) {
+                            float v = stg[rr][lane] + bv;
+                            if (relu) v = fmaxf(v, 0.f);
+                            if (maskp) v = ld_elem(maskp, mask_bf16, (long long)(row0 + rr) * msm + (long long)n * msn) > 0.f ? v : 0.f;
+                            op[(long long)rr * sm] = __float2bfloat16_rn(v);
+                        }
+                    } else {
+                        float *op = (float *)e.out + (long long)row0 * sm + (long long)n * sn;
+#pragma unroll 8
+                        for (int rr = 0; rr < rows; ++rr) {
+                            float v = stg[rr][lane] + bv;
+                            if (relu) v = fmaxf(v, 0.f);
+                            if (maskp) v = ld_elem(maskp, mask_bf16, (long long)(row0 + rr) * msm + (long long)n * msn) > 0.f ? v : 0.f;
+                            op[(long long)rr * sm] = v;
+                        }
                     }
                 } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        int n = n0 + c + j;
-                        if (n < P.N) epi_store(e, __uint_as_float(r[j]), m, n);
+#pragma unroll 4
+                    for (int rr = 0; rr < rows; ++rr) epi_store(e, stg[rr][lane], row0 + rr, n);
+                }
+            }
+            __syncwarp();
+        }
+        if (split) {
+            // split-K without a finishing launch: the last CTA to arrive on this output tile (per-tile counter behind the
+            // workspace) applies the epilogue to the summed tile and leaves workspace + counter zeroed for the next GEMM.
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            unsigned *ctr = P.ctr + blockIdx.y * gridDim.x + blockIdx.x;
+            if (threadIdx.x == 64) {
+                const unsigned old = atomicAdd(ctr, 1u);
+                const bool last = old == gridDim.z - 1;
+                if (last) *ctr = 0u;
+                *tmem_slot = last ? 1u : 0u;  // tmem_slot is dead after tmem_base was read
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (*tmem_slot) {
+                __threadfence();
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    const int n = n0 + c + lane;
+                    if (n >= Nn) break;
+                    const float bv = bias_mode == 1 ? __ldg(e.bias + n) : 0.f;
+#pragma unroll 4
+                    for (int rr = 0; rr < rows; ++rr) {
+                        float *wp = ws + (long long)(row0 + rr) * Nn + n;
+                        float v = __ldcg(wp);
+                        __stcg(wp, 0.f);
+                        if (simple) {
+                            v += bv;
+                            if (relu) v = fmaxf(v, 0.f);
+                            if (maskp) v = ld_elem(maskp, mask_bf16, (long long)(row0 + rr) * msm + (long long)n * msn) > 0.f ? v : 0.f;
+                            st_elem(e.out, out_bf16, (long long)(row0 + rr) * sm + (long long)n * sn, v);
+                        } else {
+                            epi_store(e, v, row0 + rr, n);
+                        }
                     }
                 }
             }
         }
     }
+    if (threadIdx.x == 64) dbg_stamp(P, 6);
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) dbg_stamp(P, 7);
     if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (threadIdx.x == 32) dbg_stamp(P, 8);
 }
 
 // ---------------------------------------------------------------- host side ---------------
@@ -363,8 +533,6 @@ bool tc_gemm_supported(const Operand &A, const Operand &B, int M, int N, int K) 
     return true;
 }
 
-zoo_status splitk_finish(const float *ws, int M, int N, const Epilogue &epi, cudaStream_t st);
-
 template <int EB, int BN, bool A_K, bool B_K, bool X3>
 static zoo_status launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid, cudaStream_t st) {
     using C = TcCfg<EB, BN, X3>;
@@ -409,30 +577,34 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
     const int bk = 128 / eb, mn_box = 128 / eb;
     const bool x3 = eb == 4 && epi.tf32_passes == 3;
     int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+    // one M tile (skinny batch x wide layer): many narrow N tiles first, so fewer K splits have to be summed
+    if (M <= BM && N >= 256) BN = 32;
     if (eb == 2 && BN == 32 && !B.kmajor) BN = 64;
     dim3 grid(cdiv(M, BM), cdiv(N, BN), 1);
     const int total_kb = cdiv(K, bk);
+    const long long tiles = (long long)grid.x * grid.y;
+    const long long cap_ctas = 148 * (x3 ? 1 : 2);  // resident CTAs (see TcCfg::STAGES)
     if (split_k <= 0) {
-        long long tiles = (long long)grid.x * grid.y;
+        // split only when the output grid leaves most SMs idle AND one CTA would walk a long K: each split costs
+        // atomics on the whole tile, so keep >= 4 K-blocks per CTA and stay within one resident wave
         split_k = 1;
-        if (tiles < 148 && total_kb >= 4) split_k = (int)std::min<long long>(total_kb / 2, (296 + tiles - 1) / tiles);
+        if (tiles * 2 <= cap_ctas && total_kb >= 32) split_k = (int)std::min<long long>(total_kb / 4, cap_ctas / tiles);
         if (split_k < 1) split_k = 1;
     }
-    // TMEM accumulation truncates (measured: 5.8e-5 rel after K = 7744 in one chain vs 1.4e-6 split): in the
-    // fp32-grade mode cap one accumulation chain at 32 K-blocks (1024 elements)
-    if (x3 && cdiv(total_kb, split_k) > 32) split_k = cdiv(total_kb, 32);
     split_k = std::min(split_k, total_kb);
     int kbps = cdiv(total_kb, split_k);
     split_k = cdiv(total_kb, kbps);
     grid.z = split_k;
 
     TcParams P;
-    P.M = M; P.N = N; P.K = K; P.kb_per_split = kbps; P.epi = epi; P.ws = nullptr;
+    P.M = M; P.N = N; P.K = K; P.kb_per_split = kbps; P.epi = epi; P.ws = nullptr; P.ctr = nullptr; P.dbg = g_tc_dbg;
     bool direct_acc = epi.accumulate && !epi.out_bf16;
+    if (direct_acc && split_k == 1 && epi.accumulate == 2) P.epi.accumulate = 0;  // "overwrite or accumulate": nothing to sum
     if (split_k > 1 && !direct_acc) {
-        ZOO_REQUIRE(ws && ws_elems >= (size_t)M * N, "tc_gemm: split-K workspace too small (%zu < %lld)", ws_elems, (long long)M * N);
-        ZOO_CUDA(cudaMemsetAsync(ws, 0, (size_t)M * N * sizeof(float), st));
-        P.ws = ws;
+        ZOO_REQUIRE(ws && ws_elems >= (size_t)M * N + TC_WS_COUNTERS && tiles <= TC_WS_COUNTERS,
+                    "tc_gemm: split-K workspace too small (%zu < %lld)", ws_elems, (long long)M * N + TC_WS_COUNTERS);
+        P.ws = ws;  // invariant: all-zero on entry, left all-zero by the finishing CTAs
+        P.ctr = reinterpret_cast<unsigned *>(ws + ws_elems - TC_WS_COUNTERS);
     }
     CUtensorMap tmA, tmB;
     if (A.kmajor) ZOO_TRY(make_map(&tmA, A.p, eb, K, M, A.ld, bk, BM, false));
@@ -443,7 +615,6 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
     if (eb == 2) ZOO_TRY((launch_tc_bn<2, false>(BN, A.kmajor, B.kmajor, tmA, tmB, P, grid, st)));
     else if (x3) ZOO_TRY((launch_tc_bn<4, true>(BN, A.kmajor, B.kmajor, tmA, tmB, P, grid, st)));
     else ZOO_TRY((launch_tc_bn<4, false>(BN, A.kmajor, B.kmajor, tmA, tmB, P, grid, st)));
-    if (P.ws) ZOO_TRY(splitk_finish(P.ws, M, N, epi, st));
     return ZOO_OK;
 }
 

@@ -362,7 +362,7 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
         Operand dYt{L.dout, dy_bf, L.cout, 0};
         prof_label("wgrad:t%d[%dx%lldx%lld]", L.wt, L.cout, L.K, M);
         Epilogue ew;
-        ew.out = net->grads + W.offset; ew.sm = L.K; ew.sn = 1; ew.accumulate = 1; ew.tf32_passes = net->tf32_passes;
+        ew.out = net->grads + W.offset; ew.sm = L.K; ew.sn = 1; ew.accumulate = 2;  /* grads are zeroed per update: store, or add when split */ ew.tf32_passes = net->tf32_passes;
         ZOO_TRY(gemm(dYt, X, L.cout, (int)L.K, (int)M, ew, 0, net->ws, net->ws_elems, st));
         // dgrad
         if (li == 0 && !dx) continue;
@@ -680,8 +680,15 @@ zoo_status zoo_net_create(const zoo_net_desc *d, zoo_net **out) {
         ZOO_TRY(alloc_chain(net, net->b, rows_a, nullptr));
         ZOO_TRY(alloc_chain(net, net->c, rows_a, nullptr));
     }
-    net->ws_elems = (size_t)6 << 20;  // 24 MB split-K workspace (largest split-K output: 148 tiles of 128 x 128 fp32)
+    // split-K workspace (all-zero between launches): voluntary splits cover < 74 output tiles of 128 x 128 fp32; the
+    // fp32-grade mode also splits every contraction longer than 1024 (dense layers fed by the flattened conv stack)
+    size_t ws_need = (size_t)2 << 20;
+    for (Chain *ch : {&net->a, &net->b, &net->c})
+        for (auto &L : ch->layers)
+            if (L.K > 1024) ws_need = std::max<size_t>(ws_need, (size_t)(ch->rows_cap * L.opr * L.cout));
+    net->ws_elems = ws_need + 4096;
     ZOO_CUDA(cudaMalloc(&net->ws, net->ws_elems * sizeof(float)));
+    ZOO_CUDA(cudaMemset(net->ws, 0, net->ws_elems * sizeof(float)));
     ZOO_CUDA(cudaMalloc(&net->obs, (size_t)rows_a * obs_elems(net) * sizeof(float)));
     *out = net;
     return ZOO_OK;
