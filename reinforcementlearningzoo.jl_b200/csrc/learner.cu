@@ -119,6 +119,7 @@ struct zoo_learner {
     int graph_key = -1;  // encodes (has_priority, has_mask, has_tau, obs_dtype, full)
     int graph_launches = 0;
     int warm = 0;
+    bool target_forked = false;
 };
 
 static zoo_status opt_step(zoo_opt *o, cudaStream_t st) {
@@ -136,6 +137,22 @@ static zoo_status opt_step(zoo_opt *o, cudaStream_t st) {
     ZOO_LAUNCH_CHECK();
     o->host_t += 1;
     return ZOO_OK;
+}
+
+// The target net's forward depends on nothing the online net produces (PrioritizedDQN / Rainbow / DQN): it runs on the
+// online net's side lane, concurrently with the online forward, and is joined back before the loss head.
+static zoo_status target_forward(zoo_learner *L, zoo_net *tg, const void *s2, const float *tau, int n_tau, cudaStream_t st) {
+    zoo_net *on = L->online;
+    const bool par = on->side && !g_prof_on;
+    if (par) ZOO_TRY(net_side_fork(on, st));
+    zoo_status s = net_forward(tg, s2, L->obs_dtype, L->B, tau, n_tau, par ? on->side : st);
+    L->target_forked = par;
+    return s;
+}
+static zoo_status target_join(zoo_learner *L, cudaStream_t st) {
+    if (!L->target_forked) return ZOO_OK;
+    L->target_forked = false;
+    return net_side_join(L->online, st);
 }
 
 // everything between "batch is on the device" and "results are on the device"
@@ -168,12 +185,14 @@ static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bo
         bwd_rows = 2 * B;
     } else if (c.kind == ZOO_LEARNER_DQN || c.kind == ZOO_LEARNER_PRIORITIZED_DQN) {
         const int dbl = c.kind == ZOO_LEARNER_DQN && c.double_dqn;
+        ZOO_TRY(target_forward(L, tg, s2_ptr, nullptr, 0, st));  // side lane, rejoined before the head
         ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, dbl ? 2 * B : B, nullptr, 0, st));
-        ZOO_TRY(net_forward(tg, s2_ptr, L->obs_dtype, B, nullptr, 0, st));
+        ZOO_TRY(target_join(L, st));
         prof_label("head"); ZOO_TRY(launch_dqn_head(c.kind, dbl, h, on->out_final, tg->out_final, L->gamma_n, on->dout_final, st));
     } else if (c.kind == ZOO_LEARNER_RAINBOW) {
+        ZOO_TRY(target_forward(L, tg, s2_ptr, nullptr, 0, st));
         ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, B, nullptr, 0, st));
-        ZOO_TRY(net_forward(tg, s2_ptr, L->obs_dtype, B, nullptr, 0, st));
+        ZOO_TRY(target_join(L, st));
         prof_label("head"); ZOO_TRY(launch_c51_head(h, c.n_atoms, tg->out_final, on->out_final, L->d_support, c.delta_z, c.v_min, c.v_max, L->gamma_n,
                                 on->dout_final, L->d_tdist, st));
     } else {  // IQN

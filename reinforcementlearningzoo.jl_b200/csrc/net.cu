@@ -352,8 +352,15 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
         const TensorInfo &W = net->tensors[L.wt];
         const TensorInfo &Bt = net->tensors[L.bt];
         const int dy_bf = L.out_fp32 ? 0 : bf;
+        // bias grad + wgrad only need this layer's dout, which is complete on `st` here: they go to the side lane and
+        // overlap the dgrad chain (the critical path) that continues on `st`
+        const bool par = net->side && !g_prof_on;
+        cudaStream_t sw = par ? net->side : st;
+        float *wsw = par ? net->ws_side : net->ws;
+        const size_t wsw_elems = par ? net->ws_side_elems : net->ws_elems;
+        if (par) ZOO_TRY(net_side_fork(net, st));
         prof_label("bgrad:t%d", L.bt);
-        ZOO_TRY(launch_colsum(L.dout, dy_bf, M, L.cout, net->grads + Bt.offset, st));
+        ZOO_TRY(launch_colsum(L.dout, dy_bf, M, L.cout, net->grads + Bt.offset, sw));
         // wgrad: dW[cout][K] += dY^T X   (both operands MN-major: stored [rows][features])
         Operand X;
         if (L.kind == ZOO_LAYER_CONV) X = Operand{L.cols, bf, L.K, 0};
@@ -362,8 +369,9 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
         Operand dYt{L.dout, dy_bf, L.cout, 0};
         prof_label("wgrad:t%d[%dx%lldx%lld]", L.wt, L.cout, L.K, M);
         Epilogue ew;
-        ew.out = net->grads + W.offset; ew.sm = L.K; ew.sn = 1; ew.accumulate = 2;  /* grads are zeroed per update: store, or add when split */ ew.tf32_passes = net->tf32_passes;
-        ZOO_TRY(gemm(dYt, X, L.cout, (int)L.K, (int)M, ew, 0, net->ws, net->ws_elems, st));
+        ew.out = net->grads + W.offset; ew.sm = L.K; ew.sn = 1; ew.tf32_passes = net->tf32_passes;
+        ew.accumulate = 2;  // grads are zeroed per update: plain store, or atomic add when the GEMM is K-split
+        ZOO_TRY(gemm(dYt, X, L.cout, (int)L.K, (int)M, ew, 0, wsw, wsw_elems, sw));
         // dgrad
         if (li == 0 && !dx) continue;
         Operand dY{L.dout, dy_bf, L.cout, 1};
@@ -390,6 +398,17 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
             ZOO_TRY(gemm(dY, Wn, (int)M, (int)L.K, L.cout, ed, 0, net->ws, net->ws_elems, st));
         }
     }
+    return ZOO_OK;
+}
+
+zoo_status net_side_fork(zoo_net *net, cudaStream_t main) {
+    ZOO_CUDA(cudaEventRecord(net->ev_fork, main));
+    ZOO_CUDA(cudaStreamWaitEvent(net->side, net->ev_fork, 0));
+    return ZOO_OK;
+}
+zoo_status net_side_join(zoo_net *net, cudaStream_t main) {
+    ZOO_CUDA(cudaEventRecord(net->ev_join, net->side));
+    ZOO_CUDA(cudaStreamWaitEvent(main, net->ev_join, 0));
     return ZOO_OK;
 }
 
@@ -430,8 +449,18 @@ zoo_status net_forward(zoo_net *net, const void *obs, int obs_dtype, int rows, c
     return chain_forward(net, net->c, net->merged, 2, R, st);
 }
 
+static zoo_status net_backward_impl(zoo_net *net, int obs_dtype, const void *obs, int rows, int n_tau, cudaStream_t st);
 zoo_status net_backward(zoo_net *net, int obs_dtype, const void *obs, int rows, int n_tau, cudaStream_t st) {
     ZOO_REQUIRE(net->bwd_ready && net->grads, "backward: net has no gradient buffers (attach an optimiser/learner first)");
+    zoo_status s = net_backward_impl(net, obs_dtype, obs, rows, n_tau, st);
+    if (net->side && !g_prof_on) {  // the side lane always rejoins, also on error (an open fork would poison a stream capture)
+        zoo_status j = net_side_join(net, st);
+        if (s == ZOO_OK) s = j;
+    }
+    return s;
+}
+
+static zoo_status net_backward_impl(zoo_net *net, int obs_dtype, const void *obs, int rows, int n_tau, cudaStream_t st) {
     const int bf = is_bf(net);
     const int in_kind = obs_dtype == ZOO_OBS_U8 ? 0 : 1;
     if (net->desc.kind == ZOO_NET_CHAIN) return chain_backward(net, net->a, obs, in_kind, rows, nullptr, nullptr, st);
@@ -577,6 +606,12 @@ zoo_status net_alloc_backward(zoo_net *net) {
         ZOO_CUDA(cudaMalloc(&net->dh1, (size_t)net->a.rows_cap * net->a.out_feat * net->esz));
         ZOO_CUDA(cudaMalloc(&net->dh2, (size_t)net->a.rows_cap * net->a.out_feat * net->esz));
     }
+    ZOO_CUDA(cudaStreamCreateWithFlags(&net->side, cudaStreamNonBlocking));
+    ZOO_CUDA(cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming));
+    ZOO_CUDA(cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming));
+    net->ws_side_elems = ((size_t)2 << 20) + 4096;
+    ZOO_CUDA(cudaMalloc(&net->ws_side, net->ws_side_elems * sizeof(float)));
+    ZOO_CUDA(cudaMemset(net->ws_side, 0, net->ws_side_elems * sizeof(float)));
     net->bwd_ready = true;
     return ZOO_OK;
 }
@@ -710,8 +745,11 @@ zoo_status zoo_net_destroy(zoo_net *net) {
     free_chain(net->b, net->out_final, net->dout_final);
     free_chain(net->c, net->out_final, net->dout_final);
     void *ptrs[] = {net->params, net->shadow, net->grads, net->out_final, net->dout_final, net->emb, net->merged, net->dmerged,
-                    net->tau_dev, net->dh1, net->dh2, net->ws, net->obs, net->stage};
+                    net->tau_dev, net->dh1, net->dh2, net->ws, net->obs, net->stage, net->ws_side};
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (net->side) { cudaStreamSynchronize(net->side); cudaStreamDestroy(net->side); }
+    if (net->ev_fork) cudaEventDestroy(net->ev_fork);
+    if (net->ev_join) cudaEventDestroy(net->ev_join);
     cudaStreamDestroy(net->st);
     delete net;
     return ZOO_OK;

@@ -71,6 +71,12 @@ struct zoo_net {
     float *stage = nullptr; size_t stage_elems = 0;  // param up/download staging
     cudaStream_t st = nullptr;
     bool bwd_ready = false;
+    // side lane: a second stream (joined back with events, so it also becomes a parallel branch of a captured CUDA graph)
+    // for work that is off the critical path -- the target net's forward, and bias-grad + wgrad while dgrad proceeds
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    float *ws_side = nullptr;  // split-K workspace of the side lane
+    size_t ws_side_elems = 0;
 };
 
 namespace zoo {
@@ -81,5 +87,8 @@ zoo_status net_forward(zoo_net *net, const void *obs, int obs_dtype, int rows, c
 // consumes net->dout_final (fp32, same shape as out_final, for the first `rows` samples) and accumulates into net->grads
 zoo_status net_backward(zoo_net *net, int obs_dtype, const void *obs, int rows, int n_tau, cudaStream_t st);
 zoo_status net_refresh_shadow(zoo_net *net, cudaStream_t st);
+// side lane plumbing: fork = side waits for everything enqueued on `main` so far; join = main waits for the side lane
+zoo_status net_side_fork(zoo_net *net, cudaStream_t main);
+zoo_status net_side_join(zoo_net *net, cudaStream_t main);
 long long obs_elems(const zoo_net *net);
 }  // namespace zoo
