@@ -210,7 +210,14 @@ def roofline(profiles, w, esz, n_params, pk, traffic):
 
 
 # ----------------------------------------------------------------------------------------------- our arm
+def trace(*a):
+    if os.environ.get("ZOO_BENCH_TRACE"):
+        print("[bench r%s %.2f]" % (os.environ.get("RANK", "0"), time.time() % 1000), *a, file=sys.stderr, flush=True)
+
+
 def run_ours(args, w):
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("ZOO_BENCH_WATCHDOG_S", "900")), exit=True)  # never hang a GPU box
     import torch
     import torch.distributed as dist
 
@@ -282,6 +289,7 @@ def run_ours(args, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    trace("learner built")
     clocks = Clocks(local) if rank == 0 else None
     windows = []
     # ---- warm-up: eager pass, graph capture, replays
@@ -289,6 +297,7 @@ def run_ours(args, w):
         lrn.update(dev_pool[i % n_pool], want_loss=False, want_priorities=False)
     lrn.sync()
 
+    trace("warm-up done")
     # ---- leg 1: value (HBM-resident inputs, L2 flushed before every step, events on the learner's stream)
     K = args.steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -306,6 +315,7 @@ def run_ours(args, w):
     dev_ms = maxr(dev_ms)
     launches = lrn.last_launches() * K
 
+    trace("leg 1 done")
     # ---- leg 1b: same, back to back without the flush (weights L2-resident: the steady state of a real run)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -317,6 +327,7 @@ def run_ours(args, w):
     barrier()
     warm_ms = maxr(e0.elapsed_time(e1))
 
+    trace("leg 1b done")
     # ---- leg 2: e2e through the public API with pinned host buffers; loss (and PER priorities) read back every step
     for i in range(3):
         lrn.update(host_pool[i % n_pool][0])
@@ -330,12 +341,14 @@ def run_ours(args, w):
     barrier()
     clk = clocks.stop(windows) if clocks else None
 
+    trace("leg 2 done")
     # ---- roofline leg (rank 0 profiles; the other ranks must join the collectives, so they run the same eager updates)
     profs = []
     for i in range(4):
         pr = lrn.profile(dev_pool[i % n_pool], delay_us=3000 if B <= 64 else 20000)
         if i:
             profs.append(pr)
+    trace("profiles done")
     esz = 2 if prec == "bf16" else 4
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload + ":" + prec, {})
@@ -373,6 +386,11 @@ def run_ours(args, w):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # orderly collective teardown: learner (and its captured graph) first, then our NCCL communicator, then torch's
+        lrn.close()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dp.close()
         dist.destroy_process_group()
 
 

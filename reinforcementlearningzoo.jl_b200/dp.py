@@ -42,10 +42,10 @@ class DataParallel:
         L.check(lib.zoo_dp_init(self.unique_id.ctypes.data, self.rank, self.world, C.byref(h)))
         self.h = h
 
-    def __del__(self):
-        try:
-            if getattr(self, "h", None):
-                L.lib().zoo_dp_destroy(self.h)
-                self.h = None
-        except Exception:
-            pass
+    def close(self):
+        """ncclCommDestroy.  Collective: every rank must call it, after the learners that use this communicator are gone
+        and their streams are idle.  Deliberately NOT done from __del__: at interpreter exit the ranks reach it in
+        arbitrary order (and after torch's own process group is gone), where ncclCommDestroy can block forever."""
+        if getattr(self, "h", None):
+            L.check(L.lib().zoo_dp_destroy(self.h))
+            self.h = None

@@ -32,11 +32,14 @@ class _Learner:
         self.loss = np.float32(0)
         self._keep = None
 
+    def close(self):
+        if getattr(self, "h", None):
+            L.lib().zoo_learner_destroy(self.h)
+            self.h = None
+
     def __del__(self):
         try:
-            if getattr(self, "h", None):
-                L.lib().zoo_learner_destroy(self.h)
-                self.h = None
+            self.close()
         except Exception:
             pass
 
