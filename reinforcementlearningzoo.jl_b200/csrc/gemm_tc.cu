@@ -315,22 +315,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // MMA warp, fold finished chains into acc
             const int t = threadIdx.x - 64;  // 0..127
             int drained = 0;
+            const int va = min(BM, P.M - m0), vb = min(BN, P.N - n0);  // valid rows of the A / B tiles
+            const int a_units = (A_K ? va * 128 : ((va + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
+            const int b_units = (B_K ? vb * 128 : ((vb + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
+            const int conv_units = a_units + b_units;
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % C::STAGES;
                 const uint32_t ph = (i / C::STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
-                uint4 *raw = reinterpret_cast<uint4 *>(smem + s * C::STAGE_BYTES);
+                // tcgen05 kind::tf32 ignores the low 13 mantissa bits of an fp32 operand (measured: bit-identical results for
+                // raw and pre-truncated inputs), so the landed tile itself is the hi operand and only lo = x - trunc(x) is written
+                const uint4 *raw = reinterpret_cast<const uint4 *>(smem + s * C::STAGE_BYTES);
                 uint4 *lo = reinterpret_cast<uint4 *>(smem + s * C::STAGE_BYTES + C::RAW_BYTES);
 #pragma unroll 4
-                for (int j = t; j < C::RAW_BYTES / 16; j += 128) {
-                    uint4 v = raw[j], h, l;
-                    h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
-                    l.x = __float_as_uint(__fsub_rn(__uint_as_float(v.x), __uint_as_float(h.x)));
-                    l.y = __float_as_uint(__fsub_rn(__uint_as_float(v.y), __uint_as_float(h.y)));
-                    l.z = __float_as_uint(__fsub_rn(__uint_as_float(v.z), __uint_as_float(h.z)));
-                    l.w = __float_as_uint(__fsub_rn(__uint_as_float(v.w), __uint_as_float(h.w)));
-                    raw[j] = h;
-                    lo[j] = l;
+                for (int j = t; j < conv_units; j += 128) {
+                    const int jj = j < a_units ? j : j - a_units + C::A_BYTES / 16;  // rows past M / N are never stored: skipped
+                    const uint4 v = raw[jj];
+                    uint4 l;
+                    l.x = __float_as_uint(__fsub_rn(__uint_as_float(v.x), __uint_as_float(v.x & 0xffffe000u)));
+                    l.y = __float_as_uint(__fsub_rn(__uint_as_float(v.y), __uint_as_float(v.y & 0xffffe000u)));
+                    l.z = __float_as_uint(__fsub_rn(__uint_as_float(v.z), __uint_as_float(v.z & 0xffffe000u)));
+                    l.w = __float_as_uint(__fsub_rn(__uint_as_float(v.w), __uint_as_float(v.w & 0xffffe000u)));
+                    lo[jj] = l;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
                 mbar_arrive(&conv_bar[s]);
