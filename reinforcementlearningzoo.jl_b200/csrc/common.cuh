@@ -91,6 +91,26 @@ struct Epilogue {
     int tf32_passes = 0; // fp32 operands on tcgen05: 0 = never (CUDA cores), 1 = plain tf32, 3 = 3xTF32 (fp32-grade)
 };
 
+// Implicit-GEMM convolution: the A operand (im2col matrix) is never materialised; the tcgen05 kernel's producer warps
+// gather each 128-row x 128-byte K-block straight from the activation tensor into the swizzled shared-memory tile.
+enum { CONV_RAW_U8 = 1,   // first conv: observation [B][C][H][W] uint8, K order (c,ky,kx), optional x/255 (IEEE divide)
+       CONV_RAW_F32 = 2,  // first conv: observation [B][C][H][W] float
+       CONV_NHWC = 3,     // inner conv: activations [B][H][W][C] in the GEMM dtype, K order (ky,kx,c)
+       CONV_DGRAD = 4 };  // data gradient: A = dY [B][OH][OW][Cout] gathered transposed-conv style, K order (ky,kx,o),
+                          //   M = B*H*W input pixels, N = C;  B operand = W viewed [Cout][ks*ks*C] (MN-major)
+struct ConvGeom {
+    const void *x = nullptr;
+    int mode = 0;
+    int C = 0, H = 0, W = 0;      // input channels / spatial size (the tensor the forward conv reads)
+    int ks = 0, s = 1, p = 0;     // kernel, stride, symmetric zero pad
+    int OH = 0, OW = 0, Cout = 0; // forward output size / channels
+    int scale255 = 0;
+};
+bool tc_conv_supported(const ConvGeom &g, int is_bf16);
+// D[M][N] = sum_k A(m,k) W(n,k) with A gathered per ConvGeom; Wop: K-major [N][K] (forward) or MN-major (dgrad)
+zoo_status tc_conv_gemm(const ConvGeom &g, const Operand &Wop, int M, int N, int K, const Epilogue &epi, float *ws, size_t ws_elems,
+                        cudaStream_t st);
+
 // fp32 CUDA-core engine (any shapes, fp32 or bf16 inputs, fp32 accumulate)
 zoo_status simt_gemm(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, int split_k,
                      float *ws, size_t ws_elems, cudaStream_t st);

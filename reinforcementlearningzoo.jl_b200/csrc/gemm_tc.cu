@@ -141,6 +141,7 @@ struct TcParams {
     float *ws;      // split-K workspace [M][N] (atomic accumulate, kept all-zero between launches) or nullptr
     unsigned *ctr;  // split-K per-tile arrival counters (kept all-zero between launches)
     unsigned long long *dbg;  // test hook: CTA 0 writes %globaltimer at its phase boundaries (nullptr = off)
+    ConvGeom conv;  // GA kernels only: how the A operand is gathered
 };
 
 unsigned long long *g_tc_dbg = nullptr;  // set by zoo_test_gemm_trace
@@ -182,9 +183,122 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t ad, uint64_t bd, 
     else umma_tf32(tmem_d, ad, bd, idesc, acc);
 }
 
-template <int EB, int BN, bool A_K, bool B_K, bool X3>
+// Implicit-GEMM gather, split in two so the (row-independent) index arithmetic is done once per K-block by 8 lanes:
+//   conv_decode: K index of a 16-byte chunk -> (ky, kx, channel offset), or c < 0 past the end of K
+//   conv_fetch : that chunk of one tile row (CH = 16 / EB consecutive K elements), zero outside the image
+struct ConvTap { int ky, kx, c; };
+
+__device__ __forceinline__ ConvTap conv_decode(const ConvGeom &g, int kk, int Ktot) {
+    ConvTap t;
+    if (kk >= Ktot) { t.ky = 0; t.kx = 0; t.c = -1; return t; }
+    if (g.mode == CONV_NHWC || g.mode == CONV_DGRAD) {
+        const int cw = g.mode == CONV_NHWC ? g.C : g.Cout;
+        const int tap = kk / cw;
+        t.c = kk - tap * cw;
+        t.ky = tap / g.ks;
+        t.kx = tap - t.ky * g.ks;
+    } else {  // raw observation: K order (c, ky, kx); ks % CH == 0 keeps a chunk inside one kernel row
+        const int kk2 = g.ks * g.ks;
+        t.c = kk / kk2;
+        const int rem = kk - t.c * kk2;
+        t.ky = rem / g.ks;
+        t.kx = rem - t.ky * g.ks;
+    }
+    return t;
+}
+
+template <int EB>
+__device__ __forceinline__ uint4 conv_fetch(const ConvGeom &g, bool valid, int b, int y0, int x0, const ConvTap t) {
+    constexpr int CH = 16 / EB;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (!valid || t.c < 0) return val;
+    if (g.mode == CONV_NHWC) {
+        const int iy = y0 + t.ky, ix = x0 + t.kx;
+        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+            val = __ldg(reinterpret_cast<const uint4 *>((const uint8_t *)g.x + ((((long long)b * g.H + iy) * g.W + ix) * g.C + t.c) * EB));
+    } else if (g.mode == CONV_DGRAD) {
+        const int ty = y0 + g.p - t.ky, tx = x0 + g.p - t.kx;  // y0, x0 = input pixel
+        if (ty >= 0 && tx >= 0) {
+            const int oy = g.s == 1 ? ty : (g.s == 2 ? ty >> 1 : ty / g.s), ox = g.s == 1 ? tx : (g.s == 2 ? tx >> 1 : tx / g.s);
+            if (oy * g.s == ty && ox * g.s == tx && oy < g.OH && ox < g.OW)
+                val = __ldg(reinterpret_cast<const uint4 *>((const uint8_t *)g.x + ((((long long)b * g.OH + oy) * g.OW + ox) * g.Cout + t.c) * EB));
+        }
+    } else {
+        const int iy = y0 + t.ky;
+        if (iy >= 0 && iy < g.H) {
+            const long long rowoff = (((long long)b * g.C + t.c) * g.H + iy) * g.W;
+            float f[CH];
+#pragma unroll
+            for (int e = 0; e < CH; ++e) {
+                const int ix = x0 + t.kx + e;
+                float v = 0.f;
+                if (ix >= 0 && ix < g.W) {
+                    v = g.mode == CONV_RAW_U8 ? (float)__ldg((const uint8_t *)g.x + rowoff + ix) : __ldg((const float *)g.x + rowoff + ix);
+                    if (g.scale255) v = __fdiv_rn(v, 255.f);
+                }
+                f[e] = v;
+            }
+            if (EB == 4) {
+                val = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+            } else {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1 % CH]), h1 = __floats2bfloat162_rn(f[2 % CH], f[3 % CH]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4 % CH], f[5 % CH]), h3 = __floats2bfloat162_rn(f[6 % CH], f[7 % CH]);
+                val = make_uint4(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1), *reinterpret_cast<uint32_t *>(&h2),
+                                 *reinterpret_cast<uint32_t *>(&h3));
+            }
+        }
+    }
+    return val;
+}
+
+// global address of a chunk for the cp.async path (NHWC / DGRAD modes), nullptr = zero fill
+template <int EB>
+__device__ __forceinline__ const void *conv_src(const ConvGeom &g, bool valid, int b, int y0, int x0, const ConvTap t) {
+    if (!valid || t.c < 0) return nullptr;
+    if (g.mode == CONV_NHWC) {
+        const int iy = y0 + t.ky, ix = x0 + t.kx;
+        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) return (const uint8_t *)g.x + ((((long long)b * g.H + iy) * g.W + ix) * g.C + t.c) * EB;
+        return nullptr;
+    }
+    const int ty = y0 + g.p - t.ky, tx = x0 + g.p - t.kx;  // DGRAD: y0, x0 = input pixel
+    if (ty < 0 || tx < 0) return nullptr;
+    const int oy = g.s == 1 ? ty : (g.s == 2 ? ty >> 1 : ty / g.s), ox = g.s == 1 ? tx : (g.s == 2 ? tx >> 1 : tx / g.s);
+    if (oy * g.s != ty || ox * g.s != tx || oy >= g.OH || ox >= g.OW) return nullptr;
+    return (const uint8_t *)g.x + ((((long long)b * g.OH + oy) * g.OW + ox) * g.Cout + t.c) * EB;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, const void *fallback) {
+    const int n = src ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src ? src : fallback), "r"(n) : "memory");
+}
+
+// all 8 chunks of this thread's tile row for the K-block starting at k0 (lanes j and j+8.. decode chunk j & 7 and share it)
+template <int EB>
+__device__ __forceinline__ void conv_gather_row(const ConvGeom &g, bool valid, int b, int y0, int x0, int k0, int Ktot, int lane, uint4 (&v)[8]) {
+    const ConvTap mine = conv_decode(g, k0 + (lane & 7) * (16 / EB), Ktot);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        ConvTap t;
+        t.ky = __shfl_sync(0xffffffffu, mine.ky, j);
+        t.kx = __shfl_sync(0xffffffffu, mine.kx, j);
+        t.c = __shfl_sync(0xffffffffu, mine.c, j);
+        v[j] = conv_fetch<EB>(g, valid, b, y0, x0, t);
+    }
+}
+
+__device__ __forceinline__ uint4 tf32_lo(const uint4 v) {
+    uint4 l;
+    l.x = __float_as_uint(__fsub_rn(__uint_as_float(v.x), __uint_as_float(v.x & 0xffffe000u)));
+    l.y = __float_as_uint(__fsub_rn(__uint_as_float(v.y), __uint_as_float(v.y & 0xffffe000u)));
+    l.z = __float_as_uint(__fsub_rn(__uint_as_float(v.z), __uint_as_float(v.z & 0xffffe000u)));
+    l.w = __float_as_uint(__fsub_rn(__uint_as_float(v.w), __uint_as_float(v.w & 0xffffe000u)));
+    return l;
+}
+
+// GA: the A operand is gathered by warps 2..5 (implicit-GEMM convolution, see ConvGeom) instead of TMA-loaded.
+template <int EB, int BN, bool A_K, bool B_K, bool X3, bool GA = false>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
+    static_assert(!GA || A_K, "the gathered A operand is K-major");
     using C = TcCfg<EB, BN, X3>;
     // SWIZZLE_128B tiles need 1024-byte alignment; declaring it on the array (instead of rounding the pointer up) keeps
     // the shared address space visible to the compiler, so the epilogue staging below compiles to LDS/STS
@@ -239,21 +353,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t *sa = smem + s * C::STAGE_BYTES;
                 uint8_t *sb = sa + C::A_BYTES;
-                mbar_expect_tx(&full_bar[s], C::RAW_BYTES);
+                mbar_expect_tx(&full_bar[s], GA ? C::B_BYTES : C::RAW_BYTES);
                 const int k0 = (kb0 + i) * C::BK;
-                if (A_K) {
-                    tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box {BK k, 128 rows}
-                } else {
+                if (!GA) {
+                    if (A_K) {
+                        tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box {BK k, 128 rows}
+                    } else {
 #pragma unroll
-                    for (int h = 0; h < BM / C::MN_BOX; ++h)  // boxes {MN_BOX m, BK k}
-                        tma_load_2d(sa + h * C::BOX_BYTES, &tmA, &full_bar[s], m0 + h * C::MN_BOX, k0);
+                        for (int h = 0; h < BM / C::MN_BOX; ++h)  // boxes {MN_BOX m, BK k}
+                            tma_load_2d(sa + h * C::BOX_BYTES, &tmA, &full_bar[s], m0 + h * C::MN_BOX, k0);
+                    }
                 }
                 if (B_K) {
                     tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box {BK k, BN rows}
                 } else {
+                    // conv dgrad: K runs over (tap, o); tap t's [Cout][C] slice of W sits at column offset t*C of [Cout][ks*ks*C]
+                    int nb = n0, kb = k0;
+                    if (GA) { const int tap = k0 / P.conv.Cout; nb = n0 + tap * P.conv.C; kb = k0 - tap * P.conv.Cout; }
 #pragma unroll
                     for (int h = 0; h < BN / C::MN_BOX; ++h)
-                        tma_load_2d(sb + h * C::BOX_BYTES, &tmB, &full_bar[s], n0 + h * C::MN_BOX, k0);
+                        tma_load_2d(sb + h * C::BOX_BYTES, &tmB, &full_bar[s], nb + h * C::MN_BOX, kb);
                 }
                 if (i == 0) dbg_stamp(P, 2);
             }
@@ -270,8 +389,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&acc_empty[cb], ((chain >> 1) - 1) & 1);
                     tc_fence_after();
                 }
-                if (X3) mbar_wait(&conv_bar[s], ph);
-                else mbar_wait(&full_bar[s], ph);
+                if (X3 || GA) mbar_wait(&conv_bar[s], ph);  // converter / gather warps are done with the stage
+                if (!X3) mbar_wait(&full_bar[s], ph);       // TMA bytes have landed (the 3xTF32 converters waited for them)
                 tc_fence_after();
                 if (i == 0) dbg_stamp(P, 3);
                 const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
@@ -311,38 +430,95 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (X3) {
 #pragma unroll
             for (int j = 0; j < BN; ++j) acc[j] = 0.f;
-            // split every landed fp32 tile into hi (in place) and lo (second half of the stage); one chain behind the
-            // MMA warp, fold finished chains into acc
+        }
+        if (X3 || GA) {
+            // per K-block: (GA) gather this thread's A row into the stage -- hi and, for 3xTF32, lo -- and (3xTF32) split the
+            // TMA-landed fp32 tiles into hi (the tile itself) and lo; one chain behind the MMA warp, fold finished chains
+            // into acc
             const int t = threadIdx.x - 64;  // 0..127
             int drained = 0;
             const int va = min(BM, P.M - m0), vb = min(BN, P.N - n0);  // valid rows of the A / B tiles
-            const int a_units = (A_K ? va * 128 : ((va + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
+            const int a_units = GA ? 0 : (A_K ? va * 128 : ((va + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
             const int b_units = (B_K ? vb * 128 : ((vb + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
             const int conv_units = a_units + b_units;
+            // GA: this thread owns tile row t = output pixel (forward) / input pixel (dgrad) m0 + t
+            bool gvalid = false;
+            int gb = 0, gy0 = 0, gx0 = 0;
+            constexpr int GA_AHEAD = C::STAGES - 2;  // K-blocks of cp.async gathers in flight ahead of the one being finished
+            if (GA) {
+                const ConvGeom &g = P.conv;
+                const int m = m0 + t;
+                gvalid = m < P.M;
+                const int gw = g.mode == CONV_DGRAD ? g.W : g.OW, gh = g.mode == CONV_DGRAD ? g.H : g.OH;
+                const int px = m % gw, tmp = m / gw;
+                const int py = tmp % gh;
+                gb = tmp / gh;
+                gy0 = g.mode == CONV_DGRAD ? py : py * g.s - g.p;
+                gx0 = g.mode == CONV_DGRAD ? px : px * g.s - g.p;
+            }
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % C::STAGES;
                 const uint32_t ph = (i / C::STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
-                // tcgen05 kind::tf32 ignores the low 13 mantissa bits of an fp32 operand (measured: bit-identical results for
-                // raw and pre-truncated inputs), so the landed tile itself is the hi operand and only lo = x - trunc(x) is written
-                const uint4 *raw = reinterpret_cast<const uint4 *>(smem + s * C::STAGE_BYTES);
-                uint4 *lo = reinterpret_cast<uint4 *>(smem + s * C::STAGE_BYTES + C::RAW_BYTES);
+                uint8_t *stage = smem + s * C::STAGE_BYTES;
+                if (GA) {
+                    if (P.conv.mode == CONV_NHWC || P.conv.mode == CONV_DGRAD) {
+                        // cp.async pipeline: the 16-byte chunks of K-block i+GA_AHEAD go straight from global memory into their
+                        // swizzled slots (zero-filled outside the image) while block i, issued GA_AHEAD iterations ago, lands
+                        for (int ib = (i == 0 ? 0 : i + GA_AHEAD); ib <= i + GA_AHEAD; ++ib) {
+                            if (ib < nkb) {
+                                const int sI = ib % C::STAGES;
+                                mbar_wait(&empty_bar[sI], ((ib / C::STAGES) & 1) ^ 1);  // MMAs on the stage's old contents retired
+                                const uint32_t sbase = smem_u32(smem + sI * C::STAGE_BYTES) + t * 128;
+                                const ConvTap mine = conv_decode(P.conv, (kb0 + ib) * C::BK + (lane & 7) * (16 / EB), P.K);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    ConvTap tp;
+                                    tp.ky = __shfl_sync(0xffffffffu, mine.ky, j);
+                                    tp.kx = __shfl_sync(0xffffffffu, mine.kx, j);
+                                    tp.c = __shfl_sync(0xffffffffu, mine.c, j);
+                                    cp_async16(sbase + ((j ^ (t & 7)) << 4), conv_src<EB>(P.conv, gvalid, gb, gy0, gx0, tp), P.conv.x);
+                                }
+                            }
+                            asm volatile("cp.async.commit_group;" ::: "memory");  // one group per K-block, empty past the end
+                        }
+                        asm volatile("cp.async.wait_group %0;" ::"n"(GA_AHEAD) : "memory");  // block i's own chunks have landed
+                        if (X3) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int off = t * 128 + (j << 4);
+                                *reinterpret_cast<uint4 *>(stage + C::RAW_BYTES + off) = tf32_lo(*reinterpret_cast<const uint4 *>(stage + off));
+                            }
+                        }
+                    } else {
+                        uint4 gcur[8];
+                        conv_gather_row<EB>(P.conv, gvalid, gb, gy0, gx0, (kb0 + i) * C::BK, P.K, lane, gcur);
+                        mbar_wait(&empty_bar[s], ph ^ 1);  // the MMAs that read this stage's previous contents have retired
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int off = t * 128 + ((j ^ (t & 7)) << 4);  // SWIZZLE_128B: chunk j of row t sits at j ^ (t % 8)
+                            *reinterpret_cast<uint4 *>(stage + off) = gcur[j];
+                            if (X3) *reinterpret_cast<uint4 *>(stage + C::RAW_BYTES + off) = tf32_lo(gcur[j]);
+                        }
+                    }
+                }
+                if (X3) {
+                    mbar_wait(&full_bar[s], ph);
+                    // tcgen05 kind::tf32 ignores the low 13 mantissa bits of an fp32 operand (measured: bit-identical results
+                    // for raw and pre-truncated inputs), so the landed tile itself is the hi operand; only lo = x - trunc(x)
+                    // is written.  Rows past M / N are never stored, so they are skipped.
+                    const uint4 *raw = reinterpret_cast<const uint4 *>(stage);
+                    uint4 *lo = reinterpret_cast<uint4 *>(stage + C::RAW_BYTES);
 #pragma unroll 4
-                for (int j = t; j < conv_units; j += 128) {
-                    const int jj = j < a_units ? j : j - a_units + C::A_BYTES / 16;  // rows past M / N are never stored: skipped
-                    const uint4 v = raw[jj];
-                    uint4 l;
-                    l.x = __float_as_uint(__fsub_rn(__uint_as_float(v.x), __uint_as_float(v.x & 0xffffe000u)));
-                    l.y = __float_as_uint(__fsub_rn(__uint_as_float(v.y), __uint_as_float(v.y & 0xffffe000u)));
-                    l.z = __float_as_uint(__fsub_rn(__uint_as_float(v.z), __uint_as_float(v.z & 0xffffe000u)));
-                    l.w = __float_as_uint(__fsub_rn(__uint_as_float(v.w), __uint_as_float(v.w & 0xffffe000u)));
-                    lo[jj] = l;
+                    for (int j = t; j < conv_units; j += 128) {
+                        const int jj = j < a_units ? j : j - a_units + C::A_BYTES / 16;
+                        lo[jj] = tf32_lo(raw[jj]);
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
                 mbar_arrive(&conv_bar[s]);
                 // chain `drained` ended at K-block (drained+1)*CHAIN - 1; by the time two more blocks have been converted
                 // its MMAs have retired, so the wait below does not stall the conversion pipeline
-                if (drained < nchains - 1 && i + 1 >= (drained + 1) * CHAIN + 2) {
+                if (X3 && drained < nchains - 1 && i + 1 >= (drained + 1) * CHAIN + 2) {
                     const int cb = drained & 1;
                     mbar_wait(&acc_full[cb], (drained >> 1) & 1);
                     tc_fence_after();
@@ -351,14 +527,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         uint32_t r[32];
                         tmem_ld32(tq + (uint32_t)(cb * BN + c), r);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[c + j] = __fadd_rn(acc[c + j], __uint_as_float(r[j]));
+                        for (int j = 0; j < 32; ++j) acc[X3 ? c + j : 0] = __fadd_rn(acc[X3 ? c + j : 0], __uint_as_float(r[j]));
                     }
                     tc_fence_before();
                     mbar_arrive(&acc_empty[cb]);
                     ++drained;
                 }
             }
-            for (; drained < nchains - 1; ++drained) {  // chains whose delayed drain slot never came (short tail)
+            for (; X3 && drained < nchains - 1; ++drained) {  // chains whose delayed drain slot never came (short tail)
                 const int cb = drained & 1;
                 mbar_wait(&acc_full[cb], (drained >> 1) & 1);
                 tc_fence_after();
@@ -367,7 +543,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint32_t r[32];
                     tmem_ld32(tq + (uint32_t)(cb * BN + c), r);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c + j] = __fadd_rn(acc[c + j], __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; ++j) acc[X3 ? c + j : 0] = __fadd_rn(acc[X3 ? c + j : 0], __uint_as_float(r[j]));
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[cb]);
@@ -402,7 +578,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 float v = __uint_as_float(r[j]);
-                if (X3) v = __fadd_rn(v, acc[c + j]);
+                if (X3) v = __fadd_rn(v, acc[X3 ? c + j : 0]);
                 stg[lane][j] = v;
             }
             __syncwarp();
@@ -622,6 +798,77 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
     else if (x3) ZOO_TRY((launch_tc_bn<4, true>(BN, A.kmajor, B.kmajor, tmA, tmB, P, grid, st)));
     else ZOO_TRY((launch_tc_bn<4, false>(BN, A.kmajor, B.kmajor, tmA, tmB, P, grid, st)));
     return ZOO_OK;
+}
+
+// ---------------------------------------------------------------- implicit-GEMM convolution --------
+template <int EB, int BN, bool B_K, bool X3>
+static zoo_status launch_conv(const CUtensorMap &tmB, const TcParams &P, dim3 grid, cudaStream_t st) {
+    using C = TcCfg<EB, BN, X3>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    tc_gemm_kernel<EB, BN, true, B_K, X3, true><<<grid, TC_THREADS, C::SMEM, st>>>(tmB, tmB, P);
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+
+template <int EB, bool X3>
+static zoo_status launch_conv_bn(int BN, bool bk, const CUtensorMap &tmB, const TcParams &P, dim3 grid, cudaStream_t st) {
+    if (BN == 32) {
+        if (bk) return launch_conv<EB, 32, true, X3>(tmB, P, grid, st);
+        if (EB == 4) return launch_conv<4, 32, false, X3>(tmB, P, grid, st);
+        set_err("tc_conv_gemm: bf16 MN-major B needs BN >= 64");
+        return ZOO_BAD_ARG;
+    }
+    if (BN == 64) return bk ? launch_conv<EB, 64, true, X3>(tmB, P, grid, st) : launch_conv<EB, 64, false, X3>(tmB, P, grid, st);
+    return bk ? launch_conv<EB, 128, true, X3>(tmB, P, grid, st) : launch_conv<EB, 128, false, X3>(tmB, P, grid, st);
+}
+
+bool tc_conv_supported(const ConvGeom &g, int is_bf16) {
+    const int eb = is_bf16 ? 2 : 4, ch = 16 / eb, bk = 128 / eb;
+    if (((uintptr_t)g.x & 15) && g.mode != CONV_RAW_U8) return false;
+    if (g.mode == CONV_RAW_U8 || g.mode == CONV_RAW_F32) return g.ks % ch == 0 && ((long long)g.C * g.ks * g.ks * eb) % 16 == 0;
+    if (g.mode == CONV_NHWC) return g.C % ch == 0;
+    if (g.mode == CONV_DGRAD) return g.Cout % bk == 0 && g.C % 8 == 0 && ((long long)g.ks * g.ks * g.C * eb) % 16 == 0;
+    return false;
+}
+
+zoo_status tc_conv_gemm(const ConvGeom &g, const Operand &Wop, int M, int N, int K, const Epilogue &epi, float *ws, size_t ws_elems,
+                        cudaStream_t st) {
+    ZOO_REQUIRE(tc_conv_supported(g, Wop.is_bf16) && M > 0 && N >= 8 && ((uintptr_t)Wop.p & 15) == 0, "tc_conv_gemm: unsupported geometry");
+    const int eb = Wop.is_bf16 ? 2 : 4;
+    const int bk = 128 / eb, mn_box = 128 / eb;
+    const bool x3 = eb == 4 && epi.tf32_passes == 3;
+    ZOO_REQUIRE(g.mode == CONV_DGRAD ? !Wop.kmajor : Wop.kmajor, "tc_conv_gemm: weight operand has the wrong major");
+    int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+    if (eb == 2 && BN == 32 && !Wop.kmajor) BN = 64;
+    dim3 grid(cdiv(M, BM), cdiv(N, BN), 1);
+    const int total_kb = cdiv(K, bk);
+    const long long tiles = (long long)grid.x * grid.y;
+    const long long cap_ctas = 148 * (x3 ? 1 : 2);
+    int split_k = 1;
+    if (tiles * 2 <= cap_ctas && total_kb >= 32) split_k = (int)std::min<long long>(total_kb / 4, cap_ctas / tiles);
+    split_k = std::max(1, std::min(split_k, total_kb));
+    int kbps = cdiv(total_kb, split_k);
+    split_k = cdiv(total_kb, kbps);
+    grid.z = split_k;
+    TcParams P;
+    P.M = M; P.N = N; P.K = K; P.kb_per_split = kbps; P.epi = epi; P.ws = nullptr; P.ctr = nullptr; P.dbg = nullptr; P.conv = g;
+    const bool direct_acc = epi.accumulate && !epi.out_bf16;
+    if (direct_acc && split_k == 1 && epi.accumulate == 2) P.epi.accumulate = 0;
+    if (split_k > 1 && !direct_acc) {
+        ZOO_REQUIRE(ws && ws_elems >= (size_t)M * N + TC_WS_COUNTERS && tiles <= TC_WS_COUNTERS, "tc_conv_gemm: split-K workspace too small");
+        P.ws = ws;
+        P.ctr = reinterpret_cast<unsigned *>(ws + ws_elems - TC_WS_COUNTERS);
+    }
+    CUtensorMap tmB;
+    if (Wop.kmajor) ZOO_TRY(make_map(&tmB, Wop.p, eb, K, N, Wop.ld, bk, BN, false));
+    else ZOO_TRY(make_map(&tmB, Wop.p, eb, Wop.ld, g.Cout, Wop.ld, mn_box, bk, true));  // W as [Cout][ks*ks*C]: boxes at tap offsets
+    if (eb == 2) return launch_conv_bn<2, false>(BN, Wop.kmajor, tmB, P, grid, st);
+    if (x3) return launch_conv_bn<4, true>(BN, Wop.kmajor, tmB, P, grid, st);
+    return launch_conv_bn<4, false>(BN, Wop.kmajor, tmB, P, grid, st);
 }
 
 }  // namespace zoo

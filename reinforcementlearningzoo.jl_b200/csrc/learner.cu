@@ -145,7 +145,7 @@ static zoo_status target_forward(zoo_learner *L, zoo_net *tg, const void *s2, co
     zoo_net *on = L->online;
     const bool par = on->side && !g_prof_on;
     if (par) ZOO_TRY(net_side_fork(on, st));
-    zoo_status s = net_forward(tg, s2, L->obs_dtype, L->B, tau, n_tau, par ? on->side : st);
+    zoo_status s = net_forward(tg, s2, L->obs_dtype, L->B, tau, n_tau, par ? on->side : st, 0);
     L->target_forked = par;
     return s;
 }
@@ -180,18 +180,18 @@ static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bo
     }
     int bwd_rows = B, n_tau = 0;
     if (c.kind == ZOO_LEARNER_BASIC_DQN) {
-        ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, 2 * B, nullptr, 0, st));  // Q([s; s'])
+        ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, 2 * B, nullptr, 0, st, 2 * B));  // Q([s; s'])
         prof_label("head"); ZOO_TRY(launch_dqn_head(c.kind, 0, h, on->out_final, nullptr, c.gamma, on->dout_final, st));
         bwd_rows = 2 * B;
     } else if (c.kind == ZOO_LEARNER_DQN || c.kind == ZOO_LEARNER_PRIORITIZED_DQN) {
         const int dbl = c.kind == ZOO_LEARNER_DQN && c.double_dqn;
         ZOO_TRY(target_forward(L, tg, s2_ptr, nullptr, 0, st));  // side lane, rejoined before the head
-        ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, dbl ? 2 * B : B, nullptr, 0, st));
+        ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, dbl ? 2 * B : B, nullptr, 0, st, B));
         ZOO_TRY(target_join(L, st));
         prof_label("head"); ZOO_TRY(launch_dqn_head(c.kind, dbl, h, on->out_final, tg->out_final, L->gamma_n, on->dout_final, st));
     } else if (c.kind == ZOO_LEARNER_RAINBOW) {
         ZOO_TRY(target_forward(L, tg, s2_ptr, nullptr, 0, st));
-        ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, B, nullptr, 0, st));
+        ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, B, nullptr, 0, st, B));
         ZOO_TRY(target_join(L, st));
         prof_label("head"); ZOO_TRY(launch_c51_head(h, c.n_atoms, tg->out_final, on->out_final, L->d_support, c.delta_z, c.v_min, c.v_max, L->gamma_n,
                                 on->dout_final, L->d_tdist, st));
@@ -202,9 +202,9 @@ static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bo
             rng_tick_kernel<<<1, 1, 0, st>>>(L->opt->sc);
             ZOO_LAUNCH_CHECK();
         }
-        ZOO_TRY(net_forward(tg, s2_ptr, L->obs_dtype, B, L->d_taup, c.N_prime, st));
+        ZOO_TRY(net_forward(tg, s2_ptr, L->obs_dtype, B, L->d_taup, c.N_prime, st, 0));
         prof_label("head"); ZOO_TRY(launch_iqn_target(h, c.N_prime, tg->out_final, c.gamma, L->d_target, st));
-        ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, B, L->d_tau, c.N, st));
+        ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, B, L->d_tau, c.N, st, B));
         prof_label("head"); ZOO_TRY(launch_iqn_loss(h, c.N, c.N_prime, on->out_final, L->d_target, L->d_tau, c.kappa, on->dout_final, st));
         n_tau = c.N;
     }

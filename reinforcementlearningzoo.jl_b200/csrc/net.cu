@@ -5,6 +5,15 @@
 
 namespace zoo {
 
+// Implicit-GEMM convolutions (tc_conv_gemm: the A operand is gathered in-kernel, no im2col / col2im) are parity-tested but
+// this round still lose to explicit im2col + TMA GEMM at these layer sizes (the 4-warp gather is instruction-latency bound,
+// see DESIGN.md section 4), so they are opt-in: ZOO_IMPLICIT_CONV=1.
+static bool implicit_conv_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("ZOO_IMPLICIT_CONV"); on = (e && e[0] == '1') ? 1 : 0; }
+    return on == 1;
+}
+
 // ---------------------------------------------------------------- kernels -----------------
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
@@ -41,6 +50,23 @@ __global__ void im2col_first_kernel(const Tin *__restrict__ x, T *__restrict__ c
         }
         dst[kx] = from_f<T>(v);
     }
+}
+
+// raw observation [B][C][H][W] (u8 | f32) -> fp32 NHWC [B][H][W][C] with `x ./ 255` (IEEE divide) folded in, so the first
+// conv runs through the same implicit-GEMM gather as the inner convs.  One thread per pixel, C = 4 channels (16 bytes).
+template <typename Tin>
+__global__ void obs_to_nhwc4_kernel(const Tin *__restrict__ x, float4 *__restrict__ out, long long pixels, int HW, int scale255) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pixels) return;
+    const long long b = i / HW, p = i - b * HW;
+    const Tin *src = x + b * 4 * HW + p;
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        v[c] = to_f(src[(long long)c * HW]);
+        if (scale255) v[c] = __fdiv_rn(v[c], 255.f);
+    }
+    out[i] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 template <typename T, int VEC> struct alignas(sizeof(T) * VEC) VecT { T v[VEC]; };
@@ -298,7 +324,8 @@ static Operand weight_operand(const zoo_net *net, const TensorInfo &W, const Ope
 }
 
 // in_kind: 0 raw u8, 1 raw f32, 2 internal T
-static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_kind, long long rows, cudaStream_t st) {
+// cols_rows: leading sample rows whose im2col matrices the later wgrad needs (0 = forward only, e.g. the target net)
+static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_kind, long long rows, cudaStream_t st, long long cols_rows = 0) {
     ZOO_REQUIRE(rows <= ch.rows_cap, "forward: %lld rows exceed the capacity %lld this net was created with", rows, ch.rows_cap);
     const int bf = is_bf(net);
     const void *cur = in;
@@ -309,21 +336,60 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
         const TensorInfo &Bt = net->tensors[L.bt];
         prof_label("fwd:t%d[%lldx%dx%lld]", L.wt, M, L.cout, L.K);
         Operand A;
+        Epilogue e;
+        e.out = L.out; e.out_bf16 = L.out_fp32 ? 0 : bf; e.sm = L.cout; e.sn = 1;
+        e.bias = net->params + Bt.offset; e.bias_mode = 1; e.relu = L.relu; e.tf32_passes = net->tf32_passes;
+        if (L.kind == ZOO_LAYER_CONV && L.first_raw && net->obs_nhwc) {
+            if (cur_kind == 2) { set_err("conv: first layer expects a raw observation"); return ZOO_BAD_ARG; }
+            const long long pixels = rows * L.ih * L.iw;
+            prof_label("obs2nhwc[%lld]", pixels);
+            if (cur_kind == 0) obs_to_nhwc4_kernel<uint8_t><<<cdiv(pixels, 256), 256, 0, st>>>((const uint8_t *)cur, (float4 *)net->obs_nhwc_buf, pixels, L.ih * L.iw, L.scale255);
+            else obs_to_nhwc4_kernel<float><<<cdiv(pixels, 256), 256, 0, st>>>((const float *)cur, (float4 *)net->obs_nhwc_buf, pixels, L.ih * L.iw, L.scale255);
+            ZOO_LAUNCH_CHECK();
+            cur = net->obs_nhwc_buf;
+            cur_kind = 2;
+        }
+        const bool raw_conv = L.kind == ZOO_LAYER_CONV && L.first_raw && !net->obs_nhwc;
         if (L.kind == ZOO_LAYER_CONV) {
-            if (L.first_raw) {
-                long long total = M * L.cin * L.ksize;
-                int blocks = cdiv(total, 256);
+            // implicit GEMM on tcgen05 (the producer warps gather the im2col rows): no cols matrix on the critical path.
+            // The explicit cols that wgrad consumes are built for the first cols_rows samples on the side lane.
+            ConvGeom g;
+            g.x = cur; g.C = L.cin; g.H = L.ih; g.W = L.iw; g.ks = L.ksize; g.s = L.stride; g.p = L.pad; g.OH = L.oh; g.OW = L.ow;
+            g.Cout = L.cout; g.scale255 = L.scale255;
+            g.mode = raw_conv ? (cur_kind == 0 ? CONV_RAW_U8 : CONV_RAW_F32) : CONV_NHWC;
+            if (raw_conv && cur_kind == 2) { set_err("conv: first layer expects a raw observation"); return ZOO_BAD_ARG; }
+            // (a raw first conv -- bf16 nets -- keeps the explicit im2col + TMA GEMM path: its register gather is slower)
+            const bool implicit = implicit_conv_enabled() && net->prec != ZOO_PREC_FP32_SIMT && !raw_conv && L.cout >= 8 && tc_conv_supported(g, bf);
+            const long long Mc = implicit ? cols_rows * L.opr : M;  // rows of the explicit cols matrix to build
+            cudaStream_t sc = st;
+            const bool par = implicit && net->side && !g_prof_on;
+            if (par && Mc > 0) { ZOO_TRY(net_side_fork(net, st)); sc = net->side; }
+            if (Mc > 0) {
+                prof_label("im2col:t%d[%lldx%lld]", L.wt, Mc, L.K);
+                if (raw_conv) {
+                    long long total = Mc * L.cin * L.ksize;
+                    int blocks = cdiv(total, 256);
 #define IM2COL_FIRST(Tin, T)                                                                                              \
-    im2col_first_kernel<Tin, T><<<blocks, 256, 0, st>>>((const Tin *)cur, (T *)L.cols, total, L.cin, L.ih, L.iw, L.ksize, \
+    im2col_first_kernel<Tin, T><<<blocks, 256, 0, sc>>>((const Tin *)cur, (T *)L.cols, total, L.cin, L.ih, L.iw, L.ksize, \
                                                         L.stride, L.pad, L.oh, L.ow, L.scale255)
-                if (cur_kind == 0) { if (bf) IM2COL_FIRST(uint8_t, bf16); else IM2COL_FIRST(uint8_t, float); }
-                else if (cur_kind == 1) { if (bf) IM2COL_FIRST(float, bf16); else IM2COL_FIRST(float, float); }
-                else { set_err("conv: first layer expects a raw observation"); return ZOO_BAD_ARG; }
+                    if (cur_kind == 0) { if (bf) IM2COL_FIRST(uint8_t, bf16); else IM2COL_FIRST(uint8_t, float); }
+                    else { if (bf) IM2COL_FIRST(float, bf16); else IM2COL_FIRST(float, float); }
 #undef IM2COL_FIRST
-                ZOO_LAUNCH_CHECK();
-            } else {
-                if (bf) ZOO_TRY(launch_im2col_nhwc<bf16>(cur, L.cols, M, L, st));
-                else ZOO_TRY(launch_im2col_nhwc<float>(cur, L.cols, M, L, st));
+                    ZOO_LAUNCH_CHECK();
+                } else {
+                    if (bf) ZOO_TRY(launch_im2col_nhwc<bf16>(cur, L.cols, Mc, L, sc));
+                    else ZOO_TRY(launch_im2col_nhwc<float>(cur, L.cols, Mc, L, sc));
+                }
+            }
+            if (implicit) {
+                prof_label("fwd:t%d[%lldx%dx%lld]", L.wt, M, L.cout, L.K);
+                Operand Ad{nullptr, bf, L.K, 1};
+                Operand Wk = weight_operand(net, W, Ad, (int)M, L.cout, (int)L.K, L.K, 1);
+                if (Wk.is_bf16 != bf) { set_err("conv: weight shadow missing"); return ZOO_CUDA_ERROR; }
+                ZOO_TRY(tc_conv_gemm(g, Wk, (int)M, L.cout, (int)L.K, e, net->ws, net->ws_elems, st));
+                cur = L.out;
+                cur_kind = 2;
+                continue;
             }
             A = Operand{L.cols, bf, L.K, 1};
         } else {
@@ -331,9 +397,6 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
             A = Operand{cur, cur_kind == 2 ? bf : 0, L.K, 1};
         }
         Operand B = weight_operand(net, W, A, (int)M, L.cout, (int)L.K, L.K, 1);
-        Epilogue e;
-        e.out = L.out; e.out_bf16 = L.out_fp32 ? 0 : bf; e.sm = L.cout; e.sn = 1;
-        e.bias = net->params + Bt.offset; e.bias_mode = 1; e.relu = L.relu; e.tf32_passes = net->tf32_passes;
         ZOO_TRY(gemm(A, B, (int)M, L.cout, (int)L.K, e, 0, net->ws, net->ws_elems, st));
         cur = L.out;
         cur_kind = 2;
@@ -382,6 +445,20 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
         if (L.kind == ZOO_LAYER_CONV) {
             ZOO_REQUIRE(li > 0, "backward: gradient w.r.t. the observation is not supported");
             LayerExec &P = ch.layers[li - 1];
+            ConvGeom g;
+            g.x = L.dout; g.mode = CONV_DGRAD; g.C = L.cin; g.H = L.ih; g.W = L.iw; g.ks = L.ksize; g.s = L.stride; g.p = L.pad;
+            g.OH = L.oh; g.OW = L.ow; g.Cout = L.cout;
+            if (implicit_conv_enabled() && net->prec != ZOO_PREC_FP32_SIMT && Wn.is_bf16 == dy_bf && dy_bf == bf && L.cin >= 8 && tc_conv_supported(g, bf)) {
+                // implicit transposed-conv GEMM: dX[pixel][c] = sum_(tap,o) dY[pixel_out(tap)][o] W[o][tap][c], relu' in the
+                // epilogue -- no dcols matrix, no col2im pass
+                Operand Wt{Wn.p, Wn.is_bf16, L.K, 0};
+                ed.out = P.dout; ed.sm = L.cin; ed.sn = 1;
+                if (P.relu) { ed.mask = P.out; ed.mask_bf16 = bf; ed.mask_sm = L.cin; ed.mask_sn = 1; }
+                const long long Mi = rows * L.ih * L.iw;
+                prof_label("dgrad:t%d[%lldx%dx%lld]", L.wt, Mi, L.cin, (long long)L.ksize * L.ksize * L.cout);
+                ZOO_TRY(tc_conv_gemm(g, Wt, (int)Mi, L.cin, L.ksize * L.ksize * L.cout, ed, net->ws, net->ws_elems, st));
+                continue;
+            }
             ed.out = L.dcols;
             ZOO_TRY(gemm(dY, Wn, (int)M, (int)L.K, L.cout, ed, 0, net->ws, net->ws_elems, st));
             if (bf) ZOO_TRY(launch_col2im_nhwc<bf16>(L.dcols, P.dout, P.relu ? P.out : nullptr, rows, L, st));
@@ -421,12 +498,12 @@ zoo_status net_refresh_shadow(zoo_net *net, cudaStream_t st) {
     return ZOO_OK;
 }
 
-zoo_status net_forward(zoo_net *net, const void *obs, int obs_dtype, int rows, const float *tau, int n_tau, cudaStream_t st) {
+zoo_status net_forward(zoo_net *net, const void *obs, int obs_dtype, int rows, const float *tau, int n_tau, cudaStream_t st, int bwd_rows) {
     const int bf = is_bf(net);
     const int in_kind = obs_dtype == ZOO_OBS_U8 ? 0 : 1;
-    if (net->desc.kind == ZOO_NET_CHAIN) return chain_forward(net, net->a, obs, in_kind, rows, st);
+    if (net->desc.kind == ZOO_NET_CHAIN) return chain_forward(net, net->a, obs, in_kind, rows, st, bwd_rows);
     if (net->desc.kind == ZOO_NET_DUELING) {
-        ZOO_TRY(chain_forward(net, net->a, obs, in_kind, rows, st));
+        ZOO_TRY(chain_forward(net, net->a, obs, in_kind, rows, st, bwd_rows));
         ZOO_TRY(chain_forward(net, net->b, net->a.out(), 2, rows, st));
         ZOO_TRY(chain_forward(net, net->c, net->a.out(), 2, rows, st));
         dueling_combine_kernel<<<cdiv(rows, 128), 128, 0, st>>>((const float *)net->b.out(), (const float *)net->c.out(),
@@ -438,7 +515,7 @@ zoo_status net_forward(zoo_net *net, const void *obs, int obs_dtype, int rows, c
     ZOO_REQUIRE(tau && n_tau > 0 && n_tau <= net->max_q, "IQN forward: tau missing or n_tau %d > max_quantiles %lld", n_tau, net->max_q);
     const long long R = (long long)rows * n_tau;
     const int nem = (int)net->b.in_feat, F = (int)net->a.out_feat;
-    ZOO_TRY(chain_forward(net, net->a, obs, in_kind, rows, st));
+    ZOO_TRY(chain_forward(net, net->a, obs, in_kind, rows, st, bwd_rows));
     if (bf) embed_kernel<bf16><<<cdiv(R * nem, 256), 256, 0, st>>>(tau, (bf16 *)net->emb, R, nem);
     else embed_kernel<float><<<cdiv(R * nem, 256), 256, 0, st>>>(tau, (float *)net->emb, R, nem);
     ZOO_LAUNCH_CHECK();
@@ -520,7 +597,7 @@ static zoo_status parse_chain(zoo_net *net, const zoo_layer *Ls, int n, ParseSta
             L.ow = (S.w + 2 * l.pad - l.ksize) / l.stride + 1;
             ZOO_REQUIRE(L.oh > 0 && L.ow > 0, "%s[%d]: conv output is empty", name, i);
             L.first_raw = S.raw; L.scale255 = S.scale; L.K = (long long)l.ksize * l.ksize * l.n_in; L.opr = (long long)L.oh * L.ow;
-            TensorInfo w{}; w.kind = 1; w.n_out = l.n_out; w.n_in = l.n_in; w.ksize = l.ksize; w.conv_nhwc = !S.raw;
+            TensorInfo w{}; w.kind = 1; w.n_out = l.n_out; w.n_in = l.n_in; w.ksize = l.ksize; w.conv_nhwc = !S.raw || net->obs_nhwc;
             w.count = (long long)l.n_out * L.K;
             TensorInfo b{}; b.kind = 2; b.n_out = l.n_out; b.count = l.n_out;
             L.wt = (int)net->tensors.size(); net->tensors.push_back(w);
@@ -644,6 +721,8 @@ zoo_status zoo_net_create(const zoo_net_desc *d, zoo_net **out) {
     net->tf32_passes = d->precision == ZOO_PREC_FP32 ? 3 : (d->precision == ZOO_PREC_TF32 ? 1 : 0);
     net->max_batch = d->max_batch;
     net->max_q = d->kind == ZOO_NET_IQN ? d->max_quantiles : 0;
+    // fp32-storage nets turn the raw observation into fp32 NHWC first (4 channels = one 16-byte gather chunk)
+    net->obs_nhwc = d->precision != ZOO_PREC_BF16 && d->in_c == 4 && !(d->in_h == 1 && d->in_w == 1);
     ParseState S{d->in_c, d->in_h, d->in_w, !(d->in_h == 1 && d->in_w == 1), (long long)d->in_c, false, true, false};
     zoo_status s = ZOO_OK;
     if (d->kind == ZOO_NET_CHAIN) {
@@ -725,6 +804,7 @@ zoo_status zoo_net_create(const zoo_net_desc *d, zoo_net **out) {
     ZOO_CUDA(cudaMalloc(&net->ws, net->ws_elems * sizeof(float)));
     ZOO_CUDA(cudaMemset(net->ws, 0, net->ws_elems * sizeof(float)));
     ZOO_CUDA(cudaMalloc(&net->obs, (size_t)rows_a * obs_elems(net) * sizeof(float)));
+    if (net->obs_nhwc) ZOO_CUDA(cudaMalloc(&net->obs_nhwc_buf, (size_t)rows_a * obs_elems(net) * sizeof(float)));
     *out = net;
     return ZOO_OK;
 }
@@ -745,7 +825,7 @@ zoo_status zoo_net_destroy(zoo_net *net) {
     free_chain(net->b, net->out_final, net->dout_final);
     free_chain(net->c, net->out_final, net->dout_final);
     void *ptrs[] = {net->params, net->shadow, net->grads, net->out_final, net->dout_final, net->emb, net->merged, net->dmerged,
-                    net->tau_dev, net->dh1, net->dh2, net->ws, net->obs, net->stage, net->ws_side};
+                    net->tau_dev, net->dh1, net->dh2, net->ws, net->obs, net->stage, net->ws_side, net->obs_nhwc_buf};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (net->side) { cudaStreamSynchronize(net->side); cudaStreamDestroy(net->side); }
     if (net->ev_fork) cudaEventDestroy(net->ev_fork);
@@ -829,7 +909,7 @@ zoo_status zoo_net_forward(zoo_net *net, const void *obs_host, int32_t obs_dtype
         R = (long long)B * n_tau;
         ZOO_CUDA(cudaMemcpyAsync(net->tau_dev, tau_host, R * sizeof(float), cudaMemcpyHostToDevice, net->st));
     }
-    ZOO_TRY(net_forward(net, net->obs, obs_dtype, B, net->tau_dev, n_tau, net->st));
+    ZOO_TRY(net_forward(net, net->obs, obs_dtype, B, net->tau_dev, n_tau, net->st, 0));
     ZOO_CUDA(cudaMemcpyAsync(out_host, net->out_final, (size_t)R * net->n_out * sizeof(float), cudaMemcpyDeviceToHost, net->st));
     ZOO_CUDA(cudaStreamSynchronize(net->st));
     return ZOO_OK;

@@ -68,6 +68,8 @@ struct zoo_net {
     float *ws = nullptr;  // split-K workspace
     size_t ws_elems = 0;
     void *obs = nullptr;  // staged observation for zoo_net_forward
+    bool obs_nhwc = false;        // first conv reads an fp32 NHWC copy of the observation (fp32-storage nets, 4 channels)
+    float *obs_nhwc_buf = nullptr;
     float *stage = nullptr; size_t stage_elems = 0;  // param up/download staging
     cudaStream_t st = nullptr;
     bool bwd_ready = false;
@@ -83,7 +85,8 @@ namespace zoo {
 zoo_status net_alloc_backward(zoo_net *net);
 // obs: device pointer, raw observation rows [rows][C][H][W] (u8|f32).  tau: device [rows][n_tau] (IQN).
 // Result: net->out_final fp32 [rows (* n_tau)][n_out].
-zoo_status net_forward(zoo_net *net, const void *obs, int obs_dtype, int rows, const float *tau, int n_tau, cudaStream_t st);
+// bwd_rows: leading rows that a later net_backward will differentiate (their im2col matrices are kept for wgrad); 0 = none
+zoo_status net_forward(zoo_net *net, const void *obs, int obs_dtype, int rows, const float *tau, int n_tau, cudaStream_t st, int bwd_rows);
 // consumes net->dout_final (fp32, same shape as out_final, for the first `rows` samples) and accumulates into net->grads
 zoo_status net_backward(zoo_net *net, int obs_dtype, const void *obs, int rows, int n_tau, cudaStream_t st);
 zoo_status net_refresh_shadow(zoo_net *net, cudaStream_t st);
