@@ -125,6 +125,10 @@ zoo_status gemm(const Operand &A, const Operand &B, int M, int N, int K, const E
 __device__ __forceinline__ float ld_elem(const void *p, int is_bf16, long long i) {
     return is_bf16 ? __bfloat162float(((const bf16 *)p)[i]) : ((const float *)p)[i];
 }
+// read-only (non-coherent) variant: lets the compiler batch these loads ahead of unrelated global stores
+__device__ __forceinline__ float ldg_elem(const void *p, int is_bf16, long long i) {
+    return is_bf16 ? __bfloat162float(__ldg(((const bf16 *)p) + i)) : __ldg(((const float *)p) + i);
+}
 __device__ __forceinline__ void st_elem(void *p, int is_bf16, long long i, float v) {
     if (is_bf16) ((bf16 *)p)[i] = __float2bfloat16_rn(v);
     else ((float *)p)[i] = v;

@@ -136,6 +136,15 @@ zoo_status simt_gemm(const Operand &A, const Operand &B, int M, int N, int K, co
 zoo_status gemm(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, int split_k, float *ws,
                 size_t ws_elems, cudaStream_t st) {
     const bool want_tc = (A.is_bf16 && B.is_bf16) || (!A.is_bf16 && !B.is_bf16 && epi.tf32_passes > 0);
+    if (want_tc && M <= 64 && N >= 128 && !epi.accumulate && !epi.rowmul && tc_gemm_supported(B, A, N, M, K)) {
+        // swap-AB for a skinny batch against a wide layer: the weight matrix becomes the 128-row MMA operand (every byte of
+        // its tile is payload, instead of a 128-row activation tile that is mostly padding) and the result is written transposed
+        Epilogue t = epi;
+        t.sm = epi.sn; t.sn = epi.sm;
+        t.mask_sm = epi.mask_sn; t.mask_sn = epi.mask_sm;
+        t.bias_mode = epi.bias_mode == 1 ? 2 : (epi.bias_mode == 2 ? 1 : 0);
+        return tc_gemm(B, A, N, M, K, t, split_k, ws, ws_elems, st);
+    }
     if (want_tc && tc_gemm_supported(A, B, M, N, K)) return tc_gemm(A, B, M, N, K, epi, split_k, ws, ws_elems, st);
     return simt_gemm(A, B, M, N, K, epi, split_k, ws, ws_elems, st);
 }
