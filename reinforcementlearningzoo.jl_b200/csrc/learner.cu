@@ -31,7 +31,9 @@ __global__ void opt_tick_kernel(OptScalars *s, double b1, double b2) {
 __global__ void rng_tick_kernel(OptScalars *s) { s->rng += 1; }
 
 // RMSProp: acc = rho*acc + (1-rho)*g^2;  p -= g * eta / (sqrt(acc) + eps).  fp32 arithmetic with fp64-derived scalars.
-__global__ void rmsprop_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ acc, bf16 *__restrict__ shadow,
+// Both optimiser kernels leave the gradient buffer zeroed (the next update's split-K / bias-grad atomics accumulate into it),
+// which replaces a separate 16 MB memset per update.
+__global__ void rmsprop_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ acc, bf16 *__restrict__ shadow,
                                long long n4, float rho, float omr, float eta, float eps) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
@@ -48,6 +50,7 @@ __global__ void rmsprop_kernel(float *__restrict__ p, const float *__restrict__ 
     }
     reinterpret_cast<float4 *>(p)[i] = pv;
     reinterpret_cast<float4 *>(acc)[i] = av;
+    reinterpret_cast<float4 *>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (shadow) {
         reinterpret_cast<__nv_bfloat162 *>(shadow)[2 * i] = __floats2bfloat162_rn(pv.x, pv.y);
         reinterpret_cast<__nv_bfloat162 *>(shadow)[2 * i + 1] = __floats2bfloat162_rn(pv.z, pv.w);
@@ -55,7 +58,7 @@ __global__ void rmsprop_kernel(float *__restrict__ p, const float *__restrict__ 
 }
 
 // ADAM: m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g^2; p -= m/(1-b1^t) / (sqrt(v/(1-b2^t)) + eps) * eta
-__global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+__global__ void adam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
                             bf16 *__restrict__ shadow, long long n4, float b1, float omb1, float b2, float omb2, float eta, float eps,
                             const OptScalars *__restrict__ sc) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -77,10 +80,31 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
     reinterpret_cast<float4 *>(p)[i] = pv;
     reinterpret_cast<float4 *>(m)[i] = mv;
     reinterpret_cast<float4 *>(v)[i] = vv;
+    reinterpret_cast<float4 *>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (shadow) {
         reinterpret_cast<__nv_bfloat162 *>(shadow)[2 * i] = __floats2bfloat162_rn(pv.x, pv.y);
         reinterpret_cast<__nv_bfloat162 *>(shadow)[2 * i + 1] = __floats2bfloat162_rn(pv.z, pv.w);
     }
+}
+
+// One launch stages a device-resident batch ([state; next_state] contiguous + the small vectors) instead of 5-9 D2D copies.
+struct StageArgs {
+    const uint4 *s, *s2; uint4 *obs; long long obs16;  // 16-byte units per observation block (state / next_state)
+    const int *action; const float *reward; const uint8_t *terminal; const float *priority; const uint8_t *mask;
+    const float *tau, *taup;
+    int *d_action; float *d_reward; uint8_t *d_terminal; float *d_priority; uint8_t *d_mask; float *d_tau, *d_taup;
+    int B, A, N, Np;
+};
+__global__ void stage_batch_kernel(StageArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.obs16) { a.obs[i] = __ldg(a.s + i); a.obs[a.obs16 + i] = __ldg(a.s2 + i); }
+    if (i < a.B) {
+        a.d_action[i] = a.action[i]; a.d_reward[i] = a.reward[i]; a.d_terminal[i] = a.terminal[i];
+        if (a.priority) a.d_priority[i] = a.priority[i];
+    }
+    if (a.mask && i < (long long)a.B * a.A) a.d_mask[i] = a.mask[i];
+    if (a.tau && i < (long long)a.B * a.N) a.d_tau[i] = a.tau[i];
+    if (a.taup && i < (long long)a.B * a.Np) a.d_taup[i] = a.taup[i];
 }
 
 }  // namespace zoo
@@ -122,22 +146,42 @@ struct zoo_learner {
     bool target_forked = false;
 };
 
-static zoo_status opt_step(zoo_opt *o, cudaStream_t st) {
-    zoo_net *net = o->net;
-    const long long n4 = net->n_flat / 4;
+static zoo_status opt_tick(zoo_opt *o, cudaStream_t st) {
     prof_label("opt");
     opt_tick_kernel<<<1, 1, 0, st>>>(o->sc, o->a, o->b);
-    ZOO_LAUNCH_CHECK();
-    if (o->kind == ZOO_OPT_RMSPROP)
-        rmsprop_kernel<<<cdiv(n4, 256), 256, 0, st>>>(net->params, net->grads, o->s0, net->shadow, n4, (float)o->a, (float)(1.0 - o->a),
-                                                      (float)o->eta, (float)o->eps);
-    else
-        adam_kernel<<<cdiv(n4, 256), 256, 0, st>>>(net->params, net->grads, o->s0, o->s1, net->shadow, n4, (float)o->a, (float)(1.0 - o->a),
-                                                   (float)o->b, (float)(1.0 - o->b), (float)o->eta, (float)o->eps, o->sc);
     ZOO_LAUNCH_CHECK();
     o->host_t += 1;
     return ZOO_OK;
 }
+
+// update!(Q, gs) on the flat range [lo, hi) of the parameter / gradient / state buffers (multiples of 64 elements)
+static zoo_status opt_range(zoo_opt *o, long long lo, long long hi, cudaStream_t st) {
+    zoo_net *net = o->net;
+    const long long n4 = (hi - lo) / 4;
+    if (n4 <= 0) return ZOO_OK;
+    prof_label("opt");
+    bf16 *sh = net->shadow ? net->shadow + lo : nullptr;
+    if (o->kind == ZOO_OPT_RMSPROP)
+        rmsprop_kernel<<<cdiv(n4, 256), 256, 0, st>>>(net->params + lo, net->grads + lo, o->s0 + lo, sh, n4, (float)o->a, (float)(1.0 - o->a),
+                                                      (float)o->eta, (float)o->eps);
+    else
+        adam_kernel<<<cdiv(n4, 256), 256, 0, st>>>(net->params + lo, net->grads + lo, o->s0 + lo, o->s1 + lo, sh, n4, (float)o->a,
+                                                   (float)(1.0 - o->a), (float)o->b, (float)(1.0 - o->b), (float)o->eta, (float)o->eps, o->sc);
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+
+static zoo_status opt_step(zoo_opt *o, cudaStream_t st) {
+    ZOO_TRY(opt_tick(o, st));
+    return opt_range(o, 0, o->net->n_flat, st);
+}
+
+// Late bucket: everything from the largest weight tensor to the end of the flat buffers (fc1, fc2, ... and the loss slot)
+// is final as soon as that layer's wgrad has run on the side lane, long before the conv stack's backward ends.  Its
+// all-reduce and optimiser step are issued right there, on the side lane, overlapping the remaining backward; the small
+// early bucket follows after the join.
+struct LateCtx { zoo_learner *L; bool full; };
+static zoo_status late_bucket(void *ctx_, cudaStream_t st);
 
 // The target net's forward depends on nothing the online net produces (PrioritizedDQN / Rainbow / DQN): it runs on the
 // online net's side lane, concurrently with the online forward, and is joined back before the loss head.
@@ -156,7 +200,7 @@ static zoo_status target_join(zoo_learner *L, cudaStream_t st) {
 }
 
 // everything between "batch is on the device" and "results are on the device"
-static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bool has_tau) {
+static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bool has_tau, bool full) {
     const zoo_learner_cfg &c = L->cfg;
     zoo_net *on = L->online, *tg = L->target;
     cudaStream_t st = L->st;
@@ -165,8 +209,16 @@ static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bo
     const void *s_ptr = L->d_obs;
     const void *s2_ptr = (const uint8_t *)L->d_obs + (size_t)B * obs_row;
     const int world = L->dp ? dp_world(L->dp) : 1;
-    ZOO_CUDA(cudaMemsetAsync(on->grads, 0, (on->n_flat + 64) * sizeof(float), st));
-    if (g_prof_on) { prof_label("stage+zero_grads"); prof_mark("memcpy/memset", __LINE__); }
+    if (g_prof_on) { prof_label("stage"); prof_mark("stage_batch", __LINE__); }
+    LateCtx late{L, full};
+    const bool split = on->late_off > 0;
+    on->late_cb = split ? late_bucket : nullptr;
+    on->late_ctx = &late;
+    if (full) {  // this step's bias corrections: off the critical path, first thing on the side lane
+        const bool par = on->side && !g_prof_on;
+        if (par) ZOO_TRY(net_side_fork(on, st));
+        ZOO_TRY(opt_tick(L->opt, par ? on->side : st));
+    }
     prof_label("head");
     HeadArgs h;
     h.B = B; h.A = c.n_actions; h.action = L->d_action; h.reward = L->d_reward; h.terminal = L->d_terminal;
@@ -210,7 +262,19 @@ static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bo
     }
     prof_label("head"); ZOO_TRY(launch_loss_reduce(h, c.beta_priority, L->d_loss, L->d_prio, st));
     ZOO_TRY(net_backward(on, L->obs_dtype, s_ptr, bwd_rows, n_tau, st));
-    if (L->dp) ZOO_TRY(dp_allreduce_sum(L->dp, on->grads, on->n_flat + 64, st));  // gradients + loss in one collective
+    on->late_cb = nullptr;
+    const long long early_end = split ? on->late_off : on->n_flat + 64;  // gradients (+ loss, in the last bucket) per collective
+    if (L->dp) ZOO_TRY(dp_allreduce_sum(L->dp, on->grads, early_end, st));
+    if (full) ZOO_TRY(opt_range(L->opt, 0, split ? on->late_off : on->n_flat, st));
+    return ZOO_OK;
+}
+
+static zoo_status late_bucket(void *ctx_, cudaStream_t st) {
+    LateCtx *c = (LateCtx *)ctx_;
+    zoo_learner *L = c->L;
+    zoo_net *on = L->online;
+    if (L->dp) ZOO_TRY(dp_allreduce_sum(L->dp, on->grads + on->late_off, on->n_flat + 64 - on->late_off, st));
+    if (c->full) ZOO_TRY(opt_range(L->opt, on->late_off, on->n_flat, st));
     return ZOO_OK;
 }
 
@@ -224,6 +288,19 @@ static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b) {
     if (c.kind == ZOO_LEARNER_PRIORITIZED_DQN) ZOO_REQUIRE(b->priority, "update: PrioritizedDQNLearner needs batch.priority");
     L->obs_dtype = b->obs_dtype;
     const size_t obs_bytes = (size_t)B * obs_elems(L->online) * (b->obs_dtype == ZOO_OBS_U8 ? 1 : 4);
+    if (c.kind == ZOO_LEARNER_IQN) ZOO_REQUIRE((b->tau != nullptr) == (b->tau_prime != nullptr), "update: pass both tau and tau_prime or neither");
+    if (b->on_device && obs_bytes % 16 == 0 && ((uintptr_t)b->state & 15) == 0 && ((uintptr_t)b->next_state & 15) == 0) {
+        StageArgs a{};
+        a.s = (const uint4 *)b->state; a.s2 = (const uint4 *)b->next_state; a.obs = (uint4 *)L->d_obs; a.obs16 = (long long)(obs_bytes / 16);
+        a.action = b->action; a.reward = b->reward; a.terminal = b->terminal; a.priority = b->priority; a.mask = b->next_mask;
+        a.tau = c.kind == ZOO_LEARNER_IQN ? b->tau : nullptr; a.taup = c.kind == ZOO_LEARNER_IQN ? b->tau_prime : nullptr;
+        a.d_action = L->d_action; a.d_reward = L->d_reward; a.d_terminal = L->d_terminal; a.d_priority = L->d_priority; a.d_mask = L->d_mask;
+        a.d_tau = L->d_tau; a.d_taup = L->d_taup; a.B = B; a.A = c.n_actions; a.N = c.N; a.Np = c.N_prime;
+        long long n = std::max<long long>(a.obs16, (long long)B * std::max(std::max(c.n_actions, c.N), std::max(c.N_prime, 1)));
+        stage_batch_kernel<<<cdiv(n, 256), 256, 0, st>>>(a);
+        ZOO_LAUNCH_CHECK();
+        return ZOO_OK;
+    }
     const cudaMemcpyKind k = b->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     ZOO_CUDA(cudaMemcpyAsync(L->d_obs, b->state, obs_bytes, k, st));
     ZOO_CUDA(cudaMemcpyAsync((uint8_t *)L->d_obs + obs_bytes, b->next_state, obs_bytes, k, st));
@@ -245,6 +322,13 @@ static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b) {
 static zoo_status run_update(zoo_learner *L, const zoo_batch *b, float *loss_out, float *prio_out, bool full) {
     ZOO_REQUIRE(L, "update: null learner");
     ZOO_TRY(stage_batch(L, b));
+    // the gradient buffer must be zero on entry; the optimiser kernels leave it so, anything else (creation, a
+    // compute_grads without apply, a set of optimiser state) marks it dirty and costs one memset here, outside the graph
+    if (L->online->grads_dirty) {
+        ZOO_CUDA(cudaMemsetAsync(L->online->grads, 0, (L->online->n_flat + 64) * sizeof(float), L->st));
+        L->online->grads_dirty = false;
+    }
+    if (!full) L->online->grads_dirty = true;
     const bool has_prio = b->priority != nullptr, has_mask = b->next_mask != nullptr, has_tau = b->tau != nullptr;
     const int key = (has_prio ? 1 : 0) | (has_mask ? 2 : 0) | (has_tau ? 4 : 0) | (L->obs_dtype << 3) | (full ? 16 : 0);
     g_launches = 0;
@@ -253,8 +337,7 @@ static zoo_status run_update(zoo_learner *L, const zoo_batch *b, float *loss_out
             if (L->gexec) { cudaGraphExecDestroy(L->gexec); L->gexec = nullptr; }
             cudaGraph_t graph;
             ZOO_CUDA(cudaStreamBeginCapture(L->st, cudaStreamCaptureModeThreadLocal));
-            zoo_status s = enqueue_grads(L, has_prio, has_mask, has_tau);
-            if (s == ZOO_OK && full) s = opt_step(L->opt, L->st);
+            zoo_status s = enqueue_grads(L, has_prio, has_mask, has_tau, full);
             cudaError_t ce = cudaStreamEndCapture(L->st, &graph);
             if (s != ZOO_OK) { if (ce == cudaSuccess) cudaGraphDestroy(graph); return s; }
             ZOO_CUDA(ce);
@@ -268,8 +351,7 @@ static zoo_status run_update(zoo_learner *L, const zoo_batch *b, float *loss_out
         if (full) L->opt->host_t += 1;
         L->last_launches = L->graph_launches;
     } else {
-        ZOO_TRY(enqueue_grads(L, has_prio, has_mask, has_tau));
-        if (full) ZOO_TRY(opt_step(L->opt, L->st));
+        ZOO_TRY(enqueue_grads(L, has_prio, has_mask, has_tau, full));
         L->last_launches = g_launches;
         L->warm = 1;
     }
@@ -361,6 +443,16 @@ zoo_status zoo_learner_create(const zoo_learner_cfg *cfg, zoo_net *online, zoo_n
     ZOO_CUDA(cudaStreamCreateWithFlags(&L->st, cudaStreamNonBlocking));
     const int B = L->B, A = cfg->n_actions;
     L->d_loss = online->grads + online->n_flat;  // tail of the gradient buffer (see net_alloc_backward)
+    // late bucket = [offset of the largest weight tensor, end): valid when backward visits tensors in descending offset
+    // order (Chain, ImplicitQuantileNet); a DuelingNetwork's val / adv heads break that order, so it keeps one bucket
+    online->late_off = -1;
+    const char *lb = getenv("ZOO_LATE_BUCKET");
+    if (online->desc.kind != ZOO_NET_DUELING && !(lb && lb[0] == '0')) {
+        long long best = 0;
+        for (auto &t : online->tensors)
+            if (t.kind == 0 && t.count > best) { best = t.count; online->late_off = t.offset; }
+        if (online->late_off <= 0 || best * 2 < online->n_params) online->late_off = -1;  // not worth a second bucket
+    }
     ZOO_CUDA(cudaMalloc(&L->d_obs, (size_t)2 * B * obs_elems(online) * sizeof(float)));
     ZOO_CUDA(cudaMalloc(&L->d_action, B * sizeof(int)));
     ZOO_CUDA(cudaMalloc(&L->d_reward, B * sizeof(float)));
@@ -405,6 +497,7 @@ zoo_status zoo_learner_apply(zoo_learner *L) {
     g_launches = 0;
     ZOO_TRY(opt_step(L->opt, L->st));
     ZOO_CUDA(cudaStreamSynchronize(L->st));
+    L->online->grads_dirty = false;  // the optimiser kernels re-zero the gradients
     return ZOO_OK;
 }
 

@@ -323,6 +323,18 @@ static Operand weight_operand(const zoo_net *net, const TensorInfo &W, const Ope
     return B;
 }
 
+// Every tensor at offset >= late_off now has its gradient enqueued on the side lane, and this layer's dgrad -- the last
+// reader of those parameters -- is enqueued on `st`: once both are done the late bucket (all-reduce + optimiser) may run.
+static zoo_status net_late_bucket(zoo_net *net, cudaStream_t st, cudaStream_t sw, bool par) {
+    if (par) {
+        ZOO_CUDA(cudaEventRecord(net->ev_late, st));
+        ZOO_CUDA(cudaStreamWaitEvent(sw, net->ev_late, 0));
+    }
+    zoo_status s = net->late_cb(net->late_ctx, sw);
+    net->late_cb = nullptr;
+    return s;
+}
+
 // in_kind: 0 raw u8, 1 raw f32, 2 internal T
 // cols_rows: leading sample rows whose im2col matrices the later wgrad needs (0 = forward only, e.g. the target net)
 static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_kind, long long rows, cudaStream_t st, long long cols_rows = 0) {
@@ -435,8 +447,9 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
         ew.out = net->grads + W.offset; ew.sm = L.K; ew.sn = 1; ew.tf32_passes = net->tf32_passes;
         ew.accumulate = 2;  // grads are zeroed per update: plain store, or atomic add when the GEMM is K-split
         ZOO_TRY(gemm(dYt, X, L.cout, (int)L.K, (int)M, ew, 0, wsw, wsw_elems, sw));
+        const bool late_here = net->late_cb && W.offset == net->late_off;
         // dgrad
-        if (li == 0 && !dx) continue;
+        if (li == 0 && !dx) { if (late_here) ZOO_TRY(net_late_bucket(net, st, sw, par)); continue; }
         Operand dY{L.dout, dy_bf, L.cout, 1};
         prof_label("dgrad:t%d[%lldx%lldx%d]", L.wt, M, L.K, L.cout);
         Operand Wn = weight_operand(net, W, dY, (int)M, (int)L.K, L.cout, L.K, 0);
@@ -474,6 +487,7 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
             }
             ZOO_TRY(gemm(dY, Wn, (int)M, (int)L.K, L.cout, ed, 0, net->ws, net->ws_elems, st));
         }
+        if (late_here) ZOO_TRY(net_late_bucket(net, st, sw, par));
     }
     return ZOO_OK;
 }
@@ -686,6 +700,7 @@ zoo_status net_alloc_backward(zoo_net *net) {
     ZOO_CUDA(cudaStreamCreateWithFlags(&net->side, cudaStreamNonBlocking));
     ZOO_CUDA(cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming));
     ZOO_CUDA(cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming));
+    ZOO_CUDA(cudaEventCreateWithFlags(&net->ev_late, cudaEventDisableTiming));
     net->ws_side_elems = ((size_t)2 << 20) + 4096;
     ZOO_CUDA(cudaMalloc(&net->ws_side, net->ws_side_elems * sizeof(float)));
     ZOO_CUDA(cudaMemset(net->ws_side, 0, net->ws_side_elems * sizeof(float)));
@@ -830,6 +845,7 @@ zoo_status zoo_net_destroy(zoo_net *net) {
     if (net->side) { cudaStreamSynchronize(net->side); cudaStreamDestroy(net->side); }
     if (net->ev_fork) cudaEventDestroy(net->ev_fork);
     if (net->ev_join) cudaEventDestroy(net->ev_join);
+    if (net->ev_late) cudaEventDestroy(net->ev_late);
     cudaStreamDestroy(net->st);
     delete net;
     return ZOO_OK;

@@ -54,6 +54,7 @@ struct zoo_net {
     float *params = nullptr;   // fp32 master, internal layout
     zoo::bf16 *shadow = nullptr;  // bf16 copy (BF16 precision only), same layout
     float *grads = nullptr;    // allocated when a learner/optimiser attaches
+    bool grads_dirty = true;   // grads may be non-zero (the optimiser kernels re-zero them; see learner.cu run_update)
     zoo::Chain a, b, c;
     int fc = 0, fh = 0, fw = 0;  // flatten space
     int n_out = 0;
@@ -78,6 +79,11 @@ struct zoo_net {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     float *ws_side = nullptr;  // split-K workspace of the side lane
+    // late-bucket hook (see learner.cu): called on the side lane once every tensor at offset >= late_off has its gradient
+    long long late_off = -1;
+    zoo_status (*late_cb)(void *ctx, cudaStream_t st) = nullptr;
+    void *late_ctx = nullptr;
+    cudaEvent_t ev_late = nullptr;
     size_t ws_side_elems = 0;
 };
 
