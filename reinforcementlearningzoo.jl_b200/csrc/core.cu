@@ -15,6 +15,12 @@ void set_err(const char *fmt, ...) {
     g_err = buf;
 }
 
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("ZOO_PDL"); on = (e && e[0] == '1') ? 1 : 0; }
+    return on == 1;
+}
+
 thread_local bool g_prof_on = false;
 static thread_local cudaStream_t g_prof_stream = nullptr;
 static thread_local std::vector<cudaEvent_t> g_prof_events;

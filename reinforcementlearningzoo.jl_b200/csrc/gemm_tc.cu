@@ -342,6 +342,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) dbg_stamp(P, 1);
+    pdl_trigger();  // the next kernel in the stream may start its own prologue
+    pdl_wait();     // everything above ran under the predecessor's tail; from here on global memory is touched
 
     if (warp == 0) {
         if (lane == 0) {
@@ -753,7 +755,7 @@ static zoo_status launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, A_K, B_K, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    tc_gemm_kernel<EB, BN, A_K, B_K, X3><<<grid, TC_THREADS, C::SMEM, st>>>(tmA, tmB, P);
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, false>, grid, dim3(TC_THREADS), (size_t)C::SMEM, st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -839,7 +841,7 @@ static zoo_status launch_conv(const CUtensorMap &tmB, const TcParams &P, dim3 gr
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    tc_gemm_kernel<EB, BN, true, B_K, X3, true><<<grid, TC_THREADS, C::SMEM, st>>>(tmB, tmB, P);
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, true>, grid, dim3(TC_THREADS), (size_t)C::SMEM, st, tmB, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }

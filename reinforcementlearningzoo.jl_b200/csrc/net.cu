@@ -56,6 +56,8 @@ __global__ void im2col_first_kernel(const Tin *__restrict__ x, T *__restrict__ c
 // conv runs through the same implicit-GEMM gather as the inner convs.  One thread per pixel, C = 4 channels (16 bytes).
 template <typename Tin>
 __global__ void obs_to_nhwc4_kernel(const Tin *__restrict__ x, float4 *__restrict__ out, long long pixels, int HW, int scale255) {
+    pdl_trigger();
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pixels) return;
     const long long b = i / HW, p = i - b * HW;
@@ -75,6 +77,8 @@ template <typename T, int VEC> struct alignas(sizeof(T) * VEC) VecT { T v[VEC]; 
 template <typename T, int VEC>
 __global__ void im2col_nhwc_kernel(const T *__restrict__ x, T *__restrict__ cols, long long total, int C, int H, int W, int k,
                                    int s, int p, int OH, int OW) {
+    pdl_trigger();
+    pdl_wait();
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int cv = C / VEC;
@@ -102,6 +106,8 @@ __global__ void im2col_nhwc_kernel(const T *__restrict__ x, T *__restrict__ cols
 template <typename T, int VEC>
 __global__ void col2im_nhwc_kernel(const T *__restrict__ dcols, T *__restrict__ dx, const T *__restrict__ act, long long total,
                                    int C, int H, int W, int k, int s, int p, int OH, int OW) {
+    pdl_trigger();
+    pdl_wait();
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int cv = C / VEC;
@@ -277,12 +283,12 @@ static zoo_status launch_im2col_nhwc(const void *x, void *cols, long long M, con
     constexpr int V = 16 / sizeof(T);
     if (L.cin % V == 0) {
         long long total = M * L.ksize * L.ksize * (L.cin / V);
-        im2col_nhwc_kernel<T, V><<<cdiv(total, 256), 256, 0, st>>>((const T *)x, (T *)cols, total, L.cin, L.ih, L.iw, L.ksize,
-                                                                   L.stride, L.pad, L.oh, L.ow);
+        ZOO_CUDA(launch_pdl(im2col_nhwc_kernel<T, V>, dim3(cdiv(total, 256)), dim3(256), (size_t)0, st, (const T *)x, (T *)cols, total, L.cin, L.ih, L.iw,
+                            L.ksize, L.stride, L.pad, L.oh, L.ow));
     } else {
         long long total = M * L.ksize * L.ksize * L.cin;
-        im2col_nhwc_kernel<T, 1><<<cdiv(total, 256), 256, 0, st>>>((const T *)x, (T *)cols, total, L.cin, L.ih, L.iw, L.ksize,
-                                                                   L.stride, L.pad, L.oh, L.ow);
+        ZOO_CUDA(launch_pdl(im2col_nhwc_kernel<T, 1>, dim3(cdiv(total, 256)), dim3(256), (size_t)0, st, (const T *)x, (T *)cols, total, L.cin, L.ih, L.iw,
+                            L.ksize, L.stride, L.pad, L.oh, L.ow));
     }
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
@@ -293,12 +299,12 @@ static zoo_status launch_col2im_nhwc(const void *dcols, void *dx, const void *ac
     constexpr int V = 16 / sizeof(T);
     if (L.cin % V == 0) {
         long long total = rows * L.ih * L.iw * (L.cin / V);
-        col2im_nhwc_kernel<T, V><<<cdiv(total, 256), 256, 0, st>>>((const T *)dcols, (T *)dx, (const T *)act, total, L.cin, L.ih,
-                                                                   L.iw, L.ksize, L.stride, L.pad, L.oh, L.ow);
+        ZOO_CUDA(launch_pdl(col2im_nhwc_kernel<T, V>, dim3(cdiv(total, 256)), dim3(256), (size_t)0, st, (const T *)dcols, (T *)dx, (const T *)act, total,
+                            L.cin, L.ih, L.iw, L.ksize, L.stride, L.pad, L.oh, L.ow));
     } else {
         long long total = rows * L.ih * L.iw * L.cin;
-        col2im_nhwc_kernel<T, 1><<<cdiv(total, 256), 256, 0, st>>>((const T *)dcols, (T *)dx, (const T *)act, total, L.cin, L.ih,
-                                                                   L.iw, L.ksize, L.stride, L.pad, L.oh, L.ow);
+        ZOO_CUDA(launch_pdl(col2im_nhwc_kernel<T, 1>, dim3(cdiv(total, 256)), dim3(256), (size_t)0, st, (const T *)dcols, (T *)dx, (const T *)act, total,
+                            L.cin, L.ih, L.iw, L.ksize, L.stride, L.pad, L.oh, L.ow));
     }
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
@@ -326,11 +332,16 @@ static Operand weight_operand(const zoo_net *net, const TensorInfo &W, const Ope
 // Every tensor at offset >= late_off now has its gradient enqueued on the side lane, and this layer's dgrad -- the last
 // reader of those parameters -- is enqueued on `st`: once both are done the late bucket (all-reduce + optimiser) may run.
 static zoo_status net_late_bucket(zoo_net *net, cudaStream_t st, cudaStream_t sw, bool par) {
-    if (par) {
+    cudaStream_t sc = sw;
+    if (par) {  // third lane, so the side lane carries on with the remaining bias / weight gradients meanwhile
+        sc = net->comm;
         ZOO_CUDA(cudaEventRecord(net->ev_late, st));
-        ZOO_CUDA(cudaStreamWaitEvent(sw, net->ev_late, 0));
+        ZOO_CUDA(cudaStreamWaitEvent(sc, net->ev_late, 0));
+        ZOO_CUDA(cudaEventRecord(net->ev_late2, sw));
+        ZOO_CUDA(cudaStreamWaitEvent(sc, net->ev_late2, 0));
+        net->comm_used = true;
     }
-    zoo_status s = net->late_cb(net->late_ctx, sw);
+    zoo_status s = net->late_cb(net->late_ctx, sc);
     net->late_cb = nullptr;
     return s;
 }
@@ -547,6 +558,13 @@ zoo_status net_backward(zoo_net *net, int obs_dtype, const void *obs, int rows, 
     if (net->side && !g_prof_on) {  // the side lane always rejoins, also on error (an open fork would poison a stream capture)
         zoo_status j = net_side_join(net, st);
         if (s == ZOO_OK) s = j;
+        if (net->comm_used) {
+            net->comm_used = false;
+            if (cudaEventRecord(net->ev_comm, net->comm) != cudaSuccess || cudaStreamWaitEvent(st, net->ev_comm, 0) != cudaSuccess) {
+                set_err("backward: cannot rejoin the communication lane");
+                if (s == ZOO_OK) s = ZOO_CUDA_ERROR;
+            }
+        }
     }
     return s;
 }
@@ -701,6 +719,9 @@ zoo_status net_alloc_backward(zoo_net *net) {
     ZOO_CUDA(cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming));
     ZOO_CUDA(cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming));
     ZOO_CUDA(cudaEventCreateWithFlags(&net->ev_late, cudaEventDisableTiming));
+    ZOO_CUDA(cudaEventCreateWithFlags(&net->ev_late2, cudaEventDisableTiming));
+    ZOO_CUDA(cudaEventCreateWithFlags(&net->ev_comm, cudaEventDisableTiming));
+    ZOO_CUDA(cudaStreamCreateWithFlags(&net->comm, cudaStreamNonBlocking));
     net->ws_side_elems = ((size_t)2 << 20) + 4096;
     ZOO_CUDA(cudaMalloc(&net->ws_side, net->ws_side_elems * sizeof(float)));
     ZOO_CUDA(cudaMemset(net->ws_side, 0, net->ws_side_elems * sizeof(float)));
@@ -846,6 +867,9 @@ zoo_status zoo_net_destroy(zoo_net *net) {
     if (net->ev_fork) cudaEventDestroy(net->ev_fork);
     if (net->ev_join) cudaEventDestroy(net->ev_join);
     if (net->ev_late) cudaEventDestroy(net->ev_late);
+    if (net->ev_late2) cudaEventDestroy(net->ev_late2);
+    if (net->ev_comm) cudaEventDestroy(net->ev_comm);
+    if (net->comm) { cudaStreamSynchronize(net->comm); cudaStreamDestroy(net->comm); }
     cudaStreamDestroy(net->st);
     delete net;
     return ZOO_OK;

@@ -83,7 +83,9 @@ struct zoo_net {
     long long late_off = -1;
     zoo_status (*late_cb)(void *ctx, cudaStream_t st) = nullptr;
     void *late_ctx = nullptr;
-    cudaEvent_t ev_late = nullptr;
+    cudaEvent_t ev_late = nullptr, ev_late2 = nullptr, ev_comm = nullptr;
+    cudaStream_t comm = nullptr;  // third lane: the late bucket's all-reduce + optimiser
+    bool comm_used = false;
     size_t ws_side_elems = 0;
 };
 
