@@ -75,6 +75,32 @@ simt_gemm_kernel(Operand A, Operand B, int M, int N, int K, Epilogue epi, int k_
     }
 }
 
+// Narrow output layers (fc2: N = n_actions): one CTA per row, every thread strides over K with N accumulators, warp-shuffle +
+// shared-memory reduction, bias / relu in place.  One launch, no split-K workspace.
+template <int NMAX>
+__global__ void __launch_bounds__(128) dense_narrow_kernel(Operand A, Operand B, int N, int K, Epilogue epi) {
+    const int m = blockIdx.x;
+    float acc[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+    for (int k = threadIdx.x; k < K; k += 128) {
+        const float a = ld_elem(A.p, A.is_bf16, (long long)m * A.ld + k);
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n)
+            if (n < N) acc[n] = fmaf(a, ld_elem(B.p, B.is_bf16, (long long)n * B.ld + k), acc[n]);
+    }
+    __shared__ float red[4][NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) {
+        float v = acc[n];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][n] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < N) epi_store(epi, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x], m, threadIdx.x);
+}
+
 // finishes a split-K GEMM whose partial sums were atomically accumulated in ws[M][N]
 // (and re-zeroes ws: the split-K workspace is all-zero between launches, shared with the tcgen05 engine)
 __global__ void splitk_finish_kernel(float *ws, int M, int N, Epilogue epi) {
@@ -96,6 +122,12 @@ zoo_status splitk_finish(float *ws, int M, int N, const Epilogue &epi, cudaStrea
 zoo_status simt_gemm(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, int split_k,
                      float *ws, size_t ws_elems, cudaStream_t st) {
     if (M <= 0 || N <= 0) return ZOO_OK;
+    if (N <= 16 && A.kmajor && B.kmajor && !epi.accumulate && split_k <= 0 && M <= 65535) {
+        if (N <= 8) dense_narrow_kernel<8><<<M, 128, 0, st>>>(A, B, N, K, epi);
+        else dense_narrow_kernel<16><<<M, 128, 0, st>>>(A, B, N, K, epi);
+        ZOO_LAUNCH_CHECK();
+        return ZOO_OK;
+    }
     dim3 grid(cdiv(M, SBM), cdiv(N, SBN), 1);
     int kblocks = cdiv(K, SBK);
     if (split_k <= 0) {  // auto: fill ~2 waves of 148 SMs when the output grid alone cannot
