@@ -65,8 +65,8 @@ zoo_status require_sm100();
 
 // Programmatic dependent launch: a kernel launched through launch_pdl may become resident while its stream predecessor is
 // still draining, and runs its prologue (barrier init, TMEM allocation, index setup) there; it must call pdl_wait() before it
-// touches global memory.  Measured slightly slower on the B=32 update (341 vs 326 us: early-resident CTAs compete with the
-// predecessor's tail), so it is opt-in: ZOO_PDL=1.
+// touches global memory, and calls pdl_trigger() once its main loop is done (triggering at kernel entry was measured slower:
+// early-resident dependents take SMs from the predecessor's second wave).  +4 % on the B=32 update; ZOO_PDL=0 disables it.
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {

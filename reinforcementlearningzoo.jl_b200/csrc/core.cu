@@ -17,7 +17,7 @@ void set_err(const char *fmt, ...) {
 
 bool pdl_enabled() {
     static int on = -1;
-    if (on < 0) { const char *e = getenv("ZOO_PDL"); on = (e && e[0] == '1') ? 1 : 0; }
+    if (on < 0) { const char *e = getenv("ZOO_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
     return on == 1;
 }
 

@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(256)
 simt_gemm_kernel(Operand A, Operand B, int M, int N, int K, Epilogue epi, int k_per_split, float *ws) {
     __shared__ __align__(16) float As[SBK][SBM + 4];
     __shared__ __align__(16) float Bs[SBK][SBN + 4];
+    pdl_wait();
+    pdl_trigger();
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.x * SBM, n0 = blockIdx.y * SBN;
@@ -79,6 +81,8 @@ simt_gemm_kernel(Operand A, Operand B, int M, int N, int K, Epilogue epi, int k_
 // shared-memory reduction, bias / relu in place.  One launch, no split-K workspace.
 template <int NMAX>
 __global__ void __launch_bounds__(128) dense_narrow_kernel(Operand A, Operand B, int N, int K, Epilogue epi) {
+    pdl_wait();
+    pdl_trigger();
     const int m = blockIdx.x;
     float acc[NMAX];
 #pragma unroll
@@ -123,8 +127,8 @@ zoo_status simt_gemm(const Operand &A, const Operand &B, int M, int N, int K, co
                      float *ws, size_t ws_elems, cudaStream_t st) {
     if (M <= 0 || N <= 0) return ZOO_OK;
     if (N <= 16 && A.kmajor && B.kmajor && !epi.accumulate && split_k <= 0 && M <= 65535) {
-        if (N <= 8) dense_narrow_kernel<8><<<M, 128, 0, st>>>(A, B, N, K, epi);
-        else dense_narrow_kernel<16><<<M, 128, 0, st>>>(A, B, N, K, epi);
+        if (N <= 8) ZOO_CUDA(launch_pdl(dense_narrow_kernel<8>, dim3(M), dim3(128), (size_t)0, st, A, B, N, K, epi));
+        else ZOO_CUDA(launch_pdl(dense_narrow_kernel<16>, dim3(M), dim3(128), (size_t)0, st, A, B, N, K, epi));
         ZOO_LAUNCH_CHECK();
         return ZOO_OK;
     }
@@ -154,7 +158,7 @@ zoo_status simt_gemm(const Operand &A, const Operand &B, int M, int N, int K, co
             wsp = ws;  // all-zero on entry (invariant), re-zeroed by splitk_finish
         }
     }
-#define LAUNCH(AKv, BKv) simt_gemm_kernel<AKv, BKv><<<grid, 256, 0, st>>>(A, B, M, N, K, e, kps, wsp)
+#define LAUNCH(AKv, BKv) ZOO_CUDA(launch_pdl(simt_gemm_kernel<AKv, BKv>, grid, dim3(256), (size_t)0, st, A, B, M, N, K, e, kps, wsp))
     if (A.kmajor && B.kmajor) LAUNCH(true, true);
     else if (A.kmajor && !B.kmajor) LAUNCH(true, false);
     else if (!A.kmajor && B.kmajor) LAUNCH(false, true);

@@ -342,8 +342,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) dbg_stamp(P, 1);
-    pdl_trigger();  // the next kernel in the stream may start its own prologue
-    pdl_wait();     // everything above ran under the predecessor's tail; from here on global memory is touched
+    pdl_wait();  // everything above ran under the predecessor's tail; from here on global memory is touched
 
     if (warp == 0) {
         if (lane == 0) {
@@ -557,6 +556,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int lastc = nchains - 1, lb = lastc & 1;
         mbar_wait(&acc_full[lb], (lastc >> 1) & 1);
         tc_fence_after();
+        pdl_trigger();  // main loop done: the next kernel may become resident and run its prologue under this epilogue
         if (threadIdx.x == 64) dbg_stamp(P, 5);
         float(*stg)[33] = reinterpret_cast<float(*)[33]>(smem) + q * 32;  // 32 x 33 floats per warp, in pipeline stage 0
         const int row0 = m0 + q * 32;

@@ -62,6 +62,8 @@ __global__ void __launch_bounds__(1024) per_weights_kernel(const float *__restri
 // dqn.jl:115-142, prioritized_dqn.jl:129-146, basic_dqn.jl:78-87
 __global__ void dqn_head_kernel(int kind, int double_dqn, HeadArgs h, const float *__restrict__ q_on, const float *__restrict__ q_t,
                                 float gamma_n, float *__restrict__ dout) {
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= h.B) return;
     const int A = h.A;
@@ -217,6 +219,8 @@ __global__ void iqn_loss_kernel(HeadArgs h, int N, int Np, const float *__restri
 }
 
 __global__ void __launch_bounds__(1024) loss_reduce_kernel(HeadArgs h, float beta, float *__restrict__ loss, float *__restrict__ prio_out) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float red[32];
     float acc = 0.f;
     for (int b = threadIdx.x; b < h.B; b += blockDim.x) {
@@ -249,7 +253,7 @@ zoo_status launch_per_weights(const float *priority, float beta, int B, float *w
 }
 zoo_status launch_dqn_head(int kind, int double_dqn, const HeadArgs &h, const float *q_on, const float *q_t, float gamma_n,
                            float *dout, cudaStream_t st) {
-    dqn_head_kernel<<<cdiv(h.B, 128), 128, 0, st>>>(kind, double_dqn, h, q_on, q_t, gamma_n, dout);
+    ZOO_CUDA(launch_pdl(dqn_head_kernel, dim3(cdiv(h.B, 128)), dim3(128), (size_t)0, st, kind, double_dqn, h, q_on, q_t, gamma_n, dout));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -279,7 +283,7 @@ zoo_status launch_iqn_loss(const HeadArgs &h, int N, int Np, const float *z, con
     return ZOO_OK;
 }
 zoo_status launch_loss_reduce(const HeadArgs &h, float beta, float *loss, float *prio_out, cudaStream_t st) {
-    loss_reduce_kernel<<<1, 1024, 0, st>>>(h, beta, loss, prio_out);
+    ZOO_CUDA(launch_pdl(loss_reduce_kernel, dim3(1), dim3(1024), (size_t)0, st, h, beta, loss, prio_out));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }

@@ -35,6 +35,7 @@ __global__ void rng_tick_kernel(OptScalars *s) { s->rng += 1; }
 // which replaces a separate 16 MB memset per update.
 __global__ void rmsprop_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ acc, bf16 *__restrict__ shadow,
                                long long n4, float rho, float omr, float eta, float eps) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float4 pv = reinterpret_cast<float4 *>(p)[i];
@@ -61,6 +62,7 @@ __global__ void rmsprop_kernel(float *__restrict__ p, float *__restrict__ g, flo
 __global__ void adam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
                             bf16 *__restrict__ shadow, long long n4, float b1, float omb1, float b2, float omb2, float eta, float eps,
                             const OptScalars *__restrict__ sc) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     const float c1 = sc->c1, c2 = sc->c2;
@@ -162,11 +164,12 @@ static zoo_status opt_range(zoo_opt *o, long long lo, long long hi, cudaStream_t
     prof_label("opt");
     bf16 *sh = net->shadow ? net->shadow + lo : nullptr;
     if (o->kind == ZOO_OPT_RMSPROP)
-        rmsprop_kernel<<<cdiv(n4, 256), 256, 0, st>>>(net->params + lo, net->grads + lo, o->s0 + lo, sh, n4, (float)o->a, (float)(1.0 - o->a),
-                                                      (float)o->eta, (float)o->eps);
+        ZOO_CUDA(launch_pdl(rmsprop_kernel, dim3(cdiv(n4, 256)), dim3(256), (size_t)0, st, net->params + lo, net->grads + lo, o->s0 + lo, sh, n4,
+                            (float)o->a, (float)(1.0 - o->a), (float)o->eta, (float)o->eps));
     else
-        adam_kernel<<<cdiv(n4, 256), 256, 0, st>>>(net->params + lo, net->grads + lo, o->s0 + lo, o->s1 + lo, sh, n4, (float)o->a,
-                                                   (float)(1.0 - o->a), (float)o->b, (float)(1.0 - o->b), (float)o->eta, (float)o->eps, o->sc);
+        ZOO_CUDA(launch_pdl(adam_kernel, dim3(cdiv(n4, 256)), dim3(256), (size_t)0, st, net->params + lo, net->grads + lo, o->s0 + lo, o->s1 + lo, sh,
+                            n4, (float)o->a, (float)(1.0 - o->a), (float)o->b, (float)(1.0 - o->b), (float)o->eta, (float)o->eps,
+                            (const OptScalars *)o->sc));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }

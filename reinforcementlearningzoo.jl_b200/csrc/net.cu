@@ -52,11 +52,12 @@ __global__ void im2col_first_kernel(const Tin *__restrict__ x, T *__restrict__ c
     }
 }
 
-// raw observation [B][C][H][W] (u8 | f32) -> fp32 NHWC [B][H][W][C] with `x ./ 255` (IEEE divide) folded in, so the first
+template <typename T, int VEC> struct alignas(sizeof(T) * VEC) VecT { T v[VEC]; };
+
+// raw observation [B][C][H][W] (u8 | f32) -> NHWC in the net's activation type [B][H][W][C] with `x ./ 255` (IEEE divide) folded in, so the first
 // conv runs through the same implicit-GEMM gather as the inner convs.  One thread per pixel, C = 4 channels (16 bytes).
-template <typename Tin>
-__global__ void obs_to_nhwc4_kernel(const Tin *__restrict__ x, float4 *__restrict__ out, long long pixels, int HW, int scale255) {
-    pdl_trigger();
+template <typename Tin, typename Tout>
+__global__ void obs_to_nhwc4_kernel(const Tin *__restrict__ x, Tout *__restrict__ out, long long pixels, int HW, int scale255) {
     pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pixels) return;
@@ -68,16 +69,17 @@ __global__ void obs_to_nhwc4_kernel(const Tin *__restrict__ x, float4 *__restric
         v[c] = to_f(src[(long long)c * HW]);
         if (scale255) v[c] = __fdiv_rn(v[c], 255.f);
     }
-    out[i] = make_float4(v[0], v[1], v[2], v[3]);
+    VecT<Tout, 4> o;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o.v[c] = from_f<Tout>(v[c]);
+    pdl_trigger();
+    *reinterpret_cast<VecT<Tout, 4> *>(out + i * 4) = o;
 }
-
-template <typename T, int VEC> struct alignas(sizeof(T) * VEC) VecT { T v[VEC]; };
 
 // conv reading internal NHWC activations: cols[M][k*k*C] with k index (ky,kx,c); VEC channels per thread
 template <typename T, int VEC>
 __global__ void im2col_nhwc_kernel(const T *__restrict__ x, T *__restrict__ cols, long long total, int C, int H, int W, int k,
                                    int s, int p, int OH, int OW) {
-    pdl_trigger();
     pdl_wait();
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -99,6 +101,7 @@ __global__ void im2col_nhwc_kernel(const T *__restrict__ x, T *__restrict__ cols
 #pragma unroll
         for (int i = 0; i < VEC; ++i) v.v[i] = from_f<T>(0.f);
     }
+    pdl_trigger();
     *reinterpret_cast<VecT<T, VEC> *>(cols + idx * VEC) = v;
 }
 
@@ -106,7 +109,6 @@ __global__ void im2col_nhwc_kernel(const T *__restrict__ x, T *__restrict__ cols
 template <typename T, int VEC>
 __global__ void col2im_nhwc_kernel(const T *__restrict__ dcols, T *__restrict__ dx, const T *__restrict__ act, long long total,
                                    int C, int H, int W, int k, int s, int p, int OH, int OW) {
-    pdl_trigger();
     pdl_wait();
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -145,12 +147,15 @@ __global__ void col2im_nhwc_kernel(const T *__restrict__ dcols, T *__restrict__ 
 #pragma unroll
         for (int i = 0; i < VEC; ++i) o.v[i] = from_f<T>(acc[i]);
     }
+    pdl_trigger();
     *reinterpret_cast<VecT<T, VEC> *>(dx + idx * VEC) = o;
 }
 
 // bias gradient: db[n] += sum_m dy[m][n]
 template <typename T>
 __global__ void colsum_kernel(const T *__restrict__ dy, long long M, int N, float *__restrict__ db) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float red[8][33];
     int n = blockIdx.x * 32 + threadIdx.x;
     float acc = 0.f;
@@ -186,6 +191,52 @@ __global__ void iqn_merge_kernel(const T *__restrict__ feat, const T *__restrict
     int f = (int)(idx % F);
     long long r = idx / F;
     merged[idx] = from_f<T>(to_f(feat[(r / N) * F + f]) * to_f(ea[idx]));
+}
+
+template <typename T, int VEC>
+__global__ void iqn_merge_vec_kernel(const T *__restrict__ feat, const T *__restrict__ ea, T *__restrict__ merged, long long rows, int F, int N) {
+    const int fv = F / VEC;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * fv) return;
+    const int f = (int)(idx % fv);
+    const long long r = idx / fv;
+    const VecT<T, VEC> a = *reinterpret_cast<const VecT<T, VEC> *>(feat + (r / N) * F + (long long)f * VEC);
+    const VecT<T, VEC> e = *reinterpret_cast<const VecT<T, VEC> *>(ea + idx * VEC);
+    VecT<T, VEC> o;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o.v[i] = from_f<T>(to_f(a.v[i]) * to_f(e.v[i]));
+    *reinterpret_cast<VecT<T, VEC> *>(merged + idx * VEC) = o;
+}
+
+template <typename T, int VEC>
+__global__ void iqn_merge_bwd_vec_kernel(const T *__restrict__ dm, const T *__restrict__ feat, const T *__restrict__ ea, T *__restrict__ dea,
+                                         T *__restrict__ dfeat, int B, int F, int N, int phi_relu, int psi_relu) {
+    const int fv = F / VEC;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * fv) return;
+    const int f = (int)(idx % fv);
+    const long long b = idx / fv;
+    const VecT<T, VEC> ftv = *reinterpret_cast<const VecT<T, VEC> *>(feat + b * F + (long long)f * VEC);
+    float ft[VEC], acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { ft[i] = to_f(ftv.v[i]); acc[i] = 0.f; }
+    for (int n = 0; n < N; ++n) {
+        const long long o = (b * N + n) * F + (long long)f * VEC;
+        const VecT<T, VEC> d = *reinterpret_cast<const VecT<T, VEC> *>(dm + o);
+        const VecT<T, VEC> e = *reinterpret_cast<const VecT<T, VEC> *>(ea + o);
+        VecT<T, VEC> out;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float dd = to_f(d.v[i]), ee = to_f(e.v[i]);
+            out.v[i] = from_f<T>((!phi_relu || ee > 0.f) ? dd * ft[i] : 0.f);
+            acc[i] += dd * ee;
+        }
+        *reinterpret_cast<VecT<T, VEC> *>(dea + o) = out;
+    }
+    VecT<T, VEC> of;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) of.v[i] = from_f<T>((!psi_relu || ft[i] > 0.f) ? acc[i] : 0.f);
+    *reinterpret_cast<VecT<T, VEC> *>(dfeat + b * F + (long long)f * VEC) = of;
 }
 
 // adjoint of the merge: dea = dm * feat * relu'(ea);  dfeat[b] = relu'(feat) * sum_n dm * ea
@@ -281,6 +332,13 @@ static inline bool is_bf(const zoo_net *n) { return n->prec == ZOO_PREC_BF16; }
 template <typename T>
 static zoo_status launch_im2col_nhwc(const void *x, void *cols, long long M, const LayerExec &L, cudaStream_t st) {
     constexpr int V = 16 / sizeof(T);
+    if (L.cin % V != 0 && L.cin % (V / 2) == 0) {  // e.g. the 4-channel bf16 frame stack: 8-byte chunks
+        long long total = M * L.ksize * L.ksize * (L.cin / (V / 2));
+        ZOO_CUDA(launch_pdl(im2col_nhwc_kernel<T, V / 2>, dim3(cdiv(total, 256)), dim3(256), (size_t)0, st, (const T *)x, (T *)cols, total, L.cin, L.ih,
+                            L.iw, L.ksize, L.stride, L.pad, L.oh, L.ow));
+        ZOO_LAUNCH_CHECK();
+        return ZOO_OK;
+    }
     if (L.cin % V == 0) {
         long long total = M * L.ksize * L.ksize * (L.cin / V);
         ZOO_CUDA(launch_pdl(im2col_nhwc_kernel<T, V>, dim3(cdiv(total, 256)), dim3(256), (size_t)0, st, (const T *)x, (T *)cols, total, L.cin, L.ih, L.iw,
@@ -311,10 +369,11 @@ static zoo_status launch_col2im_nhwc(const void *dcols, void *dx, const void *ac
 }
 
 static zoo_status launch_colsum(const void *dy, int dy_bf16, long long M, int N, float *db, cudaStream_t st) {
-    dim3 grid(cdiv(N, 32), (unsigned)std::max<long long>(1, std::min<long long>(64, M / 64)));
+    const int xb = cdiv(N, 32);
+    dim3 grid(xb, (unsigned)std::max<long long>(1, std::min<long long>(std::max(64, 2368 / xb), M / 64)));
     dim3 block(32, 8);
-    if (dy_bf16) colsum_kernel<bf16><<<grid, block, 0, st>>>((const bf16 *)dy, M, N, db);
-    else colsum_kernel<float><<<grid, block, 0, st>>>((const float *)dy, M, N, db);
+    if (dy_bf16) ZOO_CUDA(launch_pdl(colsum_kernel<bf16>, grid, block, (size_t)0, st, (const bf16 *)dy, M, N, db));
+    else ZOO_CUDA(launch_pdl(colsum_kernel<float>, grid, block, (size_t)0, st, (const float *)dy, M, N, db));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -366,8 +425,10 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
             if (cur_kind == 2) { set_err("conv: first layer expects a raw observation"); return ZOO_BAD_ARG; }
             const long long pixels = rows * L.ih * L.iw;
             prof_label("obs2nhwc[%lld]", pixels);
-            if (cur_kind == 0) obs_to_nhwc4_kernel<uint8_t><<<cdiv(pixels, 256), 256, 0, st>>>((const uint8_t *)cur, (float4 *)net->obs_nhwc_buf, pixels, L.ih * L.iw, L.scale255);
-            else obs_to_nhwc4_kernel<float><<<cdiv(pixels, 256), 256, 0, st>>>((const float *)cur, (float4 *)net->obs_nhwc_buf, pixels, L.ih * L.iw, L.scale255);
+#define OBS2NHWC(Tin, Tout) obs_to_nhwc4_kernel<Tin, Tout><<<cdiv(pixels, 256), 256, 0, st>>>((const Tin *)cur, (Tout *)net->obs_nhwc_buf, pixels, L.ih * L.iw, L.scale255)
+            if (cur_kind == 0) { if (bf) OBS2NHWC(uint8_t, bf16); else OBS2NHWC(uint8_t, float); }
+            else { if (bf) OBS2NHWC(float, bf16); else OBS2NHWC(float, float); }
+#undef OBS2NHWC
             ZOO_LAUNCH_CHECK();
             cur = net->obs_nhwc_buf;
             cur_kind = 2;
@@ -545,7 +606,10 @@ zoo_status net_forward(zoo_net *net, const void *obs, int obs_dtype, int rows, c
     else embed_kernel<float><<<cdiv(R * nem, 256), 256, 0, st>>>(tau, (float *)net->emb, R, nem);
     ZOO_LAUNCH_CHECK();
     ZOO_TRY(chain_forward(net, net->b, net->emb, 2, R, st));
-    if (bf) iqn_merge_kernel<bf16><<<cdiv(R * F, 256), 256, 0, st>>>((const bf16 *)net->a.out(), (const bf16 *)net->b.out(), (bf16 *)net->merged, R, F, n_tau);
+    prof_label("iqn_merge[%lldx%d]", R, F);
+    if (bf && F % 8 == 0) iqn_merge_vec_kernel<bf16, 8><<<cdiv(R * (F / 8), 256), 256, 0, st>>>((const bf16 *)net->a.out(), (const bf16 *)net->b.out(), (bf16 *)net->merged, R, F, n_tau);
+    else if (!bf && F % 4 == 0) iqn_merge_vec_kernel<float, 4><<<cdiv(R * (F / 4), 256), 256, 0, st>>>((const float *)net->a.out(), (const float *)net->b.out(), (float *)net->merged, R, F, n_tau);
+    else if (bf) iqn_merge_kernel<bf16><<<cdiv(R * F, 256), 256, 0, st>>>((const bf16 *)net->a.out(), (const bf16 *)net->b.out(), (bf16 *)net->merged, R, F, n_tau);
     else iqn_merge_kernel<float><<<cdiv(R * F, 256), 256, 0, st>>>((const float *)net->a.out(), (const float *)net->b.out(), (float *)net->merged, R, F, n_tau);
     ZOO_LAUNCH_CHECK();
     return chain_forward(net, net->c, net->merged, 2, R, st);
@@ -592,7 +656,10 @@ static zoo_status net_backward_impl(zoo_net *net, int obs_dtype, const void *obs
     LayerExec &Pphi = net->b.layers.back();
     LayerExec &Ppsi = net->a.layers.back();
     long long n = (long long)rows * F;
-    if (bf) iqn_merge_bwd_kernel<bf16><<<cdiv(n, 256), 256, 0, st>>>((const bf16 *)net->dmerged, (const bf16 *)Ppsi.out, (const bf16 *)Pphi.out, (bf16 *)Pphi.dout, (bf16 *)Ppsi.dout, rows, F, n_tau, Pphi.relu, Ppsi.relu);
+    prof_label("iqn_merge_bwd[%lldx%d]", (long long)rows * n_tau, F);
+    if (bf && F % 8 == 0) iqn_merge_bwd_vec_kernel<bf16, 8><<<cdiv(n / 8, 128), 128, 0, st>>>((const bf16 *)net->dmerged, (const bf16 *)Ppsi.out, (const bf16 *)Pphi.out, (bf16 *)Pphi.dout, (bf16 *)Ppsi.dout, rows, F, n_tau, Pphi.relu, Ppsi.relu);
+    else if (!bf && F % 4 == 0) iqn_merge_bwd_vec_kernel<float, 4><<<cdiv(n / 4, 128), 128, 0, st>>>((const float *)net->dmerged, (const float *)Ppsi.out, (const float *)Pphi.out, (float *)Pphi.dout, (float *)Ppsi.dout, rows, F, n_tau, Pphi.relu, Ppsi.relu);
+    else if (bf) iqn_merge_bwd_kernel<bf16><<<cdiv(n, 256), 256, 0, st>>>((const bf16 *)net->dmerged, (const bf16 *)Ppsi.out, (const bf16 *)Pphi.out, (bf16 *)Pphi.dout, (bf16 *)Ppsi.dout, rows, F, n_tau, Pphi.relu, Ppsi.relu);
     else iqn_merge_bwd_kernel<float><<<cdiv(n, 256), 256, 0, st>>>((const float *)net->dmerged, (const float *)Ppsi.out, (const float *)Pphi.out, (float *)Pphi.dout, (float *)Ppsi.dout, rows, F, n_tau, Pphi.relu, Ppsi.relu);
     ZOO_LAUNCH_CHECK();
     ZOO_TRY(chain_backward(net, net->b, net->emb, 2, R, nullptr, nullptr, st));
@@ -757,8 +824,9 @@ zoo_status zoo_net_create(const zoo_net_desc *d, zoo_net **out) {
     net->tf32_passes = d->precision == ZOO_PREC_FP32 ? 3 : (d->precision == ZOO_PREC_TF32 ? 1 : 0);
     net->max_batch = d->max_batch;
     net->max_q = d->kind == ZOO_NET_IQN ? d->max_quantiles : 0;
-    // fp32-storage nets turn the raw observation into fp32 NHWC first (4 channels = one 16-byte gather chunk)
-    net->obs_nhwc = d->precision != ZOO_PREC_BF16 && d->in_c == 4 && !(d->in_h == 1 && d->in_w == 1);
+    // 4-channel frame stacks are first turned into NHWC in the activation type (x ./ 255 folded in), so the first conv is
+    // an ordinary inner conv
+    net->obs_nhwc = d->in_c == 4 && !(d->in_h == 1 && d->in_w == 1);
     ParseState S{d->in_c, d->in_h, d->in_w, !(d->in_h == 1 && d->in_w == 1), (long long)d->in_c, false, true, false};
     zoo_status s = ZOO_OK;
     if (d->kind == ZOO_NET_CHAIN) {

@@ -70,7 +70,7 @@ struct zoo_net {
     size_t ws_elems = 0;
     void *obs = nullptr;  // staged observation for zoo_net_forward
     bool obs_nhwc = false;        // first conv reads an fp32 NHWC copy of the observation (fp32-storage nets, 4 channels)
-    float *obs_nhwc_buf = nullptr;
+    void *obs_nhwc_buf = nullptr;
     float *stage = nullptr; size_t stage_elems = 0;  // param up/download staging
     cudaStream_t st = nullptr;
     bool bwd_ready = false;
