@@ -178,7 +178,7 @@ def kernel_work(label, w, esz, n_params):
         out_b = 4 if label.startswith("wgrad") else esz
         return 2.0 * M * N * K, float((M * K + N * K) * esz + M * N * out_b)
     if label.startswith("opt"):
-        per = 5 if w["opt"][0] == "rmsprop" else 7  # p r/w, g r, state r/w
+        per = 6 if w["opt"][0] == "rmsprop" else 8  # p r/w, g r + re-zero, state r/w
         return 0.0, float(n_params * 4 * per + (n_params * 2 if esz == 2 else 0))
     return 0.0, 0.0
 

@@ -139,15 +139,29 @@ sumtree_update_parents_kernel(float *__restrict__ tree, int depth, const long lo
         keys[k] = key;
     }
     bitonic_sort(keys, n2);
+    // Sorted copies (node id, change) so that the serial part below walks two dense arrays: the loop-carried dependency is
+    // then only the fp32 add itself (the order of additions per node is the batch order -- that is what makes this bit-exact
+    // with the reference's sequential `tree[node] += change`; near the root one thread adds thousands of terms).
+    float *sch = ch + n2;
+    unsigned *nd = (unsigned *)(sch + n2);
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const unsigned long long a = keys[j] >> KBITS;
-        if (j > 0 && (keys[j - 1] >> KBITS) == a) continue;
+        const unsigned long long key = keys[j];
+        nd[j] = (unsigned)(key >> KBITS);
+        sch[j] = ch[key & (UPD_CHUNK - 1)];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const unsigned a = nd[j];
+        if (j > 0 && nd[j - 1] == a) continue;
         float acc = tree[a];
         int jj = j;
-        do {
-            acc = __fadd_rn(acc, ch[keys[jj] & (UPD_CHUNK - 1)]);
-            ++jj;
-        } while (jj < n && (keys[jj] >> KBITS) == a);
+        // runs of 8 with the membership tests hoisted: the adds of a full group issue back to back
+        while (jj + 8 <= n && nd[jj + 7] == a) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, sch[jj + u]);
+            jj += 8;
+        }
+        while (jj < n && nd[jj] == a) { acc = __fadd_rn(acc, sch[jj]); ++jj; }
         tree[a] = acc;
     }
 }
@@ -191,7 +205,7 @@ zoo_status zoo_sumtree_create(int64_t capacity, zoo_sumtree **out) {
     ZOO_CUDA(cudaMemsetAsync(t->tree, 0, (t->tree_len + 1) * sizeof(float), t->st));
     ZOO_CUDA(cudaMalloc(&t->d_heap, UPD_CHUNK * sizeof(long long)));
     ZOO_CUDA(cudaMalloc(&t->d_change, UPD_CHUNK * sizeof(float)));
-    ZOO_CUDA(cudaFuncSetAttribute(sumtree_update_parents_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UPD_CHUNK * 12));
+    ZOO_CUDA(cudaFuncSetAttribute(sumtree_update_parents_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UPD_CHUNK * 20));
     ZOO_CUDA(cudaStreamSynchronize(t->st));
     *out = t;
     return ZOO_OK;
@@ -216,7 +230,7 @@ static zoo_status update_dev_impl(zoo_sumtree *t, const long long *idx_dev, cons
                                                                     idx_dev + off, p_dev + off, m, n2, t->d_heap, t->d_change);
         ZOO_LAUNCH_CHECK();
         if (t->depth > 0) {
-            sumtree_update_parents_kernel<<<t->depth, threads, n2 * 12, t->st>>>(t->tree, t->depth, t->d_heap, t->d_change, m, n2);
+            sumtree_update_parents_kernel<<<t->depth, threads, n2 * 20, t->st>>>(t->tree, t->depth, t->d_heap, t->d_change, m, n2);
             ZOO_LAUNCH_CHECK();
         }
     }
