@@ -105,6 +105,32 @@ __global__ void __launch_bounds__(128) dense_narrow_kernel(Operand A, Operand B,
     if (threadIdx.x < N) epi_store(epi, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x], m, threadIdx.x);
 }
 
+// many rows (IQN: batch x quantiles): one warp per row, grid-stride, no shared memory
+template <int NMAX>
+__global__ void __launch_bounds__(256) dense_narrow_rows_kernel(Operand A, Operand B, int M, int N, int K, Epilogue epi) {
+    pdl_wait();
+    pdl_trigger();
+    const int lane = threadIdx.x & 31;
+    for (int m = blockIdx.x * 8 + (threadIdx.x >> 5); m < M; m += gridDim.x * 8) {
+        float acc[NMAX];
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+        for (int k = lane; k < K; k += 32) {
+            const float a = ld_elem(A.p, A.is_bf16, (long long)m * A.ld + k);
+#pragma unroll
+            for (int n = 0; n < NMAX; ++n)
+                if (n < N) acc[n] = fmaf(a, ldg_elem(B.p, B.is_bf16, (long long)n * B.ld + k), acc[n]);
+        }
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n) {
+            float v = acc[n];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == n) epi_store(epi, v, m, n);
+        }
+    }
+}
+
 // finishes a split-K GEMM whose partial sums were atomically accumulated in ws[M][N]
 // (and re-zeroes ws: the split-K workspace is all-zero between launches, shared with the tcgen05 engine)
 __global__ void splitk_finish_kernel(float *ws, int M, int N, Epilogue epi) {
@@ -126,6 +152,13 @@ zoo_status splitk_finish(float *ws, int M, int N, const Epilogue &epi, cudaStrea
 zoo_status simt_gemm(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, int split_k,
                      float *ws, size_t ws_elems, cudaStream_t st) {
     if (M <= 0 || N <= 0) return ZOO_OK;
+    if (N <= 16 && A.kmajor && B.kmajor && !epi.accumulate && split_k <= 0 && M > 1024) {
+        const int blocks = (int)std::min<long long>(cdiv(M, 8), 148 * 8);
+        if (N <= 8) ZOO_CUDA(launch_pdl(dense_narrow_rows_kernel<8>, dim3(blocks), dim3(256), (size_t)0, st, A, B, M, N, K, epi));
+        else ZOO_CUDA(launch_pdl(dense_narrow_rows_kernel<16>, dim3(blocks), dim3(256), (size_t)0, st, A, B, M, N, K, epi));
+        ZOO_LAUNCH_CHECK();
+        return ZOO_OK;
+    }
     if (N <= 16 && A.kmajor && B.kmajor && !epi.accumulate && split_k <= 0 && M <= 65535) {
         if (N <= 8) ZOO_CUDA(launch_pdl(dense_narrow_kernel<8>, dim3(M), dim3(128), (size_t)0, st, A, B, N, K, epi));
         else ZOO_CUDA(launch_pdl(dense_narrow_kernel<16>, dim3(M), dim3(128), (size_t)0, st, A, B, N, K, epi));

@@ -574,6 +574,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const void *const maskp = e.mask;
         const int mask_bf16 = e.mask_bf16;
         const long long msm = e.mask_sm, msn = e.mask_sn;
+        // bf16 output, plain row-major store: 64 columns at a time so that every lane writes a packed bf16x2 (128-byte row
+        // segments instead of 64-byte ones) -- the wide, K-short GEMMs (IQN phi: K = 64, 0.5 GB of output) are store-bound
+        if (BN >= 64 && !X3 && simple && !trans && !split && !e.accumulate && out_bf16 && sn == 1 && (Nn & 1) == 0 && (sm & 1) == 0 &&
+            (!maskp || (mask_bf16 && msn == 1 && (msm & 1) == 0))) {
+            float(*stw)[66] = reinterpret_cast<float(*)[66]>(smem) + q * 32;  // 32 x 66 floats per warp (spans idle stages)
+#pragma unroll
+            for (int c = 0; c < BN; c += 64) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t r[32];
+                    tmem_ld32(tq + (uint32_t)(lb * BN + c + 32 * h), r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) stw[lane][32 * h + j] = __uint_as_float(r[j]);
+                }
+                __syncwarp();
+                const int n = n0 + c + 2 * lane;
+                if (n < Nn) {
+                    float b0 = 0.f, b1 = 0.f;
+                    if (bias_mode == 1) { b0 = __ldg(e.bias + n); b1 = __ldg(e.bias + n + 1); }
+                    __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>((bf16 *)e.out + (long long)row0 * sm + n);
+                    const __nv_bfloat162 *mp = maskp ? reinterpret_cast<const __nv_bfloat162 *>((const bf16 *)maskp + (long long)row0 * msm + n) : nullptr;
+#pragma unroll 8
+                    for (int rr = 0; rr < rows; ++rr) {
+                        const float2 v2 = *reinterpret_cast<const float2 *>(&stw[rr][2 * lane]);
+                        float v0 = v2.x + b0, v1 = v2.y + b1;
+                        if (bias_mode == 2) { const float bm = __ldg(e.bias + row0 + rr); v0 += bm; v1 += bm; }
+                        if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                        if (mp) {
+                            const __nv_bfloat162 mk = __ldg(mp + (long long)rr * (msm >> 1));
+                            v0 = __low2float(mk) > 0.f ? v0 : 0.f;
+                            v1 = __high2float(mk) > 0.f ? v1 : 0.f;
+                        }
+                        op[(long long)rr * (sm >> 1)] = __floats2bfloat162_rn(v0, v1);
+                    }
+                }
+                __syncwarp();
+            }
+        } else
 #pragma unroll
         for (int c = 0; c < BN; c += 32) {
             uint32_t r[32];
