@@ -63,6 +63,7 @@ int dp_world(const zoo_dp *dp) { return dp ? dp->world : 1; }
 zoo_status dp_allreduce_sum(zoo_dp *dp, float *buf, long long n, cudaStream_t st) {
     if (!dp || dp->world == 1) return ZOO_OK;
     ZOO_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat, ncclSum, dp->comm, st));
+    if (g_prof_on) { prof_label("allreduce[%lld]", n); prof_mark("ncclAllReduce", __LINE__); }
     return ZOO_OK;
 }
 zoo_status dp_allreduce_max(zoo_dp *dp, float *buf, long long n, cudaStream_t st) {

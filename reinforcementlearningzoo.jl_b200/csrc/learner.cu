@@ -2,6 +2,7 @@
 // Reference: update!(learner, batch) basic_dqn.jl:69-90, dqn.jl:102-145, prioritized_dqn.jl:111-151,
 //            rainbow.jl:126-196, iqn.jl:159-237; update!(Q, gs) -> Flux.Optimise.update!.
 #include <cmath>
+#include <cstring>
 
 #include "heads.cuh"
 #include "net.cuh"
@@ -136,6 +137,12 @@ struct zoo_learner {
     uint8_t *d_mask = nullptr; float *d_tau = nullptr, *d_taup = nullptr;
     float *d_support = nullptr, *d_target = nullptr, *d_tdist = nullptr;
     float *d_per = nullptr, *d_prio = nullptr, *d_wraw = nullptr, *d_wmax = nullptr;
+    // the small per-sample vectors above live in one device block mirrored by a pinned host block: one H2D per update
+    uint8_t *d_pack = nullptr, *h_pack = nullptr;
+    size_t pack_bytes = 0;
+    size_t off_action = 0, off_reward = 0, off_terminal = 0, off_priority = 0, off_mask = 0, off_tau = 0, off_taup = 0;
+    cudaEvent_t ev_pack = nullptr;
+    bool pack_inflight = false;
     float *d_loss = nullptr;  // lives at grads[n_flat] so one all-reduce covers gradients and loss
     float gamma_n;
     int last_launches = 0;
@@ -304,7 +311,28 @@ static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b) {
         ZOO_LAUNCH_CHECK();
         return ZOO_OK;
     }
-    const cudaMemcpyKind k = b->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (!b->on_device) {
+        // host batch: the two frame blocks go straight from the caller's arrays; the small vectors are packed into the pinned
+        // mirror of d_pack and cross PCIe in one copy (seven tiny copies cost ~5 us of launch latency each)
+        ZOO_CUDA(cudaMemcpyAsync(L->d_obs, b->state, obs_bytes, cudaMemcpyHostToDevice, st));
+        ZOO_CUDA(cudaMemcpyAsync((uint8_t *)L->d_obs + obs_bytes, b->next_state, obs_bytes, cudaMemcpyHostToDevice, st));
+        if (L->pack_inflight) ZOO_CUDA(cudaEventSynchronize(L->ev_pack));  // the previous update's copy has read h_pack
+        memcpy(L->h_pack + L->off_action, b->action, (size_t)B * sizeof(int));
+        memcpy(L->h_pack + L->off_reward, b->reward, (size_t)B * sizeof(float));
+        memcpy(L->h_pack + L->off_terminal, b->terminal, (size_t)B);
+        if (b->priority) memcpy(L->h_pack + L->off_priority, b->priority, (size_t)B * sizeof(float));
+        if (b->next_mask) memcpy(L->h_pack + L->off_mask, b->next_mask, (size_t)B * c.n_actions);
+        if (c.kind == ZOO_LEARNER_IQN && b->tau) {
+            memcpy(L->h_pack + L->off_tau, b->tau, (size_t)B * c.N * sizeof(float));
+            memcpy(L->h_pack + L->off_taup, b->tau_prime, (size_t)B * c.N_prime * sizeof(float));
+        }
+        const size_t used = (c.kind == ZOO_LEARNER_IQN && !b->tau) ? L->off_tau : L->pack_bytes;  // device-drawn tau stays untouched
+        ZOO_CUDA(cudaMemcpyAsync(L->d_pack, L->h_pack, used, cudaMemcpyHostToDevice, st));
+        ZOO_CUDA(cudaEventRecord(L->ev_pack, st));
+        L->pack_inflight = true;
+        return ZOO_OK;
+    }
+    const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;  // device batch whose frame blocks are not 16-byte aligned
     ZOO_CUDA(cudaMemcpyAsync(L->d_obs, b->state, obs_bytes, k, st));
     ZOO_CUDA(cudaMemcpyAsync((uint8_t *)L->d_obs + obs_bytes, b->next_state, obs_bytes, k, st));
     ZOO_CUDA(cudaMemcpyAsync(L->d_action, b->action, B * sizeof(int), k, st));
@@ -312,12 +340,9 @@ static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b) {
     ZOO_CUDA(cudaMemcpyAsync(L->d_terminal, b->terminal, B, k, st));
     if (b->priority) ZOO_CUDA(cudaMemcpyAsync(L->d_priority, b->priority, B * sizeof(float), k, st));
     if (b->next_mask) ZOO_CUDA(cudaMemcpyAsync(L->d_mask, b->next_mask, (size_t)B * c.n_actions, k, st));
-    if (c.kind == ZOO_LEARNER_IQN) {
-        ZOO_REQUIRE((b->tau != nullptr) == (b->tau_prime != nullptr), "update: pass both tau and tau_prime or neither");
-        if (b->tau) {
-            ZOO_CUDA(cudaMemcpyAsync(L->d_tau, b->tau, (size_t)B * c.N * sizeof(float), k, st));
-            ZOO_CUDA(cudaMemcpyAsync(L->d_taup, b->tau_prime, (size_t)B * c.N_prime * sizeof(float), k, st));
-        }
+    if (c.kind == ZOO_LEARNER_IQN && b->tau) {
+        ZOO_CUDA(cudaMemcpyAsync(L->d_tau, b->tau, (size_t)B * c.N * sizeof(float), k, st));
+        ZOO_CUDA(cudaMemcpyAsync(L->d_taup, b->tau_prime, (size_t)B * c.N_prime * sizeof(float), k, st));
     }
     return ZOO_OK;
 }
@@ -457,11 +482,29 @@ zoo_status zoo_learner_create(const zoo_learner_cfg *cfg, zoo_net *online, zoo_n
         if (online->late_off <= 0 || best * 2 < online->n_params) online->late_off = -1;  // not worth a second bucket
     }
     ZOO_CUDA(cudaMalloc(&L->d_obs, (size_t)2 * B * obs_elems(online) * sizeof(float)));
-    ZOO_CUDA(cudaMalloc(&L->d_action, B * sizeof(int)));
-    ZOO_CUDA(cudaMalloc(&L->d_reward, B * sizeof(float)));
-    ZOO_CUDA(cudaMalloc(&L->d_terminal, B));
-    ZOO_CUDA(cudaMalloc(&L->d_priority, B * sizeof(float)));
-    ZOO_CUDA(cudaMalloc(&L->d_mask, (size_t)B * A));
+    {
+        auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+        size_t o = 0;
+        L->off_action = o; o = up(o + (size_t)B * sizeof(int));
+        L->off_reward = o; o = up(o + (size_t)B * sizeof(float));
+        L->off_terminal = o; o = up(o + (size_t)B);
+        L->off_priority = o; o = up(o + (size_t)B * sizeof(float));
+        L->off_mask = o; o = up(o + (size_t)B * A);
+        if (iqn) {
+            L->off_tau = o; o = up(o + (size_t)B * cfg->N * sizeof(float));
+            L->off_taup = o; o = up(o + (size_t)B * cfg->N_prime * sizeof(float));
+        }
+        L->pack_bytes = o;
+        ZOO_CUDA(cudaMalloc(&L->d_pack, o));
+        ZOO_CUDA(cudaHostAlloc(&L->h_pack, o, cudaHostAllocDefault));
+        ZOO_CUDA(cudaEventCreateWithFlags(&L->ev_pack, cudaEventDisableTiming));
+        L->d_action = (int *)(L->d_pack + L->off_action);
+        L->d_reward = (float *)(L->d_pack + L->off_reward);
+        L->d_terminal = L->d_pack + L->off_terminal;
+        L->d_priority = (float *)(L->d_pack + L->off_priority);
+        L->d_mask = L->d_pack + L->off_mask;
+        if (iqn) { L->d_tau = (float *)(L->d_pack + L->off_tau); L->d_taup = (float *)(L->d_pack + L->off_taup); }
+    }
     ZOO_CUDA(cudaMalloc(&L->d_per, B * sizeof(float)));
     ZOO_CUDA(cudaMalloc(&L->d_prio, B * sizeof(float)));
     ZOO_CUDA(cudaMalloc(&L->d_wraw, B * sizeof(float)));
@@ -472,8 +515,6 @@ zoo_status zoo_learner_create(const zoo_learner_cfg *cfg, zoo_net *online, zoo_n
         ZOO_CUDA(cudaMalloc(&L->d_tdist, (size_t)B * cfg->n_atoms * sizeof(float)));
     }
     if (iqn) {
-        ZOO_CUDA(cudaMalloc(&L->d_tau, (size_t)B * cfg->N * sizeof(float)));
-        ZOO_CUDA(cudaMalloc(&L->d_taup, (size_t)B * cfg->N_prime * sizeof(float)));
         ZOO_CUDA(cudaMalloc(&L->d_target, (size_t)B * cfg->N_prime * sizeof(float)));
     }
     *out = L;
@@ -484,7 +525,9 @@ zoo_status zoo_learner_destroy(zoo_learner *L) {
     if (!L) return ZOO_OK;
     cudaStreamSynchronize(L->st);
     if (L->gexec) cudaGraphExecDestroy(L->gexec);
-    void *ptrs[] = {L->d_obs, L->d_action, L->d_reward, L->d_terminal, L->d_priority, L->d_mask, L->d_tau, L->d_taup, L->d_support,
+    if (L->h_pack) cudaFreeHost(L->h_pack);
+    if (L->ev_pack) cudaEventDestroy(L->ev_pack);
+    void *ptrs[] = {L->d_obs, L->d_pack, L->d_support,
                     L->d_target, L->d_tdist, L->d_per, L->d_prio, L->d_wraw, L->d_wmax};
     for (void *p : ptrs) if (p) cudaFree(p);
     cudaStreamDestroy(L->st);
