@@ -117,8 +117,9 @@ struct Epilogue {
 enum { CONV_RAW_U8 = 1,   // first conv: observation [B][C][H][W] uint8, K order (c,ky,kx), optional x/255 (IEEE divide)
        CONV_RAW_F32 = 2,  // first conv: observation [B][C][H][W] float
        CONV_NHWC = 3,     // inner conv: activations [B][H][W][C] in the GEMM dtype, K order (ky,kx,c)
-       CONV_DGRAD = 4 };  // data gradient: A = dY [B][OH][OW][Cout] gathered transposed-conv style, K order (ky,kx,o),
+       CONV_DGRAD = 4,    // data gradient: A = dY [B][OH][OW][Cout] gathered transposed-conv style, K order (ky,kx,o),
                           //   M = B*H*W input pixels, N = C;  B operand = W viewed [Cout][ks*ks*C] (MN-major)
+       CONV_TMA = 5 };    // forward conv on NHWC activations with TMA-fetched im2col rows (4-D boxes), K order (ky,kx,c)
 struct ConvGeom {
     const void *x = nullptr;
     int mode = 0;
@@ -126,6 +127,9 @@ struct ConvGeom {
     int ks = 0, s = 1, p = 0;     // kernel, stride, symmetric zero pad
     int OH = 0, OW = 0, Cout = 0; // forward output size / channels
     int scale255 = 0;
+    // CONV_TMA: M tiles are R whole output rows of one image (tpi tiles per image); one K-block is one tap x one 128-byte
+    // channel block (cblocks per tap), or -- `first`: zero-padded 4-channel frame stack -- one kernel row (ks taps x C)
+    int tpi = 0, R = 0, cblocks = 1, first = 0;
 };
 bool tc_conv_supported(const ConvGeom &g, int is_bf16);
 // D[M][N] = sum_k A(m,k) W(n,k) with A gathered per ConvGeom; Wop: K-major [N][K] (forward) or MN-major (dgrad)

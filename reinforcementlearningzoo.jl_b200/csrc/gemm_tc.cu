@@ -294,11 +294,14 @@ __device__ __forceinline__ uint4 tf32_lo(const uint4 v) {
     return l;
 }
 
-// GA: the A operand is gathered by warps 2..5 (implicit-GEMM convolution, see ConvGeom) instead of TMA-loaded.
-template <int EB, int BN, bool A_K, bool B_K, bool X3, bool GA = false>
+// GA = 1: the A operand is gathered by warps 2..5 (implicit-GEMM convolution, see ConvGeom) instead of TMA-loaded.
+// GA = 2: implicit-GEMM convolution with the im2col rows fetched by TMA itself: one M tile = R whole output rows of one
+//         image, one K-block = one kernel tap (or kernel row), loaded as a single 4-D box of the NHWC activation tensor
+//         (element strides = conv stride, out-of-bounds = zero padding).
+template <int EB, int BN, bool A_K, bool B_K, bool X3, int GA = 0>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
-    static_assert(!GA || A_K, "the gathered A operand is K-major");
+    static_assert(GA == 0 || A_K, "the gathered A operand is K-major");
     using C = TcCfg<EB, BN, X3>;
     // SWIZZLE_128B tiles need 1024-byte alignment; declaring it on the array (instead of rounding the pointer up) keeps
     // the shared address space visible to the compiler, so the epilogue staging below compiles to LDS/STS
@@ -312,7 +315,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    int m0 = blockIdx.x * BM, vrows = min(BM, P.M - (int)blockIdx.x * BM);  // first output row / valid rows of this M tile
+    int cimg = 0, coy0 = 0;
+    if (GA == 2) {
+        cimg = blockIdx.x / P.conv.tpi;
+        coy0 = (blockIdx.x - cimg * P.conv.tpi) * P.conv.R;
+        m0 = (cimg * P.conv.OH + coy0) * P.conv.OW;
+        vrows = min(P.conv.R, P.conv.OH - coy0) * P.conv.OW;
+    }
+    const int n0 = blockIdx.y * BN;
     if (threadIdx.x == 0) dbg_stamp(P, 0);
     const int total_kb = (P.K + C::BK - 1) / C::BK;
     const int kb0 = blockIdx.z * P.kb_per_split;
@@ -354,9 +365,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t *sa = smem + s * C::STAGE_BYTES;
                 uint8_t *sb = sa + C::A_BYTES;
-                mbar_expect_tx(&full_bar[s], GA ? C::B_BYTES : C::RAW_BYTES);
+                mbar_expect_tx(&full_bar[s], GA == 1 ? C::B_BYTES : (GA == 2 ? P.conv.R * P.conv.OW * 128 + C::B_BYTES : C::RAW_BYTES));
                 const int k0 = (kb0 + i) * C::BK;
-                if (!GA) {
+                if (GA == 2) {
+                    const ConvGeom &g = P.conv;
+                    const int kb = kb0 + i;
+                    int c0, c1, c2;
+                    if (g.first) { c0 = 0; c1 = 0; c2 = coy0 * g.s + kb; }  // K-block = kernel row ky of the padded frame stack
+                    else {
+                        const int tap = kb / g.cblocks, ky = tap / g.ks, kx = tap - ky * g.ks;
+                        c0 = (kb - tap * g.cblocks) * C::BK; c1 = kx - g.p; c2 = coy0 * g.s + ky - g.p;
+                    }
+                    asm volatile(
+                        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                        ::"r"(smem_u32(sa)), "l"(&tmA), "r"(smem_u32(&full_bar[s])), "r"(c0), "r"(c1), "r"(c2), "r"(cimg)
+                        : "memory");
+                }
+                if (GA == 0) {
                     if (A_K) {
                         tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box {BK k, 128 rows}
                     } else {
@@ -370,7 +395,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else {
                     // conv dgrad: K runs over (tap, o); tap t's [Cout][C] slice of W sits at column offset t*C of [Cout][ks*ks*C]
                     int nb = n0, kb = k0;
-                    if (GA) { const int tap = k0 / P.conv.Cout; nb = n0 + tap * P.conv.C; kb = k0 - tap * P.conv.Cout; }
+                    if (GA == 1) { const int tap = k0 / P.conv.Cout; nb = n0 + tap * P.conv.C; kb = k0 - tap * P.conv.Cout; }
 #pragma unroll
                     for (int h = 0; h < BN / C::MN_BOX; ++h)
                         tma_load_2d(sb + h * C::BOX_BYTES, &tmB, &full_bar[s], nb + h * C::MN_BOX, kb);
@@ -390,7 +415,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&acc_empty[cb], ((chain >> 1) - 1) & 1);
                     tc_fence_after();
                 }
-                if (X3 || GA) mbar_wait(&conv_bar[s], ph);  // converter / gather warps are done with the stage
+                if (X3 || GA == 1) mbar_wait(&conv_bar[s], ph);  // converter / gather warps are done with the stage
                 if (!X3) mbar_wait(&full_bar[s], ph);       // TMA bytes have landed (the 3xTF32 converters waited for them)
                 tc_fence_after();
                 if (i == 0) dbg_stamp(P, 3);
@@ -432,21 +457,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < BN; ++j) acc[j] = 0.f;
         }
-        if (X3 || GA) {
+        if (X3 || GA == 1) {
             // per K-block: (GA) gather this thread's A row into the stage -- hi and, for 3xTF32, lo -- and (3xTF32) split the
             // TMA-landed fp32 tiles into hi (the tile itself) and lo; one chain behind the MMA warp, fold finished chains
             // into acc
             const int t = threadIdx.x - 64;  // 0..127
             int drained = 0;
-            const int va = min(BM, P.M - m0), vb = min(BN, P.N - n0);  // valid rows of the A / B tiles
-            const int a_units = GA ? 0 : (A_K ? va * 128 : ((va + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
+            const int va = vrows, vb = min(BN, P.N - n0);  // valid rows of the A / B tiles
+            const int a_units = GA == 1 ? 0 : (A_K ? va * 128 : ((va + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
             const int b_units = (B_K ? vb * 128 : ((vb + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
             const int conv_units = a_units + b_units;
             // GA: this thread owns tile row t = output pixel (forward) / input pixel (dgrad) m0 + t
             bool gvalid = false;
             int gb = 0, gy0 = 0, gx0 = 0;
             constexpr int GA_AHEAD = C::STAGES - 2;  // K-blocks of cp.async gathers in flight ahead of the one being finished
-            if (GA) {
+            if (GA == 1) {
                 const ConvGeom &g = P.conv;
                 const int m = m0 + t;
                 gvalid = m < P.M;
@@ -461,7 +486,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int s = i % C::STAGES;
                 const uint32_t ph = (i / C::STAGES) & 1;
                 uint8_t *stage = smem + s * C::STAGE_BYTES;
-                if (GA) {
+                if (GA == 1) {
                     if (P.conv.mode == CONV_NHWC || P.conv.mode == CONV_DGRAD) {
                         // cp.async pipeline: the 16-byte chunks of K-block i+GA_AHEAD go straight from global memory into their
                         // swizzled slots (zero-filled outside the image) while block i, issued GA_AHEAD iterations ago, lands
@@ -560,7 +585,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (threadIdx.x == 64) dbg_stamp(P, 5);
         float(*stg)[33] = reinterpret_cast<float(*)[33]>(smem) + q * 32;  // 32 x 33 floats per warp, in pipeline stage 0
         const int row0 = m0 + q * 32;
-        const int rows = min(32, P.M - row0);
+        const int rows = max(0, min(32, vrows - q * 32));
         // the epilogue description is copied out of the parameter bank once: re-reading it per row costs a chain of
         // uniform constant loads per store (measured 100 ns per row)
         const Epilogue e = P.epi;
@@ -776,6 +801,23 @@ static zoo_status make_map(CUtensorMap *tm, const void *p, int eb, long long d0,
     return ZOO_OK;
 }
 
+// 4-D tensor map over an NHWC activation tensor (or an overlapping-window view of it) for the CONV_TMA A operand
+static zoo_status make_map4(CUtensorMap *tm, const void *p, int eb, const cuuint64_t dims[4], const cuuint64_t strides_bytes[3],
+                            const cuuint32_t box[4], const cuuint32_t estr[4]) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_err("cuTensorMapEncodeTiled not available from the driver"); return ZOO_CUDA_ERROR; }
+    CUresult r = enc(tm, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(p), dims, strides_bytes,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_err("cuTensorMapEncodeTiled(4D) failed (%d): dims %llu %llu %llu %llu box %u %u %u %u estr %u %u %u %u", (int)r, (unsigned long long)dims[0],
+                (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3], box[0], box[1], box[2], box[3], estr[0], estr[1],
+                estr[2], estr[3]);
+        return ZOO_CUDA_ERROR;
+    }
+    return ZOO_OK;
+}
+
 bool tc_gemm_supported(const Operand &A, const Operand &B, int M, int N, int K) {
     if (A.is_bf16 != B.is_bf16) return false;
     const int al = A.is_bf16 ? 8 : 4;  // elements per 16 bytes
@@ -790,10 +832,10 @@ static zoo_status launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
     using C = TcCfg<EB, BN, X3>;
     static bool attr_set = false;
     if (!attr_set) {
-        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, A_K, B_K, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, false>, grid, dim3(TC_THREADS), (size_t)C::SMEM, st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, grid, dim3(TC_THREADS), (size_t)C::SMEM, st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -876,10 +918,23 @@ static zoo_status launch_conv(const CUtensorMap &tmB, const TcParams &P, dim3 gr
     using C = TcCfg<EB, BN, X3>;
     static bool attr_set = false;
     if (!attr_set) {
-        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, true>, grid, dim3(TC_THREADS), (size_t)C::SMEM, st, tmB, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, grid, dim3(TC_THREADS), (size_t)C::SMEM, st, tmB, tmB, P));
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+
+template <int EB, int BN, bool X3>
+static zoo_status launch_conv_tma(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid, cudaStream_t st) {
+    using C = TcCfg<EB, BN, X3>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, true, X3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, true, X3, 2>, grid, dim3(TC_THREADS), (size_t)C::SMEM, st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -902,12 +957,60 @@ bool tc_conv_supported(const ConvGeom &g, int is_bf16) {
     if (g.mode == CONV_RAW_U8 || g.mode == CONV_RAW_F32) return g.ks % ch == 0 && ((long long)g.C * g.ks * g.ks * eb) % 16 == 0;
     if (g.mode == CONV_NHWC) return g.C % ch == 0;
     if (g.mode == CONV_DGRAD) return g.Cout % bk == 0 && g.C % 8 == 0 && ((long long)g.ks * g.ks * g.C * eb) % 16 == 0;
+    if (g.mode == CONV_TMA) {
+        if (g.OW > 128 || g.OW < 1) return false;
+        if (g.first) return g.ks * g.C * eb == 128 && g.p == 0 && (g.s * g.C * eb) % 16 == 0 && g.OW <= 256 && ((128 / g.OW - 1) * g.s + 1) <= 256;
+        const int R = std::min(g.OH, 128 / g.OW);
+        return (g.C * eb) % 128 == 0 && (g.OW - 1) * g.s + 1 <= 256 && (R - 1) * g.s + 1 <= 256;
+    }
     return false;
+}
+
+// forward conv with TMA-fetched im2col rows.  g.x: NHWC activations [images][H][W][C] (for `first`: already zero-padded, p = 0)
+static zoo_status tc_conv_tma(ConvGeom g, const Operand &Wop, int images, int N, int K, const Epilogue &epi, cudaStream_t st) {
+    const int eb = Wop.is_bf16 ? 2 : 4;
+    const int bk = 128 / eb;
+    const bool x3 = eb == 4 && epi.tf32_passes == 3;
+    ZOO_REQUIRE(Wop.kmajor && K % bk == 0, "tc_conv_tma: K %d is not a whole number of K-blocks", K);
+    int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+    g.R = std::min(g.OH, 128 / g.OW);
+    g.tpi = cdiv(g.OH, g.R);
+    g.cblocks = g.first ? 1 : (g.C * eb) / 128;
+    dim3 grid(images * g.tpi, cdiv(N, BN), 1);
+    TcParams P;
+    P.M = images * g.OH * g.OW; P.N = N; P.K = K; P.kb_per_split = K / bk; P.epi = epi; P.ws = nullptr; P.ctr = nullptr; P.dbg = nullptr; P.conv = g;
+    if (P.epi.accumulate == 2) P.epi.accumulate = 0;
+    CUtensorMap tmA, tmB;
+    const cuuint64_t sC = (cuuint64_t)g.C * eb, sW = (cuuint64_t)g.W * sC, sH = (cuuint64_t)g.H * sW;
+    if (g.first) {
+        // view of the padded frame stack: d0 = one kernel row (ks taps x C channels, contiguous), d1 = output column (overlapping
+        // windows, stride s pixels), d2 = input row (the box steps s rows per output row), d3 = image
+        const cuuint64_t dims[4] = {(cuuint64_t)(g.ks * g.C), (cuuint64_t)g.OW, (cuuint64_t)g.H, (cuuint64_t)images};
+        const cuuint64_t str[3] = {(cuuint64_t)g.s * sC, sW, sH};
+        const cuuint32_t box[4] = {(cuuint32_t)(g.ks * g.C), (cuuint32_t)g.OW, (cuuint32_t)((g.R - 1) * g.s + 1), 1};
+        const cuuint32_t es[4] = {1, 1, (cuuint32_t)g.s, 1};
+        ZOO_TRY(make_map4(&tmA, g.x, eb, dims, str, box, es));
+    } else {
+        const cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)images};
+        const cuuint64_t str[3] = {sC, sW, sH};
+        const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)((g.OW - 1) * g.s + 1), (cuuint32_t)((g.R - 1) * g.s + 1), 1};
+        const cuuint32_t es[4] = {1, (cuuint32_t)g.s, (cuuint32_t)g.s, 1};
+        ZOO_TRY(make_map4(&tmA, g.x, eb, dims, str, box, es));
+    }
+    ZOO_TRY(make_map(&tmB, Wop.p, eb, K, N, Wop.ld, bk, BN, false));
+#define CONV_TMA_BN(EBv, X3v)                                                                  \
+    (BN == 32 ? launch_conv_tma<EBv, 32, X3v>(tmA, tmB, P, grid, st)                            \
+              : (BN == 64 ? launch_conv_tma<EBv, 64, X3v>(tmA, tmB, P, grid, st) : launch_conv_tma<EBv, 128, X3v>(tmA, tmB, P, grid, st)))
+    if (eb == 2) return CONV_TMA_BN(2, false);
+    if (x3) return CONV_TMA_BN(4, true);
+    return CONV_TMA_BN(4, false);
+#undef CONV_TMA_BN
 }
 
 zoo_status tc_conv_gemm(const ConvGeom &g, const Operand &Wop, int M, int N, int K, const Epilogue &epi, float *ws, size_t ws_elems,
                         cudaStream_t st) {
     ZOO_REQUIRE(tc_conv_supported(g, Wop.is_bf16) && M > 0 && N >= 8 && ((uintptr_t)Wop.p & 15) == 0, "tc_conv_gemm: unsupported geometry");
+    if (g.mode == CONV_TMA) return tc_conv_tma(g, Wop, M / (g.OH * g.OW), N, K, epi, st);
     const int eb = Wop.is_bf16 ? 2 : 4;
     const int bk = 128 / eb, mn_box = 128 / eb;
     const bool x3 = eb == 4 && epi.tf32_passes == 3;

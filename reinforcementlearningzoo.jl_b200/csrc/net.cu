@@ -8,6 +8,12 @@ namespace zoo {
 // Implicit-GEMM convolutions (tc_conv_gemm: the A operand is gathered in-kernel, no im2col / col2im) are parity-tested but
 // this round still lose to explicit im2col + TMA GEMM at these layer sizes (the 4-warp gather is instruction-latency bound,
 // see DESIGN.md section 4), so they are opt-in: ZOO_IMPLICIT_CONV=1.
+// forward convs with TMA-fetched im2col rows (CONV_TMA) are the default where the layer geometry allows; ZOO_TMA_CONV=0 disables
+static bool tma_conv_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("ZOO_TMA_CONV"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
 static bool implicit_conv_enabled() {
     static int on = -1;
     if (on < 0) { const char *e = getenv("ZOO_IMPLICIT_CONV"); on = (e && e[0] == '1') ? 1 : 0; }
@@ -57,10 +63,12 @@ template <typename T, int VEC> struct alignas(sizeof(T) * VEC) VecT { T v[VEC]; 
 // raw observation [B][C][H][W] (u8 | f32) -> NHWC in the net's activation type [B][H][W][C] with `x ./ 255` (IEEE divide) folded in, so the first
 // conv runs through the same implicit-GEMM gather as the inner convs.  One thread per pixel, C = 4 channels (16 bytes).
 template <typename Tin, typename Tout>
-__global__ void obs_to_nhwc4_kernel(const Tin *__restrict__ x, Tout *__restrict__ out, long long pixels, int HW, int scale255) {
+__global__ void obs_to_nhwc4_kernel(const Tin *__restrict__ x, Tout *__restrict__ out, long long pixels, int H, int W, int pad,
+                                    int scale255) {
     pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pixels) return;
+    const int HW = H * W;
     const long long b = i / HW, p = i - b * HW;
     const Tin *src = x + b * 4 * HW + p;
     float v[4];
@@ -73,7 +81,11 @@ __global__ void obs_to_nhwc4_kernel(const Tin *__restrict__ x, Tout *__restrict_
 #pragma unroll
     for (int c = 0; c < 4; ++c) o.v[c] = from_f<Tout>(v[c]);
     pdl_trigger();
-    *reinterpret_cast<VecT<Tout, 4> *>(out + i * 4) = o;
+    // the copy is physically zero-padded ([B][H + 2 pad][W + 2 pad][4], border written once at creation): the first conv then
+    // needs no bounds checks, which is what lets its im2col rows be expressed as plain (overlapping) TMA boxes
+    const int y = (int)(p / W), xx = (int)(p - (long long)y * W);
+    const long long o_idx = (b * (H + 2 * pad) + y + pad) * (W + 2 * pad) + xx + pad;
+    *reinterpret_cast<VecT<Tout, 4> *>(out + o_idx * 4) = o;
 }
 
 // conv reading internal NHWC activations: cols[M][k*k*C] with k index (ky,kx,c); VEC channels per thread
@@ -423,9 +435,10 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
         e.bias = net->params + Bt.offset; e.bias_mode = 1; e.relu = L.relu; e.tf32_passes = net->tf32_passes;
         if (L.kind == ZOO_LAYER_CONV && L.first_raw && net->obs_nhwc) {
             if (cur_kind == 2) { set_err("conv: first layer expects a raw observation"); return ZOO_BAD_ARG; }
-            const long long pixels = rows * L.ih * L.iw;
+            const int oh_ = net->desc.in_h, ow_ = net->desc.in_w, op_ = (L.ih - oh_) / 2;  // L.ih / L.iw describe the padded copy
+            const long long pixels = rows * oh_ * ow_;
             prof_label("obs2nhwc[%lld]", pixels);
-#define OBS2NHWC(Tin, Tout) obs_to_nhwc4_kernel<Tin, Tout><<<cdiv(pixels, 256), 256, 0, st>>>((const Tin *)cur, (Tout *)net->obs_nhwc_buf, pixels, L.ih * L.iw, L.scale255)
+#define OBS2NHWC(Tin, Tout) obs_to_nhwc4_kernel<Tin, Tout><<<cdiv(pixels, 256), 256, 0, st>>>((const Tin *)cur, (Tout *)net->obs_nhwc_buf, pixels, oh_, ow_, op_, L.scale255)
             if (cur_kind == 0) { if (bf) OBS2NHWC(uint8_t, bf16); else OBS2NHWC(uint8_t, float); }
             else { if (bf) OBS2NHWC(float, bf16); else OBS2NHWC(float, float); }
 #undef OBS2NHWC
@@ -443,7 +456,14 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
             g.mode = raw_conv ? (cur_kind == 0 ? CONV_RAW_U8 : CONV_RAW_F32) : CONV_NHWC;
             if (raw_conv && cur_kind == 2) { set_err("conv: first layer expects a raw observation"); return ZOO_BAD_ARG; }
             // (a raw first conv -- bf16 nets -- keeps the explicit im2col + TMA GEMM path: its register gather is slower)
-            const bool implicit = implicit_conv_enabled() && net->prec != ZOO_PREC_FP32_SIMT && !raw_conv && L.cout >= 8 && tc_conv_supported(g, bf);
+            bool implicit = implicit_conv_enabled() && net->prec != ZOO_PREC_FP32_SIMT && !raw_conv && L.cout >= 8 && tc_conv_supported(g, bf);
+            if (!raw_conv && net->prec != ZOO_PREC_FP32_SIMT && L.cout >= 8 && tma_conv_enabled()) {
+                // preferred: im2col rows fetched by TMA (4-D boxes) -- the producer stays one asynchronous thread
+                ConvGeom gt = g;
+                gt.mode = CONV_TMA;
+                gt.first = (L.first_raw && net->obs_nhwc) ? 1 : 0;
+                if (tc_conv_supported(gt, bf)) { g = gt; implicit = true; }
+            }
             const long long Mc = implicit ? cols_rows * L.opr : M;  // rows of the explicit cols matrix to build
             cudaStream_t sc = st;
             const bool par = implicit && net->side && !g_prof_on;
@@ -696,6 +716,7 @@ static zoo_status parse_chain(zoo_net *net, const zoo_layer *Ls, int n, ParseSta
             L.ow = (S.w + 2 * l.pad - l.ksize) / l.stride + 1;
             ZOO_REQUIRE(L.oh > 0 && L.ow > 0, "%s[%d]: conv output is empty", name, i);
             L.first_raw = S.raw; L.scale255 = S.scale; L.K = (long long)l.ksize * l.ksize * l.n_in; L.opr = (long long)L.oh * L.ow;
+            if (S.raw && net->obs_nhwc) { L.ih += 2 * l.pad; L.iw += 2 * l.pad; L.pad = 0; }  // reads the zero-padded NHWC copy
             TensorInfo w{}; w.kind = 1; w.n_out = l.n_out; w.n_in = l.n_in; w.ksize = l.ksize; w.conv_nhwc = !S.raw || net->obs_nhwc;
             w.count = (long long)l.n_out * L.K;
             TensorInfo b{}; b.kind = 2; b.n_out = l.n_out; b.count = l.n_out;
@@ -908,7 +929,12 @@ zoo_status zoo_net_create(const zoo_net_desc *d, zoo_net **out) {
     ZOO_CUDA(cudaMalloc(&net->ws, net->ws_elems * sizeof(float)));
     ZOO_CUDA(cudaMemset(net->ws, 0, net->ws_elems * sizeof(float)));
     ZOO_CUDA(cudaMalloc(&net->obs, (size_t)rows_a * obs_elems(net) * sizeof(float)));
-    if (net->obs_nhwc) ZOO_CUDA(cudaMalloc(&net->obs_nhwc_buf, (size_t)rows_a * obs_elems(net) * sizeof(float)));
+    if (net->obs_nhwc) {
+        const LayerExec &L0 = net->a.layers.front();
+        const size_t nb = (size_t)rows_a * L0.ih * L0.iw * 4 * sizeof(float);
+        ZOO_CUDA(cudaMalloc(&net->obs_nhwc_buf, nb));
+        ZOO_CUDA(cudaMemset(net->obs_nhwc_buf, 0, nb));  // the zero border is never written again
+    }
     *out = net;
     return ZOO_OK;
 }
