@@ -25,7 +25,10 @@ if mode == "launches":
     for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
         print("%5d launches %9.1f us  %5.1f%%  avg %7.2f us  %s" % (n, t / 1e3, 100 * t / tot, t / n / 1e3, k))
 else:
-    out = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"], text=True, stderr=subprocess.DEVNULL)
+    if path.endswith(".csv"):  # already exported on the GPU box (the .ncu-rep itself can exceed the 64 MiB return limit)
+        out = open(path).read()
+    else:
+        out = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"], text=True, stderr=subprocess.DEVNULL)
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[0]
     want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
