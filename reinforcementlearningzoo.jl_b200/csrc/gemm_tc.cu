@@ -1,764 +1,19 @@
-// tcgen05 GEMM engine for sm_100a.
-//   D(m,n) = sum_k A(m,k) B(n,k), fp32 accumulation in TMEM, three operand modes:
-//     bf16    (EB = 2)        kind::f16  on bf16 operands                          -- ZOO_PREC_BF16
-//     tf32    (EB = 4)        kind::tf32 on fp32 operands, one pass                -- ZOO_PREC_TF32
-//     3xtf32  (EB = 4, X3)    error-compensated: every fp32 operand tile is split in shared memory into
-//                             hi = x & 0xffffe000 and lo = x - hi by the (otherwise idle) epilogue warps and
-//                             the MMA warp issues hi*hi + hi*lo + lo*hi: fp32-grade results -- ZOO_PREC_FP32
-// One 128 x BN output tile (x one K-split) per CTA:
-//   warp 0      TMA producer  (cp.async.bulk.tensor 2D, SWIZZLE_128B, 4-stage mbarrier ring)
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, kind::f16, M=128, N=BN, K=16)
-//   warps 2..5  epilogue: tcgen05.ld 32x32b -> bias / relu / relu' mask / Hadamard -> global (fp32 | bf16 | atomic add)
-// Operands may be K-major ([rows][K]) or MN-major ([K][rows]); the latter is what dgrad (W as [N'][K']) and
-// wgrad (dY and X as [batch rows][features]) need, so no operand is ever transposed in memory.
-// Contractions served: CrossCor-as-GEMM and Dense forward / dgrad / wgrad of the Nature-CNN and the IQN net
-// (reference layers: src/experiments/atari/Dopamine_DQN_Atari.jl:26-35, Dopamine_IQN_Atari.jl:30-44).
+// Host side of the tcgen05 GEMM engine: tensor maps, tiling / split-K policy, dispatch to the per-mode translation units
+// (the kernel itself lives in gemm_tc.cuh).
 #include <algorithm>
 #include <mutex>
 
-#include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace zoo {
 
-static constexpr int BM = 128;      // UMMA M (cta_group::1)
-// per stage: one 128-byte swizzle span of K per row -> BK = 128 / EB elements, 4 MMAs of K = 32 / EB each
-static constexpr int TC_THREADS = 192;
-static constexpr int X3_CHAIN_KB = 4;         // 3xTF32: K-blocks (of 32 floats) per TMEM accumulation chain (see the kernel)
-static constexpr int TC_WS_COUNTERS = 4096;  // tail of the split-K workspace: per-tile arrival counters
-
-// ---------------------------------------------------------------- PTX wrappers ------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in [0,14),
-// leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version = 1 in [46,48),
-// layout type SWIZZLE_128B = 2 in [61,64).
-// 32-bit MN-major operands must use SWIZZLE_128B_BASE32B = 1 (32-byte swizzle atoms, pattern period 4 rows).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)layout_type << 61;
-    return d;
-}
-
-// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 at [4,6), a/b format BF16 = 1 at [7,10)/[10,13),
-// a_major at 15, b_major at 16 (0 = K-major, 1 = MN-major), N >> 3 at [17,23), M >> 4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, uint32_t fmt /*1 = BF16, 2 = TF32*/) {
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-
-struct TcParams {
-    int M, N, K;
-    int kb_per_split;  // K blocks (of 128 bytes of K) per grid.z slice
-    Epilogue epi;
-    float *ws;      // split-K workspace [M][N] (atomic accumulate, kept all-zero between launches) or nullptr
-    unsigned *ctr;  // split-K per-tile arrival counters (kept all-zero between launches)
-    unsigned long long *dbg;  // test hook: CTA 0 writes %globaltimer at its phase boundaries (nullptr = off)
-    ConvGeom conv;  // GA kernels only: how the A operand is gathered
-};
-
 unsigned long long *g_tc_dbg = nullptr;  // set by zoo_test_gemm_trace
 
-__device__ __forceinline__ void dbg_stamp(const TcParams &P, int slot) {
-    if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        P.dbg[slot] = t;
-    }
-}
-
-// EB: operand element bytes (2 = bf16, 4 = fp32 consumed as tf32).  X3: 3xTF32 split (EB = 4 only).
-// smem per stage: A tile 128 rows x 128 B (16 KB) + B tile BN rows x 128 B; X3 doubles it for the lo tiles.
-template <int EB, int BN, bool X3>
-struct TcCfg {
-    static constexpr int BK = 128 / EB;          // K elements per stage
-    static constexpr int UMMA_K = 32 / EB;       // K elements per tcgen05.mma
-    static constexpr int MN_BOX = 128 / EB;      // MN elements per 128-byte row of an MN-major box
-    static constexpr int BOX_BYTES = BK * 128;   // one MN-major box: BK k-rows x 128 B
-    static constexpr int KSTEP_MN = UMMA_K * 128;  // MN-major: one 128-byte row per k
-    // MN-major swizzle atoms: bf16 -> 8 k-rows (SWIZZLE_128B); fp32 -> 4 k-rows (SWIZZLE_128B_BASE32B, the only
-    // MN-major layout tcgen05 accepts for 32-bit operands)
-    static constexpr int MN_SBO = EB == 2 ? 1024 : 512;
-    static constexpr int MN_LAYOUT = EB == 2 ? 2 : 1;
-    static constexpr int A_BYTES = BM * 128;
-    static constexpr int B_BYTES = BN * 128;
-    static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGE_BYTES = RAW_BYTES * (X3 ? 2 : 1);
-    // bf16 / tf32: two CTAs per SM (<= ~97 KB each); 3xTF32 owns an SM (TMA -> split -> MMA needs the deeper ring)
-    static constexpr int STAGES = X3 ? (BN >= 128 ? 3 : 4) : (BN >= 128 ? 3 : 4);
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 256 /*barriers*/;
-    static constexpr int TMEM_COLS = X3 ? 2 * BN : (BN < 32 ? 32 : BN);  // 3xTF32: two accumulators (chains alternate)
-};
-
-template <int EB>
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
-    if (EB == 2) umma_bf16(tmem_d, ad, bd, idesc, acc);
-    else umma_tf32(tmem_d, ad, bd, idesc, acc);
-}
-
-// Implicit-GEMM gather, split in two so the (row-independent) index arithmetic is done once per K-block by 8 lanes:
-//   conv_decode: K index of a 16-byte chunk -> (ky, kx, channel offset), or c < 0 past the end of K
-//   conv_fetch : that chunk of one tile row (CH = 16 / EB consecutive K elements), zero outside the image
-struct ConvTap { int ky, kx, c; };
-
-__device__ __forceinline__ ConvTap conv_decode(const ConvGeom &g, int kk, int Ktot) {
-    ConvTap t;
-    if (kk >= Ktot) { t.ky = 0; t.kx = 0; t.c = -1; return t; }
-    if (g.mode == CONV_NHWC || g.mode == CONV_DGRAD) {
-        const int cw = g.mode == CONV_NHWC ? g.C : g.Cout;
-        const int tap = kk / cw;
-        t.c = kk - tap * cw;
-        t.ky = tap / g.ks;
-        t.kx = tap - t.ky * g.ks;
-    } else {  // raw observation: K order (c, ky, kx); ks % CH == 0 keeps a chunk inside one kernel row
-        const int kk2 = g.ks * g.ks;
-        t.c = kk / kk2;
-        const int rem = kk - t.c * kk2;
-        t.ky = rem / g.ks;
-        t.kx = rem - t.ky * g.ks;
-    }
-    return t;
-}
-
-template <int EB>
-__device__ __forceinline__ uint4 conv_fetch(const ConvGeom &g, bool valid, int b, int y0, int x0, const ConvTap t) {
-    constexpr int CH = 16 / EB;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (!valid || t.c < 0) return val;
-    if (g.mode == CONV_NHWC) {
-        const int iy = y0 + t.ky, ix = x0 + t.kx;
-        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
-            val = __ldg(reinterpret_cast<const uint4 *>((const uint8_t *)g.x + ((((long long)b * g.H + iy) * g.W + ix) * g.C + t.c) * EB));
-    } else if (g.mode == CONV_DGRAD) {
-        const int ty = y0 + g.p - t.ky, tx = x0 + g.p - t.kx;  // y0, x0 = input pixel
-        if (ty >= 0 && tx >= 0) {
-            const int oy = g.s == 1 ? ty : (g.s == 2 ? ty >> 1 : ty / g.s), ox = g.s == 1 ? tx : (g.s == 2 ? tx >> 1 : tx / g.s);
-            if (oy * g.s == ty && ox * g.s == tx && oy < g.OH && ox < g.OW)
-                val = __ldg(reinterpret_cast<const uint4 *>((const uint8_t *)g.x + ((((long long)b * g.OH + oy) * g.OW + ox) * g.Cout + t.c) * EB));
-        }
-    } else {
-        const int iy = y0 + t.ky;
-        if (iy >= 0 && iy < g.H) {
-            const long long rowoff = (((long long)b * g.C + t.c) * g.H + iy) * g.W;
-            float f[CH];
-#pragma unroll
-            for (int e = 0; e < CH; ++e) {
-                const int ix = x0 + t.kx + e;
-                float v = 0.f;
-                if (ix >= 0 && ix < g.W) {
-                    v = g.mode == CONV_RAW_U8 ? (float)__ldg((const uint8_t *)g.x + rowoff + ix) : __ldg((const float *)g.x + rowoff + ix);
-                    if (g.scale255) v = __fdiv_rn(v, 255.f);
-                }
-                f[e] = v;
-            }
-            if (EB == 4) {
-                val = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
-            } else {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1 % CH]), h1 = __floats2bfloat162_rn(f[2 % CH], f[3 % CH]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4 % CH], f[5 % CH]), h3 = __floats2bfloat162_rn(f[6 % CH], f[7 % CH]);
-                val = make_uint4(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1), *reinterpret_cast<uint32_t *>(&h2),
-                                 *reinterpret_cast<uint32_t *>(&h3));
-            }
-        }
-    }
-    return val;
-}
-
-// global address of a chunk for the cp.async path (NHWC / DGRAD modes), nullptr = zero fill
-template <int EB>
-__device__ __forceinline__ const void *conv_src(const ConvGeom &g, bool valid, int b, int y0, int x0, const ConvTap t) {
-    if (!valid || t.c < 0) return nullptr;
-    if (g.mode == CONV_NHWC) {
-        const int iy = y0 + t.ky, ix = x0 + t.kx;
-        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) return (const uint8_t *)g.x + ((((long long)b * g.H + iy) * g.W + ix) * g.C + t.c) * EB;
-        return nullptr;
-    }
-    const int ty = y0 + g.p - t.ky, tx = x0 + g.p - t.kx;  // DGRAD: y0, x0 = input pixel
-    if (ty < 0 || tx < 0) return nullptr;
-    const int oy = g.s == 1 ? ty : (g.s == 2 ? ty >> 1 : ty / g.s), ox = g.s == 1 ? tx : (g.s == 2 ? tx >> 1 : tx / g.s);
-    if (oy * g.s != ty || ox * g.s != tx || oy >= g.OH || ox >= g.OW) return nullptr;
-    return (const uint8_t *)g.x + ((((long long)b * g.OH + oy) * g.OW + ox) * g.Cout + t.c) * EB;
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, const void *fallback) {
-    const int n = src ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src ? src : fallback), "r"(n) : "memory");
-}
-
-// all 8 chunks of this thread's tile row for the K-block starting at k0 (lanes j and j+8.. decode chunk j & 7 and share it)
-template <int EB>
-__device__ __forceinline__ void conv_gather_row(const ConvGeom &g, bool valid, int b, int y0, int x0, int k0, int Ktot, int lane, uint4 (&v)[8]) {
-    const ConvTap mine = conv_decode(g, k0 + (lane & 7) * (16 / EB), Ktot);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        ConvTap t;
-        t.ky = __shfl_sync(0xffffffffu, mine.ky, j);
-        t.kx = __shfl_sync(0xffffffffu, mine.kx, j);
-        t.c = __shfl_sync(0xffffffffu, mine.c, j);
-        v[j] = conv_fetch<EB>(g, valid, b, y0, x0, t);
-    }
-}
-
-__device__ __forceinline__ uint4 tf32_lo(const uint4 v) {
-    uint4 l;
-    l.x = __float_as_uint(__fsub_rn(__uint_as_float(v.x), __uint_as_float(v.x & 0xffffe000u)));
-    l.y = __float_as_uint(__fsub_rn(__uint_as_float(v.y), __uint_as_float(v.y & 0xffffe000u)));
-    l.z = __float_as_uint(__fsub_rn(__uint_as_float(v.z), __uint_as_float(v.z & 0xffffe000u)));
-    l.w = __float_as_uint(__fsub_rn(__uint_as_float(v.w), __uint_as_float(v.w & 0xffffe000u)));
-    return l;
-}
-
-// GA = 1: the A operand is gathered by warps 2..5 (implicit-GEMM convolution, see ConvGeom) instead of TMA-loaded.
-// GA = 2: implicit-GEMM convolution with the im2col rows fetched by TMA itself: one M tile = R whole output rows of one
-//         image, one K-block = one kernel tap (or kernel row), loaded as a single 4-D box of the NHWC activation tensor
-//         (element strides = conv stride, out-of-bounds = zero padding).
-template <int EB, int BN, bool A_K, bool B_K, bool X3, int GA = 0>
-__global__ void __launch_bounds__(TC_THREADS)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
-    static_assert(GA == 0 || A_K, "the gathered A operand is K-major");
-    using C = TcCfg<EB, BN, X3>;
-    // SWIZZLE_128B tiles need 1024-byte alignment; declaring it on the array (instead of rounding the pointer up) keeps
-    // the shared address space visible to the compiler, so the epilogue staging below compiles to LDS/STS
-    extern __shared__ __align__(1024) uint8_t smem[];
-    if ((smem_u32(smem) & 1023u) != 0u) __trap();
-    uint64_t *full_bar = (uint64_t *)(smem + C::STAGES * C::STAGE_BYTES);
-    uint64_t *empty_bar = full_bar + C::STAGES;
-    uint64_t *conv_bar = empty_bar + C::STAGES;  // X3: lo tiles written (128 converter threads arrive)
-    uint64_t *acc_full = conv_bar + C::STAGES;   // [2] accumulator buffer b holds a finished chain (tcgen05.commit)
-    uint64_t *acc_empty = acc_full + 2;          // [2] buffer b has been drained to registers (128 threads arrive)
-    uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int m0 = blockIdx.x * BM, vrows = min(BM, P.M - (int)blockIdx.x * BM);  // first output row / valid rows of this M tile
-    int cimg = 0, coy0 = 0;
-    if (GA == 2) {
-        cimg = blockIdx.x / P.conv.tpi;
-        coy0 = (blockIdx.x - cimg * P.conv.tpi) * P.conv.R;
-        m0 = (cimg * P.conv.OH + coy0) * P.conv.OW;
-        vrows = min(P.conv.R, P.conv.OH - coy0) * P.conv.OW;
-    }
-    const int n0 = blockIdx.y * BN;
-    if (threadIdx.x == 0) dbg_stamp(P, 0);
-    const int total_kb = (P.K + C::BK - 1) / C::BK;
-    const int kb0 = blockIdx.z * P.kb_per_split;
-    const int kb1 = min(total_kb, kb0 + P.kb_per_split);
-    const int nkb = kb1 - kb0;  // host guarantees >= 1
-    // 3xTF32: the K loop is cut into chains of CHAIN K-blocks that alternate between two TMEM accumulators; the
-    // converter warps sum finished chains in registers with round-to-nearest fp32 adds, because a TMEM accumulator
-    // truncates on every add and that bias grows with the chain length.  Other modes: one chain, one accumulator.
-    constexpr int CHAIN = X3 ? X3_CHAIN_KB : (1 << 30);
-    const int nchains = (nkb + CHAIN - 1) / CHAIN;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < C::STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-            mbar_init(&conv_bar[s], 128);
-        }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 128);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    if (threadIdx.x == 0) dbg_stamp(P, 1);
-    pdl_wait();  // everything above ran under the predecessor's tail; from here on global memory is touched
-
-    if (warp == 0) {
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % C::STAGES;
-                const uint32_t ph = (i / C::STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t *sa = smem + s * C::STAGE_BYTES;
-                uint8_t *sb = sa + C::A_BYTES;
-                mbar_expect_tx(&full_bar[s], GA == 1 ? C::B_BYTES : (GA == 2 ? P.conv.R * P.conv.OW * 128 + C::B_BYTES : C::RAW_BYTES));
-                const int k0 = (kb0 + i) * C::BK;
-                if (GA == 2) {
-                    const ConvGeom &g = P.conv;
-                    const int kb = kb0 + i;
-                    int c0, c1, c2;
-                    if (g.first) { c0 = 0; c1 = 0; c2 = coy0 * g.s + kb; }  // K-block = kernel row ky of the padded frame stack
-                    else {
-                        const int tap = kb / g.cblocks, ky = tap / g.ks, kx = tap - ky * g.ks;
-                        c0 = (kb - tap * g.cblocks) * C::BK; c1 = kx - g.p; c2 = coy0 * g.s + ky - g.p;
-                    }
-                    asm volatile(
-                        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                        ::"r"(smem_u32(sa)), "l"(&tmA), "r"(smem_u32(&full_bar[s])), "r"(c0), "r"(c1), "r"(c2), "r"(cimg)
-                        : "memory");
-                }
-                if (GA == 0) {
-                    if (A_K) {
-                        tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box {BK k, 128 rows}
-                    } else {
-#pragma unroll
-                        for (int h = 0; h < BM / C::MN_BOX; ++h)  // boxes {MN_BOX m, BK k}
-                            tma_load_2d(sa + h * C::BOX_BYTES, &tmA, &full_bar[s], m0 + h * C::MN_BOX, k0);
-                    }
-                }
-                if (B_K) {
-                    tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box {BK k, BN rows}
-                } else {
-                    // conv dgrad: K runs over (tap, o); tap t's [Cout][C] slice of W sits at column offset t*C of [Cout][ks*ks*C]
-                    int nb = n0, kb = k0;
-                    if (GA == 1) { const int tap = k0 / P.conv.Cout; nb = n0 + tap * P.conv.C; kb = k0 - tap * P.conv.Cout; }
-#pragma unroll
-                    for (int h = 0; h < BN / C::MN_BOX; ++h)
-                        tma_load_2d(sb + h * C::BOX_BYTES, &tmB, &full_bar[s], nb + h * C::MN_BOX, kb);
-                }
-                if (i == 0) dbg_stamp(P, 2);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN, !A_K, !B_K, EB == 2 ? 1u : 2u);
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % C::STAGES;
-                const uint32_t ph = (i / C::STAGES) & 1;
-                const int chain = i / CHAIN, cb = chain & 1;
-                const bool chain_start = (i % CHAIN) == 0;
-                if (X3 && chain_start && chain >= 2) {  // the buffer's previous chain must have been drained
-                    mbar_wait(&acc_empty[cb], ((chain >> 1) - 1) & 1);
-                    tc_fence_after();
-                }
-                if (X3 || GA == 1) mbar_wait(&conv_bar[s], ph);  // converter / gather warps are done with the stage
-                if (!X3) mbar_wait(&full_bar[s], ph);       // TMA bytes have landed (the 3xTF32 converters waited for them)
-                tc_fence_after();
-                if (i == 0) dbg_stamp(P, 3);
-                const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
-                const uint32_t sb = sa + C::A_BYTES;
-                const uint32_t td = tmem_base + (uint32_t)(cb * BN);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // K-major SW128: 8-row groups 1024 B apart (SBO); one MMA's K slice = 32 B inside the swizzle span.
-                    // MN-major SW128: MN blocks of 128 B BOX_BYTES apart (LBO), 8-k groups 1024 B apart (SBO).
-                    const uint32_t ao = A_K ? k * 32 : k * C::KSTEP_MN;
-                    const uint32_t bo = B_K ? k * 32 : k * C::KSTEP_MN;
-                    const uint64_t ad = A_K ? make_smem_desc(sa + ao, 16, 1024) : make_smem_desc(sa + ao, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
-                    const uint64_t bd = B_K ? make_smem_desc(sb + bo, 16, 1024) : make_smem_desc(sb + bo, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
-                    if (X3) {
-                        // lo tiles live RAW_BYTES above the (in-place truncated) hi tiles, same layout; small terms first
-                        const uint64_t adl = A_K ? make_smem_desc(sa + C::RAW_BYTES + ao, 16, 1024)
-                                                 : make_smem_desc(sa + C::RAW_BYTES + ao, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
-                        const uint64_t bdl = B_K ? make_smem_desc(sb + C::RAW_BYTES + bo, 16, 1024)
-                                                 : make_smem_desc(sb + C::RAW_BYTES + bo, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
-                        umma<EB>(td, ad, bdl, idesc, !(chain_start && k == 0));
-                        umma<EB>(td, adl, bd, idesc, 1);
-                        umma<EB>(td, ad, bd, idesc, 1);
-                    } else {
-                        umma<EB>(td, ad, bd, idesc, (i | k) != 0);
-                    }
-                }
-                umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
-                if ((i % CHAIN) == CHAIN - 1 || i == nkb - 1) umma_commit(&acc_full[cb]);  // chain complete
-            }
-            dbg_stamp(P, 4);
-        }
-    } else {
-        // warps 2..5: TMEM lane quadrant = warp % 4, thread = accumulator row.
-        const int q = warp & 3;
-        const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
-        float acc[X3 ? BN : 1];  // running fp32 sum of the drained chains (3xTF32 only)
-        if (X3) {
-#pragma unroll
-            for (int j = 0; j < BN; ++j) acc[j] = 0.f;
-        }
-        if (X3 || GA == 1) {
-            // per K-block: (GA) gather this thread's A row into the stage -- hi and, for 3xTF32, lo -- and (3xTF32) split the
-            // TMA-landed fp32 tiles into hi (the tile itself) and lo; one chain behind the MMA warp, fold finished chains
-            // into acc
-            const int t = threadIdx.x - 64;  // 0..127
-            int drained = 0;
-            const int va = vrows, vb = min(BN, P.N - n0);  // valid rows of the A / B tiles
-            const int a_units = GA == 1 ? 0 : (A_K ? va * 128 : ((va + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
-            const int b_units = (B_K ? vb * 128 : ((vb + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
-            const int conv_units = a_units + b_units;
-            // GA: this thread owns tile row t = output pixel (forward) / input pixel (dgrad) m0 + t
-            bool gvalid = false;
-            int gb = 0, gy0 = 0, gx0 = 0;
-            constexpr int GA_AHEAD = C::STAGES - 2;  // K-blocks of cp.async gathers in flight ahead of the one being finished
-            if (GA == 1) {
-                const ConvGeom &g = P.conv;
-                const int m = m0 + t;
-                gvalid = m < P.M;
-                const int gw = g.mode == CONV_DGRAD ? g.W : g.OW, gh = g.mode == CONV_DGRAD ? g.H : g.OH;
-                const int px = m % gw, tmp = m / gw;
-                const int py = tmp % gh;
-                gb = tmp / gh;
-                gy0 = g.mode == CONV_DGRAD ? py : py * g.s - g.p;
-                gx0 = g.mode == CONV_DGRAD ? px : px * g.s - g.p;
-            }
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % C::STAGES;
-                const uint32_t ph = (i / C::STAGES) & 1;
-                uint8_t *stage = smem + s * C::STAGE_BYTES;
-                if (GA == 1) {
-                    if (P.conv.mode == CONV_NHWC || P.conv.mode == CONV_DGRAD) {
-                        // cp.async pipeline: the 16-byte chunks of K-block i+GA_AHEAD go straight from global memory into their
-                        // swizzled slots (zero-filled outside the image) while block i, issued GA_AHEAD iterations ago, lands
-                        for (int ib = (i == 0 ? 0 : i + GA_AHEAD); ib <= i + GA_AHEAD; ++ib) {
-                            if (ib < nkb) {
-                                const int sI = ib % C::STAGES;
-                                mbar_wait(&empty_bar[sI], ((ib / C::STAGES) & 1) ^ 1);  // MMAs on the stage's old contents retired
-                                const uint32_t sbase = smem_u32(smem + sI * C::STAGE_BYTES) + t * 128;
-                                const ConvTap mine = conv_decode(P.conv, (kb0 + ib) * C::BK + (lane & 7) * (16 / EB), P.K);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    ConvTap tp;
-                                    tp.ky = __shfl_sync(0xffffffffu, mine.ky, j);
-                                    tp.kx = __shfl_sync(0xffffffffu, mine.kx, j);
-                                    tp.c = __shfl_sync(0xffffffffu, mine.c, j);
-                                    cp_async16(sbase + ((j ^ (t & 7)) << 4), conv_src<EB>(P.conv, gvalid, gb, gy0, gx0, tp), P.conv.x);
-                                }
-                            }
-                            asm volatile("cp.async.commit_group;" ::: "memory");  // one group per K-block, empty past the end
-                        }
-                        asm volatile("cp.async.wait_group %0;" ::"n"(GA_AHEAD) : "memory");  // block i's own chunks have landed
-                        if (X3) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int off = t * 128 + (j << 4);
-                                *reinterpret_cast<uint4 *>(stage + C::RAW_BYTES + off) = tf32_lo(*reinterpret_cast<const uint4 *>(stage + off));
-                            }
-                        }
-                    } else {
-                        uint4 gcur[8];
-                        conv_gather_row<EB>(P.conv, gvalid, gb, gy0, gx0, (kb0 + i) * C::BK, P.K, lane, gcur);
-                        mbar_wait(&empty_bar[s], ph ^ 1);  // the MMAs that read this stage's previous contents have retired
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int off = t * 128 + ((j ^ (t & 7)) << 4);  // SWIZZLE_128B: chunk j of row t sits at j ^ (t % 8)
-                            *reinterpret_cast<uint4 *>(stage + off) = gcur[j];
-                            if (X3) *reinterpret_cast<uint4 *>(stage + C::RAW_BYTES + off) = tf32_lo(gcur[j]);
-                        }
-                    }
-                }
-                if (X3) {
-                    mbar_wait(&full_bar[s], ph);
-                    // tcgen05 kind::tf32 ignores the low 13 mantissa bits of an fp32 operand (measured: bit-identical results
-                    // for raw and pre-truncated inputs), so the landed tile itself is the hi operand; only lo = x - trunc(x)
-                    // is written.  Rows past M / N are never stored, so they are skipped.
-                    const uint4 *raw = reinterpret_cast<const uint4 *>(stage);
-                    uint4 *lo = reinterpret_cast<uint4 *>(stage + C::RAW_BYTES);
-#pragma unroll 4
-                    for (int j = t; j < conv_units; j += 128) {
-                        const int jj = j < a_units ? j : j - a_units + C::A_BYTES / 16;
-                        lo[jj] = tf32_lo(raw[jj]);
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
-                mbar_arrive(&conv_bar[s]);
-                // chain `drained` ended at K-block (drained+1)*CHAIN - 1; by the time two more blocks have been converted
-                // its MMAs have retired, so the wait below does not stall the conversion pipeline
-                if (X3 && drained < nchains - 1 && i + 1 >= (drained + 1) * CHAIN + 2) {
-                    const int cb = drained & 1;
-                    mbar_wait(&acc_full[cb], (drained >> 1) & 1);
-                    tc_fence_after();
-#pragma unroll
-                    for (int c = 0; c < BN; c += 32) {
-                        uint32_t r[32];
-                        tmem_ld32(tq + (uint32_t)(cb * BN + c), r);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[X3 ? c + j : 0] = __fadd_rn(acc[X3 ? c + j : 0], __uint_as_float(r[j]));
-                    }
-                    tc_fence_before();
-                    mbar_arrive(&acc_empty[cb]);
-                    ++drained;
-                }
-            }
-            for (; X3 && drained < nchains - 1; ++drained) {  // chains whose delayed drain slot never came (short tail)
-                const int cb = drained & 1;
-                mbar_wait(&acc_full[cb], (drained >> 1) & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int c = 0; c < BN; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tq + (uint32_t)(cb * BN + c), r);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[X3 ? c + j : 0] = __fadd_rn(acc[X3 ? c + j : 0], __uint_as_float(r[j]));
-                }
-                tc_fence_before();
-                mbar_arrive(&acc_empty[cb]);
-            }
-        }
-        // epilogue.  Each warp pulls 32 x 32 chunks of the last chain's accumulator, adds the register sums, transposes
-        // the chunk through shared memory (the pipeline stages are idle once the last chain has been committed) and then
-        // walks the rows with lane = column, so every global access below is one coalesced 128-byte row segment.
-        const int lastc = nchains - 1, lb = lastc & 1;
-        mbar_wait(&acc_full[lb], (lastc >> 1) & 1);
-        tc_fence_after();
-        pdl_trigger();  // main loop done: the next kernel may become resident and run its prologue under this epilogue
-        if (threadIdx.x == 64) dbg_stamp(P, 5);
-        float(*stg)[33] = reinterpret_cast<float(*)[33]>(smem) + q * 32;  // 32 x 33 floats per warp, in pipeline stage 0
-        const int row0 = m0 + q * 32;
-        const int rows = max(0, min(32, vrows - q * 32));
-        // the epilogue description is copied out of the parameter bank once: re-reading it per row costs a chain of
-        // uniform constant loads per store (measured 100 ns per row)
-        const Epilogue e = P.epi;
-        const bool split = P.ws != nullptr;
-        float *const ws = P.ws;
-        const int Nn = P.N;
-        const int bias_mode = e.bias_mode, relu = e.relu, out_bf16 = e.out_bf16;
-        const long long sm = e.sm, sn = e.sn;
-        const bool simple = !e.rowmul;
-        const bool trans = simple && sm == 1 && sn != 1;
-        const void *const maskp = e.mask;
-        const int mask_bf16 = e.mask_bf16;
-        const long long msm = e.mask_sm, msn = e.mask_sn;
-        // bf16 output, plain row-major store: 64 columns at a time so that every lane writes a packed bf16x2 (128-byte row
-        // segments instead of 64-byte ones) -- the wide, K-short GEMMs (IQN phi: K = 64, 0.5 GB of output) are store-bound
-        if (BN >= 64 && !X3 && simple && !trans && !split && !e.accumulate && out_bf16 && sn == 1 && (Nn & 1) == 0 && (sm & 1) == 0 &&
-            (!maskp || (mask_bf16 && msn == 1 && (msm & 1) == 0))) {
-            float(*stw)[66] = reinterpret_cast<float(*)[66]>(smem) + q * 32;  // 32 x 66 floats per warp (spans idle stages)
-#pragma unroll
-            for (int c = 0; c < BN; c += 64) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t r[32];
-                    tmem_ld32(tq + (uint32_t)(lb * BN + c + 32 * h), r);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) stw[lane][32 * h + j] = __uint_as_float(r[j]);
-                }
-                __syncwarp();
-                const int n = n0 + c + 2 * lane;
-                if (n < Nn) {
-                    float b0 = 0.f, b1 = 0.f;
-                    if (bias_mode == 1) { b0 = __ldg(e.bias + n); b1 = __ldg(e.bias + n + 1); }
-                    __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>((bf16 *)e.out + (long long)row0 * sm + n);
-                    const __nv_bfloat162 *mp = maskp ? reinterpret_cast<const __nv_bfloat162 *>((const bf16 *)maskp + (long long)row0 * msm + n) : nullptr;
-#pragma unroll 8
-                    for (int rr = 0; rr < rows; ++rr) {
-                        const float2 v2 = *reinterpret_cast<const float2 *>(&stw[rr][2 * lane]);
-                        float v0 = v2.x + b0, v1 = v2.y + b1;
-                        if (bias_mode == 2) { const float bm = __ldg(e.bias + row0 + rr); v0 += bm; v1 += bm; }
-                        if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                        if (mp) {
-                            const __nv_bfloat162 mk = __ldg(mp + (long long)rr * (msm >> 1));
-                            v0 = __low2float(mk) > 0.f ? v0 : 0.f;
-                            v1 = __high2float(mk) > 0.f ? v1 : 0.f;
-                        }
-                        op[(long long)rr * (sm >> 1)] = __floats2bfloat162_rn(v0, v1);
-                    }
-                }
-                __syncwarp();
-            }
-        } else
-#pragma unroll
-        for (int c = 0; c < BN; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(tq + (uint32_t)(lb * BN + c), r);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float v = __uint_as_float(r[j]);
-                if (X3) v = __fadd_rn(v, acc[X3 ? c + j : 0]);
-                stg[lane][j] = v;
-            }
-            __syncwarp();
-            const int n = n0 + c + lane;
-            if (trans && !split && !e.accumulate) {
-                // transposed output (swap-AB dispatch: consecutive m are contiguous in memory): lane = tile row
-                const int m = row0 + lane;
-                const int ncols = min(32, Nn - (n0 + c));
-                if (lane < rows) {
-                    const float bm = bias_mode == 2 ? __ldg(e.bias + m) : 0.f;
-#pragma unroll 8
-                    for (int cc = 0; cc < ncols; ++cc) {
-                        const int nn = n0 + c + cc;
-                        float v = stg[lane][cc] + bm;
-                        if (bias_mode == 1) v += __ldg(e.bias + nn);
-                        if (relu) v = fmaxf(v, 0.f);
-                        if (maskp) v = ldg_elem(maskp, mask_bf16, (long long)m * msm + (long long)nn * msn) > 0.f ? v : 0.f;
-                        st_elem(e.out, out_bf16, (long long)m * sm + (long long)nn * sn, v);
-                    }
-                }
-            } else if (n < Nn) {
-                if (split) {
-                    float *wp = ws + (long long)row0 * Nn + n;
-#pragma unroll 8
-                    for (int rr = 0; rr < rows; ++rr) atomicAdd(wp + (long long)rr * Nn, stg[rr][lane]);
-                } else if (e.accumulate) {
-                    float *op = (float *)e.out + (long long)row0 * sm + (long long)n * sn;
-#pragma unroll 8
-                    for (int rr = 0; rr < rows; ++rr) atomicAdd(op + (long long)rr * sm, stg[rr][lane]);
-                } else if (simple && !trans) {
-                    const float bv = bias_mode == 1 ? __ldg(e.bias + n) : 0.f;
-                    if (out_bf16) {
-                        bf16 *op = (bf16 *)e.out + (long long)row0 * sm + (long long)n * sn;
-#pragma unroll 8
-                        for (int rr = 0; rr < rows; ++rr) {
-                            float v = stg[rr][lane] + bv;
-                            if (bias_mode == 2) v += __ldg(e.bias + row0 + rr);
-                            if (relu) v = fmaxf(v, 0.f);
-                            if (maskp) v = ldg_elem(maskp, mask_bf16, (long long)(row0 + rr) * msm + (long long)n * msn) > 0.f ? v : 0.f;
-                            op[(long long)rr * sm] = __float2bfloat16_rn(v);
-                        }
-                    } else {
-                        float *op = (float *)e.out + (long long)row0 * sm + (long long)n * sn;
-#pragma unroll 8
-                        for (int rr = 0; rr < rows; ++rr) {
-                            float v = stg[rr][lane] + bv;
-                            if (bias_mode == 2) v += __ldg(e.bias + row0 + rr);
-                            if (relu) v = fmaxf(v, 0.f);
-                            if (maskp) v = ldg_elem(maskp, mask_bf16, (long long)(row0 + rr) * msm + (long long)n * msn) > 0.f ? v : 0.f;
-                            op[(long long)rr * sm] = v;
-                        }
-                    }
-                } else {
-#pragma unroll 4
-                    for (int rr = 0; rr < rows; ++rr) epi_store(e, stg[rr][lane], row0 + rr, n);
-                }
-            }
-            __syncwarp();
-        }
-        if (split) {
-            // split-K without a finishing launch: the last CTA to arrive on this output tile (per-tile counter behind the
-            // workspace) applies the epilogue to the summed tile and leaves workspace + counter zeroed for the next GEMM.
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            unsigned *ctr = P.ctr + blockIdx.y * gridDim.x + blockIdx.x;
-            if (threadIdx.x == 64) {
-                const unsigned old = atomicAdd(ctr, 1u);
-                const bool last = old == gridDim.z - 1;
-                if (last) *ctr = 0u;
-                *tmem_slot = last ? 1u : 0u;  // tmem_slot is dead after tmem_base was read
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (*tmem_slot) {
-                __threadfence();
-#pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
-                    const int n = n0 + c + lane;
-                    if (n >= Nn) break;
-                    const float bv = bias_mode == 1 ? __ldg(e.bias + n) : 0.f;
-                    // 16 rows at a time: all loads first (the compiler must not be left to order each load behind the
-                    // previous row's store -- that serialises 128 x BN / 128 L2 round trips, measured +25 us)
-#pragma unroll 1
-                    for (int r8 = 0; r8 < rows; r8 += 16) {
-                        float v[16];
-#pragma unroll
-                        for (int u = 0; u < 16; ++u) v[u] = r8 + u < rows ? __ldcg(ws + (long long)(row0 + r8 + u) * Nn + n) : 0.f;
-#pragma unroll
-                        for (int u = 0; u < 16; ++u)
-                            if (r8 + u < rows) __stcg(ws + (long long)(row0 + r8 + u) * Nn + n, 0.f);
-#pragma unroll
-                        for (int u = 0; u < 16; ++u) {
-                            if (r8 + u >= rows) continue;
-                            const int m = row0 + r8 + u;
-                            if (simple) {
-                                float x = v[u] + bv;
-                                if (bias_mode == 2) x += __ldg(e.bias + m);
-                                if (relu) x = fmaxf(x, 0.f);
-                                if (maskp) x = ldg_elem(maskp, mask_bf16, (long long)m * msm + (long long)n * msn) > 0.f ? x : 0.f;
-                                st_elem(e.out, out_bf16, (long long)m * sm + (long long)n * sn, x);
-                            } else {
-                                epi_store(e, v[u], m, n);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-    }
-    if (threadIdx.x == 64) dbg_stamp(P, 6);
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) dbg_stamp(P, 7);
-    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
-    if (threadIdx.x == 32) dbg_stamp(P, 8);
+static zoo_status tc_launch(int eb, bool x3, int kind, int BN, bool ak, bool bk, const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P,
+                            dim3 grid, cudaStream_t st) {
+    if (eb == 2) return tc_launch_bf16(kind, BN, ak, bk, tmA, tmB, P, grid, st);
+    if (x3) return tc_launch_x3(kind, BN, ak, bk, tmA, tmB, P, grid, st);
+    return tc_launch_tf32(kind, BN, ak, bk, tmA, tmB, P, grid, st);
 }
 
 // ---------------------------------------------------------------- host side ---------------
@@ -827,42 +82,6 @@ bool tc_gemm_supported(const Operand &A, const Operand &B, int M, int N, int K) 
     return true;
 }
 
-template <int EB, int BN, bool A_K, bool B_K, bool X3>
-static zoo_status launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid, cudaStream_t st) {
-    using C = TcCfg<EB, BN, X3>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr_set = true;
-    }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, grid, dim3(TC_THREADS), (size_t)C::SMEM, st, tmA, tmB, P));
-    ZOO_LAUNCH_CHECK();
-    return ZOO_OK;
-}
-
-template <int EB, int BN, bool X3>
-static zoo_status launch_tc_major(bool ak, bool bk, const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid,
-                                  cudaStream_t st) {
-    if (ak && bk) return launch_tc<EB, BN, true, true, X3>(tmA, tmB, P, grid, st);
-    if (ak && !bk) return launch_tc<EB, BN, true, false, X3>(tmA, tmB, P, grid, st);
-    if (!ak && bk) return launch_tc<EB, BN, false, true, X3>(tmA, tmB, P, grid, st);
-    return launch_tc<EB, BN, false, false, X3>(tmA, tmB, P, grid, st);
-}
-
-template <int EB, bool X3>
-static zoo_status launch_tc_bn(int BN, bool ak, bool bk, const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid,
-                               cudaStream_t st) {
-    if (BN == 32) {
-        if (EB == 2) {  // bf16 MN-major boxes are 64 wide: BN = 32 only with a K-major B
-            if (ak) return launch_tc<EB, 32, true, true, X3>(tmA, tmB, P, grid, st);
-            return launch_tc<EB, 32, false, true, X3>(tmA, tmB, P, grid, st);
-        }
-        return launch_tc_major<EB, 32, X3>(ak, bk, tmA, tmB, P, grid, st);
-    }
-    if (BN == 64) return launch_tc_major<EB, 64, X3>(ak, bk, tmA, tmB, P, grid, st);
-    return launch_tc_major<EB, 128, X3>(ak, bk, tmA, tmB, P, grid, st);
-}
-
 // tf32_passes: for fp32 operands 1 (plain tf32) or 3 (3xTF32); ignored for bf16 operands
 zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, int split_k, float *ws,
                    size_t ws_elems, cudaStream_t st) {
@@ -906,51 +125,11 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
     if (B.kmajor) ZOO_TRY(make_map(&tmB, B.p, eb, K, N, B.ld, bk, BN, false));
     else ZOO_TRY(make_map(&tmB, B.p, eb, N, K, B.ld, mn_box, bk, true));
 
-    if (eb == 2) ZOO_TRY((launch_tc_bn<2, false>(BN, A.kmajor, B.kmajor, tmA, tmB, P, grid, st)));
-    else if (x3) ZOO_TRY((launch_tc_bn<4, true>(BN, A.kmajor, B.kmajor, tmA, tmB, P, grid, st)));
-    else ZOO_TRY((launch_tc_bn<4, false>(BN, A.kmajor, B.kmajor, tmA, tmB, P, grid, st)));
+    ZOO_TRY(tc_launch(eb, x3, 0, BN, A.kmajor, B.kmajor, tmA, tmB, P, grid, st));
     return ZOO_OK;
 }
 
 // ---------------------------------------------------------------- implicit-GEMM convolution --------
-template <int EB, int BN, bool B_K, bool X3>
-static zoo_status launch_conv(const CUtensorMap &tmB, const TcParams &P, dim3 grid, cudaStream_t st) {
-    using C = TcCfg<EB, BN, X3>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr_set = true;
-    }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, grid, dim3(TC_THREADS), (size_t)C::SMEM, st, tmB, tmB, P));
-    ZOO_LAUNCH_CHECK();
-    return ZOO_OK;
-}
-
-template <int EB, int BN, bool X3>
-static zoo_status launch_conv_tma(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid, cudaStream_t st) {
-    using C = TcCfg<EB, BN, X3>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, true, X3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr_set = true;
-    }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, true, X3, 2>, grid, dim3(TC_THREADS), (size_t)C::SMEM, st, tmA, tmB, P));
-    ZOO_LAUNCH_CHECK();
-    return ZOO_OK;
-}
-
-template <int EB, bool X3>
-static zoo_status launch_conv_bn(int BN, bool bk, const CUtensorMap &tmB, const TcParams &P, dim3 grid, cudaStream_t st) {
-    if (BN == 32) {
-        if (bk) return launch_conv<EB, 32, true, X3>(tmB, P, grid, st);
-        if (EB == 4) return launch_conv<4, 32, false, X3>(tmB, P, grid, st);
-        set_err("tc_conv_gemm: bf16 MN-major B needs BN >= 64");
-        return ZOO_BAD_ARG;
-    }
-    if (BN == 64) return bk ? launch_conv<EB, 64, true, X3>(tmB, P, grid, st) : launch_conv<EB, 64, false, X3>(tmB, P, grid, st);
-    return bk ? launch_conv<EB, 128, true, X3>(tmB, P, grid, st) : launch_conv<EB, 128, false, X3>(tmB, P, grid, st);
-}
-
 bool tc_conv_supported(const ConvGeom &g, int is_bf16) {
     const int eb = is_bf16 ? 2 : 4, ch = 16 / eb, bk = 128 / eb;
     if (((uintptr_t)g.x & 15) && g.mode != CONV_RAW_U8) return false;
@@ -998,13 +177,7 @@ static zoo_status tc_conv_tma(ConvGeom g, const Operand &Wop, int images, int N,
         ZOO_TRY(make_map4(&tmA, g.x, eb, dims, str, box, es));
     }
     ZOO_TRY(make_map(&tmB, Wop.p, eb, K, N, Wop.ld, bk, BN, false));
-#define CONV_TMA_BN(EBv, X3v)                                                                  \
-    (BN == 32 ? launch_conv_tma<EBv, 32, X3v>(tmA, tmB, P, grid, st)                            \
-              : (BN == 64 ? launch_conv_tma<EBv, 64, X3v>(tmA, tmB, P, grid, st) : launch_conv_tma<EBv, 128, X3v>(tmA, tmB, P, grid, st)))
-    if (eb == 2) return CONV_TMA_BN(2, false);
-    if (x3) return CONV_TMA_BN(4, true);
-    return CONV_TMA_BN(4, false);
-#undef CONV_TMA_BN
+    return tc_launch(eb, x3, 2, BN, true, true, tmA, tmB, P, grid, st);
 }
 
 zoo_status tc_conv_gemm(const ConvGeom &g, const Operand &Wop, int M, int N, int K, const Epilogue &epi, float *ws, size_t ws_elems,
@@ -1039,9 +212,7 @@ zoo_status tc_conv_gemm(const ConvGeom &g, const Operand &Wop, int M, int N, int
     CUtensorMap tmB;
     if (Wop.kmajor) ZOO_TRY(make_map(&tmB, Wop.p, eb, K, N, Wop.ld, bk, BN, false));
     else ZOO_TRY(make_map(&tmB, Wop.p, eb, Wop.ld, g.Cout, Wop.ld, mn_box, bk, true));  // W as [Cout][ks*ks*C]: boxes at tap offsets
-    if (eb == 2) return launch_conv_bn<2, false>(BN, Wop.kmajor, tmB, P, grid, st);
-    if (x3) return launch_conv_bn<4, true>(BN, Wop.kmajor, tmB, P, grid, st);
-    return launch_conv_bn<4, false>(BN, Wop.kmajor, tmB, P, grid, st);
+    return tc_launch(eb, x3, 1, BN, true, Wop.kmajor, tmB, tmB, P, grid, st);
 }
 
 }  // namespace zoo
