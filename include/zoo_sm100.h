@@ -132,7 +132,10 @@ enum { ZOO_LEARNER_BASIC_DQN = 0,       /* basic_dqn.jl:69-90        */
        ZOO_LEARNER_DQN = 1,             /* dqn.jl:102-145            */
        ZOO_LEARNER_PRIORITIZED_DQN = 2, /* prioritized_dqn.jl:111-151 */
        ZOO_LEARNER_RAINBOW = 3,         /* rainbow.jl:126-221        */
-       ZOO_LEARNER_IQN = 4 };           /* iqn.jl:159-237            */
+       ZOO_LEARNER_IQN = 4,             /* iqn.jl:159-237            */
+       ZOO_LEARNER_QR_DQN = 5,          /* qr_dqn.jl:106-138: cfg.N = n_quantile, cfg.kappa; net outputs n_quantile*n_actions   */
+       ZOO_LEARNER_REM_DQN = 6 };       /* rem_dqn.jl:100-145: cfg.N = ensemble_num; batch.tau = the E convex weights (required);
+                                           net outputs n_actions*ensemble_num */
 
 typedef struct {
     int32_t kind;            /* ZOO_LEARNER_* */

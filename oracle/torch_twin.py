@@ -225,6 +225,42 @@ def iqn_grads(net, params, tparams, batch, tau, tau_prime, gamma=0.99, kappa=1.0
     return _finish(loss, ps, extra)
 
 
+def qr_dqn_grads(net, params, tparams, batch, n_actions, N, gamma=0.99, kappa=1.0, dtype=torch.float32):
+    """qr_dqn.jl:3-14,106-138 with autograd."""
+    ps, tps = _leaf(params, dtype), [_t(p, dtype) for p in tparams]
+    a = torch.as_tensor(np.asarray(batch["action"], np.int64))
+    B = len(a)
+    ar = torch.arange(B)
+    with torch.no_grad():
+        zt = forward(net, tps, _t(batch["next_state"], dtype)).reshape(B, n_actions, N)
+        at = zt.mean(dim=2).argmax(dim=1)
+        y = _t(batch["reward"], dtype)[:, None] + float(np.float32(gamma)) * (1 - _t(batch["terminal"], dtype))[:, None] * zt[ar, at]
+    yhat = forward(net, ps, _t(batch["state"], dtype)).reshape(B, n_actions, N)[ar, a]
+    D = y[:, :, None] - yhat[:, None, :]
+    ae = D.abs()
+    quad = torch.clamp(ae, max=kappa)
+    hub = 0.5 * quad * quad + kappa * (ae - quad)
+    cp = torch.as_tensor((np.float64(np.float32(0.5) / np.float32(N)) + np.arange(N) * np.float64(np.float32(1.0) / np.float32(N))), dtype=dtype)
+    w = (cp[None, :, None] - (D < 0).to(dtype)).abs().detach()
+    per = (w * hub).sum(dim=1).mean(dim=1)
+    return _finish(per.mean(), ps, {"per_sample": per.detach().numpy().copy()})
+
+
+def rem_dqn_grads(net, params, tparams, batch, n_actions, E, w, gamma=0.99, n=1, dtype=torch.float32):
+    """rem_dqn.jl:100-145 with autograd."""
+    ps, tps = _leaf(params, dtype), [_t(p, dtype) for p in tparams]
+    a = torch.as_tensor(np.asarray(batch["action"], np.int64))
+    B = len(a)
+    wt = _t(np.asarray(w), dtype)
+    with torch.no_grad():
+        tq = (wt[None, :, None] * forward(net, tps, _t(batch["next_state"], dtype)).reshape(B, E, n_actions)).sum(dim=1)
+        tq = _mask_add(tq, batch)
+        G = _t(batch["reward"], dtype) + _gn(gamma, n) * (1 - _t(batch["terminal"], dtype)) * tq.max(dim=1).values
+    q = (wt[None, :, None] * forward(net, ps, _t(batch["state"], dtype)).reshape(B, E, n_actions)).sum(dim=1)[torch.arange(B), a]
+    per = _huber(G, q)
+    return _finish(per.mean(), ps, {"per_sample": per.detach().numpy().copy()})
+
+
 # ---- optimisers, Flux 0.11 formulas (SURVEY.md A.5), plain fp32 torch ops (for the CPU arm) ----
 class RMSProp:
     def __init__(self, params, eta=0.00025, rho=0.95):

@@ -588,6 +588,70 @@ def iqn_grads(net, params, tparams, batch, tau, tau_prime, gamma=0.99, kappa=1.0
     return out
 
 
+def qr_cum_prob(N, dtype=F32):
+    """``range(0.5f0 / N; length = N, step = 1.0f0 / N)`` -- qr_dqn.jl:11 (Float32 range: reference value and step are
+    Float32, the elements are evaluated in higher precision and rounded once)."""
+    first, step = np.float64(F32(0.5) / F32(N)), np.float64(F32(1.0) / F32(N))
+    return (first + np.arange(N, dtype=np.float64) * step).astype(dtype)
+
+
+def quantile_huber_loss_qr(yhat, y, kappa=1.0):
+    """``quantile_huber_loss(ŷ, y; κ)`` -- qr_dqn.jl:3-14.  ŷ, y: [B, N].  Δ[b,i,j] = y[b,i] − ŷ[b,j]; the cumulative
+    probabilities are broadcast along the FIRST Julia axis, i.e. the target index i (as written in the reference);
+    loss = mean over (j, b) of Σ_i.  Returns (per-sample loss [B] = mean_j Σ_i, d per_sample_b / d ŷ[b,j])."""
+    dt = y.dtype.type
+    k = dt(kappa)
+    N = y.shape[1]
+    D = y[:, :, None] - yhat[:, None, :]
+    ae = np.abs(D)
+    quad = np.minimum(ae, k)
+    lin = ae - quad
+    hub = dt(0.5) * quad * quad + k * lin
+    cp = qr_cum_prob(N, y.dtype)
+    w = np.abs(cp[None, :, None] - (D < 0).astype(y.dtype))
+    per = (w * hub).sum(axis=1).mean(axis=1, dtype=y.dtype)
+    dyhat = -(w * np.clip(D, -k, k)).sum(axis=1) / dt(N)
+    return per.astype(y.dtype), dyhat.astype(y.dtype)
+
+
+def qr_dqn_grads(net, params, tparams, batch, n_actions, N, gamma=0.99, kappa=1.0, dtype=F32):
+    """``update!(::QRDQNLearner, batch)`` -- qr_dqn.jl:106-138.  Net output per sample is N*n_actions values, quantile index
+    fastest (reshape(Q(s), N, :, B)).  Target: mean over quantiles -> first-max action -> y = r + γ(1−t)·z_t[:, a*]
+    (γ, not γⁿ, as written: qr_dqn.jl:123).  No legal-action mask, no PER."""
+    a = batch["action"]
+    B = len(a)
+    zt, _ = net_forward(net, tparams, batch["next_state"], dtype=dtype)
+    zt = zt.reshape(B, n_actions, N)
+    at = _first_argmax(zt.mean(axis=2, dtype=dtype))
+    y = batch["reward"].astype(dtype)[:, None] + dtype(np.float32(gamma)) * (1 - batch["terminal"].astype(dtype))[:, None] * zt[np.arange(B), at]
+    z_all, c = net_forward(net, params, batch["state"], dtype=dtype)
+    z = z_all.reshape(B, n_actions, N)
+    per, dq = quantile_huber_loss_qr(z[np.arange(B), a], y.astype(dtype), kappa)
+    d = np.zeros_like(z)
+    d[np.arange(B), a] = dq / dtype(B)
+    return {"loss": dtype(per.mean(dtype=dtype)), "grads": net_backward(net, params, c, d.reshape(B, -1)), "per_sample": per, "y": y}
+
+
+def rem_dqn_grads(net, params, tparams, batch, n_actions, E, w, gamma=0.99, n=1, dtype=F32):
+    """``update!(::REMDQNLearner, batch)`` -- rem_dqn.jl:100-145.  Net output per sample is n_actions*E values, action index
+    fastest (reshape(q, :, E, B)); w [E] is the convex combination (``rand`` normalised, or ones/E), an input here because
+    the reference draws it from a host RNG.  loss_func = huber_loss (JuliaRL_REMDQN_CartPole.jl:40)."""
+    a = batch["action"]
+    B = len(a)
+    w = np.asarray(w, dtype)
+    qt, _ = net_forward(net, tparams, batch["next_state"], dtype=dtype)
+    tq = (w[None, :, None] * qt.reshape(B, E, n_actions)).sum(axis=1, dtype=dtype)
+    tq = _mask_add(tq, batch.get("next_legal_actions_mask"))
+    G = batch["reward"].astype(dtype) + gamma_n(gamma, n, dtype) * (1 - batch["terminal"].astype(dtype)) * tq.max(axis=1)
+    q_all, c = net_forward(net, params, batch["state"], dtype=dtype)
+    qe = q_all.reshape(B, E, n_actions)
+    q = (w[None, :, None] * qe).sum(axis=1, dtype=dtype)[np.arange(B), a]
+    per, dq, _ = huber_per_sample(G.astype(dtype), q)
+    d = np.zeros_like(qe)
+    d[np.arange(B), :, a] = (dq / dtype(B))[:, None] * w[None, :]
+    return {"loss": dtype(per.mean(dtype=dtype)), "grads": net_backward(net, params, c, d.reshape(B, -1)), "per_sample": per, "G": G, "q": q}
+
+
 # --------------------------------------------------------------------------------------
 # optimisers (Flux 0.11, SURVEY.md A.5): Float64 scalars x Float32 arrays -> each fused
 # broadcast line is evaluated per element in Float64 and rounded once on store.

@@ -6,8 +6,8 @@ The names mirror the reference (``BasicDQNLearner`` … ``IQNLearner``, ``Neural
 ``libzoo_sm100.so`` (csrc/, C ABI in include/zoo_sm100.h).  There is no CPU fallback."""
 from ._lib import LIB_PATH, ZooError, lib  # noqa: F401
 from .dp import DataParallel, shard_batch, shard_bounds  # noqa: F401
-from .learners import (SARTS, BasicDQNLearner, DQNLearner, IQNLearner, PrioritizedDQNLearner, RainbowLearner,  # noqa: F401
-                       update, update_trajectory)
+from .learners import (SARTS, BasicDQNLearner, DQNLearner, IQNLearner, PrioritizedDQNLearner, QRDQNLearner, RainbowLearner,  # noqa: F401
+                       REMDQNLearner, update, update_trajectory)
 from .nn import (ADAM, Chain, CrossCor, Dense, DuelingNetwork, Flatten, ImplicitQuantileNet, NatureCNN,  # noqa: F401
                  NeuralNetworkApproximator, RMSProp, Scale255, from_oracle_net)
 from .sumtree import SumTree  # noqa: F401

@@ -14,7 +14,7 @@ NET_CHAIN, NET_IQN, NET_DUELING = 0, 1, 2
 PREC_FP32, PREC_BF16, PREC_TF32, PREC_FP32_SIMT = 0, 1, 2, 3
 OBS_U8, OBS_F32 = 0, 1
 OPT_RMSPROP, OPT_ADAM = 0, 1
-LEARNER_BASIC_DQN, LEARNER_DQN, LEARNER_PRIORITIZED_DQN, LEARNER_RAINBOW, LEARNER_IQN = range(5)
+LEARNER_BASIC_DQN, LEARNER_DQN, LEARNER_PRIORITIZED_DQN, LEARNER_RAINBOW, LEARNER_IQN, LEARNER_QR_DQN, LEARNER_REM_DQN = range(7)
 DRAW_F32, DRAW_F64 = 0, 1
 SAMPLE_INDEPENDENT, SAMPLE_STRATIFIED = 0, 1
 STATUS = {0: "OK", 1: "BAD_ARG", 2: "CUDA_ERROR", 3: "NCCL_ERROR", 4: "UNSUPPORTED_ARCH"}

@@ -218,6 +218,84 @@ __global__ void iqn_loss_kernel(HeadArgs h, int N, int Np, const float *__restri
     }
 }
 
+// qr_dqn.jl:118-122: net output (N, A, B) column-major == [B][A][N]; mean over the N quantiles, first-max action,
+// y = r + gamma * (1 - t) * z_t[:, a*]   (gamma, not gamma^n -- as written in the reference)
+__global__ void qr_target_kernel(HeadArgs h, int N, const float *__restrict__ zt, float gamma, float *__restrict__ y) {
+    __shared__ float red[32];
+    const int b = blockIdx.x, i = threadIdx.x, A = h.A;
+    const bool valid = i < N;
+    float best = 0.f;
+    int sel = 0;
+    for (int a = 0; a < A; ++a) {
+        const float s = block_sum(valid ? zt[((size_t)b * A + a) * N + i] : 0.f, red);
+        const float avg = __fdiv_rn(s, (float)N);
+        if (a == 0 || better(avg, best)) { best = avg; sel = a; }
+    }
+    if (valid) {
+        const float disc = __fmul_rn(gamma, h.terminal[b] ? 0.f : 1.f);
+        y[(size_t)b * N + i] = __fadd_rn(h.reward[b], __fmul_rn(disc, zt[((size_t)b * A + sel) * N + i]));
+    }
+}
+
+// quantile_huber_loss(y_hat, y) -- qr_dqn.jl:3-14.  D[i,j] = y[i] - y_hat[j]; the cumulative probabilities
+// cum_prob[i] = (i + 0.5) / N broadcast along the FIRST axis (the target index i, as written); loss = mean_{j,b} sum_i
+__global__ void qr_loss_kernel(HeadArgs h, int N, const float *__restrict__ z, const float *__restrict__ y, float kappa,
+                               float *__restrict__ dout) {
+    extern __shared__ float tgt[];  // N
+    __shared__ float red[32];
+    const int b = blockIdx.x, j = threadIdx.x, A = h.A;
+    for (int i = j; i < N; i += blockDim.x) tgt[i] = y[(size_t)b * N + i];
+    __syncthreads();
+    const bool valid = j < N;
+    const int a_b = h.action[b];
+    float acc = 0.f, dacc = 0.f;
+    if (valid) {
+        const float q = z[((size_t)b * A + a_b) * N + j];
+        const float step = __fdiv_rn(1.0f, (float)N), first = __fdiv_rn(0.5f, (float)N);
+        for (int i = 0; i < N; ++i) {
+            const float D = __fsub_rn(tgt[i], q);
+            const float ae = fabsf(D);
+            const float quad = fminf(ae, kappa);
+            const float lin = __fsub_rn(ae, quad);
+            const float hub = __fadd_rn(__fmul_rn(__fmul_rn(0.5f, quad), quad), __fmul_rn(kappa, lin));
+            const float cp = __fadd_rn(first, __fmul_rn((float)i, step));  // range(0.5f0 / N; length = N, step = 1f0 / N)
+            const float wgt = fabsf(__fsub_rn(cp, D < 0.f ? 1.f : 0.f));
+            acc = __fadd_rn(acc, __fmul_rn(wgt, hub));
+            dacc += wgt * fminf(fmaxf(D, -kappa), kappa);
+        }
+    }
+    const float tot = block_sum(acc, red);
+    if (j == 0) h.per_sample[b] = __fdiv_rn(tot, (float)N);
+    for (int idx = j; idx < A * N; idx += blockDim.x) dout[(size_t)b * A * N + idx] = 0.f;
+    __syncthreads();
+    if (valid) dout[((size_t)b * A + a_b) * N + j] = -dacc / (float)N * sample_scale(h, b);
+}
+
+// rem_dqn.jl:100-145: net output (A, E, B) column-major == [B][E][A]; q = sum_e w_e Q[:, e]; target from the target net
+// (no double-DQN), legal-action mask, G = r + gamma^n (1 - t) max_a q_t; loss = huber(G, q[a]) (mean)
+__global__ void rem_head_kernel(HeadArgs h, int E, const float *__restrict__ q_on, const float *__restrict__ q_t, const float *__restrict__ w,
+                                float gamma_n, float *__restrict__ dout) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= h.B) return;
+    const int A = h.A;
+    float best = 0.f;
+    for (int a = 0; a < A; ++a) {
+        float s = 0.f;
+        for (int e = 0; e < E; ++e) s = __fadd_rn(s, __fmul_rn(w[e], q_t[((size_t)b * E + e) * A + a]));
+        if (h.mask && !h.mask[(size_t)b * A + a]) s += -INFINITY;
+        if (a == 0 || better(s, best)) best = s;
+    }
+    const float G = __fadd_rn(h.reward[b], __fmul_rn(__fmul_rn(gamma_n, h.terminal[b] ? 0.f : 1.f), best));
+    const int a_b = h.action[b];
+    float q = 0.f;
+    for (int e = 0; e < E; ++e) q = __fadd_rn(q, __fmul_rn(w[e], q_on[((size_t)b * E + e) * A + a_b]));
+    const float err = __fsub_rn(G, q), ae = fabsf(err);
+    h.per_sample[b] = ae < 1.f ? __fmul_rn(__fmul_rn(0.5f, ae), ae) : __fsub_rn(ae, 0.5f);  // Flux huber_loss, delta = 1, strict <
+    const float dq = -fminf(fmaxf(err, -1.f), 1.f) * sample_scale(h, b);
+    for (int e = 0; e < E; ++e)
+        for (int a = 0; a < A; ++a) dout[((size_t)b * E + e) * A + a] = a == a_b ? w[e] * dq : 0.f;
+}
+
 __global__ void __launch_bounds__(1024) loss_reduce_kernel(HeadArgs h, float beta, float *__restrict__ loss, float *__restrict__ prio_out) {
     pdl_wait();
     pdl_trigger();
@@ -282,6 +360,25 @@ zoo_status launch_iqn_loss(const HeadArgs &h, int N, int Np, const float *z, con
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
+zoo_status launch_qr_target(const HeadArgs &h, int N, const float *zt, float gamma, float *y, cudaStream_t st) {
+    ZOO_REQUIRE(N <= 1024, "QR-DQN: n_quantile %d > 1024", N);
+    qr_target_kernel<<<h.B, std::max(32, (N + 31) / 32 * 32), 0, st>>>(h, N, zt, gamma, y);
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+zoo_status launch_qr_loss(const HeadArgs &h, int N, const float *z, const float *y, float kappa, float *dout, cudaStream_t st) {
+    ZOO_REQUIRE(N <= 1024, "QR-DQN: n_quantile %d > 1024", N);
+    qr_loss_kernel<<<h.B, std::max(32, (N + 31) / 32 * 32), N * sizeof(float), st>>>(h, N, z, y, kappa, dout);
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+zoo_status launch_rem_head(const HeadArgs &h, int E, const float *q_on, const float *q_t, const float *w, float gamma_n, float *dout,
+                           cudaStream_t st) {
+    rem_head_kernel<<<cdiv(h.B, 128), 128, 0, st>>>(h, E, q_on, q_t, w, gamma_n, dout);
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+
 zoo_status launch_loss_reduce(const HeadArgs &h, float beta, float *loss, float *prio_out, cudaStream_t st) {
     ZOO_CUDA(launch_pdl(loss_reduce_kernel, dim3(1), dim3(1024), (size_t)0, st, h, beta, loss, prio_out));
     ZOO_LAUNCH_CHECK();

@@ -30,6 +30,12 @@ zoo_status launch_c51_head(const HeadArgs &h, int n_atoms, const float *tlogits,
 zoo_status launch_iqn_target(const HeadArgs &h, int Np, const float *zt, float gamma, float *target, cudaStream_t st);
 zoo_status launch_iqn_loss(const HeadArgs &h, int N, int Np, const float *z, const float *target, const float *tau, float kappa,
                            float *dout, cudaStream_t st);
+// QR-DQN (qr_dqn.jl:106-138): zt / z are [B][A][N]; y [B][N]
+zoo_status launch_qr_target(const HeadArgs &h, int N, const float *zt, float gamma, float *y, cudaStream_t st);
+zoo_status launch_qr_loss(const HeadArgs &h, int N, const float *z, const float *y, float kappa, float *dout, cudaStream_t st);
+// REM-DQN (rem_dqn.jl:100-145): q_on / q_t are [B][E][A]; w [E] the convex combination
+zoo_status launch_rem_head(const HeadArgs &h, int E, const float *q_on, const float *q_t, const float *w, float gamma_n, float *dout,
+                           cudaStream_t st);
 // loss = sum_b scale_b * per_b  (scale = w/B for PER, 1/B otherwise); priorities = (per + 1e-10)^beta
 zoo_status launch_loss_reduce(const HeadArgs &h, float beta, float *loss, float *prio_out, cudaStream_t st);
 zoo_status launch_tau(float *tau, long long n, unsigned long long seed, const unsigned long long *counter, int stream_id, cudaStream_t st);

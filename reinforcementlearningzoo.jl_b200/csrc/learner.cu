@@ -96,7 +96,8 @@ struct StageArgs {
     const int *action; const float *reward; const uint8_t *terminal; const float *priority; const uint8_t *mask;
     const float *tau, *taup;
     int *d_action; float *d_reward; uint8_t *d_terminal; float *d_priority; uint8_t *d_mask; float *d_tau, *d_taup;
-    int B, A, N, Np;
+    int B, A;
+    long long n_tau, n_taup;  // element counts of tau / tau_prime (IQN: B*N, B*N'; REM-DQN: E convex weights, 0)
 };
 __global__ void stage_batch_kernel(StageArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,8 +107,8 @@ __global__ void stage_batch_kernel(StageArgs a) {
         if (a.priority) a.d_priority[i] = a.priority[i];
     }
     if (a.mask && i < (long long)a.B * a.A) a.d_mask[i] = a.mask[i];
-    if (a.tau && i < (long long)a.B * a.N) a.d_tau[i] = a.tau[i];
-    if (a.taup && i < (long long)a.B * a.Np) a.d_taup[i] = a.taup[i];
+    if (a.tau && i < a.n_tau) a.d_tau[i] = a.tau[i];
+    if (a.taup && i < a.n_taup) a.d_taup[i] = a.taup[i];
 }
 
 }  // namespace zoo
@@ -257,6 +258,18 @@ static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bo
         ZOO_TRY(target_join(L, st));
         prof_label("head"); ZOO_TRY(launch_c51_head(h, c.n_atoms, tg->out_final, on->out_final, L->d_support, c.delta_z, c.v_min, c.v_max, L->gamma_n,
                                 on->dout_final, L->d_tdist, st));
+    } else if (c.kind == ZOO_LEARNER_QR_DQN) {
+        ZOO_TRY(target_forward(L, tg, s2_ptr, nullptr, 0, st));
+        ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, B, nullptr, 0, st, B));
+        ZOO_TRY(target_join(L, st));
+        prof_label("head"); ZOO_TRY(launch_qr_target(h, c.N, tg->out_final, c.gamma, L->d_target, st));
+        ZOO_TRY(launch_qr_loss(h, c.N, on->out_final, L->d_target, c.kappa, on->dout_final, st));
+    } else if (c.kind == ZOO_LEARNER_REM_DQN) {
+        ZOO_REQUIRE(has_tau, "update: REMDQNLearner needs the convex weights in batch.tau (ensemble_num floats)");
+        ZOO_TRY(target_forward(L, tg, s2_ptr, nullptr, 0, st));
+        ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, B, nullptr, 0, st, B));
+        ZOO_TRY(target_join(L, st));
+        prof_label("head"); ZOO_TRY(launch_rem_head(h, c.N, on->out_final, tg->out_final, L->d_tau, L->gamma_n, on->dout_final, st));
     } else {  // IQN
         if (!has_tau) {
             prof_label("head"); ZOO_TRY(launch_tau(L->d_taup, (long long)B * c.N_prime, c.seed, &L->opt->sc->rng, 0, st));
@@ -303,9 +316,11 @@ static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b) {
         StageArgs a{};
         a.s = (const uint4 *)b->state; a.s2 = (const uint4 *)b->next_state; a.obs = (uint4 *)L->d_obs; a.obs16 = (long long)(obs_bytes / 16);
         a.action = b->action; a.reward = b->reward; a.terminal = b->terminal; a.priority = b->priority; a.mask = b->next_mask;
-        a.tau = c.kind == ZOO_LEARNER_IQN ? b->tau : nullptr; a.taup = c.kind == ZOO_LEARNER_IQN ? b->tau_prime : nullptr;
+        const bool rem = c.kind == ZOO_LEARNER_REM_DQN;
+        a.tau = (c.kind == ZOO_LEARNER_IQN || rem) ? b->tau : nullptr; a.taup = c.kind == ZOO_LEARNER_IQN ? b->tau_prime : nullptr;
+        a.n_tau = rem ? c.N : (long long)B * c.N; a.n_taup = (long long)B * c.N_prime;
         a.d_action = L->d_action; a.d_reward = L->d_reward; a.d_terminal = L->d_terminal; a.d_priority = L->d_priority; a.d_mask = L->d_mask;
-        a.d_tau = L->d_tau; a.d_taup = L->d_taup; a.B = B; a.A = c.n_actions; a.N = c.N; a.Np = c.N_prime;
+        a.d_tau = L->d_tau; a.d_taup = L->d_taup; a.B = B; a.A = c.n_actions;
         long long n = std::max<long long>(a.obs16, (long long)B * std::max(std::max(c.n_actions, c.N), std::max(c.N_prime, 1)));
         stage_batch_kernel<<<cdiv(n, 256), 256, 0, st>>>(a);
         ZOO_LAUNCH_CHECK();
@@ -326,6 +341,7 @@ static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b) {
             memcpy(L->h_pack + L->off_tau, b->tau, (size_t)B * c.N * sizeof(float));
             memcpy(L->h_pack + L->off_taup, b->tau_prime, (size_t)B * c.N_prime * sizeof(float));
         }
+        if (c.kind == ZOO_LEARNER_REM_DQN && b->tau) memcpy(L->h_pack + L->off_tau, b->tau, (size_t)c.N * sizeof(float));
         const size_t used = (c.kind == ZOO_LEARNER_IQN && !b->tau) ? L->off_tau : L->pack_bytes;  // device-drawn tau stays untouched
         ZOO_CUDA(cudaMemcpyAsync(L->d_pack, L->h_pack, used, cudaMemcpyHostToDevice, st));
         ZOO_CUDA(cudaEventRecord(L->ev_pack, st));
@@ -344,6 +360,7 @@ static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b) {
         ZOO_CUDA(cudaMemcpyAsync(L->d_tau, b->tau, (size_t)B * c.N * sizeof(float), k, st));
         ZOO_CUDA(cudaMemcpyAsync(L->d_taup, b->tau_prime, (size_t)B * c.N_prime * sizeof(float), k, st));
     }
+    if (c.kind == ZOO_LEARNER_REM_DQN && b->tau) ZOO_CUDA(cudaMemcpyAsync(L->d_tau, b->tau, (size_t)c.N * sizeof(float), k, st));
     return ZOO_OK;
 }
 
@@ -447,7 +464,7 @@ zoo_status zoo_opt_set_step(zoo_opt *o, int64_t t) {
 
 zoo_status zoo_learner_create(const zoo_learner_cfg *cfg, zoo_net *online, zoo_net *target, zoo_opt *opt, zoo_dp *dp, zoo_learner **out) {
     ZOO_REQUIRE(cfg && online && opt && out, "zoo_learner_create: null argument");
-    ZOO_REQUIRE(cfg->kind >= ZOO_LEARNER_BASIC_DQN && cfg->kind <= ZOO_LEARNER_IQN, "zoo_learner_create: unknown learner kind %d", cfg->kind);
+    ZOO_REQUIRE(cfg->kind >= ZOO_LEARNER_BASIC_DQN && cfg->kind <= ZOO_LEARNER_REM_DQN, "zoo_learner_create: unknown learner kind %d", cfg->kind);
     ZOO_REQUIRE(cfg->kind == ZOO_LEARNER_BASIC_DQN || target, "zoo_learner_create: this learner needs a target network");
     ZOO_REQUIRE(opt->net == online, "zoo_learner_create: the optimiser must belong to the online network");
     ZOO_REQUIRE(cfg->batch_size > 0 && cfg->batch_size <= online->max_batch, "zoo_learner_create: batch_size %d exceeds the net's max_batch %lld",
@@ -459,6 +476,9 @@ zoo_status zoo_learner_create(const zoo_learner_cfg *cfg, zoo_net *online, zoo_n
     if (cfg->kind == ZOO_LEARNER_RAINBOW) {
         ZOO_REQUIRE(cfg->n_atoms >= 2 && cfg->support && online->n_out == cfg->n_atoms * cfg->n_actions,
                     "zoo_learner_create: Rainbow net must output n_atoms*n_actions = %d logits (has %d)", cfg->n_atoms * cfg->n_actions, online->n_out);
+    } else if (cfg->kind == ZOO_LEARNER_QR_DQN || cfg->kind == ZOO_LEARNER_REM_DQN) {
+        ZOO_REQUIRE(cfg->N >= 1 && online->n_out == cfg->N * cfg->n_actions,
+                    "zoo_learner_create: QR-DQN / REM-DQN net must output N*n_actions = %d values (has %d)", cfg->N * cfg->n_actions, online->n_out);
     } else {
         ZOO_REQUIRE(online->n_out == cfg->n_actions, "zoo_learner_create: net outputs %d values, n_actions is %d", online->n_out, cfg->n_actions);
     }
@@ -490,10 +510,9 @@ zoo_status zoo_learner_create(const zoo_learner_cfg *cfg, zoo_net *online, zoo_n
         L->off_terminal = o; o = up(o + (size_t)B);
         L->off_priority = o; o = up(o + (size_t)B * sizeof(float));
         L->off_mask = o; o = up(o + (size_t)B * A);
-        if (iqn) {
-            L->off_tau = o; o = up(o + (size_t)B * cfg->N * sizeof(float));
-            L->off_taup = o; o = up(o + (size_t)B * cfg->N_prime * sizeof(float));
-        }
+        const bool rem = cfg->kind == ZOO_LEARNER_REM_DQN;
+        if (iqn || rem) { L->off_tau = o; o = up(o + (size_t)(rem ? 1 : B) * cfg->N * sizeof(float)); }
+        if (iqn) { L->off_taup = o; o = up(o + (size_t)B * cfg->N_prime * sizeof(float)); }
         L->pack_bytes = o;
         ZOO_CUDA(cudaMalloc(&L->d_pack, o));
         ZOO_CUDA(cudaHostAlloc(&L->h_pack, o, cudaHostAllocDefault));
@@ -503,7 +522,8 @@ zoo_status zoo_learner_create(const zoo_learner_cfg *cfg, zoo_net *online, zoo_n
         L->d_terminal = L->d_pack + L->off_terminal;
         L->d_priority = (float *)(L->d_pack + L->off_priority);
         L->d_mask = L->d_pack + L->off_mask;
-        if (iqn) { L->d_tau = (float *)(L->d_pack + L->off_tau); L->d_taup = (float *)(L->d_pack + L->off_taup); }
+        if (iqn || rem) L->d_tau = (float *)(L->d_pack + L->off_tau);
+        if (iqn) L->d_taup = (float *)(L->d_pack + L->off_taup);
     }
     ZOO_CUDA(cudaMalloc(&L->d_per, B * sizeof(float)));
     ZOO_CUDA(cudaMalloc(&L->d_prio, B * sizeof(float)));
@@ -514,6 +534,7 @@ zoo_status zoo_learner_create(const zoo_learner_cfg *cfg, zoo_net *online, zoo_n
         ZOO_CUDA(cudaMemcpy(L->d_support, cfg->support, cfg->n_atoms * sizeof(float), cudaMemcpyHostToDevice));
         ZOO_CUDA(cudaMalloc(&L->d_tdist, (size_t)B * cfg->n_atoms * sizeof(float)));
     }
+    if (cfg->kind == ZOO_LEARNER_QR_DQN) ZOO_CUDA(cudaMalloc(&L->d_target, (size_t)B * cfg->N * sizeof(float)));
     if (iqn) {
         ZOO_CUDA(cudaMalloc(&L->d_target, (size_t)B * cfg->N_prime * sizeof(float)));
     }

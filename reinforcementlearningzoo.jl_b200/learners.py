@@ -240,6 +240,63 @@ class IQNLearner(_Learner):
         return self.approximator(np.asarray(obs)[None], tau)[0].mean(axis=0)
 
 
+class QRDQNLearner(_Learner):
+    """qr_dqn.jl:53-93.  The approximator outputs ``n_quantile * n_actions`` values per state (quantile index fastest);
+    loss_func is ``quantile_huber_loss`` (qr_dqn.jl:3-14, κ = 1)."""
+
+    def __init__(self, approximator, target_approximator, n_actions, gamma=0.99, batch_size=32, update_horizon=1, min_replay_history=32,
+                 update_freq=1, n_quantile=1, target_update_freq=100, update_step=0, kappa=1.0, stack_size=None, dp=None):
+        approximator.copyto(target_approximator)
+        self.approximator, self.target_approximator = approximator, target_approximator
+        self.n_actions, self.n_quantile = n_actions, n_quantile
+        self.gamma, self.batch_size, self.update_horizon = gamma, batch_size, update_horizon
+        self.min_replay_history, self.update_freq, self.target_update_freq, self.update_step = min_replay_history, update_freq, target_update_freq, update_step
+        c = _cfg(L.LEARNER_QR_DQN, batch_size, n_actions, gamma, update_horizon, 0)
+        c.kappa, c.N = float(kappa), int(n_quantile)
+        self._create(c, dp)
+
+    def __call__(self, obs):  # qr_dqn.jl:98-103: mean over the quantiles
+        return self.approximator(np.asarray(obs)[None])[0].reshape(self.n_actions, self.n_quantile).mean(axis=1)
+
+
+class REMDQNLearner(_Learner):
+    """rem_dqn.jl:50-92.  The approximator outputs ``n_actions * ensemble_num`` values per state (action index fastest);
+    loss_func is Flux ``huber_loss`` (JuliaRL_REMDQN_CartPole.jl:40).  The convex combination is drawn on the host, as the
+    reference does (rem_dqn.jl:110-116), from ``rng``; pass ``convex_polygon`` to ``update`` to fix it (parity)."""
+
+    def __init__(self, approximator, target_approximator, n_actions, gamma=0.99, batch_size=32, update_horizon=1, min_replay_history=32,
+                 update_freq=1, ensemble_num=1, ensemble_method="rand", target_update_freq=100, update_step=0, rng=None, stack_size=None,
+                 dp=None):
+        approximator.copyto(target_approximator)
+        self.approximator, self.target_approximator = approximator, target_approximator
+        self.n_actions, self.ensemble_num, self.ensemble_method = n_actions, ensemble_num, ensemble_method
+        self.gamma, self.batch_size, self.update_horizon = gamma, batch_size, update_horizon
+        self.min_replay_history, self.update_freq, self.target_update_freq, self.update_step = min_replay_history, update_freq, target_update_freq, update_step
+        self.rng = rng if rng is not None else np.random.default_rng()
+        c = _cfg(L.LEARNER_REM_DQN, batch_size, n_actions, gamma, update_horizon, 0)
+        c.N = int(ensemble_num)
+        self._create(c, dp)
+
+    def _polygon(self):
+        w = self.rng.random(self.ensemble_num, dtype=np.float32) if self.ensemble_method == "rand" else np.ones(self.ensemble_num, np.float32)
+        return (w / w.sum(dtype=np.float32)).astype(np.float32)
+
+    def update(self, batch, convex_polygon=None, **kw):
+        return super().update(batch, tau=self._polygon() if convex_polygon is None else np.asarray(convex_polygon, np.float32), **kw)
+
+    def compute_grads(self, batch, convex_polygon=None):
+        prio = self.update(batch, convex_polygon=convex_polygon, apply=False)
+        grads = []
+        for i, shp in enumerate(self.approximator.shapes):
+            buf = np.empty(int(np.prod(shp)), np.float32)
+            L.check(L.lib().zoo_learner_get_grad(self.h, i, buf.ctypes.data, buf.size))
+            grads.append(buf.reshape(shp[1], shp[0]).T.copy() if len(shp) == 2 else buf.reshape(shp).copy())
+        return self.loss, grads, prio
+
+    def __call__(self, obs):  # rem_dqn.jl:94-98: mean over the ensemble
+        return self.approximator(np.asarray(obs)[None])[0].reshape(self.ensemble_num, self.n_actions).mean(axis=0)
+
+
 def update(learner, x, **kw):
     """``RLBase.update!``: dispatches on the second argument like the reference's methods --
     a batch (dict with the SARTS keys) or a trajectory (anything with ``sample`` / ``set_priority``)."""

@@ -33,6 +33,9 @@ def cases():
         "rainbow_atari_b8": dict(net=O.chain_net(O.nature_cnn(6 * 51)), kind="rainbow", B=8, atari=True, A=6, seeds=(1, 2, 12),
                                  priority=True, vmax=10.0, vmin=-10.0, n=3),
         "iqn_atari_b4": dict(net=O.atari_iqn_net(6), kind="iqn", B=4, atari=True, A=6, seeds=(1, 2, 13), N=64, Np=64),
+        "qr_dqn_cartpole_b32": dict(net=O.chain_net(O.mlp([4, 128, 128, 2 * 10])), kind="qr", B=32, atari=False, A=2, seeds=(1, 2, 14), N=10),
+        "rem_dqn_cartpole_b32": dict(net=O.chain_net(O.mlp([4, 128, 128, 2 * 16])), kind="rem", B=32, atari=False, A=2, seeds=(1, 2, 15), N=16,
+                                     mask=True),
     }
 
 
@@ -46,6 +49,9 @@ def inputs(c):
     if c["kind"] == "iqn":
         rng = np.random.default_rng(sb + 100)
         tau, taup = rng.random((c["B"], c["N"]), dtype=np.float32), rng.random((c["B"], c["Np"]), dtype=np.float32)
+    if c["kind"] == "rem":  # the convex combination travels in the tau slot
+        w = np.random.default_rng(sb + 100).random(c["N"], dtype=np.float32)
+        tau = (w / w.sum(dtype=np.float32)).astype(np.float32)
     return p, tp, b, tau, taup
 
 
@@ -60,6 +66,10 @@ def run_oracle(c):
         return O.prioritized_dqn_grads(c["net"], p, tp, b)
     if k == "rainbow":
         return O.rainbow_grads(c["net"], p, tp, b, c["A"], 51, c["vmax"], c["vmin"], 0.99, c["n"])
+    if k == "qr":
+        return O.qr_dqn_grads(c["net"], p, tp, b, c["A"], c["N"])
+    if k == "rem":
+        return O.rem_dqn_grads(c["net"], p, tp, b, c["A"], c["N"], tau)
     return O.iqn_grads(c["net"], p, tp, b, tau, taup)
 
 

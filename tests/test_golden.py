@@ -55,8 +55,8 @@ def device_learner(zoo, c, prec="fp32"):
     B, k = c["B"], c["kind"]
     iqn = k == "iqn"
     opt = zoo.ADAM()
-    app = make_approx(zoo, c["net"], p, opt, max_batch=B, max_q=c.get("N", 0), precision=prec)
-    tapp = None if k == "basic" else make_approx(zoo, c["net"], tp, max_batch=B, max_q=c.get("Np", 0), precision=prec)
+    app = make_approx(zoo, c["net"], p, opt, max_batch=B, max_q=c.get("N", 0) if iqn else 0, precision=prec)
+    tapp = None if k == "basic" else make_approx(zoo, c["net"], tp, max_batch=B, max_q=c.get("Np", 0) if iqn else 0, precision=prec)
     if k == "basic":
         lrn = zoo.BasicDQNLearner(app, batch_size=B)
     elif k == "dqn":
@@ -65,10 +65,14 @@ def device_learner(zoo, c, prec="fp32"):
         lrn = zoo.PrioritizedDQNLearner(app, tapp, batch_size=B)
     elif k == "rainbow":
         lrn = zoo.RainbowLearner(app, tapp, n_actions=c["A"], Vmax=c["vmax"], Vmin=c["vmin"], update_horizon=c["n"], batch_size=B)
+    elif k == "qr":
+        lrn = zoo.QRDQNLearner(app, tapp, n_actions=c["A"], n_quantile=c["N"], batch_size=B)
+    elif k == "rem":
+        lrn = zoo.REMDQNLearner(app, tapp, n_actions=c["A"], ensemble_num=c["N"], batch_size=B)
     else:
         lrn = zoo.IQNLearner(app, tapp, n_actions=c["A"], N=c["N"], N_prime=c["Np"], N_em=c["net"]["phi"][0][1], batch_size=B)
     app.set_params(p)  # undo the constructor's online := target force-sync
-    kw = dict(tau=tau, tau_prime=taup) if iqn else {}
+    kw = dict(tau=tau, tau_prime=taup) if iqn else (dict(convex_polygon=tau) if k == "rem" else {})
     return lrn, b, kw
 
 

@@ -134,6 +134,45 @@ def test_iqn_cartpole(zoo, prec):
 
 
 @pytest.mark.parametrize("prec", PRECS)
+def test_qr_dqn_cartpole(zoo, prec):
+    net = O.chain_net(O.mlp([4, 128, 128, 2 * 10]))
+    p, tp = O.init_params(net, 1, 0.1), O.init_params(net, 2, 0.1)
+    b = cartpole_batch(14)
+    app = make_approx(zoo, net, p, zoo.ADAM(), precision=prec)
+    tapp = make_approx(zoo, net, tp, precision=prec)
+    lrn = zoo.QRDQNLearner(app, tapp, n_actions=2, n_quantile=10, batch_size=32)
+    app.set_params(p)
+    check(zoo, lrn, O.qr_dqn_grads(net, p, tp, b, 2, 10), b, prec, "QR-DQN CartPole")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("mask", [False, True])
+def test_rem_dqn_cartpole(zoo, prec, mask):
+    net = O.chain_net(O.mlp([4, 128, 128, 2 * 16]))
+    p, tp = O.init_params(net, 1, 0.1), O.init_params(net, 2, 0.1)
+    b = cartpole_batch(15, mask=mask)
+    w = np.random.default_rng(3).random(16, dtype=np.float32)
+    w = (w / w.sum(dtype=np.float32)).astype(np.float32)
+    app = make_approx(zoo, net, p, zoo.ADAM(), precision=prec)
+    tapp = make_approx(zoo, net, tp, precision=prec)
+    lrn = zoo.REMDQNLearner(app, tapp, n_actions=2, ensemble_num=16, batch_size=32)
+    app.set_params(p)
+    check(zoo, lrn, O.rem_dqn_grads(net, p, tp, b, 2, 16, w), b, prec, "REM-DQN CartPole", convex_polygon=w)
+
+
+def test_qr_dqn_atari(zoo):
+    B, N = 8, 32
+    net = O.chain_net(O.nature_cnn(6 * N))
+    p, tp = O.init_params(net, 1, 0.05), O.init_params(net, 2, 0.05)
+    b = atari_batch(16, B)
+    app = make_approx(zoo, net, p, zoo.ADAM(0.00005), max_batch=B)
+    tapp = make_approx(zoo, net, tp, max_batch=B)
+    lrn = zoo.QRDQNLearner(app, tapp, n_actions=6, n_quantile=N, batch_size=B)
+    app.set_params(p)
+    check(zoo, lrn, O.qr_dqn_grads(net, p, tp, b, 6, N), b, "fp32", "QR-DQN Atari")
+
+
+@pytest.mark.parametrize("prec", PRECS)
 def test_dqn_atari(zoo, prec):
     B = 8
     net = O.chain_net(O.nature_cnn(6))

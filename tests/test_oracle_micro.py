@@ -89,6 +89,15 @@ def test_quantile_huber_sum_over_target_mean_over_online():
     assert np.allclose(per, raw.sum(axis=1).mean(axis=1), atol=1e-6)
 
 
+def test_qr_quantile_huber_micro():
+    # qr_dqn.jl:3-14 with N = 2, B = 1, kappa = 1: y = [1, 0], y_hat = [0.2, 0.5]; cum_prob = [0.25, 0.75] along the TARGET axis
+    per, d = O.quantile_huber_loss_qr(np.array([[0.2, 0.5]], F), np.array([[1.0, 0.0]], F), 1.0)
+    # D[i,j] = y[i]-yhat[j] = [[0.8, 0.5], [-0.2, -0.5]]; huber = [[.32, .125], [.02, .125]]; w = [[.25, .25], [.25, .25]]
+    assert np.isclose(per[0], ((0.25 * 0.32 + 0.25 * 0.02) + (0.25 * 0.125 + 0.25 * 0.125)) / 2, atol=1e-6)
+    assert np.allclose(d[0], [-(0.25 * 0.8 + 0.25 * -0.2) / 2, -(0.25 * 0.5 + 0.25 * -0.5) / 2], atol=1e-6)
+    assert np.allclose(O.qr_cum_prob(4), [0.125, 0.375, 0.625, 0.875])
+
+
 @pytest.mark.parametrize("Tree", [CSumTree, PySumTree])
 def test_sumtree_docstring_example(Tree):
     # RLCore docstring example: SumTree(8), push 1..16 -> leaves 9..16, root 100, node2 42, node3 58

@@ -67,6 +67,23 @@ def test_iqn():
     _cmp(O.iqn_grads(net, p, tp, b, tau, taup), T.iqn_grads(net, p, tp, b, tau, taup), "iqn")
 
 
+def test_qr_dqn():
+    # qr_dqn.jl: N quantiles per action, quantile index fastest
+    net = O.chain_net(O.mlp([4, 128, 128, 2 * 10]))
+    p, tp, b = O.init_params(net, 1, 0.1), O.init_params(net, 2, 0.1), cartpole(14)
+    _cmp(O.qr_dqn_grads(net, p, tp, b, 2, 10), T.qr_dqn_grads(net, p, tp, b, 2, 10), "qr-dqn")
+
+
+@pytest.mark.parametrize("mask", [False, True])
+def test_rem_dqn(mask):
+    # JuliaRL_REMDQN_CartPole.jl: 16 heads, random convex combination
+    net = O.chain_net(O.mlp([4, 128, 128, 2 * 16]))
+    p, tp, b = O.init_params(net, 1, 0.1), O.init_params(net, 2, 0.1), cartpole(15, mask=mask)
+    w = np.random.default_rng(3).random(16, dtype=np.float32)
+    w = (w / w.sum(dtype=np.float32)).astype(np.float32)
+    _cmp(O.rem_dqn_grads(net, p, tp, b, 2, 16, w), T.rem_dqn_grads(net, p, tp, b, 2, 16, w), "rem-dqn")
+
+
 def test_dqn_nature_cnn_small_batch():
     net = O.chain_net(O.nature_cnn(6))
     p, tp = O.init_params(net, 1, 0.05), O.init_params(net, 2, 0.05)
