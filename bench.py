@@ -342,6 +342,34 @@ def run_ours(args, w):
     clk = clocks.stop(windows) if clocks else None
 
     trace("leg 2 done")
+    # ---- leg 3 (DQN workload): the same update fed from a device-resident replay shard: per step the host
+    # pushes 4 new frames (update_freq = 4, Dopamine_DQN_Atari.jl:45) and sends B uniform draws; sampling, frame stacking, the
+    # n-step fold and the update stay on the device; the loss is read back every step
+    e2e_replay = None
+    if kind == "dqn" and w["atari"]:
+        shard = zoo.ReplayShard(100_000, (84, 84), 4, w["n"], 0.99, max_batch=B)
+        rng = np.random.default_rng(rank)
+        nfill = 20_000
+        shard.push_many(rng.integers(0, 256, (nfill, 84, 84), dtype=np.uint8), rng.integers(0, w["A"], nfill), rng.integers(-1, 2, nfill).astype(np.float32),
+                        (rng.random(nfill) < 0.02))
+        newf = rng.integers(0, 256, (64, 84, 84), dtype=np.uint8)
+        draws = rng.random((K + 8, B))
+        for i in range(3):
+            shard.update(lrn, draws[i])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            for j in range(4):
+                shard.push(newf[(4 * i + j) % 64], 1, 0.0, False)
+            shard.update(lrn, draws[i + 3])
+        torch.cuda.synchronize()
+        rp_s = maxr(time.perf_counter() - t0)
+        e2e_replay = {"value": world * K / rp_s, "unit": "updates/s", "h2d_bytes_per_step": 4 * (84 * 84 + 9) + B * 8, "d2h_bytes_per_step": 4,
+                      "note": "update!(learner, trajectory) on a device-resident replay shard: 4 frame pushes + B draws per step"}
+        shard.close()
+        barrier()
+    trace("leg 3 done")
+
     # ---- roofline leg (rank 0 profiles; the other ranks must join the collectives, so they run the same eager updates)
     profs = []
     for i in range(4):
@@ -381,6 +409,7 @@ def run_ours(args, w):
             "roofline": roof,
             "cpu_baseline": cpu,
             "e2e": {"value": world * K / e2e_s, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e_replay": e2e_replay,
             "gpu_launches": launches,
             "clocks": clk,
         }

@@ -228,6 +228,35 @@ ZOO_API zoo_status zoo_sumtree_update_dev(zoo_sumtree *t, const int64_t *idx_dev
 ZOO_API zoo_status zoo_sumtree_stream(zoo_sumtree *t, void **stream);
 ZOO_API zoo_status zoo_sumtree_sync(zoo_sumtree *t);
 
+/* ------------------------------------------------------------------ device-resident replay ---- */
+/* The batch assembly behind `sample(rng, t, sampler)` (common.jl:18; trajectory + NStepBatchSampler built at
+ * Dopamine_DQN_Atari.jl:55-66, implemented in RLCore 0.7.2) on the device: uint8 single-frame ring, 4-frame stacking, n-step
+ * reward fold with terminal truncation, uniform or SumTree-prioritized indices, priority write-back -- no host round trip
+ * between sampling and the update.  Semantics: csrc/replay.cu header. */
+typedef struct zoo_replay zoo_replay;
+enum { ZOO_REPLAY_UNIFORM = 2 /* besides ZOO_SAMPLE_INDEPENDENT / ZOO_SAMPLE_STRATIFIED for a prioritized shard */ };
+ZOO_API zoo_status zoo_replay_create(int64_t capacity, int32_t frame_h, int32_t frame_w, int32_t stack_size, int32_t n_step, float gamma,
+                                     int32_t max_batch, int32_t prioritized, zoo_replay **out);
+ZOO_API zoo_status zoo_replay_destroy(zoo_replay *r);
+/* push!(trajectory, ...) of one transition: its (single) state frame [h][w] uint8, action (0-based), reward, terminal,
+ * and -- prioritized shard -- push!(t[:priority], priority) (common.jl:28-37) */
+ZOO_API zoo_status zoo_replay_push(zoo_replay *r, const uint8_t *frame_host, int32_t action, float reward, uint8_t terminal, float priority);
+/* bulk push of n transitions: frames [n][h][w]; priority may be NULL (default_priority 100) */
+ZOO_API zoo_status zoo_replay_push_many(zoo_replay *r, const uint8_t *frames_host, const int32_t *action, const float *reward,
+                                        const uint8_t *terminal, const float *priority, int64_t n);
+ZOO_API zoo_status zoo_replay_length(const zoo_replay *r, int64_t *length, int64_t *first);
+/* u_host: B uniform draws (f32 | f64).  Fills `batch` with device pointers (on_device = 1; valid until the next sample),
+ * enqueued on `stream` (pass zoo_learner_stream).  inds_out: optional host array of the 1-based logical indices (synchronises). */
+ZOO_API zoo_status zoo_replay_sample(zoo_replay *r, void *stream, const void *u_host, int32_t u_dtype, int32_t B, int32_t mode, zoo_batch *batch,
+                                     int64_t *inds_out);
+/* t[:priority][inds] .= priorities (common.jl:22) for the last sample; prio_dev = device pointer, e.g. zoo_learner_priorities_dev */
+ZOO_API zoo_status zoo_replay_update_priorities(zoo_replay *r, void *stream, const float *prio_dev);
+/* PER draws that fell outside the valid range (the reference redraws them; here they are clamped and counted) */
+ZOO_API zoo_status zoo_replay_invalid_count(zoo_replay *r, uint32_t *n);
+ZOO_API zoo_status zoo_replay_sumtree(zoo_replay *r, zoo_sumtree **tree);
+/* device buffer [B] of the learner's new priorities (batch_losses .+ 1f-10).^beta of the last update */
+ZOO_API zoo_status zoo_learner_priorities_dev(zoo_learner *lrn, float **dev_ptr);
+
 /* ------------------------------------------------------------------ data parallel ------- */
 /* One process per GPU.  Rank 0 calls zoo_dp_unique_id, the host shares the 128 bytes with the other
  * ranks (torch.distributed / MPI / a file), every rank calls zoo_dp_init.  A learner created with a

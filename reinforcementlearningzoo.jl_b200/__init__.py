@@ -10,4 +10,5 @@ from .learners import (SARTS, BasicDQNLearner, DQNLearner, IQNLearner, Prioritiz
                        REMDQNLearner, update, update_trajectory)
 from .nn import (ADAM, Chain, CrossCor, Dense, DuelingNetwork, Flatten, ImplicitQuantileNet, NatureCNN,  # noqa: F401
                  NeuralNetworkApproximator, RMSProp, Scale255, from_oracle_net)
+from .replay import ReplayShard  # noqa: F401
 from .sumtree import SumTree  # noqa: F401

@@ -16,7 +16,7 @@ OBS_U8, OBS_F32 = 0, 1
 OPT_RMSPROP, OPT_ADAM = 0, 1
 LEARNER_BASIC_DQN, LEARNER_DQN, LEARNER_PRIORITIZED_DQN, LEARNER_RAINBOW, LEARNER_IQN, LEARNER_QR_DQN, LEARNER_REM_DQN = range(7)
 DRAW_F32, DRAW_F64 = 0, 1
-SAMPLE_INDEPENDENT, SAMPLE_STRATIFIED = 0, 1
+SAMPLE_INDEPENDENT, SAMPLE_STRATIFIED, REPLAY_UNIFORM = 0, 1, 2
 STATUS = {0: "OK", 1: "BAD_ARG", 2: "CUDA_ERROR", 3: "NCCL_ERROR", 4: "UNSUPPORTED_ARCH"}
 
 
@@ -101,6 +101,16 @@ SIGNATURES = {
     "zoo_sumtree_update_dev": [V, V, V, I64],
     "zoo_sumtree_stream": [V, PV],
     "zoo_sumtree_sync": [V],
+    "zoo_replay_create": [I64, I32, I32, I32, I32, F32, I32, I32, PV],
+    "zoo_replay_destroy": [V],
+    "zoo_replay_push": [V, V, I32, F32, C.c_uint8, F32],
+    "zoo_replay_push_many": [V, V, V, V, V, V, I64],
+    "zoo_replay_length": [V, C.POINTER(I64), C.POINTER(I64)],
+    "zoo_replay_sample": [V, V, V, I32, I32, I32, C.POINTER(Batch), V],
+    "zoo_replay_update_priorities": [V, V, V],
+    "zoo_replay_invalid_count": [V, C.POINTER(C.c_uint32)],
+    "zoo_replay_sumtree": [V, PV],
+    "zoo_learner_priorities_dev": [V, PV],
     "zoo_dp_unique_id": [V],
     "zoo_dp_init": [V, I32, I32, PV],
     "zoo_dp_destroy": [V],

@@ -588,6 +588,12 @@ zoo_status zoo_learner_get_per_sample_loss(const zoo_learner *L, float *host, in
     return ZOO_OK;
 }
 
+zoo_status zoo_learner_priorities_dev(zoo_learner *L, float **dev_ptr) {
+    ZOO_REQUIRE(L && dev_ptr, "zoo_learner_priorities_dev: null argument");
+    *dev_ptr = L->d_prio;
+    return ZOO_OK;
+}
+
 zoo_status zoo_learner_stream(zoo_learner *L, void **stream) {
     ZOO_REQUIRE(L && stream, "zoo_learner_stream: null argument");
     *stream = (void *)L->st;

@@ -220,17 +220,18 @@ zoo_status zoo_sumtree_destroy(zoo_sumtree *t) {
     return ZOO_OK;
 }
 
-static zoo_status update_dev_impl(zoo_sumtree *t, const long long *idx_dev, const float *p_dev, long long n, int physical) {
+static zoo_status update_dev_impl(zoo_sumtree *t, const long long *idx_dev, const float *p_dev, long long n, int physical, cudaStream_t st = nullptr) {
+    if (!st) st = t->st;
     for (long long off = 0; off < n; off += UPD_CHUNK) {
         int m = (int)std::min<long long>(UPD_CHUNK, n - off);
         int n2 = 32;
         while (n2 < m) n2 <<= 1;
         int threads = std::min(1024, std::max(32, n2 / 2));
-        sumtree_update_leaves_kernel<<<1, threads, n2 * 8, t->st>>>(t->tree, t->nparents, t->capacity, t->first, physical,
+        sumtree_update_leaves_kernel<<<1, threads, n2 * 8, st>>>(t->tree, t->nparents, t->capacity, t->first, physical,
                                                                     idx_dev + off, p_dev + off, m, n2, t->d_heap, t->d_change);
         ZOO_LAUNCH_CHECK();
         if (t->depth > 0) {
-            sumtree_update_parents_kernel<<<t->depth, threads, n2 * 20, t->st>>>(t->tree, t->depth, t->d_heap, t->d_change, m, n2);
+            sumtree_update_parents_kernel<<<t->depth, threads, n2 * 20, st>>>(t->tree, t->depth, t->d_heap, t->d_change, m, n2);
             ZOO_LAUNCH_CHECK();
         }
     }
@@ -284,13 +285,14 @@ zoo_status zoo_sumtree_push_many(zoo_sumtree *t, const float *p, int64_t n) {
 zoo_status zoo_sumtree_push(zoo_sumtree *t, float p) { return zoo_sumtree_push_many(t, &p, 1); }
 
 static zoo_status sample_dev_impl(zoo_sumtree *t, const void *u_dev, int u_dtype, long long n, int mode, long long *idx_dev,
-                                  float *prio_dev) {
+                                  float *prio_dev, cudaStream_t st = nullptr) {
+    if (!st) st = t->st;
     int blocks = cdiv(n, 256);
     if (u_dtype == ZOO_DRAW_F64)
-        sumtree_sample_kernel<double><<<blocks, 256, 0, t->st>>>(t->tree, t->tree_len, t->nparents, t->capacity, t->first,
+        sumtree_sample_kernel<double><<<blocks, 256, 0, st>>>(t->tree, t->tree_len, t->nparents, t->capacity, t->first,
                                                                  (const double *)u_dev, n, mode, idx_dev, prio_dev);
     else
-        sumtree_sample_kernel<float><<<blocks, 256, 0, t->st>>>(t->tree, t->tree_len, t->nparents, t->capacity, t->first,
+        sumtree_sample_kernel<float><<<blocks, 256, 0, st>>>(t->tree, t->tree_len, t->nparents, t->capacity, t->first,
                                                                 (const float *)u_dev, n, mode, idx_dev, prio_dev);
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
@@ -381,3 +383,14 @@ zoo_status zoo_sumtree_sync(zoo_sumtree *t) {
 }
 
 }  // extern "C"
+
+// internal: the same device-side sample / update enqueued on a caller-chosen stream (replay.cu)
+namespace zoo {
+zoo_status sumtree_sample_on(zoo_sumtree *t, cudaStream_t st, const void *u_dev, int u_dtype, long long n, int mode, long long *idx_dev, float *prio_dev) {
+    return sample_dev_impl(t, u_dev, u_dtype, n, mode, idx_dev, prio_dev, st);
+}
+zoo_status sumtree_update_on(zoo_sumtree *t, cudaStream_t st, const long long *idx_dev, const float *p_dev, long long n) {
+    return update_dev_impl(t, idx_dev, p_dev, n, 0, st);
+}
+void sumtree_state(const zoo_sumtree *t, long long *length, long long *first) { *length = t->length; *first = t->first; }
+}  // namespace zoo
