@@ -21,6 +21,7 @@ bool pdl_enabled() {
     return on == 1;
 }
 
+int g_sm_budget = 148;
 thread_local bool g_prof_on = false;
 static thread_local cudaStream_t g_prof_stream = nullptr;
 static thread_local std::vector<cudaEvent_t> g_prof_events;
