@@ -275,6 +275,10 @@ ZOO_API zoo_status zoo_dp_destroy(zoo_dp *dp);
 ZOO_API zoo_status zoo_prof_begin(void *stream, int32_t delay_us);
 ZOO_API zoo_status zoo_prof_end(int32_t *n_launches);
 ZOO_API zoo_status zoo_prof_get(int32_t i, char *name, int32_t name_cap, float *ms);
+/* Timeline mode: zoo_prof_timeline(1, NULL); run one eager update (its lanes stay concurrent); zoo_prof_timeline(0, &n).  Record i =
+ * one kernel launch: its phase label, the stream it ran on, start / end in microseconds since the first launch. */
+ZOO_API zoo_status zoo_prof_timeline(int32_t on, int32_t *n_records);
+ZOO_API zoo_status zoo_prof_timeline_get(int32_t i, char *name, int32_t name_cap, uint64_t *stream, float *start_us, float *end_us);
 
 /* ------------------------------------------------------------------ test hooks ---------- */
 /* Stand-alone GEMM of the two contraction engines, for parity tests of the kernels themselves:

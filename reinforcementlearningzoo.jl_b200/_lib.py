@@ -116,6 +116,8 @@ SIGNATURES = {
     "zoo_dp_destroy": [V],
     "zoo_prof_begin": [V, I32],
     "zoo_prof_end": [C.POINTER(I32)],
+    "zoo_prof_timeline": [I32, C.POINTER(I32)],
+    "zoo_prof_timeline_get": [I32, C.c_char_p, I32, C.POINTER(C.c_uint64), C.POINTER(F32), C.POINTER(F32)],
     "zoo_prof_get": [I32, C.c_char_p, I32, C.POINTER(F32)],
     "zoo_test_gemm": [I32, I32, I32, I32, V, I32, V, I32, V, I32],
     "zoo_test_gemm_trace": [I32, I32, I32, I32, I32, I32, I32, V],

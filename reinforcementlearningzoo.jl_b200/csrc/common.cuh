@@ -71,8 +71,20 @@ extern int g_sm_budget;
 // touches global memory, and calls pdl_trigger() once its main loop is done (triggering at kernel entry was measured slower:
 // early-resident dependents take SMs from the predecessor's second wave).  +4 % on the B=32 update; ZOO_PDL=0 disables it.
 bool pdl_enabled();
+// timeline profiler (zoo_prof_timeline): with the lanes running concurrently, every launch_pdl launch is bracketed by two
+// events on its own stream; zoo_prof_timeline_get returns (label, stream, start, end) relative to the first launch
+extern thread_local bool g_timeline_on;
+void timeline_mark(cudaStream_t st, int end);
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    if (g_timeline_on) {
+        timeline_mark(st, 0);
+        cudaLaunchConfig_t c0 = {};
+        c0.gridDim = grid; c0.blockDim = block; c0.dynamicSmemBytes = smem; c0.stream = st;
+        cudaError_t e = cudaLaunchKernelEx(&c0, kernel, std::forward<Args>(args)...);
+        timeline_mark(st, 1);
+        return e;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];

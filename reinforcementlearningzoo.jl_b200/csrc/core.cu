@@ -22,6 +22,10 @@ bool pdl_enabled() {
 }
 
 int g_sm_budget = 148;
+thread_local bool g_timeline_on = false;
+struct TlRec { cudaEvent_t e0, e1; cudaStream_t st; std::string label; };
+static thread_local std::vector<TlRec> g_tl;
+
 thread_local bool g_prof_on = false;
 static thread_local cudaStream_t g_prof_stream = nullptr;
 static thread_local std::vector<cudaEvent_t> g_prof_events;
@@ -30,11 +34,23 @@ static thread_local std::vector<float> g_prof_ms;
 static thread_local char g_prof_lbl[96] = "";
 
 void prof_label(const char *fmt, ...) {
-    if (!g_prof_on) return;
+    if (!g_prof_on && !g_timeline_on) return;
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_prof_lbl, sizeof(g_prof_lbl), fmt, ap);
     va_end(ap);
+}
+
+void timeline_mark(cudaStream_t st, int end) {
+    if (!end) {
+        TlRec r;
+        cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+        r.st = st; r.label = g_prof_lbl;
+        cudaEventRecord(r.e0, st);
+        g_tl.push_back(r);
+    } else if (!g_tl.empty()) {
+        cudaEventRecord(g_tl.back().e1, st);
+    }
 }
 
 void prof_mark(const char *func, int line) {
@@ -126,6 +142,30 @@ zoo_status zoo_prof_end(int32_t *n) {
     g_prof_ms.assign(g_prof_events.size(), 0.f);
     for (size_t i = 1; i < g_prof_events.size(); ++i) cudaEventElapsedTime(&g_prof_ms[i], g_prof_events[i - 1], g_prof_events[i]);
     *n = (int32_t)g_prof_events.size() - 1;
+    return ZOO_OK;
+}
+
+// timeline mode: zoo_prof_timeline(1) ... run ONE eager update ... zoo_prof_timeline(0) returns the number of records
+zoo_status zoo_prof_timeline(int32_t on, int32_t *n_records) {
+    if (on) {
+        for (auto &r : g_tl) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+        g_tl.clear();
+        g_prof_lbl[0] = 0;
+        g_timeline_on = true;
+    } else {
+        g_timeline_on = false;
+        ZOO_CUDA(cudaDeviceSynchronize());
+        if (n_records) *n_records = (int32_t)g_tl.size();
+    }
+    return ZOO_OK;
+}
+zoo_status zoo_prof_timeline_get(int32_t i, char *name, int32_t cap, uint64_t *stream, float *start_us, float *end_us) {
+    ZOO_REQUIRE(name && stream && start_us && end_us && i >= 0 && i < (int)g_tl.size() && cap > 0, "zoo_prof_timeline_get: bad index");
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, g_tl[0].e0, g_tl[i].e0);
+    cudaEventElapsedTime(&b, g_tl[0].e0, g_tl[i].e1);
+    snprintf(name, cap, "%s", g_tl[i].label.c_str());
+    *stream = (uint64_t)(uintptr_t)g_tl[i].st; *start_us = a * 1e3f; *end_us = b * 1e3f;
     return ZOO_OK;
 }
 

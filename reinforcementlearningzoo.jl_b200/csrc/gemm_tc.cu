@@ -96,7 +96,7 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
     dim3 grid(cdiv(M, BM), cdiv(N, BN), 1);
     const int total_kb = cdiv(K, bk);
     const long long tiles = (long long)grid.x * grid.y;
-    const long long cap_ctas = g_sm_budget * (x3 ? 1 : 2);  // resident CTAs (see TcCfg::STAGES)
+    const long long cap_ctas = g_sm_budget * ((x3 && BN >= 128) ? 1 : 2);  // resident CTAs (see TcCfg::STAGES)
     if (split_k <= 0) {
         // split only when the output grid leaves most SMs idle AND one CTA would walk a long K: each split costs
         // atomics on the whole tile, so keep >= 4 K-blocks per CTA and stay within one resident wave
@@ -193,7 +193,7 @@ zoo_status tc_conv_gemm(const ConvGeom &g, const Operand &Wop, int M, int N, int
     dim3 grid(cdiv(M, BM), cdiv(N, BN), 1);
     const int total_kb = cdiv(K, bk);
     const long long tiles = (long long)grid.x * grid.y;
-    const long long cap_ctas = g_sm_budget * (x3 ? 1 : 2);
+    const long long cap_ctas = g_sm_budget * ((x3 && BN >= 128) ? 1 : 2);
     int split_k = 1;
     if (tiles * 2 <= cap_ctas && total_kb >= 32) split_k = (int)std::min<long long>(total_kb / 4, cap_ctas / tiles);
     split_k = std::max(1, std::min(split_k, total_kb));

@@ -157,6 +157,9 @@ __device__ __forceinline__ void dbg_stamp(const TcParams &P, int slot) {
 
 // EB: operand element bytes (2 = bf16, 4 = fp32 consumed as tf32).  X3: 3xTF32 split (EB = 4 only).
 // smem per stage: A tile 128 rows x 128 B (16 KB) + B tile BN rows x 128 B; X3 doubles it for the lo tiles.
+#ifndef X3_STAGES_SMALL
+#define X3_STAGES_SMALL 2
+#endif
 template <int EB, int BN, bool X3>
 struct TcCfg {
     static constexpr int BK = 128 / EB;          // K elements per stage
@@ -173,7 +176,7 @@ struct TcCfg {
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGE_BYTES = RAW_BYTES * (X3 ? 2 : 1);
     // bf16 / tf32: two CTAs per SM (<= ~97 KB each); 3xTF32 owns an SM (TMA -> split -> MMA needs the deeper ring)
-    static constexpr int STAGES = X3 ? (BN >= 128 ? 3 : 4) : (BN >= 128 ? 3 : 4);
+    static constexpr int STAGES = X3 ? (BN >= 128 ? 3 : X3_STAGES_SMALL) : (BN >= 128 ? 3 : 4);
     static constexpr int SMEM = STAGES * STAGE_BYTES + 256 /*barriers*/;
     static constexpr int TMEM_COLS = X3 ? 2 * BN : (BN < 32 ? 32 : BN);  // 3xTF32: two accumulators (chains alternate)
 };
