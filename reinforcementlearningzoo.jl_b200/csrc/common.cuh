@@ -134,7 +134,9 @@ enum { CONV_RAW_U8 = 1,   // first conv: observation [B][C][H][W] uint8, K order
        CONV_NHWC = 3,     // inner conv: activations [B][H][W][C] in the GEMM dtype, K order (ky,kx,c)
        CONV_DGRAD = 4,    // data gradient: A = dY [B][OH][OW][Cout] gathered transposed-conv style, K order (ky,kx,o),
                           //   M = B*H*W input pixels, N = C;  B operand = W viewed [Cout][ks*ks*C] (MN-major)
-       CONV_TMA = 5 };    // forward conv on NHWC activations with TMA-fetched im2col rows (4-D boxes), K order (ky,kx,c)
+       CONV_TMA = 5,      // forward conv on NHWC activations with TMA-fetched im2col rows (4-D boxes), K order (ky,kx,c)
+       CONV_TMA_DGRAD = 6 };  // stride-1 data gradient the same way: A = dY boxes with mirrored taps, K order (ky,kx,o),
+                          //   M = B*H*W input pixels (tiles = whole rows of one image), N = C, W operand as for CONV_DGRAD
 struct ConvGeom {
     const void *x = nullptr;
     int mode = 0;

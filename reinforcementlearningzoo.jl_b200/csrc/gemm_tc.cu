@@ -96,7 +96,7 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
     dim3 grid(cdiv(M, BM), cdiv(N, BN), 1);
     const int total_kb = cdiv(K, bk);
     const long long tiles = (long long)grid.x * grid.y;
-    const long long cap_ctas = g_sm_budget * ((x3 && BN >= 128) ? 1 : 2);  // resident CTAs (see TcCfg::STAGES)
+    const long long cap_ctas = g_sm_budget * ((x3 && BN >= 128) ? 1 : 2);  // resident CTAs (TcCfg::TWO_CTA_STAGES)
     if (split_k <= 0) {
         // split only when the output grid leaves most SMs idle AND one CTA would walk a long K: each split costs
         // atomics on the whole tile, so keep >= 4 K-blocks per CTA and stay within one resident wave
@@ -136,6 +136,10 @@ bool tc_conv_supported(const ConvGeom &g, int is_bf16) {
     if (g.mode == CONV_RAW_U8 || g.mode == CONV_RAW_F32) return g.ks % ch == 0 && ((long long)g.C * g.ks * g.ks * eb) % 16 == 0;
     if (g.mode == CONV_NHWC) return g.C % ch == 0;
     if (g.mode == CONV_DGRAD) return g.Cout % bk == 0 && g.C % 8 == 0 && ((long long)g.ks * g.ks * g.C * eb) % 16 == 0;
+    if (g.mode == CONV_TMA_DGRAD) {  // output grid = the input pixel grid H x W; boxes over dY [B][OH][OW][Cout]
+        const int R = g.W >= 1 && g.W <= 128 ? std::min(g.H, 128 / g.W) : 0;
+        return eb == 4 && g.s == 1 && R >= 1 && (g.Cout * eb) % 128 == 0 && g.C % 32 == 0 && g.C <= 64 && g.W <= 256 && R <= 256;
+    }
     if (g.mode == CONV_TMA) {
         if (g.OW > 128 || g.OW < 1) return false;
         if (g.first) return g.ks * g.C * eb == 128 && g.p == 0 && (g.s * g.C * eb) % 16 == 0 && g.OW <= 256 && ((128 / g.OW - 1) * g.s + 1) <= 256;
@@ -184,6 +188,29 @@ zoo_status tc_conv_gemm(const ConvGeom &g, const Operand &Wop, int M, int N, int
                         cudaStream_t st) {
     ZOO_REQUIRE(tc_conv_supported(g, Wop.is_bf16) && M > 0 && N >= 8 && ((uintptr_t)Wop.p & 15) == 0, "tc_conv_gemm: unsupported geometry");
     if (g.mode == CONV_TMA) return tc_conv_tma(g, Wop, M / (g.OH * g.OW), N, K, epi, st);
+    if (g.mode == CONV_TMA_DGRAD) {
+        // the kernel's "output grid" fields describe the GEMM's rows = input pixels; dY plays the activation tensor
+        const int images = M / (g.H * g.W);
+        ConvGeom d = g;
+        d.OH = g.H; d.OW = g.W;        // rows of the GEMM: input pixels
+        d.R = std::min(g.H, 128 / g.W); d.tpi = cdiv(g.H, d.R); d.cblocks = (g.Cout * 4) / 128; d.first = 0;
+        const int eb = 4, bk = 32;
+        const bool x3 = epi.tf32_passes == 3;
+        ZOO_REQUIRE(!Wop.kmajor && !Wop.is_bf16 && K == g.ks * g.ks * g.Cout, "tc_conv_gemm: bad operands for the TMA data gradient");
+        const int BN = N <= 32 ? 32 : 64;
+        dim3 grid(images * d.tpi, cdiv(N, BN), 1);
+        TcParams P;
+        P.M = M; P.N = N; P.K = K; P.kb_per_split = K / bk; P.epi = epi; P.ws = nullptr; P.ctr = nullptr; P.dbg = nullptr; P.conv = d;
+        CUtensorMap tmA, tmB;
+        const cuuint64_t sC = (cuuint64_t)g.Cout * eb, sW = (cuuint64_t)g.OW * sC, sH = (cuuint64_t)g.OH * sW;
+        const cuuint64_t dims[4] = {(cuuint64_t)g.Cout, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)images};
+        const cuuint64_t str[3] = {sC, sW, sH};
+        const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)g.W, (cuuint32_t)d.R, 1};
+        const cuuint32_t es[4] = {1, 1, 1, 1};
+        ZOO_TRY(make_map4(&tmA, g.x, eb, dims, str, box, es));
+        ZOO_TRY(make_map(&tmB, Wop.p, eb, Wop.ld, g.Cout, Wop.ld, 32, bk, true));  // W as [Cout][ks*ks*C]: boxes at tap offsets
+        return tc_launch(eb, x3, 3, BN, true, false, tmA, tmB, P, grid, st);
+    }
     const int eb = Wop.is_bf16 ? 2 : 4;
     const int bk = 128 / eb, mn_box = 128 / eb;
     const bool x3 = eb == 4 && epi.tf32_passes == 3;

@@ -138,6 +138,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, u
 struct TcParams {
     int M, N, K;
     int kb_per_split;  // K blocks (of 128 bytes of K) per grid.z slice
+    int stages;        // depth of the shared-memory ring of this launch (<= TcCfg::MAX_STAGES)
     Epilogue epi;
     float *ws;      // split-K workspace [M][N] (atomic accumulate, kept all-zero between launches) or nullptr
     unsigned *ctr;  // split-K per-tile arrival counters (kept all-zero between launches)
@@ -157,9 +158,6 @@ __device__ __forceinline__ void dbg_stamp(const TcParams &P, int slot) {
 
 // EB: operand element bytes (2 = bf16, 4 = fp32 consumed as tf32).  X3: 3xTF32 split (EB = 4 only).
 // smem per stage: A tile 128 rows x 128 B (16 KB) + B tile BN rows x 128 B; X3 doubles it for the lo tiles.
-#ifndef X3_STAGES_SMALL
-#define X3_STAGES_SMALL 2
-#endif
 template <int EB, int BN, bool X3>
 struct TcCfg {
     static constexpr int BK = 128 / EB;          // K elements per stage
@@ -176,8 +174,13 @@ struct TcCfg {
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGE_BYTES = RAW_BYTES * (X3 ? 2 : 1);
     // bf16 / tf32: two CTAs per SM (<= ~97 KB each); 3xTF32 owns an SM (TMA -> split -> MMA needs the deeper ring)
-    static constexpr int STAGES = X3 ? (BN >= 128 ? 3 : X3_STAGES_SMALL) : (BN >= 128 ? 3 : 4);
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 256 /*barriers*/;
+    // ring depth is chosen per launch (TcParams::stages): MAX_STAGES when the grid does not fill the GPU anyway (a lone CTA per
+    // SM is TMA-latency bound, so depth is what matters), TWO_CTA_STAGES when it does (two CTAs per SM overlap instead)
+    static constexpr int MAX_STAGES = (232448 - 256) / STAGE_BYTES < 6 ? (232448 - 256) / STAGE_BYTES : 6;
+    static constexpr int TWO_CTA_STAGES = (113 * 1024) / STAGE_BYTES < 2 ? 2 : ((113 * 1024) / STAGE_BYTES > MAX_STAGES ? MAX_STAGES : (113 * 1024) / STAGE_BYTES);
+    static constexpr int STAGES = MAX_STAGES;  // barrier arrays are sized for the deepest ring
+    static constexpr int SMEM = MAX_STAGES * STAGE_BYTES + 256 /*barriers*/;
+    static constexpr int smem_for(int stages) { return stages * STAGE_BYTES + 256; }
     static constexpr int TMEM_COLS = X3 ? 2 * BN : (BN < 32 ? 32 : BN);  // 3xTF32: two accumulators (chains alternate)
 };
 
@@ -311,7 +314,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // the shared address space visible to the compiler, so the epilogue staging below compiles to LDS/STS
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
-    uint64_t *full_bar = (uint64_t *)(smem + C::STAGES * C::STAGE_BYTES);
+    const int NST = GA == 1 ? C::STAGES : P.stages;  // ring depth of this launch
+    uint64_t *full_bar = (uint64_t *)(smem + NST * C::STAGE_BYTES);
     uint64_t *empty_bar = full_bar + C::STAGES;
     uint64_t *conv_bar = empty_bar + C::STAGES;  // X3: lo tiles written (128 converter threads arrive)
     uint64_t *acc_full = conv_bar + C::STAGES;   // [2] accumulator buffer b holds a finished chain (tcgen05.commit)
@@ -340,7 +344,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nchains = (nkb + CHAIN - 1) / CHAIN;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
             mbar_init(&conv_bar[s], 128);
@@ -364,8 +368,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % C::STAGES;
-                const uint32_t ph = (i / C::STAGES) & 1;
+                const int s = i % NST;
+                const uint32_t ph = (i / NST) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t *sa = smem + s * C::STAGE_BYTES;
                 uint8_t *sb = sa + C::A_BYTES;
@@ -376,7 +380,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int kb = kb0 + i;
                     int c0, c1, c2;
                     if (g.first) { c0 = 0; c1 = 0; c2 = coy0 * g.s + kb; }  // K-block = kernel row ky of the padded frame stack
-                    else {
+                    else if (g.mode == CONV_TMA_DGRAD) {  // stride-1 data gradient: a forward conv over dY with mirrored taps
+                        const int tap = kb / g.cblocks, ky = tap / g.ks, kx = tap - ky * g.ks;
+                        c0 = (kb - tap * g.cblocks) * C::BK; c1 = g.p - kx; c2 = coy0 + g.p - ky;
+                    } else {
                         const int tap = kb / g.cblocks, ky = tap / g.ks, kx = tap - ky * g.ks;
                         c0 = (kb - tap * g.cblocks) * C::BK; c1 = kx - g.p; c2 = coy0 * g.s + ky - g.p;
                     }
@@ -399,7 +406,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else {
                     // conv dgrad: K runs over (tap, o); tap t's [Cout][C] slice of W sits at column offset t*C of [Cout][ks*ks*C]
                     int nb = n0, kb = k0;
-                    if (GA == 1) { const int tap = k0 / P.conv.Cout; nb = n0 + tap * P.conv.C; kb = k0 - tap * P.conv.Cout; }
+                    if (GA != 0) { const int tap = k0 / P.conv.Cout; nb = n0 + tap * P.conv.C; kb = k0 - tap * P.conv.Cout; }
 #pragma unroll
                     for (int h = 0; h < BN / C::MN_BOX; ++h)
                         tma_load_2d(sb + h * C::BOX_BYTES, &tmB, &full_bar[s], nb + h * C::MN_BOX, kb);
@@ -411,8 +418,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BN, !A_K, !B_K, EB == 2 ? 1u : 2u);
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % C::STAGES;
-                const uint32_t ph = (i / C::STAGES) & 1;
+                const int s = i % NST;
+                const uint32_t ph = (i / NST) & 1;
                 const int chain = i / CHAIN, cb = chain & 1;
                 const bool chain_start = (i % CHAIN) == 0;
                 if (X3 && chain_start && chain >= 2) {  // the buffer's previous chain must have been drained
@@ -487,8 +494,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 gx0 = g.mode == CONV_DGRAD ? px : px * g.s - g.p;
             }
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % C::STAGES;
-                const uint32_t ph = (i / C::STAGES) & 1;
+                const int s = i % NST;
+                const uint32_t ph = (i / NST) & 1;
                 uint8_t *stage = smem + s * C::STAGE_BYTES;
                 if (GA == 1) {
                     if (P.conv.mode == CONV_NHWC || P.conv.mode == CONV_DGRAD) {
@@ -774,7 +781,7 @@ static zoo_status launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, grid, dim3(TC_THREADS), (size_t)C::SMEM, st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, grid, dim3(TC_THREADS), (size_t)C::smem_for(P.stages), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -815,15 +822,15 @@ static zoo_status launch_conv(const CUtensorMap &tmB, const TcParams &P, dim3 gr
     return ZOO_OK;
 }
 
-template <int EB, int BN, bool X3>
+template <int EB, int BN, bool X3, bool B_K = true>
 static zoo_status launch_conv_tma(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid, cudaStream_t st) {
     using C = TcCfg<EB, BN, X3>;
     static bool attr_set = false;
     if (!attr_set) {
-        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, true, X3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, true, X3, 2>, grid, dim3(TC_THREADS), (size_t)C::SMEM, st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2>, grid, dim3(TC_THREADS), (size_t)C::smem_for(P.stages), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -842,12 +849,33 @@ static zoo_status launch_conv_bn(int BN, bool bk, const CUtensorMap &tmB, const 
 
 
 // One translation unit per operand mode (gemm_tc_bf16.cu / gemm_tc_tf32.cu / gemm_tc_x3.cu) instantiates the kernels, so the
-// three compile in parallel.  kind: 0 = plain GEMM (both operands by TMA), 1 = gathered-A conv, 2 = TMA-im2col conv.
+// three compile in parallel.  kind: 0 = plain GEMM (both operands by TMA), 1 = gathered-A conv, 2 = TMA-im2col conv, 3 = TMA-im2col data gradient.
 template <int EB, bool X3>
-static zoo_status tc_launch_mode(int kind, int BN, bool ak, bool bk, const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid,
+static int tc_pick_stages(int BN, long long ctas, int nkb) {
+    const int mx = BN == 32 ? TcCfg<EB, 32, X3>::MAX_STAGES : (BN == 64 ? TcCfg<EB, 64, X3>::MAX_STAGES : TcCfg<EB, 128, X3>::MAX_STAGES);
+    const int two = BN == 32 ? TcCfg<EB, 32, X3>::TWO_CTA_STAGES : (BN == 64 ? TcCfg<EB, 64, X3>::TWO_CTA_STAGES : TcCfg<EB, 128, X3>::TWO_CTA_STAGES);
+    static const int legacy = [] { const char *e = getenv("ZOO_TC_STAGES"); return e ? atoi(e) : 0; }();
+    int stg = ctas > g_sm_budget ? two : mx;
+    if (legacy == 1) stg = (X3 && BN < 128) ? 2 : mx;  // A/B: the fixed depths of the previous build
+    if (legacy >= 2) stg = legacy < mx ? legacy : mx;
+    if (stg > nkb + 1) stg = nkb + 1 < 2 ? 2 : nkb + 1;  // no point in a ring deeper than the K loop
+    return stg;
+}
+
+template <int EB, bool X3>
+static zoo_status tc_launch_mode(int kind, int BN, bool ak, bool bk, const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P0, dim3 grid,
                                  cudaStream_t st) {
+    TcParams P = P0;
+    P.stages = tc_pick_stages<EB, X3>(BN, (long long)grid.x * grid.y * grid.z, P0.kb_per_split);
     if (kind == 0) return launch_tc_bn<EB, X3>(BN, ak, bk, tmA, tmB, P, grid, st);
     if (kind == 1) return launch_conv_bn<EB, X3>(BN, bk, tmB, P, grid, st);
+    if (kind == 3) {  // TMA-im2col data gradient: MN-major weight operand (fp32 nets; Cin <= 64)
+        if (EB != 4) { set_err("tc_conv: the TMA data-gradient path is fp32-storage only"); return ZOO_BAD_ARG; }
+        if (BN == 32) return launch_conv_tma<4, 32, X3, false>(tmA, tmB, P, grid, st);
+        if (BN == 64) return launch_conv_tma<4, 64, X3, false>(tmA, tmB, P, grid, st);
+        set_err("tc_conv: the TMA data-gradient path covers Cin <= 64");
+        return ZOO_BAD_ARG;
+    }
     if (BN == 32) return launch_conv_tma<EB, 32, X3>(tmA, tmB, P, grid, st);
     if (BN == 64) return launch_conv_tma<EB, 64, X3>(tmA, tmB, P, grid, st);
     return launch_conv_tma<EB, 128, X3>(tmA, tmB, P, grid, st);

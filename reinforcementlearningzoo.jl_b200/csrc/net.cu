@@ -9,6 +9,10 @@ namespace zoo {
 // this round still lose to explicit im2col + TMA GEMM at these layer sizes (the 4-warp gather is instruction-latency bound,
 // see DESIGN.md section 4), so they are opt-in: ZOO_IMPLICIT_CONV=1.
 // forward convs with TMA-fetched im2col rows (CONV_TMA) are the default where the layer geometry allows; ZOO_TMA_CONV=0 disables
+static bool tma_dgrad_enabled() {
+    static const bool on = [] { const char *e = getenv("ZOO_TMA_DGRAD"); return e ? atoi(e) != 0 : false; }();  // opt-in: parity-green, but 31 CTAs lose to the 279-CTA GEMM + col2im at B=32
+    return on;
+}
 static bool tma_conv_enabled() {
     static int on = -1;
     if (on < 0) { const char *e = getenv("ZOO_TMA_CONV"); on = (e && e[0] == '0') ? 0 : 1; }
@@ -553,7 +557,13 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
             ConvGeom g;
             g.x = L.dout; g.mode = CONV_DGRAD; g.C = L.cin; g.H = L.ih; g.W = L.iw; g.ks = L.ksize; g.s = L.stride; g.p = L.pad;
             g.OH = L.oh; g.OW = L.ow; g.Cout = L.cout;
-            if (implicit_conv_enabled() && net->prec != ZOO_PREC_FP32_SIMT && Wn.is_bf16 == dy_bf && dy_bf == bf && L.cin >= 8 && tc_conv_supported(g, bf)) {
+            if (tma_conv_enabled() && tma_dgrad_enabled() && !bf && net->prec != ZOO_PREC_FP32_SIMT && !Wn.is_bf16) {
+                ConvGeom gt = g;
+                gt.mode = CONV_TMA_DGRAD;
+                if (tc_conv_supported(gt, 0)) g = gt;  // stride-1 conv: dY boxes fetched by TMA, no dcols, no col2im
+            }
+            if ((g.mode == CONV_TMA_DGRAD || implicit_conv_enabled()) && net->prec != ZOO_PREC_FP32_SIMT && Wn.is_bf16 == dy_bf && dy_bf == bf &&
+                L.cin >= 8 && tc_conv_supported(g, bf)) {
                 // implicit transposed-conv GEMM: dX[pixel][c] = sum_(tap,o) dY[pixel_out(tap)][o] W[o][tap][c], relu' in the
                 // epilogue -- no dcols matrix, no col2im pass
                 Operand Wt{Wn.p, Wn.is_bf16, L.K, 0};

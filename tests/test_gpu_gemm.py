@@ -63,12 +63,12 @@ def test_split_k_is_consistent(zoo, engine, split):
         assert run(zoo, engine, M, N, K, 1, 1, split) <= TOL[engine]  # second launch: the workspace really was left zeroed
 
 
-@pytest.mark.parametrize("env", ["ZOO_IMPLICIT_CONV", "ZOO_PDL"])
-def test_opt_in_kernels_keep_parity(env):
-    """The implicit-GEMM convolutions (gathered A operand) and the programmatic-dependent-launch path are off by default;
-    switched on, the Atari learner parity tests (fp32 and bf16) must still pass."""
+@pytest.mark.parametrize("env,val", [("ZOO_IMPLICIT_CONV", "1"), ("ZOO_TMA_DGRAD", "1"), ("ZOO_PDL", "0"), ("ZOO_TMA_CONV", "0")])
+def test_non_default_kernel_paths_keep_parity(env, val):
+    """The gathered-A implicit conv and the TMA stride-1 data gradient are opt-in; programmatic dependent launch and the
+    TMA-im2col forward conv can be switched off.  In every setting the Atari learner parity tests (fp32 and bf16) must still pass."""
     e = dict(os.environ)
-    e[env] = "1"
+    e[env] = val
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_learners.py"), "-m", "gpu", "-q", "-x", "-k",
                         "atari and not simt"], env=e, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
