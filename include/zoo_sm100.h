@@ -287,8 +287,11 @@ ZOO_API zoo_status zoo_prof_timeline_get(int32_t i, char *name, int32_t name_cap
 ZOO_API zoo_status zoo_test_gemm(int32_t engine, int32_t M, int32_t N, int32_t K, const float *A, int32_t a_kmajor,
                                  const float *B, int32_t b_kmajor, float *D, int32_t split_k);
 
+/* Tuning hook: force the tcgen05 GEMM's shared-memory ring depth (0 = chosen per launch). */
+ZOO_API zoo_status zoo_test_set_tc_stages(int32_t stages);
 /* device-time benchmark of one GEMM shape: mean microseconds over `iters` back-to-back GEMMs (operands resident, zeros).
- * mode: 0 plain store, 1 atomic accumulate (wgrad), 2 bias + relu (forward). */
+ * mode: 0 plain store, 1 atomic accumulate (wgrad), 2 bias + relu (forward); + 8 = cold operands (each launch reads its own
+ * copy of A and B, the copies together larger than L2). */
 ZOO_API zoo_status zoo_test_gemm_bench(int32_t engine, int32_t M, int32_t N, int32_t K, int32_t a_kmajor, int32_t b_kmajor,
                                        int32_t split_k, int32_t mode, int32_t iters, float *us_out);
 

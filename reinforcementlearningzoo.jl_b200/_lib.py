@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzoo_sm100.so")
+LIB_PATH = os.environ.get("ZOO_SM100_LIB") or os.path.join(_HERE, "libzoo_sm100.so")  # override: A/B runs of two builds
 
 ZOO_MAX_LAYERS = 12
 LAYER_SCALE255, LAYER_CONV, LAYER_FLATTEN, LAYER_DENSE = 0, 1, 2, 3
@@ -121,6 +121,7 @@ SIGNATURES = {
     "zoo_prof_get": [I32, C.c_char_p, I32, C.POINTER(F32)],
     "zoo_test_gemm": [I32, I32, I32, I32, V, I32, V, I32, V, I32],
     "zoo_test_gemm_trace": [I32, I32, I32, I32, I32, I32, I32, V],
+    "zoo_test_set_tc_stages": [I32],
     "zoo_test_gemm_bench": [I32, I32, I32, I32, I32, I32, I32, I32, I32, C.POINTER(F32)],
 }
 _OTHER_RESTYPE = {"zoo_last_error": ([], C.c_char_p), "zoo_version": ([], I32), "zoo_device_arch": ([], I32)}
@@ -137,6 +138,8 @@ def lib():
                               "(or ./build.sh); there is no CPU fallback" % LIB_PATH)
         l = C.CDLL(LIB_PATH)
         for name, argt in SIGNATURES.items():
+            if name.startswith("zoo_test_") and os.environ.get("ZOO_SM100_LIB") and not hasattr(l, name):
+                continue  # an older build under A/B may lack a newer test hook; product entry points stay mandatory
             f = getattr(l, name)
             f.argtypes = argt
             f.restype = I32

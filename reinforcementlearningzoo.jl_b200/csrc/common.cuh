@@ -65,6 +65,7 @@ zoo_status require_sm100();
 // SMs the GEMM split-K heuristics may plan for: 148, or fewer while a data-parallel communicator is alive (the NCCL kernel
 // of the overlapped late bucket holds SMs; a 148-CTA one-CTA-per-SM GEMM would then fall into a second wave)
 extern int g_sm_budget;
+extern int g_tc_stages_force;  // 0 = per-launch choice (tc_pick_stages); >= 2 forces the ring depth (tuning hook)
 
 // Programmatic dependent launch: a kernel launched through launch_pdl may become resident while its stream predecessor is
 // still draining, and runs its prologue (barrier init, TMEM allocation, index setup) there; it must call pdl_wait() before it

@@ -22,6 +22,7 @@ bool pdl_enabled() {
 }
 
 int g_sm_budget = 148;
+int g_tc_stages_force = [] { const char *e = getenv("ZOO_TC_STAGES"); return e ? atoi(e) : 0; }();
 thread_local bool g_timeline_on = false;
 struct TlRec { cudaEvent_t e0, e1; cudaStream_t st; std::string label; };
 static thread_local std::vector<TlRec> g_tl;
@@ -234,9 +235,15 @@ zoo_status zoo_test_gemm_trace(int32_t engine, int32_t M, int32_t N, int32_t K, 
     g_tc_dbg = d;
     if (s == ZOO_OK) s = zoo_test_gemm_bench(engine, M, N, K, a_kmajor, b_kmajor, split_k, 0, 1, &us);
     g_tc_dbg = nullptr;
-    ZOO_CUDA(cudaMemcpy(stamps9, d, 12 * 8, cudaMemcpyDeviceToHost));
+    ZOO_CUDA(cudaMemcpy(stamps9, d, 16 * 8, cudaMemcpyDeviceToHost));
     cudaFree(d);
     return s;
+}
+
+// Forces the tcgen05 GEMM's smem ring depth (0 = per-launch choice); a tuning / test hook.
+zoo_status zoo_test_set_tc_stages(int32_t stages) {
+    g_tc_stages_force = stages;
+    return ZOO_OK;
 }
 
 // Device-time benchmark of one GEMM shape (test hook): random-free (zeros) operands resident on the device, `iters`
@@ -250,12 +257,17 @@ zoo_status zoo_test_gemm_bench(int32_t engine, int32_t M, int32_t N, int32_t K, 
     const int eb = engine == 1 ? 2 : 4;
     void *dA, *dB; float *dD, *ws;
     size_t na = (size_t)M * K, nb = (size_t)N * K, nd = (size_t)M * N;
-    ZOO_CUDA(cudaMalloc(&dA, na * eb));
-    ZOO_CUDA(cudaMalloc(&dB, nb * eb));
+    // mode & 8: cold operands -- every launch reads its own copy of A and B, the copies together larger than L2 (126 MB)
+    const bool cold = (mode & 8) != 0;
+    mode &= 7;
+    int copies = 1;
+    if (cold) copies = (int)std::max<size_t>(1, std::min<size_t>((size_t)iters, (320u << 20) / ((na + nb) * eb) + 1));
+    ZOO_CUDA(cudaMalloc(&dA, na * eb * copies));
+    ZOO_CUDA(cudaMalloc(&dB, nb * eb * copies));
     ZOO_CUDA(cudaMalloc(&dD, nd * 4));
     ZOO_CUDA(cudaMalloc(&ws, (nd + 4096) * 4));
-    ZOO_CUDA(cudaMemsetAsync(dA, 0, na * eb, st));
-    ZOO_CUDA(cudaMemsetAsync(dB, 0, nb * eb, st));
+    ZOO_CUDA(cudaMemsetAsync(dA, 0, na * eb * copies, st));
+    ZOO_CUDA(cudaMemsetAsync(dB, 0, nb * eb * copies, st));
     ZOO_CUDA(cudaMemsetAsync(dD, 0, nd * 4, st));
     ZOO_CUDA(cudaMemsetAsync(ws, 0, (nd + 4096) * 4, st));
     Operand oa{dA, eb == 2, a_kmajor ? K : M, a_kmajor}, ob{dB, eb == 2, b_kmajor ? K : N, b_kmajor};
@@ -266,8 +278,16 @@ zoo_status zoo_test_gemm_bench(int32_t engine, int32_t M, int32_t N, int32_t K, 
     e.tf32_passes = engine == 2 ? 1 : (engine == 3 ? 3 : 0);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    auto one = [&]() { return engine == 0 ? simt_gemm(oa, ob, M, N, K, e, split_k, ws, nd + 4096, st) : tc_gemm(oa, ob, M, N, K, e, split_k, ws, nd + 4096, st); };
+    int turn = 0;
+    auto one = [&]() {
+        Operand a = oa, b = ob;
+        a.p = (char *)dA + (size_t)(turn % copies) * na * eb;
+        b.p = (char *)dB + (size_t)(turn % copies) * nb * eb;
+        ++turn;
+        return engine == 0 ? simt_gemm(a, b, M, N, K, e, split_k, ws, nd + 4096, st) : tc_gemm(a, b, M, N, K, e, split_k, ws, nd + 4096, st);
+    };
     for (int it = 0; it < 3; ++it) ZOO_TRY(one());
+    turn = 0;
     // the timed launches are replayed from a CUDA graph so the number is device time, not host launch rate
     cudaGraph_t graph;
     cudaGraphExec_t gexec;

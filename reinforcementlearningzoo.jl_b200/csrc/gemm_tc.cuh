@@ -139,6 +139,7 @@ struct TcParams {
     int M, N, K;
     int kb_per_split;  // K blocks (of 128 bytes of K) per grid.z slice
     int stages;        // depth of the shared-memory ring of this launch (<= TcCfg::MAX_STAGES)
+    int xmode;         // timing ablations only (results are wrong): 1 = 3xTF32 converters skip the lo split, 2 = hi x hi MMA only
     Epilogue epi;
     float *ws;      // split-K workspace [M][N] (atomic accumulate, kept all-zero between launches) or nullptr
     unsigned *ctr;  // split-K per-tile arrival counters (kept all-zero between launches)
@@ -301,6 +302,99 @@ __device__ __forceinline__ uint4 tf32_lo(const uint4 v) {
     return l;
 }
 
+// Epilogue row walkers.  One warp owns a 32 x 32 chunk staged in shared memory; lane = column, LD = row stride of the
+// staging buffer.  A single warp per scheduler runs this, so the cost is instruction count x dependent-issue latency:
+// 8 rows per batch (independent chains), 32-bit strides, output type resolved outside the loop.
+template <typename T>
+__device__ __forceinline__ void epi_put(T *p, float x);
+template <>
+__device__ __forceinline__ void epi_put<float>(float *p, float x) { *p = x; }
+template <>
+__device__ __forceinline__ void epi_put<bf16>(bf16 *p, float x) { *p = __float2bfloat16_rn(x); }
+
+// (values that originate in the kernel parameter bank are laundered through empty asm statements: otherwise the compiler
+// re-reads them from the constant bank next to every store instead of keeping them in registers.)
+template <typename P>
+__device__ __forceinline__ P *in_reg(P *p) { asm volatile("" : "+l"(p)); return p; }
+__device__ __forceinline__ int in_reg(int v) { asm volatile("" : "+r"(v)); return v; }
+
+template <typename T, int LD, bool MASK>
+__device__ __forceinline__ void epi_rows_store(const float *cp, int rows, T *op, int stride, float bv, int relu, unsigned mbits) {
+    op = in_reg(op); stride = in_reg(stride); relu = in_reg(relu);
+#pragma unroll 1
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = cp[(r0 + u) * LD];
+        T *o = op + (long long)r0 * stride;
+        const unsigned mb = mbits >> r0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float x = v[u] + bv;
+            const float xr = fmaxf(x, 0.f);
+            x = relu ? xr : x;
+            if (MASK) x = (mb & (1u << u)) ? x : 0.f;
+            v[u] = x;
+        }
+        if (r0 + 8 <= rows) {  // whole batch in range: straight-line stores, no per-row branch
+#pragma unroll
+            for (int u = 0; u < 8; ++u) epi_put<T>(o + u * stride, v[u]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (r0 + u < rows) epi_put<T>(o + u * stride, v[u]);
+        }
+    }
+}
+template <int LD>
+__device__ __forceinline__ void epi_rows_red(const float *cp, int rows, float *op, int stride) {
+    op = in_reg(op); stride = in_reg(stride);
+#pragma unroll 1
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = cp[(r0 + u) * LD];
+        float *o = op + (long long)r0 * stride;
+        if (r0 + 8 <= rows) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) atomicAdd(o + u * stride, v[u]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (r0 + u < rows) atomicAdd(o + u * stride, v[u]);
+        }
+    }
+}
+// transposed chunk (swap-AB): lane = tile row, walk the columns; the output index advances by `stride` per column
+template <typename T, bool MASK>
+__device__ __forceinline__ void epi_cols_store(const float *rp, int ncols, T *op, int stride, float bm, int relu, unsigned mbits) {
+    op = in_reg(op); stride = in_reg(stride); relu = in_reg(relu);
+#pragma unroll 1
+    for (int c0 = 0; c0 < ncols; c0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = rp[c0 + u];
+        T *o = op + (long long)c0 * stride;
+        const unsigned mb = mbits >> c0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float x = v[u] + bm;
+            const float xr = fmaxf(x, 0.f);
+            x = relu ? xr : x;
+            if (MASK) x = (mb & (1u << u)) ? x : 0.f;
+            v[u] = x;
+        }
+        if (c0 + 8 <= ncols) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) epi_put<T>(o + u * stride, v[u]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (c0 + u < ncols) epi_put<T>(o + u * stride, v[u]);
+        }
+    }
+}
+
 // GA = 1: the A operand is gathered by warps 2..5 (implicit-GEMM convolution, see ConvGeom) instead of TMA-loaded.
 // GA = 2: implicit-GEMM convolution with the im2col rows fetched by TMA itself: one M tile = R whole output rows of one
 //         image, one K-block = one kernel tap (or kernel row), loaded as a single 4-D box of the NHWC activation tensor
@@ -430,6 +524,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (!X3) mbar_wait(&full_bar[s], ph);       // TMA bytes have landed (the 3xTF32 converters waited for them)
                 tc_fence_after();
                 if (i == 0) dbg_stamp(P, 3);
+                if (i == 1) dbg_stamp(P, 12);
+                if (i == 2) dbg_stamp(P, 13);
+                if (i == nkb - 1) dbg_stamp(P, 14);
                 const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
                 const uint32_t sb = sa + C::A_BYTES;
                 const uint32_t td = tmem_base + (uint32_t)(cb * BN);
@@ -447,9 +544,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                  : make_smem_desc(sa + C::RAW_BYTES + ao, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
                         const uint64_t bdl = B_K ? make_smem_desc(sb + C::RAW_BYTES + bo, 16, 1024)
                                                  : make_smem_desc(sb + C::RAW_BYTES + bo, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
-                        umma<EB>(td, ad, bdl, idesc, !(chain_start && k == 0));
-                        umma<EB>(td, adl, bd, idesc, 1);
-                        umma<EB>(td, ad, bd, idesc, 1);
+                        if (P.xmode & 2) {
+                            umma<EB>(td, ad, bd, idesc, !(chain_start && k == 0));
+                        } else {
+                            umma<EB>(td, ad, bdl, idesc, !(chain_start && k == 0));
+                            umma<EB>(td, adl, bd, idesc, 1);
+                            umma<EB>(td, ad, bd, idesc, 1);
+                        }
                     } else {
                         umma<EB>(td, ad, bd, idesc, (i | k) != 0);
                     }
@@ -545,10 +646,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // is written.  Rows past M / N are never stored, so they are skipped.
                     const uint4 *raw = reinterpret_cast<const uint4 *>(stage);
                     uint4 *lo = reinterpret_cast<uint4 *>(stage + C::RAW_BYTES);
-#pragma unroll 4
-                    for (int j = t; j < conv_units; j += 128) {
-                        const int jj = j < a_units ? j : j - a_units + C::A_BYTES / 16;
-                        lo[jj] = tf32_lo(raw[jj]);
+                    // batches of 8 x 16 B per thread: all loads first, then all stores -- raw and lo may alias as far as the
+                    // compiler knows, so an element-wise loop serialises on shared-memory latency (measured 0.4 us per stage)
+                    for (int j0 = t; j0 < ((P.xmode & 1) ? 0 : conv_units); j0 += 8 * 128) {
+                        uint4 v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int j = j0 + u * 128;
+                            const int jj = j < a_units ? j : j - a_units + C::A_BYTES / 16;
+                            if (j < conv_units) v[u] = raw[jj];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int j = j0 + u * 128;
+                            const int jj = j < a_units ? j : j - a_units + C::A_BYTES / 16;
+                            if (j < conv_units) lo[jj] = tf32_lo(v[u]);
+                        }
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
@@ -610,14 +723,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const void *const maskp = e.mask;
         const int mask_bf16 = e.mask_bf16;
         const long long msm = e.mask_sm, msn = e.mask_sn;
+        // CODE SIZE matters here: this code runs once per CTA, so it is fetched cold -- the column-chunk loops below are
+        // deliberately NOT unrolled and the row loops only by 4 (measured: the fully unrolled epilogue took 1.4 us per
+        // 32 x 32 chunk, instruction-fetch bound).
+        // 3xTF32: the register sums are indexed statically, so one small unrolled pass first folds them into the last
+        // chain and parks the whole 32 x BN slab of this warp in shared memory (row stride BN + 1: conflict-free both ways)
+        constexpr int XLD = BN + 1;
+        float *const xst = reinterpret_cast<float *>(smem) + q * 32 * XLD;
+        if (X3) {
+#pragma unroll
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(tq + (uint32_t)(lb * BN + c), r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) xst[lane * XLD + c + j] = __fadd_rn(__uint_as_float(r[j]), acc[X3 ? c + j : 0]);
+            }
+            __syncwarp();
+            if (threadIdx.x == 64) dbg_stamp(P, 9);
+        }
         // bf16 output, plain row-major store: 64 columns at a time so that every lane writes a packed bf16x2 (128-byte row
         // segments instead of 64-byte ones) -- the wide, K-short GEMMs (IQN phi: K = 64, 0.5 GB of output) are store-bound
         if (BN >= 64 && !X3 && simple && !trans && !split && !e.accumulate && out_bf16 && sn == 1 && (Nn & 1) == 0 && (sm & 1) == 0 &&
             (!maskp || (mask_bf16 && msn == 1 && (msm & 1) == 0))) {
             float(*stw)[66] = reinterpret_cast<float(*)[66]>(smem) + q * 32;  // 32 x 66 floats per warp (spans idle stages)
-#pragma unroll
+#pragma unroll 1
             for (int c = 0; c < BN; c += 64) {
-#pragma unroll
+#pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
                     uint32_t r[32];
                     tmem_ld32(tq + (uint32_t)(lb * BN + c + 32 * h), r);
@@ -631,137 +762,166 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (bias_mode == 1) { b0 = __ldg(e.bias + n); b1 = __ldg(e.bias + n + 1); }
                     __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>((bf16 *)e.out + (long long)row0 * sm + n);
                     const __nv_bfloat162 *mp = maskp ? reinterpret_cast<const __nv_bfloat162 *>((const bf16 *)maskp + (long long)row0 * msm + n) : nullptr;
-#pragma unroll 8
-                    for (int rr = 0; rr < rows; ++rr) {
-                        const float2 v2 = *reinterpret_cast<const float2 *>(&stw[rr][2 * lane]);
-                        float v0 = v2.x + b0, v1 = v2.y + b1;
-                        if (bias_mode == 2) { const float bm = __ldg(e.bias + row0 + rr); v0 += bm; v1 += bm; }
-                        if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                        if (mp) {
-                            const __nv_bfloat162 mk = __ldg(mp + (long long)rr * (msm >> 1));
-                            v0 = __low2float(mk) > 0.f ? v0 : 0.f;
-                            v1 = __high2float(mk) > 0.f ? v1 : 0.f;
+#pragma unroll 1
+                    for (int r0 = 0; r0 < rows; r0 += 4) {
+                        float2 v2[4];
+                        __nv_bfloat162 mk[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int rr = min(r0 + u, 31);
+                            v2[u] = *reinterpret_cast<const float2 *>(&stw[rr][2 * lane]);
+                            mk[u] = mp && r0 + u < rows ? __ldg(mp + (long long)rr * (msm >> 1)) : __floats2bfloat162_rn(1.f, 1.f);
                         }
-                        op[(long long)rr * (sm >> 1)] = __floats2bfloat162_rn(v0, v1);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (r0 + u >= rows) break;
+                            float v0 = v2[u].x + b0, v1 = v2[u].y + b1;
+                            if (bias_mode == 2) { const float bm = __ldg(e.bias + row0 + r0 + u); v0 += bm; v1 += bm; }
+                            if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                            v0 = __low2float(mk[u]) > 0.f ? v0 : 0.f;
+                            v1 = __high2float(mk[u]) > 0.f ? v1 : 0.f;
+                            op[(long long)(r0 + u) * (sm >> 1)] = __floats2bfloat162_rn(v0, v1);
+                        }
                     }
                 }
                 __syncwarp();
             }
-        } else
-#pragma unroll
+        } else {
+        // Split-K without a finishing launch: pass 0 adds this CTA's partial tile into the workspace; the last CTA to arrive
+        // on the tile (per-tile counter behind the workspace) runs pass 1: it re-reads the summed chunks (coalesced, all 32
+        // rows of a column in flight at once), zeroes them for the next GEMM, restages them in shared memory and then
+        // stores them exactly like an unsplit tile -- so a transposed (swap-AB) output is written coalesced too.
+        bool red_ws = split, refill = false;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(tq + (uint32_t)(lb * BN + c), r);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float v = __uint_as_float(r[j]);
-                if (X3) v = __fadd_rn(v, acc[X3 ? c + j : 0]);
-                stg[lane][j] = v;
-            }
-            __syncwarp();
+            if (n0 + c >= Nn) break;  // the whole chunk lies past N (uniform)
+            constexpr int LDC = X3 ? XLD : 33;
+            float *const cbuf = X3 ? xst + c : &stg[0][0];  // element (r, j) of the chunk at cbuf[r * LDC + j]
             const int n = n0 + c + lane;
-            if (trans && !split && !e.accumulate) {
+            if (refill) {
+#pragma unroll 1
+                for (int h = 0; h < 32; h += 16) {  // 16 rows of the column in flight at a time
+                    float v[16];
+                    float *wp = in_reg(ws + (long long)(row0 + h) * Nn + n);  // (pins the address arithmetic inside the loop: hoisted, it spilled)
+                    if (n < Nn && h + 16 <= rows) {
+#pragma unroll
+                        for (int rr = 0; rr < 16; ++rr) v[rr] = __ldcg(wp + (long long)rr * Nn);
+#pragma unroll
+                        for (int rr = 0; rr < 16; ++rr) __stcg(wp + (long long)rr * Nn, 0.f);
+                    } else {
+#pragma unroll
+                        for (int rr = 0; rr < 16; ++rr) v[rr] = (n < Nn && h + rr < rows) ? __ldcg(wp + (long long)rr * Nn) : 0.f;
+#pragma unroll
+                        for (int rr = 0; rr < 16; ++rr)
+                            if (n < Nn && h + rr < rows) __stcg(wp + (long long)rr * Nn, 0.f);
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 16; ++rr) cbuf[(h + rr) * LDC + lane] = v[rr];
+                }
+                __syncwarp();
+            } else if (!X3) {
+                uint32_t r[32];
+                tmem_ld32(tq + (uint32_t)(lb * BN + c), r);
+                if (c == 0 && threadIdx.x == 64) dbg_stamp(P, 9);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stg[lane][j] = __uint_as_float(r[j]);
+                __syncwarp();
+            }
+            const float *const chunk = cbuf;
+            constexpr int ld = LDC;
+            if (c == 0 && threadIdx.x == 64 && !refill) dbg_stamp(P, 10);
+            const bool direct = refill || (!red_ws && !e.accumulate);
+            // relu' mask of the 32 x 32 chunk as one bit per element: 32 independent loads in flight instead of one
+            // dependent load per stored row.  Bit i = row i of column `lane` (or column i of row `lane` when transposed).
+            unsigned mbits = 0xffffffffu;
+            const void *mq = maskp;
+            asm volatile("" : "+l"(mq));  // keeps the mask loads below inside this loop body
+            if (mq && direct && simple) {
+                mbits = 0u;
+                const int cnt = trans ? min(32, Nn - (n0 + c)) : rows;
+                const bool mine = trans ? lane < rows : n < Nn;
+                const long long mbase = trans ? (long long)(row0 + lane) * msm + (long long)(n0 + c) * msn : (long long)row0 * msm + (long long)n * msn;
+                const long long mstep = trans ? msn : msm;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (mine && i < cnt) mbits |= (ldg_elem(mq, mask_bf16, mbase + i * mstep) > 0.f ? 1u : 0u) << i;
+            }
+            const bool narrow = sm < (1 << 24) && sn < (1 << 24) && Nn < (1 << 24);  // 32-bit strides inside a chunk
+            const bool hasmask = maskp != nullptr;
+            if (trans && direct && narrow && bias_mode != 1) {
                 // transposed output (swap-AB dispatch: consecutive m are contiguous in memory): lane = tile row
                 const int m = row0 + lane;
                 const int ncols = min(32, Nn - (n0 + c));
                 if (lane < rows) {
                     const float bm = bias_mode == 2 ? __ldg(e.bias + m) : 0.f;
-#pragma unroll 8
-                    for (int cc = 0; cc < ncols; ++cc) {
-                        const int nn = n0 + c + cc;
-                        float v = stg[lane][cc] + bm;
-                        if (bias_mode == 1) v += __ldg(e.bias + nn);
-                        if (relu) v = fmaxf(v, 0.f);
-                        if (maskp) v = ldg_elem(maskp, mask_bf16, (long long)m * msm + (long long)nn * msn) > 0.f ? v : 0.f;
-                        st_elem(e.out, out_bf16, (long long)m * sm + (long long)nn * sn, v);
+                    const long long o0 = (long long)m * sm + (long long)(n0 + c) * sn;
+                    const float *rp = chunk + lane * ld;
+                    if (out_bf16) {
+                        if (hasmask) epi_cols_store<bf16, true>(rp, ncols, (bf16 *)e.out + o0, (int)sn, bm, relu, mbits);
+                        else epi_cols_store<bf16, false>(rp, ncols, (bf16 *)e.out + o0, (int)sn, bm, relu, mbits);
+                    } else {
+                        if (hasmask) epi_cols_store<float, true>(rp, ncols, (float *)e.out + o0, (int)sn, bm, relu, mbits);
+                        else epi_cols_store<float, false>(rp, ncols, (float *)e.out + o0, (int)sn, bm, relu, mbits);
                     }
                 }
             } else if (n < Nn) {
-                if (split) {
-                    float *wp = ws + (long long)row0 * Nn + n;
-#pragma unroll 8
-                    for (int rr = 0; rr < rows; ++rr) atomicAdd(wp + (long long)rr * Nn, stg[rr][lane]);
-                } else if (e.accumulate) {
-                    float *op = (float *)e.out + (long long)row0 * sm + (long long)n * sn;
-#pragma unroll 8
-                    for (int rr = 0; rr < rows; ++rr) atomicAdd(op + (long long)rr * sm, stg[rr][lane]);
-                } else if (simple && !trans) {
+                if (!direct && narrow) {
+                    // split-K partial sums into the workspace, or wgrad-style accumulation into the output
+                    float *bp = red_ws ? ws + (long long)row0 * Nn + n : (float *)e.out + (long long)row0 * sm + (long long)n * sn;
+                    epi_rows_red<LDC>(chunk + lane, rows, bp, red_ws ? Nn : (int)sm);
+                } else if (direct && simple && narrow && bias_mode != 2 && !trans) {
                     const float bv = bias_mode == 1 ? __ldg(e.bias + n) : 0.f;
+                    const long long o0 = (long long)row0 * sm + (long long)n * sn;
+                    const float *cp = chunk + lane;
                     if (out_bf16) {
-                        bf16 *op = (bf16 *)e.out + (long long)row0 * sm + (long long)n * sn;
-#pragma unroll 8
-                        for (int rr = 0; rr < rows; ++rr) {
-                            float v = stg[rr][lane] + bv;
-                            if (bias_mode == 2) v += __ldg(e.bias + row0 + rr);
-                            if (relu) v = fmaxf(v, 0.f);
-                            if (maskp) v = ldg_elem(maskp, mask_bf16, (long long)(row0 + rr) * msm + (long long)n * msn) > 0.f ? v : 0.f;
-                            op[(long long)rr * sm] = __float2bfloat16_rn(v);
-                        }
+                        if (hasmask) epi_rows_store<bf16, LDC, true>(cp, rows, (bf16 *)e.out + o0, (int)sm, bv, relu, mbits);
+                        else epi_rows_store<bf16, LDC, false>(cp, rows, (bf16 *)e.out + o0, (int)sm, bv, relu, mbits);
                     } else {
-                        float *op = (float *)e.out + (long long)row0 * sm + (long long)n * sn;
-#pragma unroll 8
-                        for (int rr = 0; rr < rows; ++rr) {
-                            float v = stg[rr][lane] + bv;
-                            if (bias_mode == 2) v += __ldg(e.bias + row0 + rr);
-                            if (relu) v = fmaxf(v, 0.f);
-                            if (maskp) v = ldg_elem(maskp, mask_bf16, (long long)(row0 + rr) * msm + (long long)n * msn) > 0.f ? v : 0.f;
-                            op[(long long)rr * sm] = v;
-                        }
+                        if (hasmask) epi_rows_store<float, LDC, true>(cp, rows, (float *)e.out + o0, (int)sm, bv, relu, mbits);
+                        else epi_rows_store<float, LDC, false>(cp, rows, (float *)e.out + o0, (int)sm, bv, relu, mbits);
+                    }
+                } else if (!direct) {
+                    float *bp = red_ws ? ws + (long long)row0 * Nn + n : (float *)e.out + (long long)row0 * sm + (long long)n * sn;
+                    const long long bs = red_ws ? (long long)Nn : sm;
+#pragma unroll 1
+                    for (int rr = 0; rr < rows; ++rr) atomicAdd(bp + (long long)rr * bs, chunk[rr * ld + lane]);
+                } else if (simple) {
+#pragma unroll 1
+                    for (int rr = 0; rr < rows; ++rr) {  // rare shapes (row bias without swap-AB, very large strides): one element at a time
+                        const int m = row0 + rr;
+                        float x = chunk[rr * ld + lane];
+                        if (bias_mode == 1) x += __ldg(e.bias + n);
+                        if (bias_mode == 2) x += __ldg(e.bias + m);
+                        if (relu) x = fmaxf(x, 0.f);
+                        if (maskp) x = ldg_elem(maskp, mask_bf16, (long long)m * msm + (long long)n * msn) > 0.f ? x : 0.f;
+                        st_elem(e.out, out_bf16, (long long)m * sm + (long long)n * sn, x);
                     }
                 } else {
-#pragma unroll 4
-                    for (int rr = 0; rr < rows; ++rr) epi_store(e, stg[rr][lane], row0 + rr, n);
+#pragma unroll 1
+                    for (int rr = 0; rr < rows; ++rr) epi_store(e, chunk[rr * ld + lane], row0 + rr, n);
                 }
             }
             __syncwarp();
+            if (c == 0 && threadIdx.x == 64 && !refill) dbg_stamp(P, 11);
         }
-        if (split) {
-            // split-K without a finishing launch: the last CTA to arrive on this output tile (per-tile counter behind the
-            // workspace) applies the epilogue to the summed tile and leaves workspace + counter zeroed for the next GEMM.
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            unsigned *ctr = P.ctr + blockIdx.y * gridDim.x + blockIdx.x;
-            if (threadIdx.x == 64) {
-                const unsigned old = atomicAdd(ctr, 1u);
-                const bool last = old == gridDim.z - 1;
-                if (last) *ctr = 0u;
-                *tmem_slot = last ? 1u : 0u;  // tmem_slot is dead after tmem_base was read
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (*tmem_slot) {
-                __threadfence();
-#pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
-                    const int n = n0 + c + lane;
-                    if (n >= Nn) break;
-                    const float bv = bias_mode == 1 ? __ldg(e.bias + n) : 0.f;
-                    // 16 rows at a time: all loads first (the compiler must not be left to order each load behind the
-                    // previous row's store -- that serialises 128 x BN / 128 L2 round trips, measured +25 us)
-#pragma unroll 1
-                    for (int r8 = 0; r8 < rows; r8 += 16) {
-                        float v[16];
-#pragma unroll
-                        for (int u = 0; u < 16; ++u) v[u] = r8 + u < rows ? __ldcg(ws + (long long)(row0 + r8 + u) * Nn + n) : 0.f;
-#pragma unroll
-                        for (int u = 0; u < 16; ++u)
-                            if (r8 + u < rows) __stcg(ws + (long long)(row0 + r8 + u) * Nn + n, 0.f);
-#pragma unroll
-                        for (int u = 0; u < 16; ++u) {
-                            if (r8 + u >= rows) continue;
-                            const int m = row0 + r8 + u;
-                            if (simple) {
-                                float x = v[u] + bv;
-                                if (bias_mode == 2) x += __ldg(e.bias + m);
-                                if (relu) x = fmaxf(x, 0.f);
-                                if (maskp) x = ldg_elem(maskp, mask_bf16, (long long)m * msm + (long long)n * msn) > 0.f ? x : 0.f;
-                                st_elem(e.out, out_bf16, (long long)m * sm + (long long)n * sn, x);
-                            } else {
-                                epi_store(e, v[u], m, n);
-                            }
-                        }
-                    }
-                }
-            }
+        if (!red_ws) break;
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        unsigned *ctr = P.ctr + blockIdx.y * gridDim.x + blockIdx.x;
+        if (threadIdx.x == 64) {
+            const unsigned old = atomicAdd(ctr, 1u);
+            const bool last = old == gridDim.z - 1;
+            if (last) *ctr = 0u;
+            *tmem_slot = last ? 1u : 0u;  // tmem_slot is dead after tmem_base was read
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (!*tmem_slot) break;
+        __threadfence();
+        red_ws = false;
+        refill = true;
+        }
         }
     }
     if (threadIdx.x == 64) dbg_stamp(P, 6);
@@ -854,10 +1014,9 @@ template <int EB, bool X3>
 static int tc_pick_stages(int BN, long long ctas, int nkb) {
     const int mx = BN == 32 ? TcCfg<EB, 32, X3>::MAX_STAGES : (BN == 64 ? TcCfg<EB, 64, X3>::MAX_STAGES : TcCfg<EB, 128, X3>::MAX_STAGES);
     const int two = BN == 32 ? TcCfg<EB, 32, X3>::TWO_CTA_STAGES : (BN == 64 ? TcCfg<EB, 64, X3>::TWO_CTA_STAGES : TcCfg<EB, 128, X3>::TWO_CTA_STAGES);
-    static const int legacy = [] { const char *e = getenv("ZOO_TC_STAGES"); return e ? atoi(e) : 0; }();
     int stg = ctas > g_sm_budget ? two : mx;
-    if (legacy == 1) stg = (X3 && BN < 128) ? 2 : mx;  // A/B: the fixed depths of the previous build
-    if (legacy >= 2) stg = legacy < mx ? legacy : mx;
+    const int force = g_tc_stages_force & 0xff;  // ZOO_TC_STAGES / zoo_test_set_tc_stages
+    if (force >= 2) stg = force < mx ? force : mx;
     if (stg > nkb + 1) stg = nkb + 1 < 2 ? 2 : nkb + 1;  // no point in a ring deeper than the K loop
     return stg;
 }
@@ -867,6 +1026,7 @@ static zoo_status tc_launch_mode(int kind, int BN, bool ak, bool bk, const CUten
                                  cudaStream_t st) {
     TcParams P = P0;
     P.stages = tc_pick_stages<EB, X3>(BN, (long long)grid.x * grid.y * grid.z, P0.kb_per_split);
+    P.xmode = g_tc_stages_force >> 8;
     if (kind == 0) return launch_tc_bn<EB, X3>(BN, ak, bk, tmA, tmB, P, grid, st);
     if (kind == 1) return launch_conv_bn<EB, X3>(BN, bk, tmB, P, grid, st);
     if (kind == 3) {  // TMA-im2col data gradient: MN-major weight operand (fp32 nets; Cin <= 64)
