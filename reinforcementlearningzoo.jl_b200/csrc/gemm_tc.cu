@@ -102,6 +102,12 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
         // atomics on the whole tile, so keep >= 4 K-blocks per CTA and stay within one resident wave
         split_k = 1;
         if (tiles * 2 <= cap_ctas && total_kb >= 32) split_k = (int)std::min<long long>(total_kb / 4, cap_ctas / tiles);
+        else if (x3 && tiles * 2 <= cap_ctas && total_kb >= 16) {
+            // 3xTF32 K-blocks cost ~0.85 us each, a split ~7 us (BN = 32) to ~10 us (BN = 64) of reds + finish: measured
+            // (scripts/sweep_split.py) it pays for 61 x BN32 tiles at 4 splits and for 31 x BN64 tiles at 6+, not for 61 x BN64 at 4
+            const int s = (int)std::min<long long>(total_kb / 2, cap_ctas / tiles);
+            if (s >= (BN <= 32 ? 3 : 6)) split_k = s;
+        }
         if (split_k < 1) split_k = 1;
     }
     split_k = std::min(split_k, total_kb);

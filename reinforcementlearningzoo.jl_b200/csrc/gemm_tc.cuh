@@ -139,7 +139,8 @@ struct TcParams {
     int M, N, K;
     int kb_per_split;  // K blocks (of 128 bytes of K) per grid.z slice
     int stages;        // depth of the shared-memory ring of this launch (<= TcCfg::MAX_STAGES)
-    int xmode;         // timing ablations only (results are wrong): 1 = 3xTF32 converters skip the lo split, 2 = hi x hi MMA only
+    int xmode;         // timing ablations only (results are wrong): 1 = 3xTF32 converters skip the lo split, 2 = hi x hi MMA only,
+                       // 4 = no proxy fence after the split, 8 = split computed but not stored
     Epilogue epi;
     float *ws;      // split-K workspace [M][N] (atomic accumulate, kept all-zero between launches) or nullptr
     unsigned *ctr;  // split-K per-tile arrival counters (kept all-zero between launches)
@@ -174,6 +175,9 @@ struct TcCfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGE_BYTES = RAW_BYTES * (X3 ? 2 : 1);
+    // 3xTF32 stage: [A hi][B hi][B lo][A lo] -- B lo directly behind B hi, so that [B hi; B lo] is ONE operand of 2 BN rows
+    static constexpr int LO_B_OFF = RAW_BYTES;             // from the stage base
+    static constexpr int LO_A_OFF = RAW_BYTES + B_BYTES;
     // bf16 / tf32: two CTAs per SM (<= ~97 KB each); 3xTF32 owns an SM (TMA -> split -> MMA needs the deeper ring)
     // ring depth is chosen per launch (TcParams::stages): MAX_STAGES when the grid does not fill the GPU anyway (a lone CTA per
     // SM is TMA-latency bound, so depth is what matters), TWO_CTA_STAGES when it does (two CTAs per SM overlap instead)
@@ -182,7 +186,8 @@ struct TcCfg {
     static constexpr int STAGES = MAX_STAGES;  // barrier arrays are sized for the deepest ring
     static constexpr int SMEM = MAX_STAGES * STAGE_BYTES + 256 /*barriers*/;
     static constexpr int smem_for(int stages) { return stages * STAGE_BYTES + 256; }
-    static constexpr int TMEM_COLS = X3 ? 2 * BN : (BN < 32 ? 32 : BN);  // 3xTF32: two accumulators (chains alternate)
+    static constexpr int ACC_COLS = X3 ? 2 * BN : BN;  // 3xTF32: columns [0, BN) = hi hi + lo hi, [BN, 2 BN) = hi lo
+    static constexpr int TMEM_COLS = X3 ? 2 * ACC_COLS : (BN < 32 ? 32 : BN);  // 3xTF32: two accumulators (chains alternate)
 };
 
 template <int EB>
@@ -529,7 +534,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (i == nkb - 1) dbg_stamp(P, 14);
                 const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
                 const uint32_t sb = sa + C::A_BYTES;
-                const uint32_t td = tmem_base + (uint32_t)(cb * BN);
+                const uint32_t td = tmem_base + (uint32_t)(cb * C::ACC_COLS);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     // K-major SW128: 8-row groups 1024 B apart (SBO); one MMA's K slice = 32 B inside the swizzle span.
@@ -539,17 +544,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t ad = A_K ? make_smem_desc(sa + ao, 16, 1024) : make_smem_desc(sa + ao, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
                     const uint64_t bd = B_K ? make_smem_desc(sb + bo, 16, 1024) : make_smem_desc(sb + bo, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
                     if (X3) {
-                        // lo tiles live RAW_BYTES above the (in-place truncated) hi tiles, same layout; small terms first
-                        const uint64_t adl = A_K ? make_smem_desc(sa + C::RAW_BYTES + ao, 16, 1024)
-                                                 : make_smem_desc(sa + C::RAW_BYTES + ao, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
-                        const uint64_t bdl = B_K ? make_smem_desc(sb + C::RAW_BYTES + bo, 16, 1024)
-                                                 : make_smem_desc(sb + C::RAW_BYTES + bo, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
+                        // every tcgen05.mma costs about the same ~130 clocks for N <= 128 (measured), so the three products are
+                        // issued as TWO instructions: A hi x [B hi; B lo] (one operand of 2 BN rows -> accumulator columns
+                        // [0, BN) and [BN, 2 BN)), then A lo x B hi into [0, BN); the halves are summed in registers.
+                        constexpr uint32_t idesc2 = make_idesc(2 * BN, !A_K, !B_K, 2u);
+                        const uint64_t adl = A_K ? make_smem_desc(sa + C::LO_A_OFF + ao, 16, 1024)
+                                                 : make_smem_desc(sa + C::LO_A_OFF + ao, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
                         if (P.xmode & 2) {
                             umma<EB>(td, ad, bd, idesc, !(chain_start && k == 0));
                         } else {
-                            umma<EB>(td, ad, bdl, idesc, !(chain_start && k == 0));
+                            umma<EB>(td, ad, bd, idesc2, !(chain_start && k == 0));
                             umma<EB>(td, adl, bd, idesc, 1);
-                            umma<EB>(td, ad, bd, idesc, 1);
                         }
                     } else {
                         umma<EB>(td, ad, bd, idesc, (i | k) != 0);
@@ -624,7 +629,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const int off = t * 128 + (j << 4);
-                                *reinterpret_cast<uint4 *>(stage + C::RAW_BYTES + off) = tf32_lo(*reinterpret_cast<const uint4 *>(stage + off));
+                                *reinterpret_cast<uint4 *>(stage + C::LO_A_OFF + off) = tf32_lo(*reinterpret_cast<const uint4 *>(stage + off));
                             }
                         }
                     } else {
@@ -635,7 +640,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 8; ++j) {
                             const int off = t * 128 + ((j ^ (t & 7)) << 4);  // SWIZZLE_128B: chunk j of row t sits at j ^ (t % 8)
                             *reinterpret_cast<uint4 *>(stage + off) = gcur[j];
-                            if (X3) *reinterpret_cast<uint4 *>(stage + C::RAW_BYTES + off) = tf32_lo(gcur[j]);
+                            if (X3) *reinterpret_cast<uint4 *>(stage + C::LO_A_OFF + off) = tf32_lo(gcur[j]);
                         }
                     }
                 }
@@ -645,7 +650,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // for raw and pre-truncated inputs), so the landed tile itself is the hi operand; only lo = x - trunc(x)
                     // is written.  Rows past M / N are never stored, so they are skipped.
                     const uint4 *raw = reinterpret_cast<const uint4 *>(stage);
-                    uint4 *lo = reinterpret_cast<uint4 *>(stage + C::RAW_BYTES);
+                    uint4 *lo = reinterpret_cast<uint4 *>(stage + C::RAW_BYTES);  // [B lo][A lo]
                     // batches of 8 x 16 B per thread: all loads first, then all stores -- raw and lo may alias as far as the
                     // compiler knows, so an element-wise loop serialises on shared-memory latency (measured 0.4 us per stage)
                     for (int j0 = t; j0 < ((P.xmode & 1) ? 0 : conv_units); j0 += 8 * 128) {
@@ -659,12 +664,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             const int j = j0 + u * 128;
-                            const int jj = j < a_units ? j : j - a_units + C::A_BYTES / 16;
-                            if (j < conv_units) lo[jj] = tf32_lo(v[u]);
+                            const int jl = j < a_units ? j + C::B_BYTES / 16 : j - a_units;
+                            if (j < conv_units && !(P.xmode & 8)) lo[jl] = tf32_lo(v[u]);
                         }
                     }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
+                if (!(P.xmode & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
                 mbar_arrive(&conv_bar[s]);
                 // chain `drained` ended at K-block (drained+1)*CHAIN - 1; by the time two more blocks have been converted
                 // its MMAs have retired, so the wait below does not stall the conversion pipeline
@@ -674,10 +679,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc_fence_after();
 #pragma unroll
                     for (int c = 0; c < BN; c += 32) {
-                        uint32_t r[32];
-                        tmem_ld32(tq + (uint32_t)(cb * BN + c), r);
+                        uint32_t r[32], r2[32];
+                        tmem_ld32(tq + (uint32_t)(cb * C::ACC_COLS + c), r);
+                        tmem_ld32(tq + (uint32_t)(cb * C::ACC_COLS + BN + c), r2);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[X3 ? c + j : 0] = __fadd_rn(acc[X3 ? c + j : 0], __uint_as_float(r[j]));
+                        for (int j = 0; j < 32; ++j)
+                            acc[X3 ? c + j : 0] = __fadd_rn(acc[X3 ? c + j : 0], __fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
                     }
                     tc_fence_before();
                     mbar_arrive(&acc_empty[cb]);
@@ -690,10 +697,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < BN; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tq + (uint32_t)(cb * BN + c), r);
+                    uint32_t r[32], r2[32];
+                    tmem_ld32(tq + (uint32_t)(cb * C::ACC_COLS + c), r);
+                    tmem_ld32(tq + (uint32_t)(cb * C::ACC_COLS + BN + c), r2);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[X3 ? c + j : 0] = __fadd_rn(acc[X3 ? c + j : 0], __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; ++j)
+                        acc[X3 ? c + j : 0] = __fadd_rn(acc[X3 ? c + j : 0], __fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[cb]);
@@ -733,10 +742,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (X3) {
 #pragma unroll
             for (int c = 0; c < BN; c += 32) {
-                uint32_t r[32];
-                tmem_ld32(tq + (uint32_t)(lb * BN + c), r);
+                uint32_t r[32], r2[32];
+                tmem_ld32(tq + (uint32_t)(lb * C::ACC_COLS + c), r);
+                tmem_ld32(tq + (uint32_t)(lb * C::ACC_COLS + BN + c), r2);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) xst[lane * XLD + c + j] = __fadd_rn(__uint_as_float(r[j]), acc[X3 ? c + j : 0]);
+                for (int j = 0; j < 32; ++j)
+                    xst[lane * XLD + c + j] = __fadd_rn(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])), acc[X3 ? c + j : 0]);
             }
             __syncwarp();
             if (threadIdx.x == 64) dbg_stamp(P, 9);

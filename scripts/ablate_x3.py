@@ -16,6 +16,6 @@ for tag, M, N, K, ak, bk in [("conv2 fwd", 7744, 64, 512, 1, 1), ("conv3 fwd", 7
     row = ["%-18s" % tag]
     row.append("bf16 %.1f" % bench(1, M, N, K, ak, bk, 0, 2, 0))
     row.append("tf32 %.1f" % bench(2, M, N, K, ak, bk, 0, 2, 0))
-    for name, x in [("x3", 0), ("x3-noconv", 1), ("x3-1mma", 2), ("x3-noconv-1mma", 3)]:
+    for name, x in [("x3", 0), ("x3-noconv", 1), ("x3-1mma", 2), ("x3-noconv-1mma", 3), ("x3-nofence", 4), ("x3-nostore", 8), ("x3-nostore-nofence", 12)]:
         row.append("%s %.1f" % (name, bench(3, M, N, K, ak, bk, 0, 2, x << 8)))
     print("  ".join(row), flush=True)
