@@ -370,6 +370,49 @@ __device__ __forceinline__ void epi_rows_red(const float *cp, int rows, float *o
         }
     }
 }
+// packed bf16 rows: lane = column pair, staging row stride 66 floats; mask (relu') rows are bf16x2 as well
+template <bool MASK>
+__device__ __forceinline__ void epi_rows_store_bf16x2(const float *cp, int rows, __nv_bfloat162 *op, int stride2, float b0, float b1, int relu,
+                                                      const __nv_bfloat162 *mp, int mstride2) {
+    op = in_reg(op); stride2 = in_reg(stride2); relu = in_reg(relu);
+    if (MASK) { mp = in_reg(mp); mstride2 = in_reg(mstride2); }
+#pragma unroll 1
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+        float2 v[8];
+        __nv_bfloat162 mk[8];
+        const bool full = r0 + 8 <= rows;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float2 *>(cp + (r0 + u) * 66);
+        if (MASK) {
+            const __nv_bfloat162 *m = mp + (long long)r0 * mstride2;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) mk[u] = __ldg(m + (full ? u : min(u, rows - 1 - r0)) * mstride2);
+        }
+        __nv_bfloat162 *o = op + (long long)r0 * stride2;
+        __nv_bfloat162 w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float x0 = v[u].x + b0, x1 = v[u].y + b1;
+            const float r0f = fmaxf(x0, 0.f), r1f = fmaxf(x1, 0.f);
+            x0 = relu ? r0f : x0;
+            x1 = relu ? r1f : x1;
+            if (MASK) {
+                x0 = __low2float(mk[u]) > 0.f ? x0 : 0.f;
+                x1 = __high2float(mk[u]) > 0.f ? x1 : 0.f;
+            }
+            w[u] = __floats2bfloat162_rn(x0, x1);
+        }
+        if (full) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) o[u * stride2] = w[u];
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (r0 + u < rows) o[u * stride2] = w[u];
+        }
+    }
+}
+
 // transposed chunk (swap-AB): lane = tile row, walk the columns; the output index advances by `stride` per column
 template <typename T, bool MASK>
 __device__ __forceinline__ void epi_cols_store(const float *rp, int ncols, T *op, int stride, float bm, int relu, unsigned mbits) {
@@ -754,7 +797,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // bf16 output, plain row-major store: 64 columns at a time so that every lane writes a packed bf16x2 (128-byte row
         // segments instead of 64-byte ones) -- the wide, K-short GEMMs (IQN phi: K = 64, 0.5 GB of output) are store-bound
-        if (BN >= 64 && !X3 && simple && !trans && !split && !e.accumulate && out_bf16 && sn == 1 && (Nn & 1) == 0 && (sm & 1) == 0 &&
+        if (BN >= 64 && !X3 && simple && !trans && !split && !e.accumulate && out_bf16 && sn == 1 && (Nn & 1) == 0 && (sm & 1) == 0 && bias_mode != 2 &&
+            sm < (1 << 24) && msm < (1 << 24) &&
             (!maskp || (mask_bf16 && msn == 1 && (msm & 1) == 0))) {
             float(*stw)[66] = reinterpret_cast<float(*)[66]>(smem) + q * 32;  // 32 x 66 floats per warp (spans idle stages)
 #pragma unroll 1
@@ -773,27 +817,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (bias_mode == 1) { b0 = __ldg(e.bias + n); b1 = __ldg(e.bias + n + 1); }
                     __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>((bf16 *)e.out + (long long)row0 * sm + n);
                     const __nv_bfloat162 *mp = maskp ? reinterpret_cast<const __nv_bfloat162 *>((const bf16 *)maskp + (long long)row0 * msm + n) : nullptr;
-#pragma unroll 1
-                    for (int r0 = 0; r0 < rows; r0 += 4) {
-                        float2 v2[4];
-                        __nv_bfloat162 mk[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int rr = min(r0 + u, 31);
-                            v2[u] = *reinterpret_cast<const float2 *>(&stw[rr][2 * lane]);
-                            mk[u] = mp && r0 + u < rows ? __ldg(mp + (long long)rr * (msm >> 1)) : __floats2bfloat162_rn(1.f, 1.f);
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (r0 + u >= rows) break;
-                            float v0 = v2[u].x + b0, v1 = v2[u].y + b1;
-                            if (bias_mode == 2) { const float bm = __ldg(e.bias + row0 + r0 + u); v0 += bm; v1 += bm; }
-                            if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                            v0 = __low2float(mk[u]) > 0.f ? v0 : 0.f;
-                            v1 = __high2float(mk[u]) > 0.f ? v1 : 0.f;
-                            op[(long long)(r0 + u) * (sm >> 1)] = __floats2bfloat162_rn(v0, v1);
-                        }
-                    }
+                    if (mp) epi_rows_store_bf16x2<true>(&stw[0][2 * lane], rows, op, (int)(sm >> 1), b0, b1, relu, mp, (int)(msm >> 1));
+                    else epi_rows_store_bf16x2<false>(&stw[0][2 * lane], rows, op, (int)(sm >> 1), b0, b1, relu, nullptr, 0);
                 }
                 __syncwarp();
             }
@@ -922,6 +947,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("bar.sync 1, 128;" ::: "memory");
         unsigned *ctr = P.ctr + blockIdx.y * gridDim.x + blockIdx.x;
         if (threadIdx.x == 64) {
+            __threadfence();  // cumulative: the other 127 threads' reds, observed through the barrier, are ordered before the ticket
             const unsigned old = atomicAdd(ctr, 1u);
             const bool last = old == gridDim.z - 1;
             if (last) *ctr = 0u;
