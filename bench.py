@@ -177,6 +177,12 @@ def kernel_work(label, w, esz, n_params):
             return 0.0, float(M * K * esz * 2 if "im2col" in label else M * N * esz * 2)
         out_b = 4 if label.startswith("wgrad") else esz
         return 2.0 * M * N * K, float((M * K + N * K) * esz + M * N * out_b)
+    m2 = re.search(r"\[(\d+)x(\d+)\]", label)
+    if m2 and ("im2col" in label or "col2im" in label):  # explicit (un)folding: the cols matrix once + the activation once
+        return 0.0, float(int(m2.group(1)) * int(m2.group(2)) * esz * 2)
+    m1 = re.search(r"obs2nhwc\[(\d+)\]", label)
+    if m1:  # u8 frame stack in, 4-channel NHWC rows out
+        return 0.0, float(int(m1.group(1)) * (4 + 4 * esz))
     if label.startswith("opt"):
         per = 6 if w["opt"][0] == "rmsprop" else 8  # p r/w, g r + re-zero, state r/w
         return 0.0, float(n_params * 4 * per + (n_params * 2 if esz == 2 else 0))
