@@ -7,7 +7,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import zoo_loader
 zoo = zoo_loader.load()
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 100
-for eng, M, N, K, split in [(3, 1296, 64, 512, 8), (3, 784, 64, 576, 9), (3, 1296, 64, 512, 0), (3, 784, 64, 576, 0), (3, 7744, 32, 512, 4),
+for eng, M, N, K, split in [(3, 306, 8, 512, 8), (3, 648, 64, 512, 8), (3, 392, 64, 576, 9), (3, 306, 8, 512, 0), (3, 3136, 8, 512, 8),
+                            (3, 1296, 64, 512, 8), (3, 784, 64, 576, 9), (3, 1296, 64, 512, 0), (3, 784, 64, 576, 0), (3, 7744, 32, 512, 4),
                             (1, 1296, 64, 512, 8), (3, 512, 16, 7744, 0), (3, 3872, 64, 512, 8)]:
     rng = np.random.default_rng(1)
     A = rng.standard_normal((M, K)).astype(np.float32)
