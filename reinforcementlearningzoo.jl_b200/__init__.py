@@ -5,6 +5,7 @@ The names mirror the reference (``BasicDQNLearner`` … ``IQNLearner``, ``Neural
 ``ImplicitQuantileNet``, ``DuelingNetwork``, ``SumTree``, ``update``); all arithmetic is in
 ``libzoo_sm100.so`` (csrc/, C ABI in include/zoo_sm100.h).  There is no CPU fallback."""
 from ._lib import LIB_PATH, ZooError, lib  # noqa: F401
+from .checkpoint import load_policy, save_policy  # noqa: F401
 from .dp import DataParallel, shard_batch, shard_bounds  # noqa: F401
 from .learners import (SARTS, BasicDQNLearner, DQNLearner, IQNLearner, PrioritizedDQNLearner, QRDQNLearner, RainbowLearner,  # noqa: F401
                        REMDQNLearner, update, update_trajectory)
