@@ -2,13 +2,14 @@
 //   D(m,n) = sum_k A(m,k) B(n,k), fp32 accumulation in TMEM, three operand modes:
 //     bf16    (EB = 2)        kind::f16  on bf16 operands                          -- ZOO_PREC_BF16
 //     tf32    (EB = 4)        kind::tf32 on fp32 operands, one pass                -- ZOO_PREC_TF32
-//     3xtf32  (EB = 4, X3)    error-compensated: every fp32 operand tile is split in shared memory into
-//                             hi = x & 0xffffe000 and lo = x - hi by the (otherwise idle) epilogue warps and
-//                             the MMA warp issues hi*hi + hi*lo + lo*hi: fp32-grade results -- ZOO_PREC_FP32
+//     3xtf32  (EB = 4, X3)    error-compensated: the landed fp32 tile is the hi operand (kind::tf32 ignores the low 13
+//                             mantissa bits), the (otherwise idle) epilogue warps write lo = x - trunc(x) beside it, and
+//                             the MMA warp issues A hi x [B hi; B lo] and A lo x B hi: fp32-grade results -- ZOO_PREC_FP32
 // One 128 x BN output tile (x one K-split) per CTA:
-//   warp 0      TMA producer  (cp.async.bulk.tensor 2D, SWIZZLE_128B, 4-stage mbarrier ring)
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, kind::f16, M=128, N=BN, K=16)
-//   warps 2..5  epilogue: tcgen05.ld 32x32b -> bias / relu / relu' mask / Hadamard -> global (fp32 | bf16 | atomic add)
+//   warp 0      TMA producer  (cp.async.bulk.tensor 2D / 4D, SWIZZLE_128B, mbarrier ring whose depth is a launch parameter)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, M=128, N=BN or 2 BN, K = 32 bytes)
+//   warps 2..5  3xTF32 converters during the main loop, then the epilogue: tcgen05.ld 32x32b -> shared-memory transpose ->
+//               bias / relu / relu' mask -> global (fp32 | bf16 | red add), split-K finish by the last CTA of a tile
 // Operands may be K-major ([rows][K]) or MN-major ([K][rows]); the latter is what dgrad (W as [N'][K']) and
 // wgrad (dY and X as [batch rows][features]) need, so no operand is ever transposed in memory.
 // Contractions served: CrossCor-as-GEMM and Dense forward / dgrad / wgrad of the Nature-CNN and the IQN net
