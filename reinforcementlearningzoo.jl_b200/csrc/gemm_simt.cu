@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) dense_narrow_rows_kernel(Operand A, Opera
             float v = acc[n];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == n) epi_store(epi, v, m, n);
+            if (lane == n && n < N) epi_store(epi, v, m, n);  // (n >= N would land in the next row's first columns)
         }
     }
 }

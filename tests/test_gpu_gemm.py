@@ -54,6 +54,13 @@ def test_engines_all_majors(zoo, engine, M, N, K):
             assert err <= TOL[engine], (engine, M, N, K, ak, bk, err)
 
 
+@pytest.mark.parametrize("M,N", [(1024, 6), (1025, 6), (2048, 6), (4096, 13), (2048, 8), (2048, 16)])
+def test_narrow_heads_many_rows(zoo, M, N):
+    # fc2 of an IQN batch (batch x quantiles rows, n_actions columns): above 1024 rows the CUDA-core engine switches to its
+    # warp-per-row kernel, whose lanes N..NMAX-1 once stored into the next row's first columns
+    assert run(zoo, 0, M, N, 512, 1, 1, 0) <= TOL[0]
+
+
 @pytest.mark.parametrize("engine", [1, 3])
 @pytest.mark.parametrize("split", [1, 2, 5, 16])
 def test_split_k_is_consistent(zoo, engine, split):
