@@ -83,16 +83,13 @@ bool tc_gemm_supported(const Operand &A, const Operand &B, int M, int N, int K) 
 }
 
 static bool midk_split_enabled(const Epilogue &epi, int BN) {
-    // OFF by default.  Bit 0: unmasked GEMMs (forward), bit 1: masked ones (dgrad).  Stand-alone the split products are right
-    // (scripts/stress_split.py, 0 / 800 wrong), the masked case is parity-green in the learner tests, but with bit 0 set the
-    // explicit-conv mode (ZOO_TMA_CONV=0) failed test_rainbow_atari[fp32] 5 times in 25 (always the same 9.5e-3 on conv1's
-    // gradient) -- unexplained, and it bought no end-to-end time, so the heuristic stays a tuning knob.  What is known: the
-    // failure survives CUDA_LAUNCH_BLOCKING=1 (so it is not a race between kernels), it varies between fresh processes but not
-    // within one (initial memory contents), and it needs BOTH the BN = 64 conv splits and the BN = 32 fc2 split (bits 2 / 3
-    // alone: 0 / 16 each).  The likeliest explanation is not a defect at all: split-K sums partials with fp32 atomics in a
-    // run-dependent order, and one relu unit of that B = 8 test whose pre-activation is within rounding of zero then takes the
-    // other branch of relu' -- the same mechanism measured at large batch in tests/test_gpu_full_size.py (a single flip moves a
-    // small-batch conv gradient by ~1e-2, always by the same amount).  Unverified, hence still off.
+    // OFF by default (it bought no end-to-end time).  Bit 0: unmasked GEMMs (forward), bit 1: masked ones (dgrad); bits 2 / 3
+    // restrict it to BN >= 64 / BN <= 32.  With bit 0 set, test_rainbow_atari[fp32] in the explicit-conv mode (ZOO_TMA_CONV=0)
+    // fails about one run in four, always by the same 9.5e-3 on conv1's gradient.  scripts/midk_anomaly_probe.py shows what that
+    // is: the loss is bit-identical, fc1 / fc2 gradients stay at 3e-6, only conv3's tensors and everything below move -- one
+    // conv3 output unit of that B = 8 batch has a pre-activation within rounding of zero, split-K sums its partials with fp32
+    // atomics in a run-dependent order, and the unit takes either branch of relu'.  A property of atomics-based split-K meeting
+    // that test vector, not a defect (the split products themselves: scripts/stress_split.py, 0 / 800 wrong).
     static const int on = [] { const char *e = getenv("ZOO_MIDK_SPLIT"); return e ? atoi(e) : 0; }();
     if ((on & 4) && BN < 64) return false;   // bisecting aids: bit 2 = only BN >= 64, bit 3 = only BN <= 32
     if ((on & 8) && BN > 32) return false;
