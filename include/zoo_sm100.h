@@ -299,6 +299,14 @@ ZOO_API zoo_status zoo_test_gemm_bench(int32_t engine, int32_t M, int32_t N, int
 ZOO_API zoo_status zoo_test_gemm_trace(int32_t engine, int32_t M, int32_t N, int32_t K, int32_t a_kmajor, int32_t b_kmajor,
                                        int32_t split_k, uint64_t *stamps9);
 
+/* Parity hook (tests/test_gpu_full_size.py): raw bytes of the output buffer of parameter layer `layer` of chain `chain`
+ * (0 = Chain / psi / base, 1 = phi / val, 2 = header / adv) as the last forward left it: post-activation values, internal
+ * layout [rows][out_h][out_w][out_c] in the net's activation type.  *is_bf16 tells the element type (the network's output
+ * layer is always fp32).  The caller must have synchronised the learner (an update with loss_out does).  The test derives the
+ * relu masks the device used from it, so the CPU twin can be re-run with exactly those masks. */
+ZOO_API zoo_status zoo_test_net_activation(zoo_net *net, int32_t chain, int32_t layer, int64_t rows, void *host, int64_t host_bytes,
+                                           int32_t *is_bf16);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,17 @@ import torch
 import torch.nn.functional as Fn
 
 
-def _chain(layers, params, x):
+def _act(pre, masks, rec):
+    """relu -- or, for the full-size parity tests, `pre * mask` with the relu mask the DEVICE used for this layer (so that a
+    unit whose pre-activation is within rounding of zero takes the same branch in both); `rec` collects the pre-activations."""
+    if rec is not None:
+        rec.append(pre.detach())
+    if masks is not None:
+        return pre * masks.pop(0)
+    return torch.relu(pre)
+
+
+def _chain(layers, params, x, masks=None, rec=None):
     pi = 0
     for l in layers:
         if l[0] == "scale255":  # Dopamine_DQN_Atari.jl:28
@@ -30,7 +40,7 @@ def _chain(layers, params, x):
             x = Fn.conv2d(x, params[pi], params[pi + 1], stride=s, padding=p)
             pi += 2
             if relu:
-                x = torch.relu(x)
+                x = _act(x, masks, rec)
         elif l[0] == "flatten":
             x = x.flatten(1)
         elif l[0] == "dense":
@@ -38,7 +48,7 @@ def _chain(layers, params, x):
             x = Fn.linear(x, params[pi], params[pi + 1])
             pi += 2
             if relu:
-                x = torch.relu(x)
+                x = _act(x, masks, rec)
     return x, pi
 
 
@@ -46,26 +56,28 @@ def _nparams(layers):
     return 2 * sum(1 for l in layers if l[0] in ("conv", "dense"))
 
 
-def forward(net, params, x, tau=None):
+def forward(net, params, x, tau=None, masks=None, rec=None):
+    """masks: optional list of 0/1 tensors, one per relu layer in evaluation order (consumed); rec: optional list that
+    receives every relu layer's pre-activation (see _act)."""
     kind = net["kind"]
     if kind == "chain":
-        return _chain(net["layers"], params, x)[0]
+        return _chain(net["layers"], params, x, masks, rec)[0]
     if kind == "dueling":  # common.jl:51-56
         nb, nv = _nparams(net["base"]), _nparams(net["val"])
-        h = _chain(net["base"], params[:nb], x)[0]
-        v = _chain(net["val"], params[nb : nb + nv], h)[0]
-        a = _chain(net["adv"], params[nb + nv :], h)[0]
+        h = _chain(net["base"], params[:nb], x, masks, rec)[0]
+        v = _chain(net["val"], params[nb : nb + nv], h, masks, rec)[0]
+        a = _chain(net["adv"], params[nb + nv :], h, masks, rec)[0]
         return v + a - a.mean(dim=1, keepdim=True)
     if kind == "iqn":  # iqn.jl:25-33,157
         npsi, nphi = _nparams(net["psi"]), _nparams(net["phi"])
         n_em = net["phi"][0][1]
         B, N = tau.shape
-        feat = _chain(net["psi"], params[:npsi], x)[0]
+        feat = _chain(net["psi"], params[:npsi], x, masks, rec)[0]
         i = torch.arange(1, n_em + 1, dtype=tau.dtype)
         emb = torch.cos((torch.tensor(np.float32(np.pi), dtype=tau.dtype) * i)[None, :] * tau.reshape(-1, 1))
-        ea = _chain(net["phi"], params[npsi : npsi + nphi], emb)[0]
+        ea = _chain(net["phi"], params[npsi : npsi + nphi], emb, masks, rec)[0]
         merged = feat[:, None, :] * ea.reshape(B, N, -1)
-        z = _chain(net["header"], params[npsi + nphi :], merged.reshape(B * N, -1))[0]
+        z = _chain(net["header"], params[npsi + nphi :], merged.reshape(B * N, -1), masks, rec)[0]
         return z.reshape(B, N, -1)
     raise ValueError(kind)
 
@@ -142,30 +154,30 @@ def _dqn_target(net, ps, tps, batch, gamma, n, double, dtype):
         return _t(batch["reward"], dtype) + _gn(gamma, n) * (1 - _t(batch["terminal"], dtype)) * q2
 
 
-def dqn_grads(net, params, tparams, batch, gamma=0.99, n=1, double_dqn=True, dtype=torch.float32):
+def dqn_grads(net, params, tparams, batch, gamma=0.99, n=1, double_dqn=True, dtype=torch.float32, masks=None, rec=None):
     """dqn.jl:102-145."""
     ps, tps = _leaf(params, dtype), [_t(p, dtype) for p in tparams]
     a = torch.from_numpy(batch["action"].astype(np.int64))
     G = _dqn_target(net, ps, tps, batch, gamma, n, double_dqn, dtype)
-    q = forward(net, ps, _t(batch["state"], dtype)).gather(1, a[:, None])[:, 0]
+    q = forward(net, ps, _t(batch["state"], dtype), masks=masks, rec=rec).gather(1, a[:, None])[:, 0]
     return _finish(_huber(G, q).mean(), ps, {})
 
 
-def prioritized_dqn_grads(net, params, tparams, batch, gamma=0.99, n=1, beta=0.5, dtype=torch.float32):
+def prioritized_dqn_grads(net, params, tparams, batch, gamma=0.99, n=1, beta=0.5, dtype=torch.float32, masks=None, rec=None):
     """prioritized_dqn.jl:111-151."""
     ps, tps = _leaf(params, dtype), [_t(p, dtype) for p in tparams]
     a = torch.from_numpy(batch["action"].astype(np.int64))
     B = len(a)
     w = _per_w(batch, beta, dtype)
     G = _dqn_target(net, ps, tps, batch, gamma, n, False, dtype)
-    q = forward(net, ps, _t(batch["state"], dtype)).gather(1, a[:, None])[:, 0]
+    q = forward(net, ps, _t(batch["state"], dtype), masks=masks, rec=rec).gather(1, a[:, None])[:, 0]
     per = _huber(G, q)
     pr = ((per.detach().float() + 1e-10) ** np.float32(beta)).numpy()
     return _finish(torch.dot(w, per) / B, ps, {"priorities": pr, "per_sample": per.detach().numpy()})
 
 
 def rainbow_grads(net, params, tparams, batch, n_actions, n_atoms=51, vmax=10.0, vmin=-10.0, gamma=0.99, n=1,
-                  beta=0.5, support=None, dtype=torch.float32):
+                  beta=0.5, support=None, dtype=torch.float32, masks=None, rec=None):
     """rainbow.jl:126-221 -- projection written exactly as the reference's tiled broadcast."""
     ps, tps = _leaf(params, dtype), [_t(p, dtype) for p in tparams]
     a = torch.from_numpy(batch["action"].astype(np.int64))
@@ -185,7 +197,7 @@ def rainbow_grads(net, params, tparams, batch, n_actions, n_atoms=51, vmax=10.0,
         tiled = Tz.clamp(vmin, vmax)[:, :, None].expand(B, n_atoms, n_atoms)  # [b, i, j]
         proj = (1 - (tiled - z[None, None, :]).abs() / dz).clamp(0, 1) * wsel[:, :, None]
         target = proj.sum(1)
-    logits = forward(net, ps, _t(batch["state"], dtype)).reshape(B, n_actions, n_atoms)
+    logits = forward(net, ps, _t(batch["state"], dtype), masks=masks, rec=rec).reshape(B, n_actions, n_atoms)
     sl = logits[torch.arange(B), a]
     per = -(target * torch.log_softmax(sl, dim=1)).sum(1)
     extra = {"per_sample": per.detach().numpy(), "target_distribution": target.numpy()}
@@ -197,7 +209,7 @@ def rainbow_grads(net, params, tparams, batch, n_actions, n_atoms=51, vmax=10.0,
     return _finish(loss, ps, extra)
 
 
-def iqn_grads(net, params, tparams, batch, tau, tau_prime, gamma=0.99, kappa=1.0, beta=0.5, dtype=torch.float32):
+def iqn_grads(net, params, tparams, batch, tau, tau_prime, gamma=0.99, kappa=1.0, beta=0.5, dtype=torch.float32, masks=None, rec=None):
     """iqn.jl:159-237."""
     ps, tps = _leaf(params, dtype), [_t(p, dtype) for p in tparams]
     a = torch.from_numpy(batch["action"].astype(np.int64))
@@ -208,7 +220,7 @@ def iqn_grads(net, params, tparams, batch, tau, tau_prime, gamma=0.99, kappa=1.0
         at = _mask_add(zt.mean(1), batch).argmax(1)
         qt = zt[torch.arange(B), :, at]
         target = _t(batch["reward"], dtype)[:, None] + float(np.float32(gamma)) * (1 - _t(batch["terminal"], dtype))[:, None] * qt
-    z = forward(net, ps, _t(batch["state"], dtype), tau_t)
+    z = forward(net, ps, _t(batch["state"], dtype), tau_t, masks=masks, rec=rec)
     q = z[torch.arange(B), :, a]  # [B, N]
     TD = target[:, :, None] - q[:, None, :]
     ae = TD.abs()

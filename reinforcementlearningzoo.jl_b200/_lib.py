@@ -123,6 +123,7 @@ SIGNATURES = {
     "zoo_test_gemm_trace": [I32, I32, I32, I32, I32, I32, I32, V],
     "zoo_test_set_tc_stages": [I32],
     "zoo_test_gemm_bench": [I32, I32, I32, I32, I32, I32, I32, I32, I32, C.POINTER(F32)],
+    "zoo_test_net_activation": [V, I32, I32, I64, V, I64, C.POINTER(I32)],
 }
 _OTHER_RESTYPE = {"zoo_last_error": ([], C.c_char_p), "zoo_version": ([], I32), "zoo_device_arch": ([], I32)}
 

@@ -1059,4 +1059,19 @@ zoo_status zoo_net_forward(zoo_net *net, const void *obs_host, int32_t obs_dtype
     return ZOO_OK;
 }
 
+zoo_status zoo_test_net_activation(zoo_net *net, int32_t chain, int32_t layer, int64_t rows, void *host, int64_t host_bytes, int32_t *is_bf16) {
+    ZOO_REQUIRE(net && host && is_bf16 && chain >= 0 && chain <= 2, "zoo_test_net_activation: bad argument");
+    const Chain &ch = chain == 0 ? net->a : (chain == 1 ? net->b : net->c);
+    ZOO_REQUIRE(layer >= 0 && layer < (int)ch.layers.size() && rows > 0 && rows <= ch.rows_cap, "zoo_test_net_activation: chain %d has %d layers, %lld rows",
+                chain, (int)ch.layers.size(), ch.rows_cap);
+    const LayerExec &L = ch.layers[layer];
+    const int esz = L.out_fp32 ? 4 : net->esz;
+    const size_t need = (size_t)rows * L.opr * L.cout * esz;
+    ZOO_REQUIRE((size_t)host_bytes == need, "zoo_test_net_activation: layer holds %zu bytes for %lld rows, caller passed %lld", need, (long long)rows, (long long)host_bytes);
+    ZOO_CUDA(cudaDeviceSynchronize());
+    ZOO_CUDA(cudaMemcpy(host, L.out, need, cudaMemcpyDeviceToHost));
+    *is_bf16 = esz == 2;
+    return ZOO_OK;
+}
+
 }  // extern "C"

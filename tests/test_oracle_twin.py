@@ -149,3 +149,28 @@ def test_optimisers_match_twin():
                 opt.step(ps, [torch.from_numpy(x) for x in g])
             for a, r in zip(ps, cur):
                 assert np.abs(a.numpy() - r).max() <= 1e-7
+
+
+def test_twin_with_its_own_relu_masks_pinned_reproduces_the_free_run():
+    """The full-size GPU parity tests re-run the twin with the DEVICE's relu masks (tests/helpers.py:full_size_parity);
+    pinning the twin's own masks must change nothing -- checks the mask / pre-activation plumbing on the CPU."""
+    net = O.atari_iqn_net(6)
+    p, tp = O.init_params(net, 1, 0.05), O.init_params(net, 2, 0.05)
+    B, N = 2, 8
+    b = O.synth_batch(3, B, (4, 84, 84), 6, atari=True)
+    rng = np.random.default_rng(0)
+    tau, taup = rng.random((B, N), dtype=np.float32), rng.random((B, N), dtype=np.float32)
+    rec = []
+    free = T.iqn_grads(net, p, tp, b, tau, taup, rec=rec)
+    assert [tuple(r.shape) for r in rec] == [(B, 32, 21, 21), (B, 64, 11, 11), (B, 64, 11, 11), (B * N, 7744), (B * N, 512)]
+    pinned = T.iqn_grads(net, p, tp, b, tau, taup, masks=[(r > 0).float() for r in rec])
+    assert float(free["loss"]) == float(pinned["loss"])
+    for x, y in zip(free["grads"], pinned["grads"]):
+        assert np.array_equal(x, y)
+    net = O.chain_net(O.nature_cnn(6))
+    p, tp = O.init_params(net, 1, 0.05), O.init_params(net, 2, 0.05)
+    rec = []
+    free = T.dqn_grads(net, p, tp, b, rec=rec)
+    pinned = T.dqn_grads(net, p, tp, b, masks=[(r > 0).float() for r in rec])
+    for x, y in zip(free["grads"], pinned["grads"]):
+        assert np.array_equal(x, y)
