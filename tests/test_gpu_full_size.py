@@ -40,7 +40,9 @@ def test_bench_config_matches_the_twin_with_pinned_relu_masks(zoo, case, prec):
     for i, f in enumerate(rep["flips"]):
         assert f["worst_rel_preact"] <= FLIP_TOL[prec], "%s [%s]: relu layer %d flipped a unit with |pre-activation| = %.2e x rms" % (
             case, prec, i, f["worst_rel_preact"])
-        assert f["flipped"] <= max(8, f["units"] // 1000), (case, prec, i, f)  # ties are rare: far below 0.1 % of a layer
+        # ties are rare.  Measured (profiles/r02_full_size_parity.txt): fp32 <= 19 of 254 M units; bf16 (every operand rounded to
+        # 2^-9) 0.06-0.14 % of a layer
+        assert f["flipped"] <= (max(32, f["units"] // 100000) if prec == "fp32" else max(32, f["units"] // 200)), (case, prec, i, f)
 
 
 def part(b, lo, hi):
