@@ -81,7 +81,7 @@ def cpu_arm(w, steps, warmup, budget_s=None):
     from oracle import zoo_oracle as O
     net = oracle_net(w)
     p, tp = O.init_params(net, 1), O.init_params(net, 2)
-    kind = {"basic": "dqn"}.get(w["kind"], w["kind"])
+    kind = w["kind"]
     cfg = dict(gamma=0.99)
     if w["kind"] == "dqn":
         cfg.update(n=w["n"], double_dqn=True)
@@ -118,17 +118,51 @@ def cpu_arm(w, steps, warmup, budget_s=None):
     return rate, done, torch.get_num_threads(), sample
 
 
+def host_cores():
+    """Physical cores this process may run on (what torch picks by itself when OMP_NUM_THREADS is not forced)."""
+    cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else set(range(os.cpu_count() or 1))
+    try:
+        cores, cur = set(), {}
+        for line in open("/proc/cpuinfo"):
+            if ":" in line:
+                k, v = (x.strip() for x in line.split(":", 1))
+                cur[k] = v
+            elif cur:
+                if int(cur.get("processor", -1)) in cpus:
+                    cores.add((cur.get("physical id", "0"), cur.get("core id", cur.get("processor"))))
+                cur = {}
+        if cur and int(cur.get("processor", -1)) in cpus:
+            cores.add((cur.get("physical id", "0"), cur.get("core id", cur.get("processor"))))
+        return max(1, len(cores))
+    except Exception:
+        return max(1, len(cpus))
+
+
+def config_of(args, w, world):
+    """The `config` object of the JSON line -- the same keys and values for both arms (the driver compares them)."""
+    prec = args.precision
+    return {"workload": args.workload, "learner": w["kind"], "per_gpu_batch": w["B"], "global_batch": w["B"] * world,
+            "precision_mode": {"fp32": "fp32 storage, contractions as 3xTF32 on tcgen05 (parity 1e-4)", "bf16": "bf16 operands on tcgen05, fp32 accumulate"}.get(prec, prec),
+            "value_counts": "per-GPU minibatches of %d per second (one all-reduced optimiser step per %d of them)" % (w["B"], world),
+            "l2": "flushed (256 MB fill) before every timed step", "cuda_graph": True, "parallelism": "dp%d" % world}
+
+
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the CPU arm is ONE replica that may use every host core
+    # (the JULIA_NUM_THREADS analogue, SURVEY.md 8d), so undo that here -- rank 0 is the only rank that runs
+    torch.set_num_threads(host_cores())
     rate, done, threads, sample = cpu_arm(w, args.steps, args.warmup, budget_s=240)
     line = {
         "impl": "reference", "metric": "learner updates/s", "value": rate, "unit": "updates/s", "n_gpus": args.gpus, "steps": done,
         "warmup": args.warmup, "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "per_gpu_batch": w["B"], "learner": w["kind"],
-                   "note": "CPU arm: torch-CPU restatement of the reference update (julia absent); one replica on the host cores"},
+        "config": config_of(args, w, args.gpus),
+        "note": "CPU arm: torch-CPU restatement of the reference update (julia absent); ONE replica on all host cores, whatever --gpus says "
+                "(fp32 arithmetic; the precision_mode / l2 / cuda_graph keys describe the GPU arm it is compared with)",
         "cpu_baseline": {"value": rate, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -216,6 +250,87 @@ def roofline(profiles, w, esz, n_params, pk, traffic):
 
 
 # ----------------------------------------------------------------------------------------------- our arm
+def build_learner(zoo, w, prec, dp, rank):
+    """Learner + online / target approximators of a workload with Flux-style glorot weights (online != target, as after the
+    first target period)."""
+    from oracle import zoo_oracle as O  # weight init only
+    B, kind = w["B"], w["kind"]
+    net = oracle_net(w)
+    model = zoo.from_oracle_net(net)
+    opt = zoo.RMSProp(*w["opt"][1:]) if w["opt"][0] == "rmsprop" else zoo.ADAM(w["opt"][1])
+    obs_shape = (4, 84, 84) if w["atari"] else (4,)
+    nq = w.get("N", 0)
+    app = zoo.NeuralNetworkApproximator(model, opt, obs_shape, B, nq, prec)
+    tapp = None if kind == "basic" else zoo.NeuralNetworkApproximator(model, None, obs_shape, B, nq, prec)
+    if tapp is not None:
+        tapp.set_params(O.init_params(net, 2))
+    if kind == "basic":
+        lrn = zoo.BasicDQNLearner(app, batch_size=B, dp=dp)
+    elif kind == "dqn":
+        lrn = zoo.DQNLearner(app, tapp, batch_size=B, update_horizon=w["n"], dp=dp)  # Double-DQN on (dqn.jl:58)
+    elif kind == "rainbow":
+        lrn = zoo.RainbowLearner(app, tapp, n_actions=w["A"], Vmax=10.0, Vmin=-10.0, update_horizon=w["n"], batch_size=B, dp=dp)
+    else:
+        lrn = zoo.IQNLearner(app, tapp, n_actions=w["A"], N=nq, N_prime=nq, N_em=64, batch_size=B, update_horizon=w["n"], device_seed=rank, dp=dp)
+    app.set_params(O.init_params(net, 1))  # the constructors force-sync online := target (dqn.jl:60)
+    return lrn, app, tapp
+
+
+def make_pools(w, rank, dev, torch, n_pool=None):
+    """synthetic replay minibatches: a pool of distinct batches per rank, pinned on the host and resident on the device"""
+    n_pool = n_pool or (8 if w["B"] <= 64 else 2)
+    host_pool, dev_pool = [], []
+    for i in range(n_pool):
+        b = synth(w, 1000 * rank + i)
+        hb, db = {}, {}
+        for k, v in b.items():
+            t = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
+            hb[k] = t.numpy()
+            db[k] = t.to(dev)
+        host_pool.append((hb, [t for t in hb.values()]))
+        dev_pool.append(db)
+    return host_pool, dev_pool
+
+
+def step_work(w, B, n_params):
+    """Algorithmic work of ONE update of per-GPU batch B: flops (2*MAC, fwd + bwd) and the HBM bytes that must move
+    at least once: the u8 frames of s and s', the online and target parameters read, the optimiser state read + written and the
+    parameters written (RMSProp: 1 state tensor, Adam: 2)."""
+    flops = float(FLOP_PER_SAMPLE[w["kind"]]) * B
+    obs = (4 * 84 * 84) if w["atari"] else 4 * 4
+    states = 1 if w["opt"][0] == "rmsprop" else 2
+    targets = 0 if w["kind"] == "basic" else 1
+    byts = 2.0 * B * obs + n_params * 4.0 * (1 + targets + 2 * states + 1)
+    return flops, byts
+
+
+def step_roofline(w, B, n_params, step_s, pk, tensor_div=1.0):
+    """Whole-step roofline: the step's algorithmic flops and bytes against the measured peaks; the binding one is whichever
+    takes longer at its peak.  tensor_div: 3 for the fp32-grade mode (three TF32 products per contraction)."""
+    fl, by = step_work(w, B, n_params)
+    t_tensor = fl / (pk["tf_sus"] * 1e12 / tensor_div)
+    t_hbm = by / (pk["hbm"] * 1e9)
+    if t_tensor >= t_hbm:
+        ach = fl / step_s / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": pk["tf_sus"] / tensor_div, "unit": "TFLOP/s", "frac": ach / (pk["tf_sus"] / tensor_div),
+                "flops": fl, "bytes": by, "bound_us": t_tensor * 1e6}
+    ach = by / step_s / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "flops": fl, "bytes": by, "bound_us": t_hbm * 1e6}
+
+
+def time_updates(lrn, dev_pool, K, stream, flush, torch):
+    """K graph-replayed updates, L2 flushed before each, CUDA events on the learner's stream around each update; returns ms."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    with torch.cuda.stream(stream):
+        for i in range(K):
+            flush.fill_(i & 0xFF)
+            ev[i][0].record(stream)
+            lrn.update(dev_pool[i % len(dev_pool)], want_loss=False, want_priorities=False)
+            ev[i][1].record(stream)
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in ev)
+
+
 def trace(*a):
     if os.environ.get("ZOO_BENCH_TRACE"):
         print("[bench r%s %.2f]" % (os.environ.get("RANK", "0"), time.time() % 1000), *a, file=sys.stderr, flush=True)
@@ -241,40 +356,13 @@ def run_ours(args, w):
     dp = zoo.DataParallel(rank, world) if world > 1 else None
 
     B, kind, prec = w["B"], w["kind"], args.precision
-    net = oracle_net(w)
-    model = zoo.from_oracle_net(net)
-    opt = zoo.RMSProp(*w["opt"][1:]) if w["opt"][0] == "rmsprop" else zoo.ADAM(w["opt"][1])
-    obs_shape = (4, 84, 84) if w["atari"] else (4,)
     nq = w.get("N", 0)
-    app = zoo.NeuralNetworkApproximator(model, opt, obs_shape, B, nq, prec)
-    tapp = None if kind == "basic" else zoo.NeuralNetworkApproximator(model, None, obs_shape, B, nq, prec)
-    app.set_params(O.init_params(net, 1))
-    if tapp is not None:
-        tapp.set_params(O.init_params(net, 2))
-    if kind == "basic":
-        lrn = zoo.BasicDQNLearner(app, batch_size=B, dp=dp)
-    elif kind == "dqn":
-        lrn = zoo.DQNLearner(app, tapp, batch_size=B, update_horizon=w["n"], dp=dp)  # Double-DQN on (dqn.jl:58)
-    elif kind == "rainbow":
-        lrn = zoo.RainbowLearner(app, tapp, n_actions=w["A"], Vmax=10.0, Vmin=-10.0, update_horizon=w["n"], batch_size=B, dp=dp)
-    else:
-        lrn = zoo.IQNLearner(app, tapp, n_actions=w["A"], N=nq, N_prime=nq, N_em=64, batch_size=B, update_horizon=w["n"], device_seed=rank, dp=dp)
-    app.set_params(O.init_params(net, 1))  # online != target, as after the first target period
+    lrn, app, tapp = build_learner(zoo, w, prec, dp, rank)
     n_params = sum(int(np.prod(s)) for s in app.shapes)
     lrn.use_graph(True)
 
-    # synthetic replay minibatches: a pool of distinct batches per rank, pinned on the host and resident on the device
-    n_pool = 8 if B <= 64 else 2
-    host_pool, dev_pool = [], []
-    for i in range(n_pool):
-        b = synth(w, 1000 * rank + i)
-        hb, db = {}, {}
-        for k, v in b.items():
-            t = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
-            hb[k] = t.numpy()
-            db[k] = t.to(dev)
-        host_pool.append((hb, [t for t in hb.values()]))
-        dev_pool.append(db)
+    host_pool, dev_pool = make_pools(w, rank, dev, torch)
+    n_pool = len(dev_pool)
     h2d = sum(v.nbytes for v in host_pool[0][0].values())
     per = w.get("priority", False)
     d2h = 4 + (4 * B if per else 0)
@@ -392,6 +480,38 @@ def run_ours(args, w):
     roof = roofline(profs, w, esz, n_params, pk, traffic)
     flop_step = FLOP_PER_SAMPLE[kind] * B
     step_s = dev_ms * 1e-3 / K
+    roof["step"] = step_roofline(w, B, n_params, step_s, pk, 3.0 if prec == "fp32" else 1.0)
+
+    # ---- extra.c5: the north_star data-parallel configuration (Dopamine IQN, N = N' = 64, 512 samples per GPU = global 4096
+    # at 8 GPUs; Dopamine_IQN_Atari.jl:26-68), timed the same way (graph replay, L2 flushed, events, max over ranks) in the
+    # fp32-grade mode and in bf16.  The headline `value` stays the dqn_atari_b32 line.
+    c5 = None
+    if args.c5 and args.workload == "dqn_atari_b32":
+        lrn.close()
+        del lrn, app, tapp, dev_pool, host_pool
+        c5 = {"workload": "iqn_atari_b512", "per_gpu_batch": 512, "global_batch": 512 * world, "quantiles": "N = N' = 64",
+              "steps": args.c5_steps, "gflop_per_step_per_gpu": FLOP_PER_SAMPLE["iqn"] * 512 / 1e9}
+        w5 = WORKLOADS["iqn_atari_b512"]
+        for p5 in ("fp32", "bf16"):
+            l5, a5, t5 = build_learner(zoo, w5, p5, dp, rank)
+            l5.use_graph(True)
+            _, pool5 = make_pools(w5, rank, dev, torch, 2)
+            st5 = torch.cuda.ExternalStream(l5.stream(), device=dev)
+            for i in range(3):
+                l5.update(pool5[i % 2], want_loss=False, want_priorities=False)
+            l5.sync()
+            barrier()
+            ms5 = maxr(time_updates(l5, pool5, args.c5_steps, st5, flush, torch))
+            barrier()
+            s5 = ms5 * 1e-3 / args.c5_steps
+            np5 = sum(int(np.prod(x)) for x in a5.shapes)
+            c5[p5] = {"ms_per_step": ms5 / args.c5_steps, "updates_per_s": world / s5, "samples_per_s": world * 512 / s5,
+                      "step_tflops_per_gpu": FLOP_PER_SAMPLE["iqn"] * 512 / s5 / 1e12,
+                      "roofline_step": step_roofline(w5, 512, np5, s5, pk, 3.0 if p5 == "fp32" else 1.0), "launches_per_step": l5.last_launches()}
+            l5.close()
+            del l5, a5, t5, pool5
+            torch.cuda.synchronize()
+        trace("c5 done")
 
     if world > 1:
         dist.barrier()
@@ -404,10 +524,7 @@ def run_ours(args, w):
             "metric": "learner updates/s", "value": world * K / (dev_ms * 1e-3), "unit": "updates/s", "n_gpus": world, "steps": K,
             "warmup": max(3, args.warmup), "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if prec == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "learner": kind, "per_gpu_batch": B, "global_batch": B * world,
-                       "precision_mode": {"fp32": "fp32 storage, contractions as 3xTF32 on tcgen05 (parity 1e-4)", "bf16": "bf16 operands on tcgen05, fp32 accumulate"}.get(prec, prec),
-                       "value_counts": "per-GPU minibatches of %d per second (one all-reduced optimiser step per %d of them)" % (B, world),
-                       "l2": "flushed (256 MB fill) before every timed step", "cuda_graph": True, "parallelism": "dp%d" % world},
+            "config": config_of(args, w, world),
             "value_l2_warm": world * K / (warm_ms * 1e-3),
             "gflop_per_step_per_gpu": flop_step / 1e9,
             "step_tflops_per_gpu": flop_step / step_s / 1e12,
@@ -416,13 +533,15 @@ def run_ours(args, w):
             "cpu_baseline": cpu,
             "e2e": {"value": world * K / e2e_s, "unit": "updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "e2e_replay": e2e_replay,
+            "extra": {"c5": c5} if c5 else None,
             "gpu_launches": launches,
             "clocks": clk,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         # orderly collective teardown: learner (and its captured graph) first, then our NCCL communicator, then torch's
-        lrn.close()
+        if c5 is None:
+            lrn.close()
         torch.cuda.synchronize()
         dist.barrier()
         dp.close()
@@ -438,6 +557,8 @@ def main():
     ap.add_argument("--workload", default="dqn_atari_b32", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "tf32", "fp32_simt"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-c5", dest="c5", action="store_false", help="skip the extra.c5 block (IQN 512 per GPU, fp32 + bf16) of the default workload")
+    ap.add_argument("--c5-steps", type=int, default=10)
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

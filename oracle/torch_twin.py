@@ -305,7 +305,7 @@ class Adam:
 
 class CpuLearner:
     """The reference's update!(learner, batch) executed on the host cores with torch (MKL/oneDNN, fp32): the CPU arm
-    bench.py times (cpu_baseline / --impl reference).  kind in {"dqn", "rainbow", "iqn"}."""
+    bench.py times (cpu_baseline / --impl reference).  kind in {"basic", "dqn", "rainbow", "iqn"}."""
 
     def __init__(self, kind, net, params, tparams, opt, **cfg):
         self.kind, self.net, self.cfg = kind, net, cfg
@@ -319,7 +319,9 @@ class CpuLearner:
         try:
             for p in self.ps:
                 p.grad = None
-            if self.kind == "dqn":
+            if self.kind == "basic":
+                r = basic_dqn_grads(self.net, self.ps, batch, **self.cfg)
+            elif self.kind == "dqn":
                 r = dqn_grads(self.net, self.ps, self.tps, batch, **self.cfg)
             elif self.kind == "rainbow":
                 r = rainbow_grads(self.net, self.ps, self.tps, batch, **self.cfg)

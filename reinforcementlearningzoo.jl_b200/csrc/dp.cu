@@ -18,6 +18,12 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    // optional (NCCL >= 2.19): VMM-backed allocation + user-buffer registration, which is what lets the NVLS (in-switch) and
+    // P2P algorithms read and write the gradient buffer in place instead of staging it through NCCL's own FIFO buffers
+    ncclResult_t (*MemAlloc)(void **, size_t) = nullptr;
+    ncclResult_t (*MemFree)(void *) = nullptr;
+    ncclResult_t (*CommRegister)(const ncclComm_t, void *, size_t, void **) = nullptr;
+    ncclResult_t (*CommDeregister)(const ncclComm_t, void *) = nullptr;
 };
 static NcclApi g_nccl;
 
@@ -34,6 +40,10 @@ static zoo_status load_nccl() {
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    g_nccl.MemAlloc = (decltype(g_nccl.MemAlloc))dlsym(h, "ncclMemAlloc");
+    g_nccl.MemFree = (decltype(g_nccl.MemFree))dlsym(h, "ncclMemFree");
+    g_nccl.CommRegister = (decltype(g_nccl.CommRegister))dlsym(h, "ncclCommRegister");
+    g_nccl.CommDeregister = (decltype(g_nccl.CommDeregister))dlsym(h, "ncclCommDeregister");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.GetErrorString) {
         set_err("libnccl.so.2 lacks a required symbol");
         return ZOO_NCCL_ERROR;
@@ -66,6 +76,27 @@ zoo_status dp_allreduce_sum(zoo_dp *dp, float *buf, long long n, cudaStream_t st
     if (g_prof_on) { prof_label("allreduce[%lld]", n); prof_mark("ncclAllReduce", __LINE__); }
     return ZOO_OK;
 }
+// The flat gradient buffer of a data-parallel learner: allocated by NCCL (ncclMemAlloc: VMM-backed, multicast-capable) and
+// registered with the communicator, so that all-reduces captured into the update's CUDA graph run zero-copy (NVLS / P2P direct)
+// instead of copying through NCCL's staging buffers.  Falls back to the caller's cudaMalloc buffer when the NCCL in use has no
+// such API (returns ZOO_OK with *ptr = nullptr).  ZOO_NCCL_REG=0 disables it (A/B runs).
+zoo_status dp_alloc_registered(zoo_dp *dp, size_t bytes, void **ptr, void **handle) {
+    *ptr = nullptr; *handle = nullptr;
+    const char *e = getenv("ZOO_NCCL_REG");
+    if (!dp || dp->world == 1 || (e && e[0] == '0') || !g_nccl.MemAlloc || !g_nccl.MemFree) return ZOO_OK;
+    void *p = nullptr;
+    if (g_nccl.MemAlloc(&p, bytes) != ncclSuccess || !p) { cudaGetLastError(); return ZOO_OK; }
+    if (g_nccl.CommRegister && g_nccl.CommRegister(dp->comm, p, bytes, handle) != ncclSuccess) *handle = nullptr;
+    *ptr = p;
+    return ZOO_OK;
+}
+void dp_deregister(zoo_dp *dp, void *handle) {
+    if (dp && dp->comm && handle && g_nccl.CommDeregister) g_nccl.CommDeregister(dp->comm, handle);
+}
+void dp_free_registered(void *ptr) {
+    if (ptr && g_nccl.MemFree) g_nccl.MemFree(ptr);
+}
+
 zoo_status dp_allreduce_max(zoo_dp *dp, float *buf, long long n, cudaStream_t st) {
     if (!dp || dp->world == 1) return ZOO_OK;
     ZOO_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat, ncclMax, dp->comm, st));

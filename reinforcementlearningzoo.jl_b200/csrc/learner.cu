@@ -13,6 +13,8 @@ namespace zoo {
 zoo_status dp_allreduce_sum(zoo_dp *dp, float *buf, long long n, cudaStream_t st);
 zoo_status dp_allreduce_max(zoo_dp *dp, float *buf, long long n, cudaStream_t st);
 int dp_world(const zoo_dp *dp);
+zoo_status dp_alloc_registered(zoo_dp *dp, size_t bytes, void **ptr, void **handle);
+void dp_deregister(zoo_dp *dp, void *handle);
 
 struct OptScalars {
     double b1p, b2p;        // beta^t carried like Flux's per-array state (starts at beta)
@@ -154,6 +156,7 @@ struct zoo_learner {
     int graph_launches = 0;
     int warm = 0;
     bool target_forked = false;
+    void *nccl_reg = nullptr;  // ncclCommRegister handle of the gradient buffer (data-parallel learners)
 };
 
 static zoo_status opt_tick(zoo_opt *o, cudaStream_t st) {
@@ -490,6 +493,19 @@ zoo_status zoo_learner_create(const zoo_learner_cfg *cfg, zoo_net *online, zoo_n
     L->gamma_n = (float)std::pow((double)cfg->gamma, (double)cfg->update_horizon);  // gamma^n, gamma::Float32 (dqn.jl:133)
     ZOO_CUDA(cudaStreamCreateWithFlags(&L->st, cudaStreamNonBlocking));
     const int B = L->B, A = cfg->n_actions;
+    if (dp && dp_world(dp) > 1 && !online->grads_nccl) {
+        // data parallel: move the flat gradient buffer into NCCL-allocated, communicator-registered memory (zero-copy all-reduce)
+        void *p = nullptr, *h = nullptr;
+        const size_t bytes = (online->n_flat + 64) * sizeof(float);
+        ZOO_TRY(dp_alloc_registered(dp, bytes, &p, &h));
+        if (p) {
+            ZOO_CUDA(cudaDeviceSynchronize());
+            ZOO_CUDA(cudaMemset(p, 0, bytes));
+            ZOO_CUDA(cudaFree(online->grads));
+            online->grads = (float *)p; online->grads_nccl = true; online->grads_dirty = false;
+            L->nccl_reg = h;
+        }
+    }
     L->d_loss = online->grads + online->n_flat;  // tail of the gradient buffer (see net_alloc_backward)
     // late bucket = [offset of the largest weight tensor, end): valid when backward visits tensors in descending offset
     // order (Chain, ImplicitQuantileNet); a DuelingNetwork's val / adv heads break that order, so it keeps one bucket
@@ -546,6 +562,7 @@ zoo_status zoo_learner_destroy(zoo_learner *L) {
     if (!L) return ZOO_OK;
     cudaStreamSynchronize(L->st);
     if (L->gexec) cudaGraphExecDestroy(L->gexec);
+    if (L->nccl_reg) dp_deregister(L->dp, L->nccl_reg);
     if (L->h_pack) cudaFreeHost(L->h_pack);
     if (L->ev_pack) cudaEventDestroy(L->ev_pack);
     void *ptrs[] = {L->d_obs, L->d_pack, L->d_support,

@@ -4,6 +4,7 @@
 #include "net.cuh"
 
 namespace zoo {
+void dp_free_registered(void *ptr);  // dp.cu
 
 // Implicit-GEMM convolutions (tc_conv_gemm: the A operand is gathered in-kernel, no im2col / col2im) are parity-tested but
 // this round still lose to explicit im2col + TMA GEMM at these layer sizes (the 4-warp gather is instruction-latency bound,
@@ -964,6 +965,7 @@ zoo_status zoo_net_destroy(zoo_net *net) {
     free_chain(net->a, net->out_final, net->dout_final);
     free_chain(net->b, net->out_final, net->dout_final);
     free_chain(net->c, net->out_final, net->dout_final);
+    if (net->grads_nccl) { dp_free_registered(net->grads); net->grads = nullptr; }
     void *ptrs[] = {net->params, net->shadow, net->grads, net->out_final, net->dout_final, net->emb, net->merged, net->dmerged,
                     net->tau_dev, net->dh1, net->dh2, net->ws, net->obs, net->stage, net->ws_side, net->obs_nhwc_buf};
     for (void *p : ptrs) if (p) cudaFree(p);

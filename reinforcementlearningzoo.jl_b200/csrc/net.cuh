@@ -54,6 +54,7 @@ struct zoo_net {
     float *params = nullptr;   // fp32 master, internal layout
     zoo::bf16 *shadow = nullptr;  // bf16 copy (BF16 precision only), same layout
     float *grads = nullptr;    // allocated when a learner/optimiser attaches
+    bool grads_nccl = false;   // grads came from ncclMemAlloc (data-parallel learner: registered for zero-copy all-reduce)
     bool grads_dirty = true;   // grads may be non-zero (the optimiser kernels re-zero them; see learner.cu run_update)
     zoo::Chain a, b, c;
     int fc = 0, fh = 0, fw = 0;  // flatten space

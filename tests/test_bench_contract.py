@@ -49,3 +49,31 @@ def test_roofline_byte_model_parses_every_label_kind():
     n = 4046502
     assert bench.kernel_work("opt|opt_range:181", w, 4, n) == (0.0, n * 4 * 6.0)  # RMSProp: p r/w, g r + re-zero, acc r/w
     assert bench.kernel_work("head|launch_dqn_head:335", w, 4, n) == (0.0, 0.0)
+
+
+def test_whole_step_roofline_model_matches_the_survey_table():
+    """DQN B=32 82.7 MB (HBM-bound, 12.6 us); Rainbow B=32 ~119 MB; Rainbow B=1024 and IQN tensor-bound."""
+    import bench
+    pk = dict(hbm=6548.5, tf_burst=1598.9, tf_sus=1375.3, src="measured")
+    fl, by = bench.step_work(bench.WORKLOADS["dqn_atari_b32"], 32, 4046502)
+    assert fl == 152_836_096 * 32 and abs(by / 1e6 - 82.7) < 0.1
+    r = bench.step_roofline(bench.WORKLOADS["dqn_atari_b32"], 32, 4046502, 283.5e-6, pk, 3.0)
+    assert r["bound"] == "hbm" and abs(r["bound_us"] - 12.6) < 0.1 and abs(r["frac"] - 0.0446) < 0.001
+    _, by = bench.step_work(bench.WORKLOADS["rainbow_atari_b32"], 32, 4200402)
+    assert abs(by / 1e6 - 119.4) < 0.5
+    assert bench.step_roofline(bench.WORKLOADS["rainbow_atari_b1024"], 1024, 4200402, 1e-3, pk)["bound"] == "tensor"
+    r = bench.step_roofline(bench.WORKLOADS["iqn_atari_b512"], 512, 4549862, 4.27e-3, pk)
+    assert r["bound"] == "tensor" and abs(r["frac"] - 0.2015) < 0.002
+
+
+def test_both_arms_print_the_same_config_object():
+    import argparse
+
+    import bench
+    a = argparse.Namespace(workload="dqn_atari_b32", precision="fp32", gpus=4)
+    c = bench.config_of(a, bench.WORKLOADS["dqn_atari_b32"], 4)
+    assert c["global_batch"] == 128 and c["parallelism"] == "dp4" and "model" not in c
+    r = run_bench(["--impl", "reference", "--gpus", "4", "--steps", "1", "--warmup", "0"], {"RANK": "0", "LOCAL_RANK": "0", "WORLD_SIZE": "4", "OMP_NUM_THREADS": "1"})
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["config"] == c
+    assert d["cpu_baseline"]["cores"] == bench.host_cores()  # torchrun's OMP_NUM_THREADS=1 does not starve the CPU arm
