@@ -324,8 +324,9 @@ template <typename P>
 __device__ __forceinline__ P *in_reg(P *p) { asm volatile("" : "+l"(p)); return p; }
 __device__ __forceinline__ int in_reg(int v) { asm volatile("" : "+r"(v)); return v; }
 
+// rm: per-column multiplier applied after bias / relu (IQN: the Hadamard merge psi[b] .* relu(phi), iqn.jl:28-30; 1 otherwise)
 template <typename T, int LD, bool MASK>
-__device__ __forceinline__ void epi_rows_store(const float *cp, int rows, T *op, int stride, float bv, int relu, unsigned mbits) {
+__device__ __forceinline__ void epi_rows_store(const float *cp, int rows, T *op, int stride, float bv, int relu, unsigned mbits, float rm = 1.f) {
     op = in_reg(op); stride = in_reg(stride); relu = in_reg(relu);
 #pragma unroll 1
     for (int r0 = 0; r0 < rows; r0 += 8) {
@@ -340,7 +341,7 @@ __device__ __forceinline__ void epi_rows_store(const float *cp, int rows, T *op,
             const float xr = fmaxf(x, 0.f);
             x = relu ? xr : x;
             if (MASK) x = (mb & (1u << u)) ? x : 0.f;
-            v[u] = x;
+            v[u] = x * rm;
         }
         if (r0 + 8 <= rows) {  // whole batch in range: straight-line stores, no per-row branch
 #pragma unroll
@@ -374,7 +375,7 @@ __device__ __forceinline__ void epi_rows_red(const float *cp, int rows, float *o
 // packed bf16 rows: lane = column pair, staging row stride 66 floats; mask (relu') rows are bf16x2 as well
 template <bool MASK>
 __device__ __forceinline__ void epi_rows_store_bf16x2(const float *cp, int rows, __nv_bfloat162 *op, int stride2, float b0, float b1, int relu,
-                                                      const __nv_bfloat162 *mp, int mstride2) {
+                                                      const __nv_bfloat162 *mp, int mstride2, float rm0 = 1.f, float rm1 = 1.f) {
     op = in_reg(op); stride2 = in_reg(stride2); relu = in_reg(relu);
     if (MASK) { mp = in_reg(mp); mstride2 = in_reg(mstride2); }
 #pragma unroll 1
@@ -401,7 +402,7 @@ __device__ __forceinline__ void epi_rows_store_bf16x2(const float *cp, int rows,
                 x0 = __low2float(mk[u]) > 0.f ? x0 : 0.f;
                 x1 = __high2float(mk[u]) > 0.f ? x1 : 0.f;
             }
-            w[u] = __floats2bfloat162_rn(x0, x1);
+            w[u] = __floats2bfloat162_rn(x0 * rm0, x1 * rm1);
         }
         if (full) {
 #pragma unroll
@@ -771,8 +772,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int Nn = P.N;
         const int bias_mode = e.bias_mode, relu = e.relu, out_bf16 = e.out_bf16;
         const long long sm = e.sm, sn = e.sn;
-        const bool simple = !e.rowmul;
-        const bool trans = simple && sm == 1 && sn != 1;
+        // IQN merge in the epilogue: every row of a warp's 32-row chunk belongs to the same sample when rowmul_div % 32 == 0
+        const bool rmul = e.rowmul != nullptr && (e.rowmul_div & 31) == 0 && GA == 0 && sn == 1;
+        const void *const rmp = e.rowmul;
+        const long long rm_ld = e.rowmul_ld;
+        const int rm_div = e.rowmul_div;
+        const bool simple = !e.rowmul || rmul;
+        const bool trans = !e.rowmul && sm == 1 && sn != 1;
         const void *const maskp = e.mask;
         const int mask_bf16 = e.mask_bf16;
         const long long msm = e.mask_sm, msn = e.mask_sn;
@@ -799,7 +805,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // bf16 output, plain row-major store: 64 columns at a time so that every lane writes a packed bf16x2 (128-byte row
         // segments instead of 64-byte ones) -- the wide, K-short GEMMs (IQN phi: K = 64, 0.5 GB of output) are store-bound
         if (BN >= 64 && !X3 && simple && !trans && !split && !e.accumulate && out_bf16 && sn == 1 && (Nn & 1) == 0 && (sm & 1) == 0 && bias_mode != 2 &&
-            sm < (1 << 24) && msm < (1 << 24) &&
+            sm < (1 << 24) && msm < (1 << 24) && (!rmul || (rm_ld & 1) == 0) &&
             (!maskp || (mask_bf16 && msn == 1 && (msm & 1) == 0))) {
             float(*stw)[66] = reinterpret_cast<float(*)[66]>(smem) + q * 32;  // 32 x 66 floats per warp (spans idle stages)
 #pragma unroll 1
@@ -818,8 +824,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (bias_mode == 1) { b0 = __ldg(e.bias + n); b1 = __ldg(e.bias + n + 1); }
                     __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>((bf16 *)e.out + (long long)row0 * sm + n);
                     const __nv_bfloat162 *mp = maskp ? reinterpret_cast<const __nv_bfloat162 *>((const bf16 *)maskp + (long long)row0 * msm + n) : nullptr;
-                    if (mp) epi_rows_store_bf16x2<true>(&stw[0][2 * lane], rows, op, (int)(sm >> 1), b0, b1, relu, mp, (int)(msm >> 1));
-                    else epi_rows_store_bf16x2<false>(&stw[0][2 * lane], rows, op, (int)(sm >> 1), b0, b1, relu, nullptr, 0);
+                    float rm0 = 1.f, rm1 = 1.f;
+                    if (rmul) {
+                        const __nv_bfloat162 r2 = __ldg(reinterpret_cast<const __nv_bfloat162 *>((const bf16 *)rmp + (long long)(row0 / rm_div) * rm_ld + n));
+                        rm0 = __low2float(r2); rm1 = __high2float(r2);
+                    }
+                    if (mp) epi_rows_store_bf16x2<true>(&stw[0][2 * lane], rows, op, (int)(sm >> 1), b0, b1, relu, mp, (int)(msm >> 1), rm0, rm1);
+                    else epi_rows_store_bf16x2<false>(&stw[0][2 * lane], rows, op, (int)(sm >> 1), b0, b1, relu, nullptr, 0, rm0, rm1);
                 }
                 __syncwarp();
             }
@@ -910,14 +921,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     epi_rows_red<LDC>(chunk + lane, rows, bp, red_ws ? Nn : (int)sm);
                 } else if (direct && simple && narrow && bias_mode != 2 && !trans) {
                     const float bv = bias_mode == 1 ? __ldg(e.bias + n) : 0.f;
+                    const float rm = rmul ? ldg_elem(rmp, out_bf16, (long long)(row0 / rm_div) * rm_ld + n) : 1.f;
                     const long long o0 = (long long)row0 * sm + (long long)n * sn;
                     const float *cp = chunk + lane;
                     if (out_bf16) {
-                        if (hasmask) epi_rows_store<bf16, LDC, true>(cp, rows, (bf16 *)e.out + o0, (int)sm, bv, relu, mbits);
-                        else epi_rows_store<bf16, LDC, false>(cp, rows, (bf16 *)e.out + o0, (int)sm, bv, relu, mbits);
+                        if (hasmask) epi_rows_store<bf16, LDC, true>(cp, rows, (bf16 *)e.out + o0, (int)sm, bv, relu, mbits, rm);
+                        else epi_rows_store<bf16, LDC, false>(cp, rows, (bf16 *)e.out + o0, (int)sm, bv, relu, mbits, rm);
                     } else {
-                        if (hasmask) epi_rows_store<float, LDC, true>(cp, rows, (float *)e.out + o0, (int)sm, bv, relu, mbits);
-                        else epi_rows_store<float, LDC, false>(cp, rows, (float *)e.out + o0, (int)sm, bv, relu, mbits);
+                        if (hasmask) epi_rows_store<float, LDC, true>(cp, rows, (float *)e.out + o0, (int)sm, bv, relu, mbits, rm);
+                        else epi_rows_store<float, LDC, false>(cp, rows, (float *)e.out + o0, (int)sm, bv, relu, mbits, rm);
                     }
                 } else if (!direct) {
                     float *bp = red_ws ? ws + (long long)row0 * Nn + n : (float *)e.out + (long long)row0 * sm + (long long)n * sn;
@@ -933,6 +945,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (bias_mode == 2) x += __ldg(e.bias + m);
                         if (relu) x = fmaxf(x, 0.f);
                         if (maskp) x = ldg_elem(maskp, mask_bf16, (long long)m * msm + (long long)n * msn) > 0.f ? x : 0.f;
+                        if (rmp) x *= ldg_elem(rmp, out_bf16, (long long)(m / rm_div) * rm_ld + n);
                         st_elem(e.out, out_bf16, (long long)m * sm + (long long)n * sn, x);
                     }
                 } else {

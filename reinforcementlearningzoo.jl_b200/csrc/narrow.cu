@@ -1,0 +1,244 @@
+// Narrow output layers (the Q head: Dense(512 => n_actions), n_actions <= 8) as HBM-streaming CUDA-core kernels.
+// A 6-column GEMM has nothing for the tensor cores; what matters is reading the [rows][K] activation matrix once, with
+// 16-byte loads, and folding everything that hangs off it into the same pass:
+//   narrow_fwd_kernel : out[m][n] = b[n] + sum_k X[m][k] W[n][k]                               (one warp per row)
+//   narrow_bwd_kernel : dX = (dY W) .* relu'(X),  dW += dY^T X,  db += colsum(dY),  db_prev += colsum(dX)
+//                       -- the layer's data gradient, weight gradient, bias gradient AND the previous layer's bias
+//                       gradient in ONE pass over X (they were four launches: colsum, wgrad GEMM, dgrad GEMM, colsum)
+// Reference layers: Dense(512, n_actions) at src/experiments/atari/Dopamine_DQN_Atari.jl:34 and the IQN header
+// Dopamine_IQN_Atari.jl:40-43 (rows = batch x quantiles, 32 768 at the bench size); differentiated at dqn.jl:135, iqn.jl:203.
+#include "common.cuh"
+
+namespace zoo {
+
+static constexpr int NARROW_NMAX = 8;
+
+template <typename T> struct NarrowVec;
+template <> struct NarrowVec<float> {
+    static constexpr int V = 4;
+    typedef float4 raw;
+    static __device__ __forceinline__ void unpack(const raw &r, float (&f)[4]) { f[0] = r.x; f[1] = r.y; f[2] = r.z; f[3] = r.w; }
+    static __device__ __forceinline__ raw pack(const float (&f)[4]) { return make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <> struct NarrowVec<bf16> {
+    static constexpr int V = 8;
+    typedef uint4 raw;
+    static __device__ __forceinline__ void unpack(const raw &r, float (&f)[8]) {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            f[2 * i] = __uint_as_float(w[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ raw pack(const float (&f)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t *>(&h);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+// one warp per row (grid-stride); lane owns the 16-byte chunks lane, lane + 32, ... of the row; W lives in registers
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256) narrow_fwd_kernel(const T *__restrict__ X, const float *__restrict__ W, const float *__restrict__ bias,
+                                                         float *__restrict__ out, int M, int N, int K) {
+    using NV = NarrowVec<T>;
+    constexpr int V = NV::V;
+    extern __shared__ float w_s[];  // W [N][K], staged once per CTA with coalesced 16-byte loads
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int nchunks = K / V;
+    for (int i = threadIdx.x; i < N * K / 4; i += 256) reinterpret_cast<float4 *>(w_s)[i] = __ldg(reinterpret_cast<const float4 *>(W) + i);
+    __syncthreads();
+    float w[NARROW_NMAX][CPL * V];
+#pragma unroll
+    for (int n = 0; n < NARROW_NMAX; ++n)
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int ch = lane + 32 * c;
+#pragma unroll
+            for (int e4 = 0; e4 < V; e4 += 4) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n < N && ch < nchunks) t = *reinterpret_cast<const float4 *>(w_s + n * K + ch * V + e4);
+                w[n][c * V + e4] = t.x; w[n][c * V + e4 + 1] = t.y; w[n][c * V + e4 + 2] = t.z; w[n][c * V + e4 + 3] = t.w;
+            }
+        }
+    float bn = lane < N ? __ldg(bias + lane) : 0.f;
+    pdl_trigger();
+    for (int m = blockIdx.x * 8 + (threadIdx.x >> 5); m < M; m += gridDim.x * 8) {
+        float acc[NARROW_NMAX];
+#pragma unroll
+        for (int n = 0; n < NARROW_NMAX; ++n) acc[n] = 0.f;
+        const typename NV::raw *row = reinterpret_cast<const typename NV::raw *>(X + (long long)m * K);
+        typename NV::raw r[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+            if (lane + 32 * c < nchunks) r[c] = row[lane + 32 * c];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            if (lane + 32 * c < nchunks) {
+                float x[V];
+                NV::unpack(r[c], x);
+#pragma unroll
+                for (int n = 0; n < NARROW_NMAX; ++n)
+#pragma unroll
+                    for (int e = 0; e < V; ++e) acc[n] = fmaf(x[e], w[n][c * V + e], acc[n]);
+            }
+        }
+        float mine = 0.f;
+#pragma unroll
+        for (int n = 0; n < NARROW_NMAX; ++n) {
+            float v = acc[n];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == n) mine = v;
+        }
+        if (lane < N) out[(long long)m * N + lane] = mine + bn;
+    }
+}
+
+// TPR = K / 8 threads share a row (8 consecutive k each), 256 / TPR rows per pass; grid-stride over row groups.
+// Shared memory: dW accumulator [N][K], db_prev accumulator [K], db accumulator [N] -- flushed with one atomic per element per CTA.
+template <typename T>
+__global__ void __launch_bounds__(256) narrow_bwd_kernel(const T *__restrict__ X, const float *__restrict__ dY, const float *__restrict__ W,
+                                                         T *__restrict__ dX, float *__restrict__ dW, float *__restrict__ db, float *__restrict__ db_prev,
+                                                         int M, int N, int K, int relu_prev) {
+    extern __shared__ float acc_s[];
+    float *dWs = acc_s, *dbp_s = acc_s + NARROW_NMAX * K, *dbn_s = dbp_s + K;
+    const int TPR = K >> 3, RPP = 256 / TPR;
+    const int kq = threadIdx.x % TPR, rl = threadIdx.x / TPR;
+    pdl_wait();
+    // W is staged through the (not yet used) dW accumulator with coalesced 16-byte loads, then each thread keeps its 8 columns
+    for (int i = threadIdx.x; i < N * K / 4; i += 256) reinterpret_cast<float4 *>(dWs)[i] = __ldg(reinterpret_cast<const float4 *>(W) + i);
+    __syncthreads();
+    float w[NARROW_NMAX][8], dw[NARROW_NMAX][8], dbp[8], dbn[NARROW_NMAX];
+#pragma unroll
+    for (int n = 0; n < NARROW_NMAX; ++n) {
+        dbn[n] = 0.f;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (n < N) {
+            a = *reinterpret_cast<const float4 *>(dWs + n * K + kq * 8);
+            b = *reinterpret_cast<const float4 *>(dWs + n * K + kq * 8 + 4);
+        }
+        w[n][0] = a.x; w[n][1] = a.y; w[n][2] = a.z; w[n][3] = a.w; w[n][4] = b.x; w[n][5] = b.y; w[n][6] = b.z; w[n][7] = b.w;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dw[n][e] = 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NARROW_NMAX * K + K + NARROW_NMAX; i += 256) acc_s[i] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dbp[e] = 0.f;
+    pdl_trigger();
+    for (long long m = (long long)blockIdx.x * RPP + rl; m < M; m += (long long)gridDim.x * RPP) {
+        float x[8], dy[NARROW_NMAX];
+        if (sizeof(T) == 2) {
+            float t8[8];
+            NarrowVec<bf16>::unpack(*reinterpret_cast<const uint4 *>(reinterpret_cast<const bf16 *>(X) + m * K + kq * 8), t8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = t8[e];
+        } else {
+            const float4 a = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(X) + m * K + kq * 8);
+            const float4 b = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(X) + m * K + kq * 8 + 4);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        }
+#pragma unroll
+        for (int n = 0; n < NARROW_NMAX; ++n) dy[n] = n < N ? __ldg(dY + m * N + n) : 0.f;
+        float dx[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float s = 0.f;
+#pragma unroll
+            for (int n = 0; n < NARROW_NMAX; ++n) s = fmaf(dy[n], w[n][e], s);
+            if (relu_prev && !(x[e] > 0.f)) s = 0.f;
+            dx[e] = s;
+            dbp[e] += s;
+#pragma unroll
+            for (int n = 0; n < NARROW_NMAX; ++n) dw[n][e] = fmaf(dy[n], x[e], dw[n][e]);
+        }
+        if (sizeof(T) == 2) {
+            *reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(dX) + m * K + kq * 8) = NarrowVec<bf16>::pack(dx);
+        } else {
+            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(dX) + m * K + kq * 8) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(dX) + m * K + kq * 8 + 4) = make_float4(dx[4], dx[5], dx[6], dx[7]);
+        }
+        if (kq == 0) {
+#pragma unroll
+            for (int n = 0; n < NARROW_NMAX; ++n) dbn[n] += dy[n];
+        }
+    }
+    __syncthreads();  // accumulators zeroed
+#pragma unroll
+    for (int n = 0; n < NARROW_NMAX; ++n) {
+        if (n < N) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(dWs + n * K + kq * 8 + e, dw[n][e]);
+            if (kq == 0) atomicAdd(dbn_s + n, dbn[n]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(dbp_s + kq * 8 + e, dbp[e]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < N * K; i += 256) atomicAdd(dW + i, dWs[i]);
+    if (db_prev)
+        for (int i = threadIdx.x; i < K; i += 256) atomicAdd(db_prev + i, dbp_s[i]);
+    if (threadIdx.x < N) atomicAdd(db + threadIdx.x, dbn_s[threadIdx.x]);
+}
+
+bool narrow_supported(int N, long long K, int x_bf16) {
+    if (N < 1 || N > NARROW_NMAX || K < 8 || K % 8 || K > 2048) return false;
+    const int tpr = (int)(K / 8);
+    if (256 % tpr) return false;                       // backward: K/8 threads per row must divide the CTA
+    const int v = x_bf16 ? 8 : 4;
+    return K % v == 0 && K / v <= 32 * 4;               // forward: at most 4 chunks of 16 bytes per lane
+}
+
+zoo_status narrow_forward(const void *X, int x_bf16, const float *W, const float *bias, float *out, long long M, int N, long long K, cudaStream_t st) {
+    ZOO_REQUIRE(narrow_supported(N, K, x_bf16) && M > 0 && M < (1ll << 31), "narrow_forward: unsupported shape (N=%d K=%lld)", N, K);
+    const int v = x_bf16 ? 8 : 4;
+    const int cpl = cdiv(K / v, 32);
+    const dim3 grid((unsigned)std::min<long long>(cdiv(M, 8), 148 * 2)), block(256);
+    const size_t smem = (size_t)N * K * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        const int mx = NARROW_NMAX * 2048 * (int)sizeof(float);
+        ZOO_CUDA(cudaFuncSetAttribute(narrow_fwd_kernel<bf16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        ZOO_CUDA(cudaFuncSetAttribute(narrow_fwd_kernel<bf16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        ZOO_CUDA(cudaFuncSetAttribute(narrow_fwd_kernel<bf16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        ZOO_CUDA(cudaFuncSetAttribute(narrow_fwd_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        ZOO_CUDA(cudaFuncSetAttribute(narrow_fwd_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        ZOO_CUDA(cudaFuncSetAttribute(narrow_fwd_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        attr = true;
+    }
+#define NFWD(T, C) ZOO_CUDA(launch_pdl(narrow_fwd_kernel<T, C>, grid, block, smem, st, (const T *)X, W, bias, out, (int)M, N, (int)K))
+    if (x_bf16) { if (cpl <= 1) NFWD(bf16, 1); else if (cpl == 2) NFWD(bf16, 2); else NFWD(bf16, 4); }
+    else { if (cpl <= 1) NFWD(float, 1); else if (cpl == 2) NFWD(float, 2); else NFWD(float, 4); }
+#undef NFWD
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+
+zoo_status narrow_backward(const void *X, int x_bf16, const float *dY, const float *W, void *dX, float *dW, float *db, float *db_prev, long long M,
+                           int N, long long K, int relu_prev, cudaStream_t st) {
+    ZOO_REQUIRE(narrow_supported(N, K, x_bf16) && M > 0, "narrow_backward: unsupported shape (N=%d K=%lld)", N, K);
+    const int rpp = 256 / (int)(K / 8);
+    const dim3 grid((unsigned)std::min<long long>(cdiv(M, rpp), 148 * 2)), block(256);
+    const size_t smem = (size_t)(NARROW_NMAX * K + K + NARROW_NMAX) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        ZOO_CUDA(cudaFuncSetAttribute(narrow_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((NARROW_NMAX * 2048 + 2048 + NARROW_NMAX) * sizeof(float))));
+        ZOO_CUDA(cudaFuncSetAttribute(narrow_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((NARROW_NMAX * 2048 + 2048 + NARROW_NMAX) * sizeof(float))));
+        attr = true;
+    }
+    if (x_bf16)
+        ZOO_CUDA(launch_pdl(narrow_bwd_kernel<bf16>, grid, block, smem, st, (const bf16 *)X, dY, W, (bf16 *)dX, dW, db, db_prev, (int)M, N, (int)K, relu_prev));
+    else
+        ZOO_CUDA(launch_pdl(narrow_bwd_kernel<float>, grid, block, smem, st, (const float *)X, dY, W, (float *)dX, dW, db, db_prev, (int)M, N, (int)K, relu_prev));
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+
+}  // namespace zoo

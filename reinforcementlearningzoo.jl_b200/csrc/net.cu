@@ -5,6 +5,15 @@
 
 namespace zoo {
 void dp_free_registered(void *ptr);  // dp.cu
+// narrow.cu: the Q head (n_actions <= 8 outputs) as one streaming pass forward and one backward
+bool narrow_supported(int N, long long K, int x_bf16);
+zoo_status narrow_forward(const void *X, int x_bf16, const float *W, const float *bias, float *out, long long M, int N, long long K, cudaStream_t st);
+zoo_status narrow_backward(const void *X, int x_bf16, const float *dY, const float *W, void *dX, float *dW, float *db, float *db_prev, long long M,
+                           int N, long long K, int relu_prev, cudaStream_t st);
+static bool narrow_enabled() {
+    static const bool on = [] { const char *e = getenv("ZOO_NARROW"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 // Implicit-GEMM convolutions (tc_conv_gemm: the A operand is gathered in-kernel, no im2col / col2im) are parity-tested but
 // this round still lose to explicit im2col + TMA GEMM at these layer sizes (the 4-warp gather is instruction-latency bound,
@@ -256,6 +265,54 @@ __global__ void iqn_merge_bwd_vec_kernel(const T *__restrict__ dm, const T *__re
     *reinterpret_cast<VecT<T, VEC> *>(dfeat + b * F + (long long)f * VEC) = of;
 }
 
+// Adjoint of the FUSED merge (phi's output was never stored; merged = psi .* relu(phi), both factors >= 0):
+//   relu'(phi) = [merged > 0] wherever psi > 0, and where psi == 0 the gradient into phi is zero anyway;
+//   relu(phi)  = merged / psi wherever psi > 0, and where psi == 0 relu'(psi) = 0 kills d psi anyway.
+// so  dphi = dm .* psi .* [merged > 0],   dpsi[b] = [psi > 0] / psi .* sum_n dm .* merged,   dbias_phi += sum over rows of dphi
+// (the bias gradient of phi's last layer is folded in: it was a separate column-sum pass over the 0.5 GB dphi tensor).
+// One thread per (feature vector, group of BG samples).
+template <typename T, int VEC>
+__global__ void iqn_merge_bwd_fused_kernel(const T *__restrict__ dm, const T *__restrict__ feat, const T *__restrict__ merged, T *__restrict__ dea,
+                                           T *__restrict__ dfeat, float *__restrict__ dbias, int B, int F, int N, int BG) {
+    const int fv = F / VEC;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int groups = (B + BG - 1) / BG;
+    if (idx >= (long long)groups * fv) return;
+    const int f = (int)(idx % fv);
+    const int g = (int)(idx / fv);
+    float bsum[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) bsum[i] = 0.f;
+    for (int b = g * BG; b < min(B, (g + 1) * BG); ++b) {
+        const VecT<T, VEC> ftv = *reinterpret_cast<const VecT<T, VEC> *>(feat + (long long)b * F + (long long)f * VEC);
+        float ft[VEC], acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { ft[i] = to_f(ftv.v[i]); acc[i] = 0.f; }
+#pragma unroll 4
+        for (int n = 0; n < N; ++n) {
+            const long long o = ((long long)b * N + n) * F + (long long)f * VEC;
+            const VecT<T, VEC> d = *reinterpret_cast<const VecT<T, VEC> *>(dm + o);
+            const VecT<T, VEC> m = *reinterpret_cast<const VecT<T, VEC> *>(merged + o);
+            VecT<T, VEC> out;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float dd = to_f(d.v[i]), mm = to_f(m.v[i]);
+                const float de = mm > 0.f ? dd * ft[i] : 0.f;
+                out.v[i] = from_f<T>(de);
+                bsum[i] += to_f(out.v[i]);  // the bias gradient sums what the weight gradient will read
+                acc[i] = fmaf(dd, mm, acc[i]);
+            }
+            *reinterpret_cast<VecT<T, VEC> *>(dea + o) = out;
+        }
+        VecT<T, VEC> of;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) of.v[i] = from_f<T>(ft[i] > 0.f ? acc[i] / ft[i] : 0.f);
+        *reinterpret_cast<VecT<T, VEC> *>(dfeat + (long long)b * F + (long long)f * VEC) = of;
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) atomicAdd(dbias + (long long)f * VEC + i, bsum[i]);
+}
+
 // adjoint of the merge: dea = dm * feat * relu'(ea);  dfeat[b] = relu'(feat) * sum_n dm * ea
 template <typename T>
 __global__ void iqn_merge_bwd_kernel(const T *__restrict__ dm, const T *__restrict__ feat, const T *__restrict__ ea,
@@ -438,6 +495,7 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
         Epilogue e;
         e.out = L.out; e.out_bf16 = L.out_fp32 ? 0 : bf; e.sm = L.cout; e.sn = 1;
         e.bias = net->params + Bt.offset; e.bias_mode = 1; e.relu = L.relu; e.tf32_passes = net->tf32_passes;
+        if (L.rowmul) { e.rowmul = L.rowmul; e.rowmul_div = L.rowmul_div; e.rowmul_ld = L.rowmul_ld; }
         if (L.kind == ZOO_LAYER_CONV && L.first_raw && net->obs_nhwc) {
             if (cur_kind == 2) { set_err("conv: first layer expects a raw observation"); return ZOO_BAD_ARG; }
             const int oh_ = net->desc.in_h, ow_ = net->desc.in_w, op_ = (L.ih - oh_) / 2;  // L.ih / L.iw describe the padded copy
@@ -503,7 +561,14 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
             A = Operand{L.cols, bf, L.K, 1};
         } else {
             ZOO_REQUIRE(cur_kind != 0, "dense: uint8 observations need a conv or scale layer first");
-            A = Operand{cur, cur_kind == 2 ? bf : 0, L.K, 1};
+            const int xbf = cur_kind == 2 ? bf : 0;
+            if (L.out_fp32 && !L.relu && narrow_enabled() && narrow_supported(L.cout, L.K, xbf)) {
+                ZOO_TRY(narrow_forward(cur, xbf, net->params + W.offset, net->params + Bt.offset, (float *)L.out, M, L.cout, L.K, st));
+                cur = L.out;
+                cur_kind = 2;
+                continue;
+            }
+            A = Operand{cur, xbf, L.K, 1};
         }
         Operand B = weight_operand(net, W, A, (int)M, L.cout, (int)L.K, L.K, 1);
         ZOO_TRY(gemm(A, B, (int)M, L.cout, (int)L.K, e, 0, net->ws, net->ws_elems, st));
@@ -516,7 +581,7 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
 // Each layer's dout must already hold d(loss)/d(out) with the layer's own relu' applied.
 // dx (optional): gradient w.r.t. the chain input, internal T [rows][in_feat]; dx_mask: relu' source for it.
 static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in_kind, long long rows, void *dx, const void *dx_mask,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, int bias_done = -1) {  // bias_done: layer whose bias gradient a fused kernel already produced
     const int bf = is_bf(net);
     for (int li = (int)ch.layers.size() - 1; li >= 0; --li) {
         LayerExec &L = ch.layers[li];
@@ -524,6 +589,16 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
         const TensorInfo &W = net->tensors[L.wt];
         const TensorInfo &Bt = net->tensors[L.bt];
         const int dy_bf = L.out_fp32 ? 0 : bf;
+        if (li > 0 && L.kind == ZOO_LAYER_DENSE && L.out_fp32 && !L.relu && narrow_enabled() && narrow_supported(L.cout, L.K, bf) &&
+            !(net->late_cb && W.offset == net->late_off)) {
+            // the Q head: data, weight and bias gradient plus the previous layer's bias gradient in one pass over its input
+            LayerExec &P = ch.layers[li - 1];
+            prof_label("dgrad+wgrad:t%d[%lldx%lldx%d]", L.wt, M, L.K, L.cout);
+            ZOO_TRY(narrow_backward(P.out, bf, (const float *)L.dout, net->params + W.offset, P.dout, net->grads + W.offset, net->grads + Bt.offset,
+                                    net->grads + net->tensors[P.bt].offset, M, L.cout, L.K, P.relu, st));
+            bias_done = li - 1;
+            continue;
+        }
         // bias grad + wgrad only need this layer's dout, which is complete on `st` here: they go to the side lane and
         // overlap the dgrad chain (the critical path) that continues on `st`
         const bool par = net->side && !g_prof_on;
@@ -531,8 +606,10 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
         float *wsw = par ? net->ws_side : net->ws;
         const size_t wsw_elems = par ? net->ws_side_elems : net->ws_elems;
         if (par) ZOO_TRY(net_side_fork(net, st));
-        prof_label("bgrad:t%d", L.bt);
-        ZOO_TRY(launch_colsum(L.dout, dy_bf, M, L.cout, net->grads + Bt.offset, sw));
+        if (bias_done != li) {
+            prof_label("bgrad:t%d", L.bt);
+            ZOO_TRY(launch_colsum(L.dout, dy_bf, M, L.cout, net->grads + Bt.offset, sw));
+        }
         // wgrad: dW[cout][K] += dY^T X   (both operands MN-major: stored [rows][features])
         Operand X;
         if (L.kind == ZOO_LAYER_CONV) X = Operand{L.cols, bf, L.K, 0};
@@ -636,6 +713,12 @@ zoo_status net_forward(zoo_net *net, const void *obs, int obs_dtype, int rows, c
     if (bf) embed_kernel<bf16><<<cdiv(R * nem, 256), 256, 0, st>>>(tau, (bf16 *)net->emb, R, nem);
     else embed_kernel<float><<<cdiv(R * nem, 256), 256, 0, st>>>(tau, (float *)net->emb, R, nem);
     ZOO_LAUNCH_CHECK();
+    if (net->iqn_fused) {  // phi's last GEMM writes merged = psi[b] .* relu(W cos + b) from its epilogue (iqn.jl:27-30)
+        LayerExec &Lp = net->b.layers.back();
+        Lp.rowmul = net->a.out(); Lp.rowmul_div = n_tau; Lp.rowmul_ld = F;
+        ZOO_TRY(chain_forward(net, net->b, net->emb, 2, R, st));
+        return chain_forward(net, net->c, net->merged, 2, R, st);
+    }
     ZOO_TRY(chain_forward(net, net->b, net->emb, 2, R, st));
     prof_label("iqn_merge[%lldx%d]", R, F);
     if (bf && F % 8 == 0) iqn_merge_vec_kernel<bf16, 8><<<cdiv(R * (F / 8), 256), 256, 0, st>>>((const bf16 *)net->a.out(), (const bf16 *)net->b.out(), (bf16 *)net->merged, R, F, n_tau);
@@ -688,6 +771,18 @@ static zoo_status net_backward_impl(zoo_net *net, int obs_dtype, const void *obs
     LayerExec &Ppsi = net->a.layers.back();
     long long n = (long long)rows * F;
     prof_label("iqn_merge_bwd[%lldx%d]", (long long)rows * n_tau, F);
+    if (net->iqn_fused) {
+        const int BG = rows >= 64 ? 4 : 1;
+        const long long groups = (rows + BG - 1) / BG;
+        float *dbias = net->grads + net->tensors[Pphi.bt].offset;
+        if (bf && F % 8 == 0) iqn_merge_bwd_fused_kernel<bf16, 8><<<cdiv(groups * (F / 8), 128), 128, 0, st>>>((const bf16 *)net->dmerged, (const bf16 *)Ppsi.out, (const bf16 *)net->merged, (bf16 *)Pphi.dout, (bf16 *)Ppsi.dout, dbias, rows, F, n_tau, BG);
+        else if (!bf && F % 4 == 0) iqn_merge_bwd_fused_kernel<float, 4><<<cdiv(groups * (F / 4), 128), 128, 0, st>>>((const float *)net->dmerged, (const float *)Ppsi.out, (const float *)net->merged, (float *)Pphi.dout, (float *)Ppsi.dout, dbias, rows, F, n_tau, BG);
+        else if (bf) iqn_merge_bwd_fused_kernel<bf16, 1><<<cdiv(groups * F, 128), 128, 0, st>>>((const bf16 *)net->dmerged, (const bf16 *)Ppsi.out, (const bf16 *)net->merged, (bf16 *)Pphi.dout, (bf16 *)Ppsi.dout, dbias, rows, F, n_tau, BG);
+        else iqn_merge_bwd_fused_kernel<float, 1><<<cdiv(groups * F, 128), 128, 0, st>>>((const float *)net->dmerged, (const float *)Ppsi.out, (const float *)net->merged, (float *)Pphi.dout, (float *)Ppsi.dout, dbias, rows, F, n_tau, BG);
+        ZOO_LAUNCH_CHECK();
+        ZOO_TRY(chain_backward(net, net->b, net->emb, 2, R, nullptr, nullptr, st, (int)net->b.layers.size() - 1));
+        return chain_backward(net, net->a, obs, in_kind, rows, nullptr, nullptr, st);
+    }
     if (bf && F % 8 == 0) iqn_merge_bwd_vec_kernel<bf16, 8><<<cdiv(n / 8, 128), 128, 0, st>>>((const bf16 *)net->dmerged, (const bf16 *)Ppsi.out, (const bf16 *)Pphi.out, (bf16 *)Pphi.dout, (bf16 *)Ppsi.dout, rows, F, n_tau, Pphi.relu, Ppsi.relu);
     else if (!bf && F % 4 == 0) iqn_merge_bwd_vec_kernel<float, 4><<<cdiv(n / 4, 128), 128, 0, st>>>((const float *)net->dmerged, (const float *)Ppsi.out, (const float *)Pphi.out, (float *)Pphi.dout, (float *)Ppsi.dout, rows, F, n_tau, Pphi.relu, Ppsi.relu);
     else if (bf) iqn_merge_bwd_kernel<bf16><<<cdiv(n, 256), 256, 0, st>>>((const bf16 *)net->dmerged, (const bf16 *)Ppsi.out, (const bf16 *)Pphi.out, (bf16 *)Pphi.dout, (bf16 *)Ppsi.dout, rows, F, n_tau, Pphi.relu, Ppsi.relu);
@@ -770,11 +865,12 @@ static zoo_status parse_chain(zoo_net *net, const zoo_layer *Ls, int n, ParseSta
     return ZOO_OK;
 }
 
-static zoo_status alloc_chain(zoo_net *net, Chain &ch, long long rows_cap, float *final_out) {
+static zoo_status alloc_chain(zoo_net *net, Chain &ch, long long rows_cap, float *final_out, void *last_out_alias = nullptr) {
     ch.rows_cap = rows_cap;
     for (auto &L : ch.layers) {
         long long M = rows_cap * L.opr;
         if (L.kind == ZOO_LAYER_CONV) ZOO_CUDA(cudaMalloc(&L.cols, (size_t)M * L.K * net->esz));
+        if (last_out_alias && &L == &ch.layers.back()) { L.out = last_out_alias; continue; }
         if (L.out_fp32 && final_out) L.out = final_out;
         else ZOO_CUDA(cudaMalloc(&L.out, (size_t)M * L.cout * (L.out_fp32 ? 4 : net->esz)));
     }
@@ -919,11 +1015,15 @@ zoo_status zoo_net_create(const zoo_net_desc *d, zoo_net **out) {
     ZOO_CUDA(cudaMalloc(&net->out_final, (size_t)out_rows * net->n_out * sizeof(float)));
     if (d->kind == ZOO_NET_CHAIN) ZOO_TRY(alloc_chain(net, net->a, rows_a, net->out_final));
     else if (d->kind == ZOO_NET_IQN) {
+        ZOO_CUDA(cudaMalloc(&net->merged, (size_t)rq * net->a.out_feat * net->esz));
+        {   // fused merge: needs relu on both factors (so that merged / psi and [merged > 0] recover phi's output and mask)
+            const char *e = getenv("ZOO_IQN_FUSE");
+            net->iqn_fused = net->a.layers.back().relu && net->b.layers.back().relu && net->b.layers.back().kind == ZOO_LAYER_DENSE && !(e && e[0] == '0');
+        }
         ZOO_TRY(alloc_chain(net, net->a, rows_a, nullptr));
-        ZOO_TRY(alloc_chain(net, net->b, rq, nullptr));
+        ZOO_TRY(alloc_chain(net, net->b, rq, nullptr, net->iqn_fused ? net->merged : nullptr));
         ZOO_TRY(alloc_chain(net, net->c, rq, net->out_final));
         ZOO_CUDA(cudaMalloc(&net->emb, (size_t)rq * net->b.in_feat * net->esz));
-        ZOO_CUDA(cudaMalloc(&net->merged, (size_t)rq * net->a.out_feat * net->esz));
         ZOO_CUDA(cudaMalloc(&net->tau_dev, (size_t)rq * sizeof(float)));
     } else {
         ZOO_TRY(alloc_chain(net, net->a, rows_a, nullptr));
@@ -950,10 +1050,10 @@ zoo_status zoo_net_create(const zoo_net_desc *d, zoo_net **out) {
     return ZOO_OK;
 }
 
-static void free_chain(Chain &ch, float *fo, float *fd) {
+static void free_chain(Chain &ch, float *fo, float *fd, void *alias = nullptr) {
     for (auto &L : ch.layers) {
         if (L.cols) cudaFree(L.cols);
-        if (L.out && L.out != fo) cudaFree(L.out);
+        if (L.out && L.out != fo && L.out != alias) cudaFree(L.out);
         if (L.dout && L.dout != fd) cudaFree(L.dout);
         if (L.dcols) cudaFree(L.dcols);
     }
@@ -963,7 +1063,7 @@ zoo_status zoo_net_destroy(zoo_net *net) {
     if (!net) return ZOO_OK;
     cudaStreamSynchronize(net->st);
     free_chain(net->a, net->out_final, net->dout_final);
-    free_chain(net->b, net->out_final, net->dout_final);
+    free_chain(net->b, net->out_final, net->dout_final, net->merged);
     free_chain(net->c, net->out_final, net->dout_final);
     if (net->grads_nccl) { dp_free_registered(net->grads); net->grads = nullptr; }
     void *ptrs[] = {net->params, net->shadow, net->grads, net->out_final, net->dout_final, net->emb, net->merged, net->dmerged,

@@ -32,6 +32,8 @@ struct LayerExec {
     long long K;         // GEMM reduction length (conv: k*k*cin, dense: in)
     long long opr;       // outputs rows per sample (conv: oh*ow, dense: 1)
     void *cols = nullptr, *out = nullptr, *dout = nullptr, *dcols = nullptr;
+    // fused IQN merge (set per forward call on phi's last layer): out = relu(.) .* rowmul[row / rowmul_div]  -- iqn.jl:28-30
+    const void *rowmul = nullptr; int rowmul_div = 1; long long rowmul_ld = 0;
 };
 
 struct Chain {
@@ -62,7 +64,9 @@ struct zoo_net {
     long long max_batch = 0, max_q = 0;
     // fp32 network output / its gradient
     float *out_final = nullptr, *dout_final = nullptr;
-    // IQN extras
+    // IQN extras.  iqn_fused: phi's last GEMM multiplies by psi in its epilogue and writes `merged` directly (phi's own output
+    // is never materialised: its last layer's `out` aliases `merged`); the backward recovers what it needs from merged and psi
+    bool iqn_fused = false;
     void *emb = nullptr, *merged = nullptr, *dmerged = nullptr;
     float *tau_dev = nullptr;
     // dueling extras

@@ -135,6 +135,15 @@ def full_size_parity(zoo, case, prec, seed=33):
     del lrn, app, tapp
     rec = []
     free = twin(rec=rec)
+    if kind == "iqn":
+        # the library fuses the IQN merge into phi's GEMM epilogue and never stores phi's own output: the hook returns
+        # merged = psi .* relu(phi) for that layer, from which relu'(phi) = [merged > 0] wherever psi > 0.  Where psi == 0 the
+        # unit's branch is unobservable AND irrelevant (its gradient is multiplied by psi): those take the twin's own branch.
+        n_psi = sum(1 for l in net["psi"] if l[0] in ("conv", "dense") and l[-1])
+        psi_flat = np.repeat(acts[n_psi - 1].reshape(B, -1), N, axis=0)
+        dontcare = psi_flat == 0
+        acts[n_psi] = np.where(dontcare, rec[n_psi].numpy(), acts[n_psi])
+        del psi_flat, dontcare
     masks = [torch.from_numpy((a > 0).astype(np.float32)) for a in acts]
     assert len(masks) == len(rec)
     flips = []
