@@ -139,6 +139,20 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
         P.ws = ws;  // invariant: all-zero on entry, left all-zero by the finishing CTAs
         P.ctr = reinterpret_cast<unsigned *>(ws + ws_elems - TC_WS_COUNTERS);
     }
+    {
+        // TMA-store epilogue for plain bf16 row-major outputs (see TcParams::tma_store); ZOO_TMA_STORE=0 falls back to the
+        // per-row 128-byte stores
+        static const bool ts_on = [] { const char *e = getenv("ZOO_TMA_STORE"); return !(e && e[0] == '0'); }();
+        const Epilogue &pe = P.epi;
+        const bool rm_ok = !pe.rowmul || ((pe.rowmul_div & 31) == 0);
+        const bool mask_ok = !pe.mask || (pe.mask_bf16 && pe.mask_sn == 1 && (pe.mask_sm & 7) == 0 && ((uintptr_t)pe.mask & 15) == 0);
+        P.tma_store = 0;
+        if (ts_on && !x3 && BN >= 64 && split_k == 1 && pe.out_bf16 && !pe.accumulate && pe.bias_mode != 2 && pe.sn == 1 && (pe.sm & 7) == 0 &&
+            ((uintptr_t)pe.out & 15) == 0 && rm_ok && mask_ok) {
+            ZOO_TRY(make_map(&P.tmC, pe.out, 2, N, M, pe.sm, 64, 32, false));
+            P.tma_store = 1;
+        }
+    }
     CUtensorMap tmA, tmB;
     if (A.kmajor) ZOO_TRY(make_map(&tmA, A.p, eb, K, M, A.ld, bk, BM, false));
     else ZOO_TRY(make_map(&tmA, A.p, eb, M, K, A.ld, mn_box, bk, true));

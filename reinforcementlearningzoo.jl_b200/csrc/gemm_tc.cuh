@@ -147,6 +147,11 @@ struct TcParams {
     unsigned *ctr;  // split-K per-tile arrival counters (kept all-zero between launches)
     unsigned long long *dbg;  // test hook: CTA 0 writes %globaltimer at its phase boundaries (nullptr = off)
     ConvGeom conv;  // GA kernels only: how the A operand is gathered
+    // TMA-store epilogue (plain GEMMs with a bf16 row-major output): the warps stage finished 32 x 64 blocks in shared memory in
+    // the SWIZZLE_128B layout and one lane hands each block to the TMA unit (cp.async.bulk.tensor ... global.shared::cta), which
+    // also clips rows / columns past M / N.  tmC: 2-D map over the output, box {64 columns, 32 rows}.
+    int tma_store = 0;
+    CUtensorMap tmC;
 };
 
 extern unsigned long long *g_tc_dbg;  // set by zoo_test_gemm_trace (defined in gemm_tc.cu)
@@ -451,7 +456,7 @@ __device__ __forceinline__ void epi_cols_store(const float *rp, int ncols, T *op
 //         (element strides = conv stride, out-of-bounds = zero padding).
 template <int EB, int BN, bool A_K, bool B_K, bool X3, int GA = 0>
 __global__ void __launch_bounds__(TC_THREADS)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams P) {
     static_assert(GA == 0 || A_K, "the gathered A operand is K-major");
     using C = TcCfg<EB, BN, X3>;
     // SWIZZLE_128B tiles need 1024-byte alignment; declaring it on the array (instead of rounding the pointer up) keeps
@@ -804,6 +809,95 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // bf16 output, plain row-major store: 64 columns at a time so that every lane writes a packed bf16x2 (128-byte row
         // segments instead of 64-byte ones) -- the wide, K-short GEMMs (IQN phi: K = 64, 0.5 GB of output) are store-bound
+        if (BN >= 64 && !X3 && GA == 0 && P.tma_store) {
+            // TMA-store epilogue.  tcgen05.ld leaves lane = tile row with 32 consecutive columns in registers -- exactly one
+            // 64-byte half of a 128-byte row of the staging block, so the values go to shared memory as four 16-byte chunks per
+            // half (chunk j of row r at j ^ (r % 8): conflict-free, and the layout the SWIZZLE_128B tensor map expects) with no
+            // transpose; bias / rowmul are staged once per CTA / warp and read as broadcasts.  Two staging blocks per warp, so
+            // the bulk store of one 64-column group overlaps the conversion of the next.
+            float *const bias_s = reinterpret_cast<float *>(smem + 32768);
+            float *const rm_s = bias_s + 128 + q * 128;
+            {
+                const int t = threadIdx.x - 64;
+                if (t < BN) bias_s[t] = (bias_mode == 1 && n0 + t < Nn) ? __ldg(e.bias + n0 + t) : 0.f;
+                for (int j = lane; j < BN; j += 32) rm_s[j] = (rmul && n0 + j < Nn) ? ldg_elem(rmp, 1, (long long)(row0 / rm_div) * rm_ld + n0 + j) : 1.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const uint32_t sbase = smem_u32(smem) + q * 8192;
+            const bool rowok = lane < rows;
+            int buf = 0, issued = 0;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 64) {
+                if (n0 + c >= Nn) break;
+                if (issued >= 2) {  // the block about to be overwritten has been read by its bulk store
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                }
+                const uint32_t sb = sbase + buf * 4096 + lane * 128;
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t r[32];
+                    tmem_ld32(tq + (uint32_t)(lb * BN + c + 32 * h), r);
+                    const int nb = n0 + c + 32 * h;
+                    uint4 mk[4];
+                    if (maskp) {
+                        const bf16 *mp = (const bf16 *)maskp + (long long)(row0 + lane) * msm + nb;
+                        if (rowok && nb + 32 <= Nn) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) mk[j] = __ldg(reinterpret_cast<const uint4 *>(mp) + j);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint32_t w[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int col = j * 8 + 2 * i;
+                                    const uint32_t lo = (rowok && nb + col < Nn) ? (uint32_t)__bfloat16_as_ushort(__ldg(mp + col)) : 0u;
+                                    const uint32_t hi = (rowok && nb + col + 1 < Nn) ? (uint32_t)__bfloat16_as_ushort(__ldg(mp + col + 1)) : 0u;
+                                    w[i] = lo | (hi << 16);
+                                }
+                                mk[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        const uint32_t mw[4] = {mk[j8].x, mk[j8].y, mk[j8].z, mk[j8].w};
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int col = c + 32 * h + j8 * 8 + 2 * i;
+                            float x0 = __uint_as_float(r[j8 * 8 + 2 * i]) + bias_s[col], x1 = __uint_as_float(r[j8 * 8 + 2 * i + 1]) + bias_s[col + 1];
+                            const float r0f = fmaxf(x0, 0.f), r1f = fmaxf(x1, 0.f);
+                            x0 = relu ? r0f : x0;
+                            x1 = relu ? r1f : x1;
+                            if (maskp) {
+                                x0 = __uint_as_float(mw[i] << 16) > 0.f ? x0 : 0.f;
+                                x1 = __uint_as_float(mw[i] & 0xffff0000u) > 0.f ? x1 : 0.f;
+                            }
+                            const __nv_bfloat162 hh = __floats2bfloat162_rn(x0 * rm_s[col], x1 * rm_s[col + 1]);
+                            pk[i] = *reinterpret_cast<const uint32_t *>(&hh);
+                        }
+                        const int jc = h * 4 + j8;
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + ((uint32_t)(jc ^ (lane & 7)) << 4)), "r"(pk[0]), "r"(pk[1]),
+                                     "r"(pk[2]), "r"(pk[3])
+                                     : "memory");
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&P.tmC),
+                                 "r"(sbase + buf * 4096), "r"(n0 + c), "r"(row0)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                ++issued;
+                buf ^= 1;
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __syncwarp();
+        } else
         if (BN >= 64 && !X3 && simple && !trans && !split && !e.accumulate && out_bf16 && sn == 1 && (Nn & 1) == 0 && (sm & 1) == 0 && bias_mode != 2 &&
             sm < (1 << 24) && msm < (1 << 24) && (!rmul || (rm_ld & 1) == 0) &&
             (!maskp || (mask_bf16 && msn == 1 && (msm & 1) == 0))) {

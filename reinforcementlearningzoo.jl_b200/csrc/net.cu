@@ -270,20 +270,19 @@ __global__ void iqn_merge_bwd_vec_kernel(const T *__restrict__ dm, const T *__re
 //   relu(phi)  = merged / psi wherever psi > 0, and where psi == 0 relu'(psi) = 0 kills d psi anyway.
 // so  dphi = dm .* psi .* [merged > 0],   dpsi[b] = [psi > 0] / psi .* sum_n dm .* merged,   dbias_phi += sum over rows of dphi
 // (the bias gradient of phi's last layer is folded in: it was a separate column-sum pass over the 0.5 GB dphi tensor).
-// One thread per (feature vector, group of BG samples).
+// CTA = 32 feature vectors (x) x 8 samples (y): one thread per (feature vector, sample) walks the N quantile rows; the bias sums
+// of the 8 samples are combined in shared memory, so the CTA issues one atomic per feature.
 template <typename T, int VEC>
-__global__ void iqn_merge_bwd_fused_kernel(const T *__restrict__ dm, const T *__restrict__ feat, const T *__restrict__ merged, T *__restrict__ dea,
-                                           T *__restrict__ dfeat, float *__restrict__ dbias, int B, int F, int N, int BG) {
+__global__ void __launch_bounds__(256) iqn_merge_bwd_fused_kernel(const T *__restrict__ dm, const T *__restrict__ feat, const T *__restrict__ merged,
+                                                                  T *__restrict__ dea, T *__restrict__ dfeat, float *__restrict__ dbias, int B, int F, int N) {
+    __shared__ float red[8][32 * VEC + 1];
     const int fv = F / VEC;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int groups = (B + BG - 1) / BG;
-    if (idx >= (long long)groups * fv) return;
-    const int f = (int)(idx % fv);
-    const int g = (int)(idx / fv);
+    const int f = blockIdx.x * 32 + threadIdx.x;
+    const int b = blockIdx.y * 8 + threadIdx.y;
     float bsum[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) bsum[i] = 0.f;
-    for (int b = g * BG; b < min(B, (g + 1) * BG); ++b) {
+    if (f < fv && b < B) {
         const VecT<T, VEC> ftv = *reinterpret_cast<const VecT<T, VEC> *>(feat + (long long)b * F + (long long)f * VEC);
         float ft[VEC], acc[VEC];
 #pragma unroll
@@ -310,7 +309,17 @@ __global__ void iqn_merge_bwd_fused_kernel(const T *__restrict__ dm, const T *__
         *reinterpret_cast<VecT<T, VEC> *>(dfeat + (long long)b * F + (long long)f * VEC) = of;
     }
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) atomicAdd(dbias + (long long)f * VEC + i, bsum[i]);
+    for (int i = 0; i < VEC; ++i) red[threadIdx.y][threadIdx.x * VEC + i] = bsum[i];
+    __syncthreads();
+    for (int j = threadIdx.y * 32 + threadIdx.x; j < 32 * VEC; j += 256) {
+        const int fcol = blockIdx.x * 32 * VEC + j;
+        if (fcol < F) {
+            float s = 0.f;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) s += red[y][j];
+            atomicAdd(dbias + fcol, s);
+        }
+    }
 }
 
 // adjoint of the merge: dea = dm * feat * relu'(ea);  dfeat[b] = relu'(feat) * sum_n dm * ea
@@ -772,13 +781,14 @@ static zoo_status net_backward_impl(zoo_net *net, int obs_dtype, const void *obs
     long long n = (long long)rows * F;
     prof_label("iqn_merge_bwd[%lldx%d]", (long long)rows * n_tau, F);
     if (net->iqn_fused) {
-        const int BG = rows >= 64 ? 4 : 1;
-        const long long groups = (rows + BG - 1) / BG;
         float *dbias = net->grads + net->tensors[Pphi.bt].offset;
-        if (bf && F % 8 == 0) iqn_merge_bwd_fused_kernel<bf16, 8><<<cdiv(groups * (F / 8), 128), 128, 0, st>>>((const bf16 *)net->dmerged, (const bf16 *)Ppsi.out, (const bf16 *)net->merged, (bf16 *)Pphi.dout, (bf16 *)Ppsi.dout, dbias, rows, F, n_tau, BG);
-        else if (!bf && F % 4 == 0) iqn_merge_bwd_fused_kernel<float, 4><<<cdiv(groups * (F / 4), 128), 128, 0, st>>>((const float *)net->dmerged, (const float *)Ppsi.out, (const float *)net->merged, (float *)Pphi.dout, (float *)Ppsi.dout, dbias, rows, F, n_tau, BG);
-        else if (bf) iqn_merge_bwd_fused_kernel<bf16, 1><<<cdiv(groups * F, 128), 128, 0, st>>>((const bf16 *)net->dmerged, (const bf16 *)Ppsi.out, (const bf16 *)net->merged, (bf16 *)Pphi.dout, (bf16 *)Ppsi.dout, dbias, rows, F, n_tau, BG);
-        else iqn_merge_bwd_fused_kernel<float, 1><<<cdiv(groups * F, 128), 128, 0, st>>>((const float *)net->dmerged, (const float *)Ppsi.out, (const float *)net->merged, (float *)Pphi.dout, (float *)Ppsi.dout, dbias, rows, F, n_tau, BG);
+        const dim3 blk(32, 8);
+#define MBWD(T, V) iqn_merge_bwd_fused_kernel<T, V><<<dim3(cdiv(F / V, 32), cdiv(rows, 8)), blk, 0, st>>>((const T *)net->dmerged, (const T *)Ppsi.out, (const T *)net->merged, (T *)Pphi.dout, (T *)Ppsi.dout, dbias, rows, F, n_tau)
+        if (bf && F % 8 == 0) MBWD(bf16, 8);
+        else if (!bf && F % 4 == 0) MBWD(float, 4);
+        else if (bf) MBWD(bf16, 1);
+        else MBWD(float, 1);
+#undef MBWD
         ZOO_LAUNCH_CHECK();
         ZOO_TRY(chain_backward(net, net->b, net->emb, 2, R, nullptr, nullptr, st, (int)net->b.layers.size() - 1));
         return chain_backward(net, net->a, obs, in_kind, rows, nullptr, nullptr, st);
