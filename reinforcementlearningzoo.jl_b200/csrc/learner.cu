@@ -403,6 +403,8 @@ static zoo_status run_update(zoo_learner *L, const zoo_batch *b, float *loss_out
         L->last_launches = g_launches;
         L->warm = 1;
     }
+    ZOO_TRY(net_mark_busy(L->online, L->st));  // net-level entry points on the nets' own streams wait for this update (net.cuh)
+    if (L->target) ZOO_TRY(net_mark_busy(L->target, L->st));
     if (prio_out) ZOO_CUDA(cudaMemcpyAsync(prio_out, L->d_prio, L->B * sizeof(float), cudaMemcpyDeviceToHost, L->st));
     if (loss_out) ZOO_CUDA(cudaMemcpyAsync(loss_out, L->d_loss, sizeof(float), cudaMemcpyDeviceToHost, L->st));
     if (prio_out || loss_out) ZOO_CUDA(cudaStreamSynchronize(L->st));
@@ -580,6 +582,7 @@ zoo_status zoo_learner_apply(zoo_learner *L) {
     ZOO_REQUIRE(L, "zoo_learner_apply: null learner");
     g_launches = 0;
     ZOO_TRY(opt_step(L->opt, L->st));
+    ZOO_TRY(net_mark_busy(L->online, L->st));
     ZOO_CUDA(cudaStreamSynchronize(L->st));
     L->online->grads_dirty = false;  // the optimiser kernels re-zero the gradients
     return ZOO_OK;

@@ -692,6 +692,20 @@ zoo_status net_side_join(zoo_net *net, cudaStream_t main) {
     return ZOO_OK;
 }
 
+zoo_status net_mark_busy(zoo_net *net, cudaStream_t user) {
+    if (!net->ev_busy) ZOO_CUDA(cudaEventCreateWithFlags(&net->ev_busy, cudaEventDisableTiming));
+    ZOO_CUDA(cudaEventRecord(net->ev_busy, user));
+    net->busy_pending = true;
+    return ZOO_OK;
+}
+zoo_status net_wait_busy(zoo_net *net) {
+    if (net->busy_pending) {
+        ZOO_CUDA(cudaStreamWaitEvent(net->st, net->ev_busy, 0));
+        net->busy_pending = false;
+    }
+    return ZOO_OK;
+}
+
 long long obs_elems(const zoo_net *net) { return (long long)net->desc.in_c * net->desc.in_h * net->desc.in_w; }
 
 zoo_status net_refresh_shadow(zoo_net *net, cudaStream_t st) {
@@ -1085,6 +1099,7 @@ zoo_status zoo_net_destroy(zoo_net *net) {
     if (net->ev_late) cudaEventDestroy(net->ev_late);
     if (net->ev_late2) cudaEventDestroy(net->ev_late2);
     if (net->ev_comm) cudaEventDestroy(net->ev_comm);
+    if (net->ev_busy) cudaEventDestroy(net->ev_busy);
     if (net->comm) { cudaStreamSynchronize(net->comm); cudaStreamDestroy(net->comm); }
     cudaStreamDestroy(net->st);
     delete net;
@@ -1118,6 +1133,7 @@ zoo_status zoo_internal_tensor_io(zoo_net *net, float *flat, int32_t id, float *
     const TensorInfo &t = net->tensors[id];
     ZOO_REQUIRE(n == t.count, "tensor io: tensor %d has %lld elements, caller passed %lld", id, t.count, (long long)n);
     ZOO_TRY(ensure_stage(net, (size_t)t.count));
+    ZOO_TRY(net_wait_busy(net));
     if (to_device) {
         ZOO_CUDA(cudaMemcpyAsync(net->stage, host, t.count * sizeof(float), cudaMemcpyHostToDevice, net->st));
         permute_param_kernel<<<cdiv(t.count, 256), 256, 0, net->st>>>(flat + t.offset, net->stage, t, 0);
@@ -1147,6 +1163,8 @@ zoo_status zoo_net_get_params(const zoo_net *net, int32_t id, float *host, int64
 zoo_status zoo_net_copy(zoo_net *dst, const zoo_net *src) {
     ZOO_REQUIRE(dst && src, "zoo_net_copy: null argument");
     ZOO_REQUIRE(dst->n_flat == src->n_flat && dst->tensors.size() == src->tensors.size(), "zoo_net_copy: nets have different structure");
+    ZOO_TRY(net_wait_busy(dst));
+    if (src->busy_pending) ZOO_CUDA(cudaStreamWaitEvent(dst->st, src->ev_busy, 0));  // (src stays marked: its own stream has not waited)
     ZOO_CUDA(cudaMemcpyAsync(dst->params, src->params, src->n_flat * sizeof(float), cudaMemcpyDeviceToDevice, dst->st));
     ZOO_TRY(net_refresh_shadow(dst, dst->st));
     ZOO_CUDA(cudaStreamSynchronize(dst->st));
@@ -1158,6 +1176,7 @@ zoo_status zoo_net_forward(zoo_net *net, const void *obs_host, int32_t obs_dtype
     ZOO_REQUIRE(obs_dtype == ZOO_OBS_U8 || obs_dtype == ZOO_OBS_F32, "zoo_net_forward: bad obs dtype");
     ZOO_REQUIRE(B <= net->a.rows_cap, "zoo_net_forward: B %d exceeds capacity %lld", B, net->a.rows_cap);
     size_t ob = (size_t)B * obs_elems(net) * (obs_dtype == ZOO_OBS_U8 ? 1 : 4);
+    ZOO_TRY(net_wait_busy(net));
     ZOO_CUDA(cudaMemcpyAsync(net->obs, obs_host, ob, cudaMemcpyHostToDevice, net->st));
     long long R = B;
     if (net->desc.kind == ZOO_NET_IQN) {

@@ -78,6 +78,11 @@ struct zoo_net {
     void *obs_nhwc_buf = nullptr;
     float *stage = nullptr; size_t stage_elems = 0;  // param up/download staging
     cudaStream_t st = nullptr;
+    // stream contract: learner updates run on the learner's stream and may return before they finish (loss_out == NULL); every
+    // net-level entry point (zoo_net_copy / forward / get / set params, optimiser state io) runs on `st` and first waits, on the
+    // device, for ev_busy = the end of the last update that used this net (net_wait_busy)
+    cudaEvent_t ev_busy = nullptr;
+    bool busy_pending = false;
     bool bwd_ready = false;
     // side lane: a second stream (joined back with events, so it also becomes a parallel branch of a captured CUDA graph)
     // for work that is off the critical path -- the target net's forward, and bias-grad + wgrad while dgrad proceeds
@@ -103,6 +108,8 @@ zoo_status net_forward(zoo_net *net, const void *obs, int obs_dtype, int rows, c
 // consumes net->dout_final (fp32, same shape as out_final, for the first `rows` samples) and accumulates into net->grads
 zoo_status net_backward(zoo_net *net, int obs_dtype, const void *obs, int rows, int n_tau, cudaStream_t st);
 zoo_status net_refresh_shadow(zoo_net *net, cudaStream_t st);
+zoo_status net_mark_busy(zoo_net *net, cudaStream_t user);  // an update using `net` has been enqueued on `user`
+zoo_status net_wait_busy(zoo_net *net);                     // net->st waits for it
 // side lane plumbing: fork = side waits for everything enqueued on `main` so far; join = main waits for the side lane
 zoo_status net_side_fork(zoo_net *net, cudaStream_t main);
 zoo_status net_side_join(zoo_net *net, cudaStream_t main);

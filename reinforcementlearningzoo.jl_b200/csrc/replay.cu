@@ -97,6 +97,10 @@ struct zoo_replay {
     uint8_t *ring = nullptr;      // [capacity][rec_bytes]
     size_t rec_bytes = 0;
     cudaEvent_t ev_push = nullptr;  // last push has landed
+    // the ring is read (frame gather) on the caller's stream: ev_use marks the last such read, and the next push -- which may
+    // overwrite the oldest slot -- waits for it on the push stream
+    cudaEvent_t ev_use = nullptr;
+    bool use_pending = false;
     zoo_sumtree *tree = nullptr;  // prioritized only
     // last sampled batch (device)
     uint8_t *b_state = nullptr, *b_next = nullptr, *b_terminal = nullptr;
@@ -133,6 +137,7 @@ zoo_status zoo_replay_create(int64_t capacity, int32_t frame_h, int32_t frame_w,
     r->rec_bytes = fb + 16;
     ZOO_CUDA(cudaMalloc(&r->ring, (size_t)capacity * r->rec_bytes));
     ZOO_CUDA(cudaEventCreateWithFlags(&r->ev_push, cudaEventDisableTiming));
+    ZOO_CUDA(cudaEventCreateWithFlags(&r->ev_use, cudaEventDisableTiming));
     ZOO_CUDA(cudaMalloc(&r->b_state, (size_t)max_batch * stack_size * fb));
     ZOO_CUDA(cudaMalloc(&r->b_next, (size_t)max_batch * stack_size * fb));
     ZOO_CUDA(cudaMalloc(&r->b_action, max_batch * sizeof(int)));
@@ -153,6 +158,7 @@ zoo_status zoo_replay_destroy(zoo_replay *r) {
     if (!r) return ZOO_OK;
     cudaDeviceSynchronize();
     if (r->ev_push) cudaEventDestroy(r->ev_push);
+    if (r->ev_use) cudaEventDestroy(r->ev_use);
     void *ptrs[] = {r->ring, r->b_state, r->b_next, r->b_action, r->b_reward, r->b_terminal, r->b_priority,
                     r->b_idx, r->b_u, r->n_invalid};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -166,6 +172,7 @@ zoo_status zoo_replay_destroy(zoo_replay *r) {
 // push!(trajectory; state, action, reward, terminal) (+ push!(t[:priority], p), common.jl:28-37): one transition
 zoo_status zoo_replay_push(zoo_replay *r, const uint8_t *frame_host, int32_t action, float reward, uint8_t terminal, float priority) {
     ZOO_REQUIRE(r && frame_host, "zoo_replay_push: null argument");
+    if (r->use_pending) { ZOO_CUDA(cudaStreamWaitEvent(r->st, r->ev_use, 0)); r->use_pending = false; }
     if (r->length == r->capacity) r->first = (r->first == r->capacity) ? 1 : r->first + 1;
     else r->length += 1;
     const long long slot = (r->first - 1 + r->length - 1) % r->capacity;
@@ -188,6 +195,7 @@ zoo_status zoo_replay_push(zoo_replay *r, const uint8_t *frame_host, int32_t act
 zoo_status zoo_replay_push_many(zoo_replay *r, const uint8_t *frames_host, const int32_t *action, const float *reward, const uint8_t *terminal,
                                 const float *priority, int64_t n) {
     ZOO_REQUIRE(r && frames_host && action && reward && terminal && n >= 0, "zoo_replay_push_many: null argument");
+    if (r->use_pending) { ZOO_CUDA(cudaStreamWaitEvent(r->st, r->ev_use, 0)); r->use_pending = false; }
     const size_t fb = (size_t)r->h * r->w;
     const int64_t CH = 1024;
     uint8_t *stage = nullptr;
@@ -256,6 +264,8 @@ zoo_status zoo_replay_sample(zoo_replay *r, void *stream, const void *u_host, in
     replay_fetch_scalars_kernel<<<cdiv(B, 128), 128, 0, st>>>(v, r->b_idx, B, r->b_action, r->b_reward, r->b_terminal);
     ZOO_LAUNCH_CHECK();
     r->last_B = B;
+    ZOO_CUDA(cudaEventRecord(r->ev_use, st));
+    r->use_pending = true;
     memset(batch, 0, sizeof(*batch));
     batch->B = B; batch->obs_dtype = ZOO_OBS_U8; batch->state = r->b_state; batch->next_state = r->b_next; batch->action = r->b_action;
     batch->reward = r->b_reward; batch->terminal = r->b_terminal; batch->priority = per ? r->b_priority : nullptr; batch->on_device = 1;

@@ -166,6 +166,57 @@ sumtree_update_parents_kernel(float *__restrict__ tree, int depth, const long lo
     }
 }
 
+// Small batches (n <= SMALL_N, the Dopamine batch of 32): ONE launch of one CTA, no sort.  Thread (level, k) checks in shared
+// memory whether an earlier entry shares its node on that level; the first entry of every node ("head") applies that node's
+// changes serially in batch order -- the same order-preserving rule as the sorted path, hence still bit-exact -- and all nodes of
+// all levels proceed in parallel: latency = one L2 round trip for the leaves + one for the ancestors.
+static constexpr int SMALL_N = 256;
+__global__ void __launch_bounds__(1024)
+sumtree_update_small_kernel(float *__restrict__ tree, long long nparents, long long capacity, long long first, int depth, int physical,
+                            const long long *__restrict__ idx, const float *__restrict__ p, int n) {
+    __shared__ long long heap[SMALL_N];
+    __shared__ float pv[SMALL_N], change[SMALL_N];
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        long long s = idx[k];
+        if (!physical) { s = s + first - 1; if (s > capacity) s -= capacity; }
+        heap[k] = nparents + s;
+        pv[k] = p[k];
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {  // leaf level: change[k] = p[k] - (leaf value just before entry k)
+        const long long h = heap[k];
+        bool head = true;
+        for (int j = 0; j < k; ++j) if (heap[j] == h) { head = false; break; }
+        if (!head) continue;
+        float prev = tree[h];
+        for (int j = k; j < n; ++j)
+            if (heap[j] == h) { change[j] = __fsub_rn(pv[j], prev); prev = pv[j]; }
+        tree[h] = prev;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < depth * n; t += blockDim.x) {  // ancestors: level = t / n (shift 1 .. depth), entry k = t % n
+        const int shift = t / n + 1, k = t - (shift - 1) * n;
+        const long long a = heap[k] >> shift;
+        bool head = true;
+        for (int j = 0; j < k; ++j) if ((heap[j] >> shift) == a) { head = false; break; }
+        if (!head) continue;
+        float acc = tree[a];
+        for (int j = k; j < n; ++j)
+            if ((heap[j] >> shift) == a) acc = __fadd_rn(acc, change[j]);
+        tree[a] = acc;
+    }
+}
+
+// push! of ONE priority (common.jl:36): slot and value travel as kernel arguments (no staging copies, no host sync); lane l owns
+// the ancestor l levels above the leaf -- all distinct nodes, so the single `+= change` per node needs no ordering.
+__global__ void sumtree_push1_kernel(float *__restrict__ tree, long long leaf, float p, int depth) {
+    const int l = threadIdx.x;
+    const float change = __fsub_rn(p, tree[leaf]);  // every lane reads the old leaf value before lane 0 overwrites it
+    __syncwarp();
+    if (l == 0) tree[leaf] = p;
+    else if (l <= depth) { const long long a = leaf >> l; tree[a] = __fadd_rn(tree[a], change); }
+}
+
 }  // namespace zoo
 
 using namespace zoo;
@@ -178,7 +229,22 @@ struct zoo_sumtree {
     // scratch (device)
     void *d_u = nullptr; long long *d_idx = nullptr; float *d_p = nullptr; long long cap_scratch = 0;
     long long *d_heap = nullptr; float *d_change = nullptr;
+    // stream contract: the tree is also read / written on caller-chosen streams (sumtree_sample_on / sumtree_update_on: the
+    // learner's stream).  ev_push marks the last push on `st` (those streams wait for it before touching the tree); ev_use marks
+    // the last foreign-stream use (everything on `st` waits for it first) -- so the two streams never interleave on the tree or
+    // on the d_heap / d_change scratch.
+    cudaEvent_t ev_push = nullptr, ev_use = nullptr;
+    bool use_pending = false, push_pending = false;
 };
+
+// everything that touches the tree on t->st first waits for the last use on a foreign stream
+static zoo_status st_begin(zoo_sumtree *t) {
+    if (t->use_pending) {
+        ZOO_CUDA(cudaStreamWaitEvent(t->st, t->ev_use, 0));
+        t->use_pending = false;
+    }
+    return ZOO_OK;
+}
 
 static zoo_status st_reserve(zoo_sumtree *t, long long n) {
     if (n <= t->cap_scratch) return ZOO_OK;
@@ -201,6 +267,8 @@ zoo_status zoo_sumtree_create(int64_t capacity, zoo_sumtree **out) {
     while (p < capacity) { p <<= 1; ++d; }
     t->capacity = capacity; t->nparents = p - 1; t->tree_len = t->nparents + capacity; t->depth = d;
     ZOO_CUDA(cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
+    ZOO_CUDA(cudaEventCreateWithFlags(&t->ev_push, cudaEventDisableTiming));
+    ZOO_CUDA(cudaEventCreateWithFlags(&t->ev_use, cudaEventDisableTiming));
     ZOO_CUDA(cudaMalloc(&t->tree, (t->tree_len + 1) * sizeof(float)));
     ZOO_CUDA(cudaMemsetAsync(t->tree, 0, (t->tree_len + 1) * sizeof(float), t->st));
     ZOO_CUDA(cudaMalloc(&t->d_heap, UPD_CHUNK * sizeof(long long)));
@@ -213,7 +281,9 @@ zoo_status zoo_sumtree_create(int64_t capacity, zoo_sumtree **out) {
 
 zoo_status zoo_sumtree_destroy(zoo_sumtree *t) {
     if (!t) return ZOO_OK;
-    cudaStreamSynchronize(t->st);
+    cudaDeviceSynchronize();
+    if (t->ev_push) cudaEventDestroy(t->ev_push);
+    if (t->ev_use) cudaEventDestroy(t->ev_use);
     cudaFree(t->tree); cudaFree(t->d_u); cudaFree(t->d_idx); cudaFree(t->d_p); cudaFree(t->d_heap); cudaFree(t->d_change);
     cudaStreamDestroy(t->st);
     delete t;
@@ -222,6 +292,12 @@ zoo_status zoo_sumtree_destroy(zoo_sumtree *t) {
 
 static zoo_status update_dev_impl(zoo_sumtree *t, const long long *idx_dev, const float *p_dev, long long n, int physical, cudaStream_t st = nullptr) {
     if (!st) st = t->st;
+    if (n > 0 && n <= SMALL_N) {
+        const int threads = (int)std::min<long long>(1024, std::max<long long>(32, ((long long)(t->depth + 1) * n + 31) / 32 * 32));
+        sumtree_update_small_kernel<<<1, threads, 0, st>>>(t->tree, t->nparents, t->capacity, t->first, t->depth, physical, idx_dev, p_dev, (int)n);
+        ZOO_LAUNCH_CHECK();
+        return ZOO_OK;
+    }
     for (long long off = 0; off < n; off += UPD_CHUNK) {
         int m = (int)std::min<long long>(UPD_CHUNK, n - off);
         int n2 = 32;
@@ -240,6 +316,7 @@ static zoo_status update_dev_impl(zoo_sumtree *t, const long long *idx_dev, cons
 
 zoo_status zoo_sumtree_update_dev(zoo_sumtree *t, const int64_t *idx_dev, const float *p_dev, int64_t n) {
     ZOO_REQUIRE(t && idx_dev && p_dev && n >= 0, "zoo_sumtree_update_dev: bad argument");
+    ZOO_TRY(st_begin(t));
     return update_dev_impl(t, (const long long *)idx_dev, p_dev, n, 0);
 }
 
@@ -248,6 +325,7 @@ zoo_status zoo_sumtree_update(zoo_sumtree *t, const int64_t *idx, const float *p
     if (n == 0) return ZOO_OK;
     for (int64_t i = 0; i < n; ++i)
         ZOO_REQUIRE(idx[i] >= 1 && idx[i] <= t->capacity, "zoo_sumtree_update: index %lld out of 1..%lld", (long long)idx[i], t->capacity);
+    ZOO_TRY(st_begin(t));
     ZOO_TRY(st_reserve(t, n));
     ZOO_CUDA(cudaMemcpyAsync(t->d_idx, idx, n * sizeof(long long), cudaMemcpyHostToDevice, t->st));
     ZOO_CUDA(cudaMemcpyAsync(t->d_p, p, n * sizeof(float), cudaMemcpyHostToDevice, t->st));
@@ -262,6 +340,7 @@ zoo_status zoo_sumtree_push_many(zoo_sumtree *t, const float *p, int64_t n) {
     // one per push, so a run of pushes is one batched update on consecutive physical slots.
     int64_t done = 0;
     std::vector<long long> slots;
+    ZOO_TRY(st_begin(t));
     while (done < n) {
         int64_t m = std::min<int64_t>(std::min<int64_t>(UPD_CHUNK, t->capacity), n - done);
         slots.resize(m);
@@ -282,7 +361,22 @@ zoo_status zoo_sumtree_push_many(zoo_sumtree *t, const float *p, int64_t n) {
     return ZOO_OK;
 }
 
-zoo_status zoo_sumtree_push(zoo_sumtree *t, float p) { return zoo_sumtree_push_many(t, &p, 1); }
+// one push: asynchronous (one 32-thread launch on the tree's stream, no copies, no host sync); consumers on other streams wait
+// for ev_push, host-facing reads synchronise the tree's stream as before
+zoo_status zoo_sumtree_push(zoo_sumtree *t, float p) {
+    ZOO_REQUIRE(t, "zoo_sumtree_push: null tree");
+    ZOO_REQUIRE(t->depth < 32, "zoo_sumtree_push: tree too deep");
+    ZOO_TRY(st_begin(t));
+    if (t->length == t->capacity) t->first = (t->first == t->capacity) ? 1 : t->first + 1;
+    else t->length += 1;
+    long long k = t->length + t->first - 1;
+    if (k > t->capacity) k -= t->capacity;
+    sumtree_push1_kernel<<<1, 32, 0, t->st>>>(t->tree, t->nparents + k, p, t->depth);
+    ZOO_LAUNCH_CHECK();
+    ZOO_CUDA(cudaEventRecord(t->ev_push, t->st));
+    t->push_pending = true;
+    return ZOO_OK;
+}
 
 static zoo_status sample_dev_impl(zoo_sumtree *t, const void *u_dev, int u_dtype, long long n, int mode, long long *idx_dev,
                                   float *prio_dev, cudaStream_t st = nullptr) {
@@ -303,6 +397,7 @@ zoo_status zoo_sumtree_sample_dev(zoo_sumtree *t, const void *u_dev, int32_t u_d
     ZOO_REQUIRE(t && u_dev && idx_dev && prio_dev && n >= 0, "zoo_sumtree_sample_dev: bad argument");
     ZOO_REQUIRE(u_dtype == ZOO_DRAW_F32 || u_dtype == ZOO_DRAW_F64, "zoo_sumtree_sample_dev: bad draw dtype");
     if (n == 0) return ZOO_OK;
+    ZOO_TRY(st_begin(t));
     return sample_dev_impl(t, u_dev, u_dtype, n, mode, (long long *)idx_dev, prio_dev);
 }
 
@@ -312,6 +407,7 @@ zoo_status zoo_sumtree_sample(zoo_sumtree *t, const void *u, int32_t u_dtype, in
     ZOO_REQUIRE(u_dtype == ZOO_DRAW_F32 || u_dtype == ZOO_DRAW_F64, "zoo_sumtree_sample: bad draw dtype");
     ZOO_REQUIRE(mode == ZOO_SAMPLE_INDEPENDENT || mode == ZOO_SAMPLE_STRATIFIED, "zoo_sumtree_sample: bad mode");
     if (n == 0) return ZOO_OK;
+    ZOO_TRY(st_begin(t));
     ZOO_TRY(st_reserve(t, n));
     size_t esz = u_dtype == ZOO_DRAW_F64 ? 8 : 4;
     ZOO_CUDA(cudaMemcpyAsync(t->d_u, u, n * esz, cudaMemcpyHostToDevice, t->st));
@@ -324,6 +420,7 @@ zoo_status zoo_sumtree_sample(zoo_sumtree *t, const void *u, int32_t u_dtype, in
 
 zoo_status zoo_sumtree_total(zoo_sumtree *t, float *total) {
     ZOO_REQUIRE(t && total, "zoo_sumtree_total: bad argument");
+    ZOO_TRY(st_begin(t));
     ZOO_CUDA(cudaMemcpyAsync(total, t->tree + 1, sizeof(float), cudaMemcpyDeviceToHost, t->st));
     ZOO_CUDA(cudaStreamSynchronize(t->st));
     return ZOO_OK;
@@ -332,6 +429,7 @@ zoo_status zoo_sumtree_total(zoo_sumtree *t, float *total) {
 zoo_status zoo_sumtree_get(zoo_sumtree *t, const int64_t *idx, int64_t n, float *prio_out) {
     ZOO_REQUIRE(t && idx && prio_out && n >= 0, "zoo_sumtree_get: bad argument");
     if (n == 0) return ZOO_OK;
+    ZOO_TRY(st_begin(t));
     ZOO_TRY(st_reserve(t, n));
     ZOO_CUDA(cudaMemcpyAsync(t->d_idx, idx, n * sizeof(long long), cudaMemcpyHostToDevice, t->st));
     sumtree_get_kernel<<<cdiv(n, 256), 256, 0, t->st>>>(t->tree, t->nparents, t->capacity, t->first, t->d_idx, n, t->d_p);
@@ -356,6 +454,7 @@ zoo_status zoo_sumtree_tree_len(const zoo_sumtree *t, int64_t *n) {
 
 zoo_status zoo_sumtree_export(zoo_sumtree *t, float *host_tree, int64_t n) {
     ZOO_REQUIRE(t && host_tree && n == t->tree_len, "zoo_sumtree_export: expected %lld floats", t ? t->tree_len : 0);
+    ZOO_TRY(st_begin(t));
     ZOO_CUDA(cudaMemcpyAsync(host_tree, t->tree + 1, n * sizeof(float), cudaMemcpyDeviceToHost, t->st));
     ZOO_CUDA(cudaStreamSynchronize(t->st));
     return ZOO_OK;
@@ -364,6 +463,7 @@ zoo_status zoo_sumtree_export(zoo_sumtree *t, float *host_tree, int64_t n) {
 zoo_status zoo_sumtree_import(zoo_sumtree *t, const float *host_tree, int64_t n, int64_t length, int64_t first) {
     ZOO_REQUIRE(t && host_tree && n == t->tree_len, "zoo_sumtree_import: expected %lld floats", t ? t->tree_len : 0);
     ZOO_REQUIRE(length >= 0 && length <= t->capacity && first >= 1 && first <= t->capacity, "zoo_sumtree_import: bad length/first");
+    ZOO_TRY(st_begin(t));
     ZOO_CUDA(cudaMemcpyAsync(t->tree + 1, host_tree, n * sizeof(float), cudaMemcpyHostToDevice, t->st));
     ZOO_CUDA(cudaStreamSynchronize(t->st));
     t->length = length; t->first = first;
@@ -386,11 +486,27 @@ zoo_status zoo_sumtree_sync(zoo_sumtree *t) {
 
 // internal: the same device-side sample / update enqueued on a caller-chosen stream (replay.cu)
 namespace zoo {
+// a foreign stream first waits for the pushes enqueued on the tree's own stream, and leaves a marker the next push waits for
+static zoo_status foreign_begin(zoo_sumtree *t, cudaStream_t st) {
+    if (st != t->st && t->push_pending) ZOO_CUDA(cudaStreamWaitEvent(st, t->ev_push, 0));
+    return ZOO_OK;
+}
+static zoo_status foreign_end(zoo_sumtree *t, cudaStream_t st) {
+    if (st != t->st) {
+        ZOO_CUDA(cudaEventRecord(t->ev_use, st));
+        t->use_pending = true;
+    }
+    return ZOO_OK;
+}
 zoo_status sumtree_sample_on(zoo_sumtree *t, cudaStream_t st, const void *u_dev, int u_dtype, long long n, int mode, long long *idx_dev, float *prio_dev) {
-    return sample_dev_impl(t, u_dev, u_dtype, n, mode, idx_dev, prio_dev, st);
+    ZOO_TRY(foreign_begin(t, st));
+    ZOO_TRY(sample_dev_impl(t, u_dev, u_dtype, n, mode, idx_dev, prio_dev, st));
+    return foreign_end(t, st);
 }
 zoo_status sumtree_update_on(zoo_sumtree *t, cudaStream_t st, const long long *idx_dev, const float *p_dev, long long n) {
-    return update_dev_impl(t, idx_dev, p_dev, n, 0, st);
+    ZOO_TRY(foreign_begin(t, st));
+    ZOO_TRY(update_dev_impl(t, idx_dev, p_dev, n, 0, st));
+    return foreign_end(t, st);
 }
 void sumtree_state(const zoo_sumtree *t, long long *length, long long *first) { *length = t->length; *first = t->first; }
 }  // namespace zoo
