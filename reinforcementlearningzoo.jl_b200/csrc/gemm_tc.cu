@@ -35,7 +35,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2D tensor map: inner (contiguous) extent d0, outer extent d1, row pitch ld elements, box {b0, b1}, SWIZZLE_128B
-static zoo_status make_map(CUtensorMap *tm, const void *p, int eb, long long d0, long long d1, long long ld, int b0, int b1, bool mn_major) {
+static zoo_status make_map(CUtensorMap *tm, const void *p, int eb, long long d0, long long d1, long long ld, int b0, int b1, bool mn_major, int span = 128) {
     EncodeTiledFn enc = get_encode();
     if (!enc) {
         set_err("cuTensorMapEncodeTiled not available from the driver");
@@ -47,7 +47,7 @@ static zoo_status make_map(CUtensorMap *tm, const void *p, int eb, long long d0,
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(p), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     (eb == 4 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     span == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : ((eb == 4 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_err("cuTensorMapEncodeTiled failed (%d): dims %lld x %lld ld %lld box %d x %d ptr %p", (int)r, d0, d1, ld, b0, b1, p);
@@ -58,12 +58,12 @@ static zoo_status make_map(CUtensorMap *tm, const void *p, int eb, long long d0,
 
 // 4-D tensor map over an NHWC activation tensor (or an overlapping-window view of it) for the CONV_TMA A operand
 static zoo_status make_map4(CUtensorMap *tm, const void *p, int eb, const cuuint64_t dims[4], const cuuint64_t strides_bytes[3],
-                            const cuuint32_t box[4], const cuuint32_t estr[4]) {
+                            const cuuint32_t box[4], const cuuint32_t estr[4], int span = 128) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_err("cuTensorMapEncodeTiled not available from the driver"); return ZOO_CUDA_ERROR; }
     CUresult r = enc(tm, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(p), dims, strides_bytes,
-                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, span == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_err("cuTensorMapEncodeTiled(4D) failed (%d): dims %llu %llu %llu %llu box %u %u %u %u estr %u %u %u %u", (int)r, (unsigned long long)dims[0],
                 (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3], box[0], box[1], box[2], box[3], estr[0], estr[1],
@@ -176,9 +176,13 @@ bool tc_conv_supported(const ConvGeom &g, int is_bf16) {
     }
     if (g.mode == CONV_TMA) {
         if (g.OW > 128 || g.OW < 1) return false;
-        if (g.first) return g.ks * g.C * eb == 128 && g.p == 0 && (g.s * g.C * eb) % 16 == 0 && g.OW <= 256 && ((128 / g.OW - 1) * g.s + 1) <= 256;
+        // the innermost contiguous run (one kernel row of the padded frame stack, or one pixel's channels) must be a whole number
+        // of 128-byte spans -- or, bf16 only, exactly one 64-byte span (SWIZZLE_64B variant; N <= 64)
+        const int run = (g.first ? g.ks * g.C : g.C) * eb;
+        const bool span_ok = g.first ? (run == 128 || (eb == 2 && run == 64 && g.Cout <= 64)) : (run % 128 == 0 || (eb == 2 && run == 64 && g.Cout <= 64));
+        if (g.first) return span_ok && g.p == 0 && (g.s * g.C * eb) % 16 == 0 && g.OW <= 256 && ((128 / g.OW - 1) * g.s + 1) <= 256;
         const int R = std::min(g.OH, 128 / g.OW);
-        return (g.C * eb) % 128 == 0 && (g.OW - 1) * g.s + 1 <= 256 && (R - 1) * g.s + 1 <= 256;
+        return span_ok && (g.OW - 1) * g.s + 1 <= 256 && (R - 1) * g.s + 1 <= 256;
     }
     return false;
 }
@@ -187,16 +191,18 @@ bool tc_conv_supported(const ConvGeom &g, int is_bf16) {
 static zoo_status tc_conv_tma(ConvGeom g, const Operand &Wop, int images, int N, int K, const Epilogue &epi, float *ws, size_t ws_elems,
                               cudaStream_t st) {
     const int eb = Wop.is_bf16 ? 2 : 4;
-    const int bk = 128 / eb;
+    const int span = ((g.first ? g.ks * g.C : g.C) * eb) % 128 == 0 ? 128 : 64;
+    const int bk = span / eb;
     const bool x3 = eb == 4 && epi.tf32_passes == 3;
     ZOO_REQUIRE(Wop.kmajor && K % bk == 0, "tc_conv_tma: K %d is not a whole number of K-blocks", K);
     int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
     g.R = std::min(g.OH, 128 / g.OW);
     g.tpi = cdiv(g.OH, g.R);
-    g.cblocks = g.first ? 1 : (g.C * eb) / 128;
+    g.cblocks = g.first ? 1 : (g.C * eb) / span;
     dim3 grid(images * g.tpi, cdiv(N, BN), 1);
     TcParams P;
     P.M = images * g.OH * g.OW; P.N = N; P.K = K; P.kb_per_split = K / bk; P.epi = epi; P.ws = nullptr; P.ctr = nullptr; P.dbg = nullptr; P.conv = g;
+    P.span = span;
     if (P.epi.accumulate == 2) P.epi.accumulate = 0;
     // optional split over kernel taps (ZOO_CONV_SPLIT=n).  Measured at B = 32 (one tile per image for the 9 x 9 / 7 x 7 maps, 32-64 CTAs):
     // 2 / 4 / 8 splits cost 8 / 12 / 22 % of the whole update -- the extra CTAs and reds take the SMs the other two lanes were
@@ -224,15 +230,15 @@ static zoo_status tc_conv_tma(ConvGeom g, const Operand &Wop, int images, int N,
         const cuuint64_t str[3] = {(cuuint64_t)g.s * sC, sW, sH};
         const cuuint32_t box[4] = {(cuuint32_t)(g.ks * g.C), (cuuint32_t)g.OW, (cuuint32_t)((g.R - 1) * g.s + 1), 1};
         const cuuint32_t es[4] = {1, 1, (cuuint32_t)g.s, 1};
-        ZOO_TRY(make_map4(&tmA, g.x, eb, dims, str, box, es));
+        ZOO_TRY(make_map4(&tmA, g.x, eb, dims, str, box, es, span));
     } else {
         const cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)images};
         const cuuint64_t str[3] = {sC, sW, sH};
         const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)((g.OW - 1) * g.s + 1), (cuuint32_t)((g.R - 1) * g.s + 1), 1};
         const cuuint32_t es[4] = {1, (cuuint32_t)g.s, (cuuint32_t)g.s, 1};
-        ZOO_TRY(make_map4(&tmA, g.x, eb, dims, str, box, es));
+        ZOO_TRY(make_map4(&tmA, g.x, eb, dims, str, box, es, span));
     }
-    ZOO_TRY(make_map(&tmB, Wop.p, eb, K, N, Wop.ld, bk, BN, false));
+    ZOO_TRY(make_map(&tmB, Wop.p, eb, K, N, Wop.ld, bk, BN, false, span));
     return tc_launch(eb, x3, 2, BN, true, true, tmA, tmB, P, grid, st);
 }
 

@@ -151,6 +151,7 @@ struct TcParams {
     // the SWIZZLE_128B layout and one lane hands each block to the TMA unit (cp.async.bulk.tensor ... global.shared::cta), which
     // also clips rows / columns past M / N.  tmC: 2-D map over the output, box {64 columns, 32 rows}.
     int tma_store = 0;
+    int span = 128;  // bytes of K per stage row (TcCfg SPAN); 64 = the SWIZZLE_64B convolution variants
     CUtensorMap tmC;
 };
 
@@ -166,9 +167,15 @@ __device__ __forceinline__ void dbg_stamp(const TcParams &P, int slot) {
 
 // EB: operand element bytes (2 = bf16, 4 = fp32 consumed as tf32).  X3: 3xTF32 split (EB = 4 only).
 // smem per stage: A tile 128 rows x 128 B (16 KB) + B tile BN rows x 128 B; X3 doubles it for the lo tiles.
-template <int EB, int BN, bool X3>
+// SPAN: bytes of K per tile row and stage = the TMA / UMMA swizzle span.  128 everywhere except the bf16 TMA-im2col convolutions
+// whose innermost contiguous run is only 64 bytes (conv over a 32-channel bf16 activation tensor; the first conv's kernel row of
+// 8 taps x 4 channels): those run with SWIZZLE_64B tiles, 32 K elements per stage, two tcgen05.mma per stage.
+template <int EB, int BN, bool X3, int SPAN = 128>
 struct TcCfg {
-    static constexpr int BK = 128 / EB;          // K elements per stage
+    static constexpr int BK = SPAN / EB;         // K elements per stage
+    static constexpr int KSTEPS = SPAN / 32;     // tcgen05.mma per stage (K = 32 bytes each)
+    static constexpr int KM_SBO = 8 * SPAN;      // K-major operand: 8-row groups this far apart
+    static constexpr int KM_LAYOUT = SPAN == 128 ? 2 : 4;  // UMMA layout type: SWIZZLE_128B = 2, SWIZZLE_64B = 4
     static constexpr int UMMA_K = 32 / EB;       // K elements per tcgen05.mma
     static constexpr int MN_BOX = 128 / EB;      // MN elements per 128-byte row of an MN-major box
     static constexpr int BOX_BYTES = BK * 128;   // one MN-major box: BK k-rows x 128 B
@@ -177,8 +184,8 @@ struct TcCfg {
     // MN-major layout tcgen05 accepts for 32-bit operands)
     static constexpr int MN_SBO = EB == 2 ? 1024 : 512;
     static constexpr int MN_LAYOUT = EB == 2 ? 2 : 1;
-    static constexpr int A_BYTES = BM * 128;
-    static constexpr int B_BYTES = BN * 128;
+    static constexpr int A_BYTES = BM * SPAN;
+    static constexpr int B_BYTES = BN * SPAN;
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGE_BYTES = RAW_BYTES * (X3 ? 2 : 1);
     // 3xTF32 stage: [A hi][B hi][B lo][A lo] -- B lo directly behind B hi, so that [B hi; B lo] is ONE operand of 2 BN rows
@@ -454,11 +461,12 @@ __device__ __forceinline__ void epi_cols_store(const float *rp, int ncols, T *op
 // GA = 2: implicit-GEMM convolution with the im2col rows fetched by TMA itself: one M tile = R whole output rows of one
 //         image, one K-block = one kernel tap (or kernel row), loaded as a single 4-D box of the NHWC activation tensor
 //         (element strides = conv stride, out-of-bounds = zero padding).
-template <int EB, int BN, bool A_K, bool B_K, bool X3, int GA = 0>
+template <int EB, int BN, bool A_K, bool B_K, bool X3, int GA = 0, int SPAN = 128>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams P) {
     static_assert(GA == 0 || A_K, "the gathered A operand is K-major");
-    using C = TcCfg<EB, BN, X3>;
+    static_assert(SPAN == 128 || (SPAN == 64 && EB == 2 && GA == 2 && A_K && B_K && !X3), "64-byte spans: bf16 TMA-im2col convolutions only");
+    using C = TcCfg<EB, BN, X3, SPAN>;
     // SWIZZLE_128B tiles need 1024-byte alignment; declaring it on the array (instead of rounding the pointer up) keeps
     // the shared address space visible to the compiler, so the epilogue staging below compiles to LDS/STS
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -522,7 +530,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t *sa = smem + s * C::STAGE_BYTES;
                 uint8_t *sb = sa + C::A_BYTES;
-                mbar_expect_tx(&full_bar[s], GA == 1 ? C::B_BYTES : (GA == 2 ? P.conv.R * P.conv.OW * 128 + C::B_BYTES : C::RAW_BYTES));
+                mbar_expect_tx(&full_bar[s], GA == 1 ? C::B_BYTES : (GA == 2 ? P.conv.R * P.conv.OW * SPAN + C::B_BYTES : C::RAW_BYTES));
                 const int k0 = (kb0 + i) * C::BK;
                 if (GA == 2) {
                     const ConvGeom &g = P.conv;
@@ -586,13 +594,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t sb = sa + C::A_BYTES;
                 const uint32_t td = tmem_base + (uint32_t)(cb * C::ACC_COLS);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < C::KSTEPS; ++k) {
                     // K-major SW128: 8-row groups 1024 B apart (SBO); one MMA's K slice = 32 B inside the swizzle span.
                     // MN-major SW128: MN blocks of 128 B BOX_BYTES apart (LBO), 8-k groups 1024 B apart (SBO).
                     const uint32_t ao = A_K ? k * 32 : k * C::KSTEP_MN;
                     const uint32_t bo = B_K ? k * 32 : k * C::KSTEP_MN;
-                    const uint64_t ad = A_K ? make_smem_desc(sa + ao, 16, 1024) : make_smem_desc(sa + ao, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
-                    const uint64_t bd = B_K ? make_smem_desc(sb + bo, 16, 1024) : make_smem_desc(sb + bo, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
+                    const uint64_t ad = A_K ? make_smem_desc(sa + ao, 16, C::KM_SBO, C::KM_LAYOUT) : make_smem_desc(sa + ao, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
+                    const uint64_t bd = B_K ? make_smem_desc(sb + bo, 16, C::KM_SBO, C::KM_LAYOUT) : make_smem_desc(sb + bo, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
                     if (X3) {
                         // every tcgen05.mma costs about the same ~130 clocks for N <= 128 (measured), so the three products are
                         // issued as TWO instructions: A hi x [B hi; B lo] (one operand of 2 BN rows -> accumulator columns
@@ -1127,15 +1135,16 @@ static zoo_status launch_conv(const CUtensorMap &tmB, const TcParams &P, dim3 gr
     return ZOO_OK;
 }
 
-template <int EB, int BN, bool X3, bool B_K = true>
+static constexpr int TC_EPI_SMEM = 40 * 1024;  // the epilogue stages through the (idle) pipeline stages: never launch with less
+template <int EB, int BN, bool X3, bool B_K = true, int SPAN = 128>
 static zoo_status launch_conv_tma(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid, cudaStream_t st) {
-    using C = TcCfg<EB, BN, X3>;
+    using C = TcCfg<EB, BN, X3, SPAN>;
     static bool attr_set = false;
     if (!attr_set) {
-        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(C::SMEM, TC_EPI_SMEM)));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2>, grid, dim3(TC_THREADS), (size_t)C::smem_for(P.stages), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, grid, dim3(TC_THREADS), (size_t)std::max(C::smem_for(P.stages), TC_EPI_SMEM), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1155,14 +1164,15 @@ static zoo_status launch_conv_bn(int BN, bool bk, const CUtensorMap &tmB, const 
 
 // One translation unit per operand mode (gemm_tc_bf16.cu / gemm_tc_tf32.cu / gemm_tc_x3.cu) instantiates the kernels, so the
 // three compile in parallel.  kind: 0 = plain GEMM (both operands by TMA), 1 = gathered-A conv, 2 = TMA-im2col conv, 3 = TMA-im2col data gradient.
-template <int EB, bool X3>
+template <int EB, bool X3, int SPAN = 128>
 static int tc_pick_stages(int BN, long long ctas, int nkb) {
-    const int mx = BN == 32 ? TcCfg<EB, 32, X3>::MAX_STAGES : (BN == 64 ? TcCfg<EB, 64, X3>::MAX_STAGES : TcCfg<EB, 128, X3>::MAX_STAGES);
-    const int two = BN == 32 ? TcCfg<EB, 32, X3>::TWO_CTA_STAGES : (BN == 64 ? TcCfg<EB, 64, X3>::TWO_CTA_STAGES : TcCfg<EB, 128, X3>::TWO_CTA_STAGES);
+    const int mx = BN == 32 ? TcCfg<EB, 32, X3, SPAN>::MAX_STAGES : (BN == 64 ? TcCfg<EB, 64, X3, SPAN>::MAX_STAGES : TcCfg<EB, 128, X3, SPAN>::MAX_STAGES);
+    const int two = BN == 32 ? TcCfg<EB, 32, X3, SPAN>::TWO_CTA_STAGES : (BN == 64 ? TcCfg<EB, 64, X3, SPAN>::TWO_CTA_STAGES : TcCfg<EB, 128, X3, SPAN>::TWO_CTA_STAGES);
     int stg = ctas > g_sm_budget ? two : mx;
     const int force = g_tc_stages_force & 0xff;  // ZOO_TC_STAGES / zoo_test_set_tc_stages
     if (force >= 2) stg = force < mx ? force : mx;
     if (stg > nkb + 1) stg = nkb + 1 < 2 ? 2 : nkb + 1;  // no point in a ring deeper than the K loop
+    if (SPAN == 64 && stg < 4) stg = 4;  // the epilogue stages ~35 KB through the ring: keep the barriers behind it
     return stg;
 }
 
@@ -1172,6 +1182,14 @@ static zoo_status tc_launch_mode(int kind, int BN, bool ak, bool bk, const CUten
     TcParams P = P0;
     P.stages = tc_pick_stages<EB, X3>(BN, (long long)grid.x * grid.y * grid.z, P0.kb_per_split);
     P.xmode = g_tc_stages_force >> 8;
+    if (kind == 2 && P0.span == 64) {  // bf16 TMA-im2col convolution over 64-byte runs (SWIZZLE_64B tiles)
+        if (EB != 2 || X3) { set_err("tc_conv: 64-byte spans are a bf16 path"); return ZOO_BAD_ARG; }
+        P.stages = tc_pick_stages<2, false, 64>(BN, (long long)grid.x * grid.y * grid.z, P0.kb_per_split);
+        if (BN == 32) return launch_conv_tma<2, 32, false, true, 64>(tmA, tmB, P, grid, st);
+        if (BN == 64) return launch_conv_tma<2, 64, false, true, 64>(tmA, tmB, P, grid, st);
+        set_err("tc_conv: 64-byte spans cover N <= 64");
+        return ZOO_BAD_ARG;
+    }
     if (kind == 0) return launch_tc_bn<EB, X3>(BN, ak, bk, tmA, tmB, P, grid, st);
     if (kind == 1) return launch_conv_bn<EB, X3>(BN, bk, tmB, P, grid, st);
     if (kind == 3) {  // TMA-im2col data gradient: MN-major weight operand (fp32 nets; Cin <= 64)
