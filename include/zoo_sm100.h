@@ -251,6 +251,12 @@ ZOO_API zoo_status zoo_replay_sample(zoo_replay *r, void *stream, const void *u_
                                      int64_t *inds_out);
 /* t[:priority][inds] .= priorities (common.jl:22) for the last sample; prio_dev = device pointer, e.g. zoo_learner_priorities_dev */
 ZOO_API zoo_status zoo_replay_update_priorities(zoo_replay *r, void *stream, const float *prio_dev);
+/* RLCore's prioritized sampler REDRAWS an index that falls outside the valid range stack .. length - n (call site
+ * src/algorithms/dqns/common.jl:18).  The redraws need fresh uniforms: spare_host holds [B][n_per_sample] of them (dtype as the
+ * draws passed to zoo_replay_sample; sample b uses row b, each an independent single draw).  They are used by every following
+ * zoo_replay_sample until replaced; an index still invalid after n_per_sample redraws (or with none supplied) is clamped to the
+ * range edge, counted (zoo_replay_invalid_count) and given the priority of the transition actually fetched. */
+ZOO_API zoo_status zoo_replay_set_spare_draws(zoo_replay *r, void *stream, const void *spare_host, int32_t u_dtype, int32_t B, int32_t n_per_sample);
 /* PER draws that fell outside the valid range (the reference redraws them; here they are clamped and counted) */
 ZOO_API zoo_status zoo_replay_invalid_count(zoo_replay *r, uint32_t *n);
 ZOO_API zoo_status zoo_replay_sumtree(zoo_replay *r, zoo_sumtree **tree);

@@ -45,8 +45,11 @@ class ReplayOracle:
     def valid_range(self):
         return self.stack, self.length - self.n
 
-    def indices(self, u, mode="uniform"):
+    def indices(self, u, mode="uniform", spare=None):
         """uniform: i = lo + floor(u * n_valid) in the dtype of the draw; 'independent' / 'stratified': SumTree.
+        A prioritized index outside the valid range is REDRAWN (RLCore's sampler loops until the index is valid):
+        sample b consumes spare[b, 0], spare[b, 1], ... as independent single draws get(u * total); when the spares run out (or
+        none are given) it is clamped to the range edge and takes that transition's priority.
         Returns (indices, priorities | None, number clamped)."""
         lo, hi = self.valid_range()
         u = np.asarray(u)
@@ -55,8 +58,20 @@ class ReplayOracle:
             i = lo + (u * T(hi - lo + 1)).astype(np.int64)
             return np.minimum(i, hi), None, 0
         idx, pr = self.tree.sample(u, stratified=(mode == "stratified"))
-        bad = (idx < lo) | (idx > hi)
-        return np.clip(idx, lo, hi), pr, int(bad.sum())
+        idx, pr = np.array(idx, np.int64), np.array(pr, F32)
+        nbad = 0
+        R = 0 if spare is None else np.asarray(spare).shape[1]
+        for b in range(len(idx)):
+            r = 0
+            while (idx[b] < lo or idx[b] > hi) and r < R:
+                i1, p1 = self.tree.sample(np.asarray(spare)[b, r:r + 1].astype(u.dtype), stratified=False)
+                idx[b], pr[b] = i1[0], p1[0]
+                r += 1
+            if idx[b] < lo or idx[b] > hi:
+                nbad += 1
+                idx[b] = lo if idx[b] < lo else hi
+                pr[b] = self.tree[int(idx[b])]
+        return idx, pr, nbad
 
     def fetch(self, inds):
         B = len(inds)

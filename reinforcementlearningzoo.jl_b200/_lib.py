@@ -109,6 +109,7 @@ SIGNATURES = {
     "zoo_replay_sample": [V, V, V, I32, I32, I32, C.POINTER(Batch), V],
     "zoo_replay_update_priorities": [V, V, V],
     "zoo_replay_invalid_count": [V, C.POINTER(C.c_uint32)],
+    "zoo_replay_set_spare_draws": [V, V, V, I32, I32, I32],
     "zoo_replay_sumtree": [V, PV],
     "zoo_learner_priorities_dev": [V, PV],
     "zoo_dp_unique_id": [V],

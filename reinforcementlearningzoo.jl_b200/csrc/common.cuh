@@ -136,6 +136,8 @@ enum { CONV_RAW_U8 = 1,   // first conv: observation [B][C][H][W] uint8, K order
        CONV_DGRAD = 4,    // data gradient: A = dY [B][OH][OW][Cout] gathered transposed-conv style, K order (ky,kx,o),
                           //   M = B*H*W input pixels, N = C;  B operand = W viewed [Cout][ks*ks*C] (MN-major)
        CONV_TMA = 5,      // forward conv on NHWC activations with TMA-fetched im2col rows (4-D boxes), K order (ky,kx,c)
+       CONV_TMA_WGRAD = 7,    // weight gradient: contraction over the output pixels, dY and the activations as MN-major TMA boxes of
+                          //   R whole output rows of one image (see gemm_tc.cuh, GA = 4)
        CONV_TMA_DGRAD = 6 };  // stride-1 data gradient the same way: A = dY boxes with mirrored taps, K order (ky,kx,o),
                           //   M = B*H*W input pixels (tiles = whole rows of one image), N = C, W operand as for CONV_DGRAD
 struct ConvGeom {
@@ -148,8 +150,12 @@ struct ConvGeom {
     // CONV_TMA: M tiles are R whole output rows of one image (tpi tiles per image); one K-block is one tap x one 128-byte
     // channel block (cblocks per tap), or -- `first`: zero-padded 4-channel frame stack -- one kernel row (ks taps x C)
     int tpi = 0, R = 0, cblocks = 1, first = 0;
+    int ksteps = 4;  // CONV_TMA_WGRAD: tcgen05.mma per K-block = ceil(R * OW / UMMA_K)
 };
 bool tc_conv_supported(const ConvGeom &g, int is_bf16);
+// weight gradient of a convolution with TMA-fetched operands (no im2col matrix): dW[Cout][ks*ks*C] += dY^T im2col(X)
+bool tc_conv_wgrad_supported(const ConvGeom &g, int is_bf16);
+zoo_status tc_conv_wgrad(ConvGeom g, const void *dy, int is_bf16, int images, const Epilogue &epi, cudaStream_t st);
 // D[M][N] = sum_k A(m,k) W(n,k) with A gathered per ConvGeom; Wop: K-major [N][K] (forward) or MN-major (dgrad)
 zoo_status tc_conv_gemm(const ConvGeom &g, const Operand &Wop, int M, int N, int K, const Epilogue &epi, float *ws, size_t ws_elems,
                         cudaStream_t st);

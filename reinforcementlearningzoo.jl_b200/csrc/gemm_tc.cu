@@ -242,6 +242,97 @@ static zoo_status tc_conv_tma(ConvGeom g, const Operand &Wop, int images, int N,
     return tc_launch(eb, x3, 2, BN, true, true, tmA, tmB, P, grid, st);
 }
 
+// 3-D tensor map {d0, d1, d2} with explicit swizzle (the dY operand of the weight gradient)
+static zoo_status make_map3(CUtensorMap *tm, const void *p, int eb, const cuuint64_t dims[3], const cuuint64_t strides_bytes[2], const cuuint32_t box[3],
+                            CUtensorMapSwizzle sw) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_err("cuTensorMapEncodeTiled not available from the driver"); return ZOO_CUDA_ERROR; }
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(p), dims, strides_bytes, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_err("cuTensorMapEncodeTiled(3D) failed (%d): dims %llu %llu %llu box %u %u %u", (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                (unsigned long long)dims[2], box[0], box[1], box[2]);
+        return ZOO_CUDA_ERROR;
+    }
+    return ZOO_OK;
+}
+
+static int wgrad_span(const ConvGeom &g, int eb) {
+    const int run = (g.first ? g.ks * g.C : g.C) * eb;
+    if (run % 128 == 0) return 128;
+    return (eb == 2 && run == 64) ? 64 : 0;
+}
+
+bool tc_conv_wgrad_supported(const ConvGeom &g, int is_bf16) {
+    const int eb = is_bf16 ? 2 : 4, span = wgrad_span(g, eb);
+    if (!span) return false;
+    if (g.first && !(g.ks * g.C * eb == span && g.p == 0)) return false;
+    const int mn_rows = 128 / eb, mn_box = span / eb;
+    if (g.OW < 1 || g.OW > mn_rows || g.Cout > BM || g.Cout < 8) return false;
+    const int R = std::min(g.OH, mn_rows / g.OW);
+    if ((g.OW - 1) * g.s + 1 > 256 || (R - 1) * g.s + 1 > 256) return false;
+    if ((g.ks * g.ks * g.C) % mn_box) return false;
+    if ((g.Cout * eb) % 16 || (g.s * g.C * eb) % 16 || ((uintptr_t)g.x & 15)) return false;
+    return true;
+}
+
+// dW[Cout][ks*ks*C] += dY^T im2col(X) with both operands fetched as TMA boxes (kernel GA = 4): g.x = NHWC activations the forward
+// conv read (`first`: the zero-padded frame stack, p = 0), dy = [images][OH][OW][Cout] in the same element type; epi.out = fp32
+// [Cout][ks*ks*C], all-zero on entry (partial sums of the image splits are red-added).
+zoo_status tc_conv_wgrad(ConvGeom g, const void *dy, int is_bf16, int images, const Epilogue &epi, cudaStream_t st) {
+    ZOO_REQUIRE(tc_conv_wgrad_supported(g, is_bf16) && images > 0 && ((uintptr_t)dy & 15) == 0 && !epi.out_bf16, "tc_conv_wgrad: unsupported geometry");
+    const int eb = is_bf16 ? 2 : 4, span = wgrad_span(g, eb);
+    const int mn_rows = 128 / eb, mn_box = span / eb, umma_k = 32 / eb;
+    const bool x3 = eb == 4 && epi.tf32_passes == 3;
+    g.R = std::min(g.OH, mn_rows / g.OW);
+    g.tpi = cdiv(g.OH, g.R);
+    g.ksteps = cdiv(g.R * g.OW, umma_k);
+    g.mode = CONV_TMA_WGRAD;
+    const int N = g.ks * g.ks * g.C, BN = 128;
+    const int total_kb = images * g.tpi;
+    const int ntiles = cdiv(N, BN);
+    const long long cap = g_sm_budget * (x3 ? 1 : 2);
+    int split = (int)std::max<long long>(1, std::min<long long>(total_kb, cap / ntiles));
+    const int kbps = cdiv(total_kb, split);
+    split = cdiv(total_kb, kbps);
+    dim3 grid(1, ntiles, split);
+    TcParams P;
+    P.M = g.Cout; P.N = N; P.K = total_kb; P.kb_per_split = kbps; P.epi = epi; P.ws = nullptr; P.ctr = nullptr; P.dbg = nullptr; P.conv = g; P.span = span;
+    P.epi.sm = N; P.epi.sn = 1; P.epi.out_bf16 = 0; P.epi.bias_mode = 0; P.epi.relu = 0; P.epi.mask = nullptr; P.epi.rowmul = nullptr;
+    P.epi.accumulate = split > 1 ? 1 : 0;
+    const CUtensorMapSwizzle sw = eb == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (span == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    CUtensorMap tmA, tmB;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)g.Cout, (cuuint64_t)(g.OH * g.OW), (cuuint64_t)images};
+        const cuuint64_t str[2] = {(cuuint64_t)g.Cout * eb, (cuuint64_t)g.OH * g.OW * g.Cout * eb};
+        const cuuint32_t box[3] = {(cuuint32_t)mn_box, (cuuint32_t)(g.R * g.OW), 1};
+        ZOO_TRY(make_map3(&tmA, dy, eb, dims, str, box, sw));
+    }
+    {
+        EncodeTiledFn enc = get_encode();
+        ZOO_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+        const cuuint64_t sC = (cuuint64_t)g.C * eb, sW = (cuuint64_t)g.W * sC, sH = (cuuint64_t)g.H * sW;
+        cuuint64_t dims[4], str[3];
+        cuuint32_t box[4], es[4];
+        if (g.first) {
+            dims[0] = (cuuint64_t)(g.ks * g.C); dims[1] = (cuuint64_t)g.OW; dims[2] = (cuuint64_t)g.H; dims[3] = (cuuint64_t)images;
+            str[0] = (cuuint64_t)g.s * sC; str[1] = sW; str[2] = sH;
+            box[0] = (cuuint32_t)(g.ks * g.C); box[1] = (cuuint32_t)g.OW; box[2] = (cuuint32_t)((g.R - 1) * g.s + 1); box[3] = 1;
+            es[0] = 1; es[1] = 1; es[2] = (cuuint32_t)g.s; es[3] = 1;
+        } else {
+            dims[0] = (cuuint64_t)g.C; dims[1] = (cuuint64_t)g.W; dims[2] = (cuuint64_t)g.H; dims[3] = (cuuint64_t)images;
+            str[0] = sC; str[1] = sW; str[2] = sH;
+            box[0] = (cuuint32_t)mn_box; box[1] = (cuuint32_t)((g.OW - 1) * g.s + 1); box[2] = (cuuint32_t)((g.R - 1) * g.s + 1); box[3] = 1;
+            es[0] = 1; es[1] = (cuuint32_t)g.s; es[2] = (cuuint32_t)g.s; es[3] = 1;
+        }
+        CUresult r = enc(&tmB, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(g.x), dims, str, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_err("tc_conv_wgrad: cuTensorMapEncodeTiled(4D) failed (%d)", (int)r); return ZOO_CUDA_ERROR; }
+    }
+    return tc_launch(eb, x3, 4, BN, false, false, tmA, tmB, P, grid, st);
+}
+
 zoo_status tc_conv_gemm(const ConvGeom &g, const Operand &Wop, int M, int N, int K, const Epilogue &epi, float *ws, size_t ws_elems,
                         cudaStream_t st) {
     ZOO_REQUIRE(tc_conv_supported(g, Wop.is_bf16) && M > 0 && N >= 8 && ((uintptr_t)Wop.p & 15) == 0, "tc_conv_gemm: unsupported geometry");

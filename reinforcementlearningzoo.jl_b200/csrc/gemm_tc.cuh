@@ -170,22 +170,25 @@ __device__ __forceinline__ void dbg_stamp(const TcParams &P, int slot) {
 // SPAN: bytes of K per tile row and stage = the TMA / UMMA swizzle span.  128 everywhere except the bf16 TMA-im2col convolutions
 // whose innermost contiguous run is only 64 bytes (conv over a 32-channel bf16 activation tensor; the first conv's kernel row of
 // 8 taps x 4 channels): those run with SWIZZLE_64B tiles, 32 K elements per stage, two tcgen05.mma per stage.
-template <int EB, int BN, bool X3, int SPAN = 128>
+// MNT: both operands MN-major (a tile is then always 128 bytes of K x rows, whatever the span)
+template <int EB, int BN, bool X3, int SPAN = 128, bool MNT = false>
 struct TcCfg {
     static constexpr int BK = SPAN / EB;         // K elements per stage
     static constexpr int KSTEPS = SPAN / 32;     // tcgen05.mma per stage (K = 32 bytes each)
     static constexpr int KM_SBO = 8 * SPAN;      // K-major operand: 8-row groups this far apart
     static constexpr int KM_LAYOUT = SPAN == 128 ? 2 : 4;  // UMMA layout type: SWIZZLE_128B = 2, SWIZZLE_64B = 4
     static constexpr int UMMA_K = 32 / EB;       // K elements per tcgen05.mma
-    static constexpr int MN_BOX = 128 / EB;      // MN elements per 128-byte row of an MN-major box
-    static constexpr int BOX_BYTES = BK * 128;   // one MN-major box: BK k-rows x 128 B
-    static constexpr int KSTEP_MN = UMMA_K * 128;  // MN-major: one 128-byte row per k
-    // MN-major swizzle atoms: bf16 -> 8 k-rows (SWIZZLE_128B); fp32 -> 4 k-rows (SWIZZLE_128B_BASE32B, the only
+    // MN-major operands: boxes of MN_ROWS k-rows x SPAN bytes of MN (MN_BOX elements); BM / MN_BOX (BN / MN_BOX) boxes per tile
+    static constexpr int MN_ROWS = 128 / EB;     // k-rows per box = K elements per stage of an MN-major operand (64 bf16, 32 fp32)
+    static constexpr int MN_BOX = SPAN / EB;     // MN elements per row of a box
+    static constexpr int BOX_BYTES = MN_ROWS * SPAN;
+    static constexpr int KSTEP_MN = UMMA_K * SPAN;  // MN-major: one SPAN-byte row per k
+    // MN-major swizzle atoms: bf16 -> 8 k-rows (SWIZZLE_128B / SWIZZLE_64B); fp32 -> 4 k-rows (SWIZZLE_128B_BASE32B, the only
     // MN-major layout tcgen05 accepts for 32-bit operands)
-    static constexpr int MN_SBO = EB == 2 ? 1024 : 512;
-    static constexpr int MN_LAYOUT = EB == 2 ? 2 : 1;
-    static constexpr int A_BYTES = BM * SPAN;
-    static constexpr int B_BYTES = BN * SPAN;
+    static constexpr int MN_SBO = EB == 2 ? 8 * SPAN : 512;
+    static constexpr int MN_LAYOUT = EB == 2 ? (SPAN == 128 ? 2 : 4) : 1;
+    static constexpr int A_BYTES = BM * (MNT ? 128 : SPAN);
+    static constexpr int B_BYTES = BN * (MNT ? 128 : SPAN);
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGE_BYTES = RAW_BYTES * (X3 ? 2 : 1);
     // 3xTF32 stage: [A hi][B hi][B lo][A lo] -- B lo directly behind B hi, so that [B hi; B lo] is ONE operand of 2 BN rows
@@ -461,12 +464,19 @@ __device__ __forceinline__ void epi_cols_store(const float *rp, int ncols, T *op
 // GA = 2: implicit-GEMM convolution with the im2col rows fetched by TMA itself: one M tile = R whole output rows of one
 //         image, one K-block = one kernel tap (or kernel row), loaded as a single 4-D box of the NHWC activation tensor
 //         (element strides = conv stride, out-of-bounds = zero padding).
+// GA = 4: implicit-GEMM convolution WEIGHT gradient, dW[o][(ky,kx,c)] = sum over pixels of dY[pixel][o] * X[pixel @ tap][c]:
+//         M = Cout (one tile, rows past Cout stay zero), N = the K x K x C features, contraction over the output pixels.  Both
+//         operands are MN-major and arrive as TMA boxes of R whole output rows of one image: dY through a 3-D map
+//         {Cout, pixels, images}, the activations through the same 4-D strided boxes as the forward conv (one per tap / kernel
+//         row) -- so no im2col matrix exists in either direction.  A K-block's pixel rows past R x OW are never written
+//         (the ring is zeroed once at kernel start), grid.z splits the images, partial sums are red-added into the gradient.
 template <int EB, int BN, bool A_K, bool B_K, bool X3, int GA = 0, int SPAN = 128>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams P) {
-    static_assert(GA == 0 || A_K, "the gathered A operand is K-major");
-    static_assert(SPAN == 128 || (SPAN == 64 && EB == 2 && GA == 2 && A_K && B_K && !X3), "64-byte spans: bf16 TMA-im2col convolutions only");
-    using C = TcCfg<EB, BN, X3, SPAN>;
+    static_assert(GA == 0 || GA == 4 || A_K, "the gathered A operand is K-major");
+    static_assert(GA != 4 || (!A_K && !B_K), "the weight-gradient operands are MN-major");
+    static_assert(SPAN == 128 || (SPAN == 64 && EB == 2 && !X3 && ((GA == 2 && A_K && B_K) || GA == 4)), "64-byte spans: bf16 TMA-im2col convolutions only");
+    using C = TcCfg<EB, BN, X3, SPAN, GA == 4>;
     // SWIZZLE_128B tiles need 1024-byte alignment; declaring it on the array (instead of rounding the pointer up) keeps
     // the shared address space visible to the compiler, so the epilogue staging below compiles to LDS/STS
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -490,7 +500,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     const int n0 = blockIdx.y * BN;
     if (threadIdx.x == 0) dbg_stamp(P, 0);
-    const int total_kb = (P.K + C::BK - 1) / C::BK;
+    const int total_kb = GA == 4 ? P.K : (P.K + C::BK - 1) / C::BK;  // GA = 4: P.K counts K-blocks (images x row groups)
     const int kb0 = blockIdx.z * P.kb_per_split;
     const int kb1 = min(total_kb, kb0 + P.kb_per_split);
     const int nkb = kb1 - kb0;  // host guarantees >= 1
@@ -512,6 +522,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (GA == 4) {  // pad rows of every stage (pixel rows past R x OW, feature boxes past N, channel rows past Cout) must read as zero
+        for (int i = threadIdx.x; i < NST * C::STAGE_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
@@ -530,6 +544,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t *sa = smem + s * C::STAGE_BYTES;
                 uint8_t *sb = sa + C::A_BYTES;
+                if (GA == 4) {
+                    const ConvGeom &g = P.conv;
+                    const int kb = kb0 + i;
+                    const int img = kb / g.tpi, oy0 = (kb - img * g.tpi) * g.R;
+                    const int abox = (P.M + C::MN_BOX - 1) / C::MN_BOX;                       // Cout blocks of dY
+                    const int bbox = min(BN / C::MN_BOX, (P.N - n0 + C::MN_BOX - 1) / C::MN_BOX);  // feature blocks of this N tile
+                    const int box_bytes = g.R * g.OW * SPAN;                                   // R x OW pixel rows of SPAN bytes
+                    mbar_expect_tx(&full_bar[s], (abox + bbox) * box_bytes);
+                    for (int h = 0; h < abox; ++h)
+                        asm volatile(
+                            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                            ::"r"(smem_u32(sa + h * C::BOX_BYTES)), "l"(&tmA), "r"(smem_u32(&full_bar[s])), "r"(h * C::MN_BOX), "r"(oy0 * g.OW), "r"(img)
+                            : "memory");
+                    for (int j = 0; j < bbox; ++j) {
+                        const int f = n0 + j * C::MN_BOX;  // first feature of the box: (ky, kx, c) with c fastest
+                        int c0, c1, c2;
+                        if (g.first) { c0 = 0; c1 = 0; c2 = oy0 * g.s + f / (g.ks * g.C); }  // one kernel row of the padded frame stack
+                        else { const int tap = f / g.C, ky = tap / g.ks, kx = tap - ky * g.ks; c0 = f - tap * g.C; c1 = kx - g.p; c2 = oy0 * g.s + ky - g.p; }
+                        asm volatile(
+                            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                            ::"r"(smem_u32(sb + j * C::BOX_BYTES)), "l"(&tmB), "r"(smem_u32(&full_bar[s])), "r"(c0), "r"(c1), "r"(c2), "r"(img)
+                            : "memory");
+                    }
+                    if (i == 0) dbg_stamp(P, 2);
+                    continue;
+                }
                 mbar_expect_tx(&full_bar[s], GA == 1 ? C::B_BYTES : (GA == 2 ? P.conv.R * P.conv.OW * SPAN + C::B_BYTES : C::RAW_BYTES));
                 const int k0 = (kb0 + i) * C::BK;
                 if (GA == 2) {
@@ -593,8 +633,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
                 const uint32_t sb = sa + C::A_BYTES;
                 const uint32_t td = tmem_base + (uint32_t)(cb * C::ACC_COLS);
+                const int ksteps = GA == 4 ? P.conv.ksteps : C::KSTEPS;  // GA = 4: ceil(R x OW / UMMA_K) (pad rows are zero)
 #pragma unroll
-                for (int k = 0; k < C::KSTEPS; ++k) {
+                for (int k = 0; k < (GA == 4 ? 4 : C::KSTEPS); ++k) {
+                    if (GA == 4 && k >= ksteps) break;
                     // K-major SW128: 8-row groups 1024 B apart (SBO); one MMA's K slice = 32 B inside the swizzle span.
                     // MN-major SW128: MN blocks of 128 B BOX_BYTES apart (LBO), 8-k groups 1024 B apart (SBO).
                     const uint32_t ao = A_K ? k * 32 : k * C::KSTEP_MN;
@@ -1086,6 +1128,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------- launch templates ---------
+static constexpr int TC_EPI_SMEM = 40 * 1024;  // the epilogue stages through the (idle) pipeline stages: never launch with less
 template <int EB, int BN, bool A_K, bool B_K, bool X3>
 static zoo_status launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid, cudaStream_t st) {
     using C = TcCfg<EB, BN, X3>;
@@ -1135,7 +1178,6 @@ static zoo_status launch_conv(const CUtensorMap &tmB, const TcParams &P, dim3 gr
     return ZOO_OK;
 }
 
-static constexpr int TC_EPI_SMEM = 40 * 1024;  // the epilogue stages through the (idle) pipeline stages: never launch with less
 template <int EB, int BN, bool X3, bool B_K = true, int SPAN = 128>
 static zoo_status launch_conv_tma(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid, cudaStream_t st) {
     using C = TcCfg<EB, BN, X3, SPAN>;
@@ -1145,6 +1187,26 @@ static zoo_status launch_conv_tma(const CUtensorMap &tmA, const CUtensorMap &tmB
         attr_set = true;
     }
     ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, grid, dim3(TC_THREADS), (size_t)std::max(C::smem_for(P.stages), TC_EPI_SMEM), st, tmA, tmB, P));
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+
+template <int EB, bool X3, int SPAN>
+static zoo_status launch_conv_wgrad(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P0, dim3 grid, cudaStream_t st) {
+    using C = TcCfg<EB, 128, X3, SPAN, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    TcParams P = P0;
+    const long long ctas = (long long)grid.x * grid.y * grid.z;
+    int stg = ctas > g_sm_budget ? C::TWO_CTA_STAGES : C::MAX_STAGES;
+    if (stg > P.kb_per_split + 1) stg = P.kb_per_split + 1;
+    if (stg < 2) stg = 2;
+    P.stages = stg;
+    P.xmode = 0;
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN>, grid, dim3(TC_THREADS), (size_t)std::max(C::smem_for(stg), TC_EPI_SMEM), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1183,12 +1245,23 @@ static zoo_status tc_launch_mode(int kind, int BN, bool ak, bool bk, const CUten
     P.stages = tc_pick_stages<EB, X3>(BN, (long long)grid.x * grid.y * grid.z, P0.kb_per_split);
     P.xmode = g_tc_stages_force >> 8;
     if (kind == 2 && P0.span == 64) {  // bf16 TMA-im2col convolution over 64-byte runs (SWIZZLE_64B tiles)
-        if (EB != 2 || X3) { set_err("tc_conv: 64-byte spans are a bf16 path"); return ZOO_BAD_ARG; }
-        P.stages = tc_pick_stages<2, false, 64>(BN, (long long)grid.x * grid.y * grid.z, P0.kb_per_split);
-        if (BN == 32) return launch_conv_tma<2, 32, false, true, 64>(tmA, tmB, P, grid, st);
-        if (BN == 64) return launch_conv_tma<2, 64, false, true, 64>(tmA, tmB, P, grid, st);
-        set_err("tc_conv: 64-byte spans cover N <= 64");
+        if constexpr (EB == 2 && !X3) {
+            P.stages = tc_pick_stages<2, false, 64>(BN, (long long)grid.x * grid.y * grid.z, P0.kb_per_split);
+            if (BN == 32) return launch_conv_tma<2, 32, false, true, 64>(tmA, tmB, P, grid, st);
+            if (BN == 64) return launch_conv_tma<2, 64, false, true, 64>(tmA, tmB, P, grid, st);
+            set_err("tc_conv: 64-byte spans cover N <= 64");
+            return ZOO_BAD_ARG;
+        }
+        set_err("tc_conv: 64-byte spans are a bf16 path");
         return ZOO_BAD_ARG;
+    }
+    if (kind == 4) {  // TMA-im2col weight gradient (both operands MN-major boxes)
+        if (P0.span == 64) {
+            if constexpr (EB == 2 && !X3) return launch_conv_wgrad<2, false, 64>(tmA, tmB, P0, grid, st);
+            set_err("tc_conv_wgrad: 64-byte spans are a bf16 path");
+            return ZOO_BAD_ARG;
+        }
+        return launch_conv_wgrad<EB, X3, 128>(tmA, tmB, P0, grid, st);
     }
     if (kind == 0) return launch_tc_bn<EB, X3>(BN, ak, bk, tmA, tmB, P, grid, st);
     if (kind == 1) return launch_conv_bn<EB, X3>(BN, bk, tmB, P, grid, st);

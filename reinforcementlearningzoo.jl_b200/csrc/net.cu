@@ -28,6 +28,21 @@ static bool tma_conv_enabled() {
     if (on < 0) { const char *e = getenv("ZOO_TMA_CONV"); on = (e && e[0] == '0') ? 0 : 1; }
     return on == 1;
 }
+// weight gradients of the convolutions with TMA-fetched operands (no im2col matrix at all); ZOO_TMA_WGRAD=0 restores the explicit
+// im2col + GEMM path
+static bool tma_wgrad_enabled() {
+    static const bool on = [] { const char *e = getenv("ZOO_TMA_WGRAD"); return !(e && e[0] == '0'); }();
+    return on && tma_conv_enabled();
+}
+// geometry of layer L's weight gradient as seen by tc_conv_wgrad; x = the NHWC tensor the forward conv read
+static bool wgrad_geom(const zoo_net *net, const LayerExec &L, const void *x, ConvGeom &g) {
+    if (!tma_wgrad_enabled() || net->prec == ZOO_PREC_FP32_SIMT || L.kind != ZOO_LAYER_CONV || !x) return false;
+    if (L.first_raw && !net->obs_nhwc) return false;
+    g = ConvGeom();
+    g.x = x; g.C = L.cin; g.H = L.ih; g.W = L.iw; g.ks = L.ksize; g.s = L.stride; g.p = L.pad; g.OH = L.oh; g.OW = L.ow; g.Cout = L.cout;
+    g.first = (L.first_raw && net->obs_nhwc) ? 1 : 0;
+    return tc_conv_wgrad_supported(g, net->prec == ZOO_PREC_BF16);
+}
 static bool implicit_conv_enabled() {
     static int on = -1;
     if (on < 0) { const char *e = getenv("ZOO_IMPLICIT_CONV"); on = (e && e[0] == '1') ? 1 : 0; }
@@ -536,7 +551,9 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
                 gt.first = (L.first_raw && net->obs_nhwc) ? 1 : 0;
                 if (tc_conv_supported(gt, bf)) { g = gt; implicit = true; }
             }
-            const long long Mc = implicit ? cols_rows * L.opr : M;  // rows of the explicit cols matrix to build
+            ConvGeom gw;
+            const bool wg_implicit = implicit && wgrad_geom(net, L, cur, gw);
+            const long long Mc = implicit ? (wg_implicit ? 0 : cols_rows * L.opr) : M;  // rows of the explicit cols matrix to build
             cudaStream_t sc = st;
             const bool par = implicit && net->side && !g_prof_on;
             if (par && Mc > 0) { ZOO_TRY(net_side_fork(net, st)); sc = net->side; }
@@ -620,16 +637,25 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
             ZOO_TRY(launch_colsum(L.dout, dy_bf, M, L.cout, net->grads + Bt.offset, sw));
         }
         // wgrad: dW[cout][K] += dY^T X   (both operands MN-major: stored [rows][features])
-        Operand X;
-        if (L.kind == ZOO_LAYER_CONV) X = Operand{L.cols, bf, L.K, 0};
-        else if (li == 0) X = Operand{in, in_kind == 2 ? bf : 0, L.K, 0};
-        else X = Operand{ch.layers[li - 1].out, bf, L.K, 0};
-        Operand dYt{L.dout, dy_bf, L.cout, 0};
+        ConvGeom gw;
+        const void *xin = L.kind != ZOO_LAYER_CONV ? nullptr : (li == 0 ? ((L.first_raw && net->obs_nhwc) ? net->obs_nhwc_buf : nullptr) : ch.layers[li - 1].out);
         prof_label("wgrad:t%d[%dx%lldx%lld]", L.wt, L.cout, L.K, M);
-        Epilogue ew;
-        ew.out = net->grads + W.offset; ew.sm = L.K; ew.sn = 1; ew.tf32_passes = net->tf32_passes;
-        ew.accumulate = 2;  // grads are zeroed per update: plain store, or atomic add when the GEMM is K-split
-        ZOO_TRY(gemm(dYt, X, L.cout, (int)L.K, (int)M, ew, 0, wsw, wsw_elems, sw));
+        if (dy_bf == bf && wgrad_geom(net, L, xin, gw)) {
+            // convolution: dY and the activations arrive as TMA boxes, the im2col matrix is never built (tc_conv_wgrad)
+            Epilogue ew;
+            ew.out = net->grads + W.offset; ew.tf32_passes = net->tf32_passes;
+            ZOO_TRY(tc_conv_wgrad(gw, L.dout, bf, (int)rows, ew, sw));
+        } else {
+            Operand X;
+            if (L.kind == ZOO_LAYER_CONV) X = Operand{L.cols, bf, L.K, 0};
+            else if (li == 0) X = Operand{in, in_kind == 2 ? bf : 0, L.K, 0};
+            else X = Operand{ch.layers[li - 1].out, bf, L.K, 0};
+            Operand dYt{L.dout, dy_bf, L.cout, 0};
+            Epilogue ew;
+            ew.out = net->grads + W.offset; ew.sm = L.K; ew.sn = 1; ew.tf32_passes = net->tf32_passes;
+            ew.accumulate = 2;  // grads are zeroed per update: plain store, or atomic add when the GEMM is K-split
+            ZOO_TRY(gemm(dYt, X, L.cout, (int)L.K, (int)M, ew, 0, wsw, wsw_elems, sw));
+        }
         const bool late_here = net->late_cb && W.offset == net->late_off;
         // dgrad
         if (li == 0 && !dx) { if (late_here) ZOO_TRY(net_late_bucket(net, st, sw, par)); continue; }

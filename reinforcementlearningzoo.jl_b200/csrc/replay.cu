@@ -14,13 +14,14 @@
 //   valid i:   stack <= i <= length - n
 // Everything is enqueued on the stream the caller passes (the learner's), so sample -> update -> priority write-back is one
 // ordered device-side sequence with no host round trip.
-#include "common.cuh"
+#include "sumtree.cuh"
 
 struct zoo_sumtree;
 namespace zoo {
 zoo_status sumtree_sample_on(zoo_sumtree *t, cudaStream_t st, const void *u_dev, int u_dtype, long long n, int mode, long long *idx_dev, float *prio_dev);
 zoo_status sumtree_update_on(zoo_sumtree *t, cudaStream_t st, const long long *idx_dev, const float *p_dev, long long n);
 void sumtree_state(const zoo_sumtree *t, long long *length, long long *first);
+void sumtree_view(const zoo_sumtree *t, SumTreeView *v);
 
 struct ReplayView {
     const uint8_t *ring;
@@ -35,18 +36,33 @@ __device__ __forceinline__ int rec_action(const ReplayView &v, long long i) { re
 __device__ __forceinline__ float rec_reward(const ReplayView &v, long long i) { return *reinterpret_cast<const float *>(rec_of(v, i) + v.frame_bytes + 4); }
 __device__ __forceinline__ uint8_t rec_terminal(const ReplayView &v, long long i) { return rec_of(v, i)[v.frame_bytes + 8]; }
 
-// uniform draws -> logical indices in the valid range (PER indices come from the SumTree); out-of-range PER indices are clamped
-// into the valid range and counted (the reference redraws them, which needs a live RNG)
+// uniform draws -> logical indices in the valid range.  PER indices come from the SumTree; one that falls outside
+// stack .. length - n is REDRAWN, as RLCore's sampler does ("each redrawn while ind is not in the valid range"):
+// lane b consumes its own spare uniforms spare[b * R + r], r = 0 .. R-1, each an independent single draw get(u * total) in the
+// dtype of the draws, and takes the priority of the transition it finally fetches.  Only when all R spares are used up (or
+// none were supplied) is the index clamped to the range edge and counted in n_invalid.
 template <typename T>
 __global__ void replay_indices_kernel(ReplayView v, const T *__restrict__ u, long long *__restrict__ idx, int B, int from_tree,
-                                      unsigned *__restrict__ n_invalid) {
+                                      unsigned *__restrict__ n_invalid, SumTreeView tv, const T *__restrict__ spare, int R,
+                                      float *__restrict__ prio) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const long long lo = v.stack, hi = v.length - v.n;
     long long i;
     if (from_tree) {
         i = idx[b];
-        if (i < lo || i > hi) { atomicAdd(n_invalid, 1u); i = i < lo ? lo : hi; }
+        for (int r = 0; (i < lo || i > hi) && r < R; ++r) {
+            float p;
+            i = sumtree_descend<T>(tv, Rn<T>::mul(spare[(long long)b * R + r], (T)__ldg(tv.tree + 1)), &p);
+            prio[b] = p;
+        }
+        if (i < lo || i > hi) {
+            atomicAdd(n_invalid, 1u);
+            i = i < lo ? lo : hi;
+            long long k = i + tv.first - 1;
+            if (k > tv.capacity) k -= tv.capacity;
+            prio[b] = tv.tree[tv.nparents + k];  // the importance weight must belong to the transition that is fetched
+        }
     } else {
         i = lo + (long long)(u[b] * (T)(hi - lo + 1));
         if (i > hi) i = hi;
@@ -108,6 +124,8 @@ struct zoo_replay {
     float *b_reward = nullptr, *b_priority = nullptr;
     long long *b_idx = nullptr;
     void *b_u = nullptr;
+    void *b_spare = nullptr;  // spare uniforms for PER redraws: [max_batch][spare_R] in the dtype of the draws
+    int spare_R = 0, spare_dtype = -1;
     unsigned *n_invalid = nullptr;
     int last_B = 0;
     uint8_t *h_frame = nullptr;  // pinned staging ring (8 slots) of pushed frames + scalars
@@ -160,7 +178,7 @@ zoo_status zoo_replay_destroy(zoo_replay *r) {
     if (r->ev_push) cudaEventDestroy(r->ev_push);
     if (r->ev_use) cudaEventDestroy(r->ev_use);
     void *ptrs[] = {r->ring, r->b_state, r->b_next, r->b_action, r->b_reward, r->b_terminal, r->b_priority,
-                    r->b_idx, r->b_u, r->n_invalid};
+                    r->b_idx, r->b_u, r->n_invalid, r->b_spare};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (r->h_frame) cudaFreeHost(r->h_frame);
     if (r->tree) zoo_sumtree_destroy(r->tree);
@@ -256,8 +274,13 @@ zoo_status zoo_replay_sample(zoo_replay *r, void *stream, const void *u_host, in
         ZOO_REQUIRE(tl == r->length && tf == r->first, "zoo_replay_sample: the priority tree is out of step with the trajectory");
         ZOO_TRY(sumtree_sample_on(r->tree, st, r->b_u, u_dtype, B, mode, r->b_idx, r->b_priority));
     }
-    if (u_dtype == ZOO_DRAW_F64) replay_indices_kernel<double><<<cdiv(B, 128), 128, 0, st>>>(v, (const double *)r->b_u, r->b_idx, B, per, r->n_invalid);
-    else replay_indices_kernel<float><<<cdiv(B, 128), 128, 0, st>>>(v, (const float *)r->b_u, r->b_idx, B, per, r->n_invalid);
+    SumTreeView tv{};
+    if (per) sumtree_view(r->tree, &tv);
+    const int R = (per && r->b_spare && r->spare_dtype == u_dtype) ? r->spare_R : 0;
+    if (u_dtype == ZOO_DRAW_F64)
+        replay_indices_kernel<double><<<cdiv(B, 128), 128, 0, st>>>(v, (const double *)r->b_u, r->b_idx, B, per, r->n_invalid, tv, (const double *)r->b_spare, R, r->b_priority);
+    else
+        replay_indices_kernel<float><<<cdiv(B, 128), 128, 0, st>>>(v, (const float *)r->b_u, r->b_idx, B, per, r->n_invalid, tv, (const float *)r->b_spare, R, r->b_priority);
     ZOO_LAUNCH_CHECK();
     replay_fetch_frames_kernel<<<dim3(B, r->stack, 2), 256, 0, st>>>(v, r->b_idx, (uint4 *)r->b_state, (uint4 *)r->b_next);
     ZOO_LAUNCH_CHECK();
@@ -281,6 +304,22 @@ zoo_status zoo_replay_sample(zoo_replay *r, void *stream, const void *u_host, in
 zoo_status zoo_replay_update_priorities(zoo_replay *r, void *stream, const float *prio_dev) {
     ZOO_REQUIRE(r && r->tree && prio_dev && r->last_B > 0, "zoo_replay_update_priorities: nothing sampled / not prioritized");
     return sumtree_update_on(r->tree, (cudaStream_t)stream, r->b_idx, prio_dev, r->last_B);
+}
+
+// Spare uniforms for the redraws of out-of-range prioritized indices: spare_host [B][R] (same dtype as the draws of the next
+// zoo_replay_sample calls; lane b uses row b).  Supplied by the host so that sampling stays a deterministic function of its
+// inputs; consumed by every following sample until replaced (n_per_sample = 0 switches redraws off: clamp + count).
+zoo_status zoo_replay_set_spare_draws(zoo_replay *r, void *stream, const void *spare_host, int32_t u_dtype, int32_t B, int32_t n_per_sample) {
+    ZOO_REQUIRE(r && B >= 1 && B <= r->max_batch && n_per_sample >= 0 && n_per_sample <= 64, "zoo_replay_set_spare_draws: bad argument");
+    ZOO_REQUIRE(u_dtype == ZOO_DRAW_F32 || u_dtype == ZOO_DRAW_F64, "zoo_replay_set_spare_draws: bad draw dtype");
+    r->spare_R = 0;
+    if (n_per_sample == 0) return ZOO_OK;
+    ZOO_REQUIRE(spare_host, "zoo_replay_set_spare_draws: null draws");
+    if (!r->b_spare) ZOO_CUDA(cudaMalloc(&r->b_spare, (size_t)r->max_batch * 64 * sizeof(double)));
+    const size_t esz = u_dtype == ZOO_DRAW_F64 ? 8 : 4;
+    ZOO_CUDA(cudaMemcpyAsync(r->b_spare, spare_host, (size_t)B * n_per_sample * esz, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    r->spare_R = n_per_sample; r->spare_dtype = u_dtype;
+    return ZOO_OK;
 }
 
 zoo_status zoo_replay_invalid_count(zoo_replay *r, uint32_t *n) {

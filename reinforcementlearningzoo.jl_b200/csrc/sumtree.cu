@@ -10,7 +10,7 @@
 //    dependent, duplicates see earlier writes).  Nodes are independent of each other, so per tree
 //    level one CTA sorts (node, batch position) keys in shared memory and the head of every node's run
 //    applies that node's changes serially in batch order: parallel across nodes and levels, bit-exact.
-#include "common.cuh"
+#include "sumtree.cuh"
 
 namespace zoo {
 
@@ -18,20 +18,6 @@ static constexpr int TOP_LEVELS = 12;              // nodes 1 .. 4095 staged in 
 static constexpr int TOP_N = 1 << TOP_LEVELS;      // index bound (exclusive)
 static constexpr int UPD_CHUNK = 4096;             // batch entries per update launch
 static constexpr int KBITS = 12;                   // log2(UPD_CHUNK)
-
-template <typename T> struct Rn;
-template <> struct Rn<float> {
-    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
-    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
-    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
-    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
-};
-template <> struct Rn<double> {
-    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
-    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
-    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
-};
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -173,7 +159,7 @@ sumtree_update_parents_kernel(float *__restrict__ tree, int depth, const long lo
 static constexpr int SMALL_N = 256;
 __global__ void __launch_bounds__(1024)
 sumtree_update_small_kernel(float *__restrict__ tree, long long nparents, long long capacity, long long first, int depth, int physical,
-                            const long long *__restrict__ idx, const float *__restrict__ p, int n) {
+                            const long long *__restrict__ idx, const float *__restrict__ p, int n, int dbg) {
     __shared__ long long heap[SMALL_N];
     __shared__ float pv[SMALL_N], change[SMALL_N];
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
@@ -183,6 +169,7 @@ sumtree_update_small_kernel(float *__restrict__ tree, long long nparents, long l
         pv[k] = p[k];
     }
     __syncthreads();
+    if (!(dbg & 1))
     for (int k = threadIdx.x; k < n; k += blockDim.x) {  // leaf level: change[k] = p[k] - (leaf value just before entry k)
         const long long h = heap[k];
         bool head = true;
@@ -194,6 +181,7 @@ sumtree_update_small_kernel(float *__restrict__ tree, long long nparents, long l
         tree[h] = prev;
     }
     __syncthreads();
+    if (!(dbg & 2))
     for (int t = threadIdx.x; t < depth * n; t += blockDim.x) {  // ancestors: level = t / n (shift 1 .. depth), entry k = t % n
         const int shift = t / n + 1, k = t - (shift - 1) * n;
         const long long a = heap[k] >> shift;
@@ -292,9 +280,11 @@ zoo_status zoo_sumtree_destroy(zoo_sumtree *t) {
 
 static zoo_status update_dev_impl(zoo_sumtree *t, const long long *idx_dev, const float *p_dev, long long n, int physical, cudaStream_t st = nullptr) {
     if (!st) st = t->st;
-    if (n > 0 && n <= SMALL_N) {
+    static const bool small_on = [] { const char *e = getenv("ZOO_SUMTREE_SMALL"); return !(e && e[0] == '0'); }();
+    if (small_on && n > 0 && n <= SMALL_N) {
         const int threads = (int)std::min<long long>(1024, std::max<long long>(32, ((long long)(t->depth + 1) * n + 31) / 32 * 32));
-        sumtree_update_small_kernel<<<1, threads, 0, st>>>(t->tree, t->nparents, t->capacity, t->first, t->depth, physical, idx_dev, p_dev, (int)n);
+        static const int dbg = [] { const char *e = getenv("ZOO_ST_DBG"); return e ? atoi(e) : 0; }();
+        sumtree_update_small_kernel<<<1, (dbg & 4) ? 1024 : threads, 0, st>>>(t->tree, t->nparents, t->capacity, t->first, t->depth, physical, idx_dev, p_dev, (int)n, dbg);
         ZOO_LAUNCH_CHECK();
         return ZOO_OK;
     }
@@ -509,4 +499,7 @@ zoo_status sumtree_update_on(zoo_sumtree *t, cudaStream_t st, const long long *i
     return foreign_end(t, st);
 }
 void sumtree_state(const zoo_sumtree *t, long long *length, long long *first) { *length = t->length; *first = t->first; }
+void sumtree_view(const zoo_sumtree *t, SumTreeView *v) {
+    v->tree = t->tree; v->tree_len = t->tree_len; v->nparents = t->nparents; v->capacity = t->capacity; v->first = t->first;
+}
 }  // namespace zoo

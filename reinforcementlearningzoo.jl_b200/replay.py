@@ -51,12 +51,26 @@ class ReplayShard:
         assert f.shape[1:] == self.frame_shape and len(a) == len(r) == len(t) == f.shape[0]
         L.check(L.lib().zoo_replay_push_many(self.h, f.ctypes.data, a.ctypes.data, r.ctypes.data, t.ctypes.data, L.ptr(p), f.shape[0]))
 
-    def sample_batch(self, learner, u, mode=None, want_inds=False):
+    def set_spare_draws(self, learner, spare):
+        """Uniforms for the redraws of out-of-range prioritized indices (RLCore redraws them): ``spare`` [B, R] in
+        the dtype of the draws, sample b consumes row b; ``None`` switches redraws off (clamp + count)."""
+        if spare is None:
+            L.check(L.lib().zoo_replay_set_spare_draws(self.h, learner.stream(), None, L.DRAW_F64, 1, 0))
+            return
+        s = np.ascontiguousarray(spare)
+        if s.dtype not in (np.float32, np.float64) or s.ndim != 2:
+            raise TypeError("spare draws must be a float32 or float64 [B, R] array")
+        L.check(L.lib().zoo_replay_set_spare_draws(self.h, learner.stream(), s.ctypes.data, L.DRAW_F64 if s.dtype == np.float64 else L.DRAW_F32,
+                                                   s.shape[0], s.shape[1]))
+
+    def sample_batch(self, learner, u, mode=None, want_inds=False, spare=None):
         """Assemble a minibatch on the device from the uniform draws ``u`` (float32 | float64, len = batch size).
-        Returns (zoo_batch with device pointers, indices | None)."""
+        ``spare`` [B, R]: uniforms for prioritized redraws (see set_spare_draws).  Returns (zoo_batch with device pointers, indices | None)."""
         u = np.ascontiguousarray(u)
         if u.dtype not in (np.float32, np.float64):
             raise TypeError("draws must be float32 or float64")
+        if spare is not None:
+            self.set_spare_draws(learner, np.asarray(spare, u.dtype))
         if mode is None:
             mode = L.SAMPLE_INDEPENDENT if self.is_prioritized else L.REPLAY_UNIFORM
         b = L.Batch()
@@ -65,11 +79,11 @@ class ReplayShard:
                                           int(mode), C.byref(b), L.ptr(inds)))
         return b, inds
 
-    def update(self, learner, u, mode=None, want_loss=True):
+    def update(self, learner, u, mode=None, want_loss=True, spare=None):
         """``update!(learner, t)`` (common.jl:18-24): sample -> ``update!(learner, batch)`` -> priority write-back, all enqueued on
         the learner's stream; the only host traffic is the draws (and the loss, if wanted)."""
         lib = L.lib()
-        b, _ = self.sample_batch(learner, u, mode)
+        b, _ = self.sample_batch(learner, u, mode, spare=spare)
         loss = C.c_float(0)
         L.check(lib.zoo_learner_update(learner.h, C.byref(b), C.byref(loss) if want_loss else None, None))
         if self.is_prioritized:

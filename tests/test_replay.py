@@ -98,6 +98,47 @@ def test_device_prioritized_sample_and_write_back(zoo, mode):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_device_prioritized_redraw_matches_the_oracle(zoo, dt):
+    """RLCore redraws prioritized indices outside stack .. length - n (call site common.jl:18).  Early in training most leaves
+    still hold default_priority 100, the newest n of them are invalid, so redraws are frequent: here 40 % of the mass sits on
+    the invalid ends.  The device redraw loop consumes the host's spare uniforms exactly as the oracle does; with too few spares
+    the leftover is clamped, counted, and weighted with the priority of the transition actually fetched."""
+    cap, stack, n, B = 256, 4, 3, 32
+    lrn = _tiny_learner(zoo, B, stack, per=True)
+    shard = zoo.ReplayShard(cap, (8, 8), stack, n, 0.99, max_batch=B, prioritized=True)
+    o = ReplayOracle(cap, (8, 8), stack, n, 0.99, prioritized=True)
+    rng = np.random.default_rng(11)
+    frames = rng.integers(0, 256, (200, 8, 8), dtype=np.uint8)
+    act, rew, term = rng.integers(0, 6, 200).astype(np.int32), rng.integers(-1, 2, 200).astype(F), (rng.random(200) < 0.1).astype(np.uint8)
+    pri = (rng.random(200, dtype=F) + F(0.1)).astype(F)
+    pri[:3] = F(20.0)   # indices 1..3 < stack: invalid
+    pri[-3:] = F(20.0)  # indices > length - n: invalid
+    for i in range(200):
+        o.push(frames[i], act[i], rew[i], term[i], pri[i])
+    shard.push_many(frames, act, rew, term, pri)
+    from rlzoo_b200 import _lib as ZL
+    u = rng.random(B).astype(dt)
+    for R in (8, 1, 0):
+        spare = rng.random((B, max(R, 1))).astype(dt)[:, :R] if R else None
+        before = shard.invalid_count()
+        if spare is None:
+            shard.set_spare_draws(lrn, None)
+        b, inds = shard.sample_batch(lrn, u, mode=ZL.SAMPLE_INDEPENDENT, want_inds=True, spare=spare)
+        oi, opr, nbad = o.indices(u, "independent", spare=spare)
+        assert np.array_equal(inds, oi), R
+        assert shard.invalid_count() - before == nbad
+        got = _read_batch(b, B, stack, (8, 8), priority=True)
+        assert np.array_equal(got["priority"], opr), R
+        lo, hi = o.valid_range()
+        assert inds.min() >= lo and inds.max() <= hi
+        if R == 8:
+            assert nbad == 0  # 0.4^9 per sample: the redraws resolve every index
+        if R == 0:
+            assert nbad > 0   # and without spares the old clamp-and-count behaviour remains
+
+
+@pytest.mark.gpu
 def test_update_from_shard_equals_update_from_batch(zoo):
     """sample -> update on the device == the oracle's batch fed through update!(learner, batch)."""
     cap, stack, n, B = 256, 4, 1, 8
