@@ -138,8 +138,11 @@ enum { CONV_RAW_U8 = 1,   // first conv: observation [B][C][H][W] uint8, K order
        CONV_TMA = 5,      // forward conv on NHWC activations with TMA-fetched im2col rows (4-D boxes), K order (ky,kx,c)
        CONV_TMA_WGRAD = 7,    // weight gradient: contraction over the output pixels, dY and the activations as MN-major TMA boxes of
                           //   R whole output rows of one image (see gemm_tc.cuh, GA = 4)
-       CONV_TMA_DGRAD = 6 };  // stride-1 data gradient the same way: A = dY boxes with mirrored taps, K order (ky,kx,o),
-                          //   M = B*H*W input pixels (tiles = whole rows of one image), N = C, W operand as for CONV_DGRAD
+       CONV_TMA_DGRAD = 6 };  // data gradient the same way, any stride (sub-pixel decomposition): grid.z = the s*s residue classes
+                          //   (py, px) of the input pixel grid; class pixels (s*yy + py, s*xx + px) only receive the taps
+                          //   ky = (py + p) % s + a*s, i.e. a stride-1 convolution of dY with the class's sub-kernel: A = dY boxes,
+                          //   K order (a, b, o), M = class pixels (tiles = whole class rows of one image), N = C, W operand as for
+                          //   CONV_DGRAD; the tile goes back to the strided class view of dX with one TMA store
 struct ConvGeom {
     const void *x = nullptr;
     int mode = 0;

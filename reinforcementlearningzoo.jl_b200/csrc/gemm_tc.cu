@@ -170,9 +170,13 @@ bool tc_conv_supported(const ConvGeom &g, int is_bf16) {
     if (g.mode == CONV_RAW_U8 || g.mode == CONV_RAW_F32) return g.ks % ch == 0 && ((long long)g.C * g.ks * g.ks * eb) % 16 == 0;
     if (g.mode == CONV_NHWC) return g.C % ch == 0;
     if (g.mode == CONV_DGRAD) return g.Cout % bk == 0 && g.C % 8 == 0 && ((long long)g.ks * g.ks * g.C * eb) % 16 == 0;
-    if (g.mode == CONV_TMA_DGRAD) {  // output grid = the input pixel grid H x W; boxes over dY [B][OH][OW][Cout]
-        const int R = g.W >= 1 && g.W <= 128 ? std::min(g.H, 128 / g.W) : 0;
-        return eb == 4 && g.s == 1 && R >= 1 && (g.Cout * eb) % 128 == 0 && g.C % 32 == 0 && g.C <= 64 && g.W <= 256 && R <= 256;
+    if (g.mode == CONV_TMA_DGRAD) {  // rows = the pixels of one residue class of the input grid; boxes over dY [B][OH][OW][Cout]
+        if (g.s < 1 || g.s > 2 || g.W < 1 || g.H < 1) return false;  // s*s <= 4 class maps (TcParams::tmC4)
+        const int cols = cdiv(g.W, g.s), rows = cdiv(g.H, g.s);
+        if (cols > 128) return false;
+        const int R = std::min(rows, 128 / cols);
+        // dY channel blocks of 128 bytes (K-major A), C <= 64 output columns whose rows are whole 16-byte chunks, W boxes of MN_BOX
+        return R >= 1 && R <= 256 && cols <= 256 && (g.Cout * eb) % 128 == 0 && g.C <= 64 && (g.C * eb) % 64 == 0 && g.ks >= g.s;
     }
     if (g.mode == CONV_TMA) {
         if (g.OW > 128 || g.OW < 1) return false;
@@ -338,26 +342,46 @@ zoo_status tc_conv_gemm(const ConvGeom &g, const Operand &Wop, int M, int N, int
     ZOO_REQUIRE(tc_conv_supported(g, Wop.is_bf16) && M > 0 && N >= 8 && ((uintptr_t)Wop.p & 15) == 0, "tc_conv_gemm: unsupported geometry");
     if (g.mode == CONV_TMA) return tc_conv_tma(g, Wop, M / (g.OH * g.OW), N, K, epi, ws, ws_elems, st);
     if (g.mode == CONV_TMA_DGRAD) {
-        // the kernel's "output grid" fields describe the GEMM's rows = input pixels; dY plays the activation tensor
+        // data gradient by sub-pixel decomposition (kernel: GA = 2 with mode CONV_TMA_DGRAD): grid.z = the s*s residue classes
         const int images = M / (g.H * g.W);
+        const int eb = Wop.is_bf16 ? 2 : 4, bk = 128 / eb, mn_box = 128 / eb;
+        const bool x3 = eb == 4 && epi.tf32_passes == 3;
+        ZOO_REQUIRE(!Wop.kmajor && K == g.ks * g.ks * g.Cout && N == g.C && epi.out && ((uintptr_t)epi.out & 15) == 0 && (epi.out_bf16 != 0) == (eb == 2),
+                    "tc_conv_gemm: bad operands for the TMA data gradient");
         ConvGeom d = g;
-        d.OH = g.H; d.OW = g.W;        // rows of the GEMM: input pixels
-        d.R = std::min(g.H, 128 / g.W); d.tpi = cdiv(g.H, d.R); d.cblocks = (g.Cout * 4) / 128; d.first = 0;
-        const int eb = 4, bk = 32;
-        const bool x3 = epi.tf32_passes == 3;
-        ZOO_REQUIRE(!Wop.kmajor && !Wop.is_bf16 && K == g.ks * g.ks * g.Cout, "tc_conv_gemm: bad operands for the TMA data gradient");
-        const int BN = N <= 32 ? 32 : 64;
-        dim3 grid(images * d.tpi, cdiv(N, BN), 1);
+        const int cols = cdiv(g.W, g.s), rows = cdiv(g.H, g.s);
+        d.R = std::min(rows, 128 / cols); d.tpi = cdiv(rows, d.R); d.cblocks = (g.Cout * eb) / 128; d.first = 0;
+        const int BN = eb == 2 ? 64 : (N <= 32 ? 32 : 64);  // bf16 MN-major W boxes are 64 columns wide (N = 32: the upper half is never stored)
+        dim3 grid(images * d.tpi, 1, g.s * g.s);
         TcParams P;
-        P.M = M; P.N = N; P.K = K; P.kb_per_split = K / bk; P.epi = epi; P.ws = nullptr; P.ctr = nullptr; P.dbg = nullptr; P.conv = d;
+        const int kt = cdiv(g.ks, g.s);
+        P.M = M; P.N = N; P.K = K; P.kb_per_split = kt * kt * d.cblocks; P.epi = epi; P.ws = nullptr; P.ctr = nullptr; P.dbg = nullptr; P.conv = d;
+        P.tpi_max = d.tpi; P.tma_store = 2;
+        const int esz = eb;
+        P.ts_span = std::min(128, N * esz);
+        const CUtensorMapSwizzle osw = P.ts_span == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (P.ts_span == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+        EncodeTiledFn enc = get_encode();
+        ZOO_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+        for (int py = 0; py < g.s; ++py)
+            for (int px = 0; px < g.s; ++px) {  // the class's strided view of dX [images][H][W][C]
+                const int rows_c = (g.H - py + g.s - 1) / g.s, cols_c = (g.W - px + g.s - 1) / g.s;
+                const cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)cols_c, (cuuint64_t)rows_c, (cuuint64_t)images};
+                const cuuint64_t str[3] = {(cuuint64_t)g.s * g.C * esz, (cuuint64_t)g.s * g.W * g.C * esz, (cuuint64_t)g.H * g.W * g.C * esz};
+                const cuuint32_t box[4] = {(cuuint32_t)(P.ts_span / esz), (cuuint32_t)cols, (cuuint32_t)d.R, 1};
+                const cuuint32_t es[4] = {1, 1, 1, 1};
+                void *base = (uint8_t *)epi.out + ((size_t)py * g.W + px) * g.C * esz;
+                CUresult r = enc(&P.tmC4[py * g.s + px], eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, str, box, es,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, osw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) { set_err("tc_conv_gemm: output map of class (%d,%d) failed (%d)", py, px, (int)r); return ZOO_CUDA_ERROR; }
+            }
         CUtensorMap tmA, tmB;
         const cuuint64_t sC = (cuuint64_t)g.Cout * eb, sW = (cuuint64_t)g.OW * sC, sH = (cuuint64_t)g.OH * sW;
         const cuuint64_t dims[4] = {(cuuint64_t)g.Cout, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)images};
         const cuuint64_t str[3] = {sC, sW, sH};
-        const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)g.W, (cuuint32_t)d.R, 1};
+        const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)cols, (cuuint32_t)d.R, 1};
         const cuuint32_t es[4] = {1, 1, 1, 1};
         ZOO_TRY(make_map4(&tmA, g.x, eb, dims, str, box, es));
-        ZOO_TRY(make_map(&tmB, Wop.p, eb, Wop.ld, g.Cout, Wop.ld, 32, bk, true));  // W as [Cout][ks*ks*C]: boxes at tap offsets
+        ZOO_TRY(make_map(&tmB, Wop.p, eb, Wop.ld, g.Cout, Wop.ld, mn_box, bk, true));  // W as [Cout][ks*ks*C]: boxes at tap offsets
         return tc_launch(eb, x3, 3, BN, true, false, tmA, tmB, P, grid, st);
     }
     const int eb = Wop.is_bf16 ? 2 : 4;

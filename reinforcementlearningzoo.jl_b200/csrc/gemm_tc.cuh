@@ -153,6 +153,11 @@ struct TcParams {
     int tma_store = 0;
     int span = 128;  // bytes of K per stage row (TcCfg SPAN); 64 = the SWIZZLE_64B convolution variants
     CUtensorMap tmC;
+    // tma_store == 2 (TMA data gradient): the whole tile is staged [rows][ts_span-byte column blocks] and stored with one 4-D box
+    // per column block into the class's strided view of dX; one map per residue class (grid.z), tpi_max = tiles per image of the
+    // largest class (grid.x = images * tpi_max; smaller classes' surplus CTAs exit)
+    int ts_span = 128, tpi_max = 1;
+    CUtensorMap tmC4[4];
 };
 
 extern unsigned long long *g_tc_dbg;  // set by zoo_test_gemm_trace (defined in gemm_tc.cu)
@@ -492,17 +497,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int m0 = blockIdx.x * BM, vrows = min(BM, P.M - (int)blockIdx.x * BM);  // first output row / valid rows of this M tile
     int cimg = 0, coy0 = 0;
-    if (GA == 2) {
+    // TMA data gradient (GA = 2, CONV_TMA_DGRAD): geometry of this CTA's residue class (see common.cuh)
+    const bool dgrad = GA == 2 && P.conv.mode == CONV_TMA_DGRAD;
+    int cls_py = 0, cls_px = 0, cols_c = 0, cls_R = 0, ky0 = 0, kx0 = 0, kt_x = 1, dy0 = 0, dx0 = 0, cls_kb = 0;
+    if (GA == 2 && !dgrad) {
         cimg = blockIdx.x / P.conv.tpi;
         coy0 = (blockIdx.x - cimg * P.conv.tpi) * P.conv.R;
         m0 = (cimg * P.conv.OH + coy0) * P.conv.OW;
         vrows = min(P.conv.R, P.conv.OH - coy0) * P.conv.OW;
     }
+    if (dgrad) {
+        const ConvGeom &g = P.conv;
+        cls_py = blockIdx.z / g.s; cls_px = blockIdx.z - cls_py * g.s;
+        // every class is tiled like the largest one (ceil(H/s) x ceil(W/s) pixels, the A boxes are the same shape for all):
+        // pixels a smaller class does not have are computed and then clipped by its output map
+        const int rows_c = (g.H + g.s - 1) / g.s;
+        cols_c = (g.W + g.s - 1) / g.s;
+        cls_R = min(rows_c, BM / cols_c);
+        cimg = blockIdx.x / P.tpi_max;
+        coy0 = (blockIdx.x - cimg * P.tpi_max) * cls_R;
+        vrows = min(cls_R, rows_c - coy0) * cols_c;
+        m0 = 0;
+        ky0 = (cls_py + g.p) % g.s; kx0 = (cls_px + g.p) % g.s;
+        const int kt_y = (g.ks - ky0 + g.s - 1) / g.s;
+        kt_x = (g.ks - kx0 + g.s - 1) / g.s;
+        dy0 = (cls_py + g.p - ky0) / g.s; dx0 = (cls_px + g.p - kx0) / g.s;
+        cls_kb = kt_y * kt_x * g.cblocks;
+    }
     const int n0 = blockIdx.y * BN;
     if (threadIdx.x == 0) dbg_stamp(P, 0);
-    const int total_kb = GA == 4 ? P.K : (P.K + C::BK - 1) / C::BK;  // GA = 4: P.K counts K-blocks (images x row groups)
-    const int kb0 = blockIdx.z * P.kb_per_split;
-    const int kb1 = min(total_kb, kb0 + P.kb_per_split);
+    const int total_kb = GA == 4 ? P.K : (dgrad ? cls_kb : (P.K + C::BK - 1) / C::BK);  // GA = 4: P.K counts K-blocks (images x row groups)
+    const int kb0 = dgrad ? 0 : blockIdx.z * P.kb_per_split;
+    const int kb1 = dgrad ? total_kb : min(total_kb, kb0 + P.kb_per_split);
     const int nkb = kb1 - kb0;  // host guarantees >= 1
     // 3xTF32: the K loop is cut into chains of CHAIN K-blocks that alternate between two TMEM accumulators; the
     // converter warps sum finished chains in registers with round-to-nearest fp32 adds, because a TMEM accumulator
@@ -570,16 +596,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (i == 0) dbg_stamp(P, 2);
                     continue;
                 }
-                mbar_expect_tx(&full_bar[s], GA == 1 ? C::B_BYTES : (GA == 2 ? P.conv.R * P.conv.OW * SPAN + C::B_BYTES : C::RAW_BYTES));
+                mbar_expect_tx(&full_bar[s], GA == 1 ? C::B_BYTES : (GA == 2 ? (dgrad ? cls_R * cols_c : P.conv.R * P.conv.OW) * SPAN + C::B_BYTES : C::RAW_BYTES));
                 const int k0 = (kb0 + i) * C::BK;
                 if (GA == 2) {
                     const ConvGeom &g = P.conv;
                     const int kb = kb0 + i;
                     int c0, c1, c2;
                     if (g.first) { c0 = 0; c1 = 0; c2 = coy0 * g.s + kb; }  // K-block = kernel row ky of the padded frame stack
-                    else if (g.mode == CONV_TMA_DGRAD) {  // stride-1 data gradient: a forward conv over dY with mirrored taps
-                        const int tap = kb / g.cblocks, ky = tap / g.ks, kx = tap - ky * g.ks;
-                        c0 = (kb - tap * g.cblocks) * C::BK; c1 = g.p - kx; c2 = coy0 + g.p - ky;
+                    else if (g.mode == CONV_TMA_DGRAD) {  // data gradient: a stride-1 conv of dY with the class's (mirrored) sub-kernel
+                        const int t = kb / g.cblocks, a = t / kt_x, b = t - a * kt_x;
+                        c0 = (kb - t * g.cblocks) * C::BK; c1 = dx0 - b; c2 = coy0 + dy0 - a;
                     } else {
                         const int tap = kb / g.cblocks, ky = tap / g.ks, kx = tap - ky * g.ks;
                         c0 = (kb - tap * g.cblocks) * C::BK; c1 = kx - g.p; c2 = coy0 * g.s + ky - g.p;
@@ -603,7 +629,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else {
                     // conv dgrad: K runs over (tap, o); tap t's [Cout][C] slice of W sits at column offset t*C of [Cout][ks*ks*C]
                     int nb = n0, kb = k0;
-                    if (GA != 0) { const int tap = k0 / P.conv.Cout; nb = n0 + tap * P.conv.C; kb = k0 - tap * P.conv.Cout; }
+                    if (GA != 0 && !dgrad) { const int tap = k0 / P.conv.Cout; nb = n0 + tap * P.conv.C; kb = k0 - tap * P.conv.Cout; }
+                    if (dgrad) {  // class tap (a, b) -> kernel tap (ky0 + a s, kx0 + b s)
+                        const int kbi = kb0 + i, t = kbi / P.conv.cblocks, a = t / kt_x, b = t - a * kt_x;
+                        const int tap = (ky0 + a * P.conv.s) * P.conv.ks + kx0 + b * P.conv.s;
+                        nb = n0 + tap * P.conv.C; kb = (kbi - t * P.conv.cblocks) * C::BK;
+                    }
 #pragma unroll
                     for (int h = 0; h < BN / C::MN_BOX; ++h)
                         tma_load_2d(sb + h * C::BOX_BYTES, &tmB, &full_bar[s], nb + h * C::MN_BOX, kb);
@@ -859,6 +890,111 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // bf16 output, plain row-major store: 64 columns at a time so that every lane writes a packed bf16x2 (128-byte row
         // segments instead of 64-byte ones) -- the wide, K-short GEMMs (IQN phi: K = 64, 0.5 GB of output) are store-bound
+        if (GA == 2 && P.tma_store == 2) {
+            // Whole-tile TMA store (data gradient).  Lane = tile row: every thread converts its row (32 columns per tcgen05.ld),
+            // applies relu' of the pixel it belongs to and writes 16-byte chunks into the staging tile [column block][row][ts_span
+            // bytes] (swizzled like the tensor map: conflict-free); one thread then issues one 4-D box per column block into the
+            // residue class's strided view of dX -- rows past the class's last row are clipped by the map.
+            const int vN = min(BN, Nn - n0);
+            const int esz = out_bf16 ? 2 : 4;
+            const int span = P.ts_span;
+            const int r = q * 32 + lane;
+            const uint32_t swz = span == 128 ? (uint32_t)(r & 7) : (span == 64 ? (uint32_t)((r >> 1) & 3) : 0u);
+            const uint32_t stg0 = smem_u32(smem);
+            const uint8_t *mrow = nullptr;
+            if (maskp && r < vrows) {
+                const int ry = r / cols_c, rx = r - ry * cols_c;
+                const int y = (coy0 + ry) * P.conv.s + cls_py, xx = rx * P.conv.s + cls_px;
+                if (y < P.conv.H && xx < P.conv.W)
+                    mrow = (const uint8_t *)maskp + ((((long long)cimg * P.conv.H + y) * P.conv.W + xx) * msm + n0) * (mask_bf16 ? 2 : 4);
+            }
+#pragma unroll
+            for (int c = 0; c < BN; c += 32) {
+                if (c < vN) {
+                    uint32_t rr[32];
+                    float x[32];
+                    tmem_ld32(tq + (uint32_t)(lb * C::ACC_COLS + c), rr);
+                    if (X3) {
+                        uint32_t r2[32];
+                        tmem_ld32(tq + (uint32_t)(lb * C::ACC_COLS + BN + c), r2);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = __fadd_rn(__fadd_rn(__uint_as_float(rr[j]), __uint_as_float(r2[j])), acc[X3 ? c + j : 0]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(rr[j]);
+                    }
+                    if (bias_mode == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] += (n0 + c + j < Nn) ? __ldg(e.bias + n0 + c + j) : 0.f;
+                    }
+                    if (relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+                    }
+                    if (maskp) {
+                        if (!mrow) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) x[j] = 0.f;
+                        } else if (mask_bf16) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                uint4 mk = make_uint4(0u, 0u, 0u, 0u);
+                                if (c + j4 * 8 + 8 <= vN) mk = __ldg(reinterpret_cast<const uint4 *>(mrow + (c + j4 * 8) * 2));
+                                const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    if (!(__uint_as_float(mw[i] << 16) > 0.f)) x[j4 * 8 + 2 * i] = 0.f;
+                                    if (!(__uint_as_float(mw[i] & 0xffff0000u) > 0.f)) x[j4 * 8 + 2 * i + 1] = 0.f;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (c + j4 * 4 + 4 <= vN) mk = __ldg(reinterpret_cast<const float4 *>(mrow + (c + j4 * 4) * 4));
+                                if (!(mk.x > 0.f)) x[j4 * 4] = 0.f;
+                                if (!(mk.y > 0.f)) x[j4 * 4 + 1] = 0.f;
+                                if (!(mk.z > 0.f)) x[j4 * 4 + 2] = 0.f;
+                                if (!(mk.w > 0.f)) x[j4 * 4 + 3] = 0.f;
+                            }
+                        }
+                    }
+                    if (out_bf16) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const __nv_bfloat162 hh = __floats2bfloat162_rn(x[j4 * 8 + 2 * i], x[j4 * 8 + 2 * i + 1]);
+                                pk[i] = *reinterpret_cast<const uint32_t *>(&hh);
+                            }
+                            const int off = c * 2 + j4 * 16, box = off / span, chunk = (off - box * span) >> 4;
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg0 + (uint32_t)(box * BM * span + r * span) + (((uint32_t)chunk ^ swz) << 4)),
+                                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                        }
+                    } else {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const int off = c * 4 + j4 * 16, box = off / span, chunk = (off - box * span) >> 4;
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg0 + (uint32_t)(box * BM * span + r * span) + (((uint32_t)chunk ^ swz) << 4)),
+                                         "r"(__float_as_uint(x[j4 * 4])), "r"(__float_as_uint(x[j4 * 4 + 1])), "r"(__float_as_uint(x[j4 * 4 + 2])),
+                                         "r"(__float_as_uint(x[j4 * 4 + 3])) : "memory");
+                        }
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) {
+                const int nbox = (vN * esz + span - 1) / span;
+                for (int bx = 0; bx < nbox; ++bx)
+                    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&P.tmC4[blockIdx.z]),
+                                 "r"(stg0 + (uint32_t)(bx * BM * span)), "r"(n0 + bx * (span / esz)), "r"(0), "r"(coy0), "r"(cimg)
+                                 : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            }
+        } else
         if (BN >= 64 && !X3 && GA == 0 && P.tma_store) {
             // TMA-store epilogue.  tcgen05.ld leaves lane = tile row with 32 consecutive columns in registers -- exactly one
             // 64-byte half of a 128-byte row of the staging block, so the values go to shared memory as four 16-byte chunks per
@@ -1265,10 +1401,13 @@ static zoo_status tc_launch_mode(int kind, int BN, bool ak, bool bk, const CUten
     }
     if (kind == 0) return launch_tc_bn<EB, X3>(BN, ak, bk, tmA, tmB, P, grid, st);
     if (kind == 1) return launch_conv_bn<EB, X3>(BN, bk, tmB, P, grid, st);
-    if (kind == 3) {  // TMA-im2col data gradient: MN-major weight operand (fp32 nets; Cin <= 64)
-        if (EB != 4) { set_err("tc_conv: the TMA data-gradient path is fp32-storage only"); return ZOO_BAD_ARG; }
-        if (BN == 32) return launch_conv_tma<4, 32, X3, false>(tmA, tmB, P, grid, st);
-        if (BN == 64) return launch_conv_tma<4, 64, X3, false>(tmA, tmB, P, grid, st);
+    if (kind == 3) {  // TMA-im2col data gradient: MN-major weight operand (Cin <= 64)
+        if constexpr (EB == 4) {
+            if (BN == 32) return launch_conv_tma<4, 32, X3, false>(tmA, tmB, P, grid, st);
+            if (BN == 64) return launch_conv_tma<4, 64, X3, false>(tmA, tmB, P, grid, st);
+        } else {
+            if (BN == 64) return launch_conv_tma<2, 64, false, false>(tmA, tmB, P, grid, st);
+        }
         set_err("tc_conv: the TMA data-gradient path covers Cin <= 64");
         return ZOO_BAD_ARG;
     }

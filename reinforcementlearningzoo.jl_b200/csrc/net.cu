@@ -670,10 +670,10 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
             ConvGeom g;
             g.x = L.dout; g.mode = CONV_DGRAD; g.C = L.cin; g.H = L.ih; g.W = L.iw; g.ks = L.ksize; g.s = L.stride; g.p = L.pad;
             g.OH = L.oh; g.OW = L.ow; g.Cout = L.cout;
-            if (tma_conv_enabled() && tma_dgrad_enabled() && !bf && net->prec != ZOO_PREC_FP32_SIMT && !Wn.is_bf16) {
+            if (tma_conv_enabled() && tma_dgrad_enabled() && net->prec != ZOO_PREC_FP32_SIMT && Wn.is_bf16 == bf) {
                 ConvGeom gt = g;
                 gt.mode = CONV_TMA_DGRAD;
-                if (tc_conv_supported(gt, 0)) g = gt;  // stride-1 conv: dY boxes fetched by TMA, no dcols, no col2im
+                if (tc_conv_supported(gt, bf)) g = gt;  // dY boxes fetched by TMA per residue class, no dcols, no col2im
             }
             if ((g.mode == CONV_TMA_DGRAD || implicit_conv_enabled()) && net->prec != ZOO_PREC_FP32_SIMT && Wn.is_bf16 == dy_bf && dy_bf == bf &&
                 L.cin >= 8 && tc_conv_supported(g, bf)) {
