@@ -126,6 +126,9 @@ ZOO_API zoo_status zoo_opt_get_state(const zoo_opt *opt, int32_t slot, int32_t t
 ZOO_API zoo_status zoo_opt_set_state(zoo_opt *opt, int32_t slot, int32_t tensor_id, const float *host, int64_t n_elem);
 ZOO_API zoo_status zoo_opt_get_step(const zoo_opt *opt, int64_t *t);
 ZOO_API zoo_status zoo_opt_set_step(zoo_opt *opt, int64_t t);
+/* counter of the on-device Philox tau stream (IQN updates that draw their own quantiles tick it once); part of a checkpoint */
+ZOO_API zoo_status zoo_opt_get_rng(const zoo_opt *opt, uint64_t *counter);
+ZOO_API zoo_status zoo_opt_set_rng(zoo_opt *opt, uint64_t counter);
 
 /* ------------------------------------------------------------------ learners ------------ */
 enum { ZOO_LEARNER_BASIC_DQN = 0,       /* basic_dqn.jl:69-90        */

@@ -73,6 +73,8 @@ SIGNATURES = {
     "zoo_opt_set_state": [V, I32, I32, V, I64],
     "zoo_opt_get_step": [V, C.POINTER(I64)],
     "zoo_opt_set_step": [V, I64],
+    "zoo_opt_get_rng": [V, C.POINTER(C.c_uint64)],
+    "zoo_opt_set_rng": [V, C.c_uint64],
     "zoo_learner_create": [C.POINTER(LearnerCfg), V, V, V, V, PV],
     "zoo_learner_destroy": [V],
     "zoo_learner_update": [V, C.POINTER(Batch), V, V],

@@ -1,7 +1,8 @@
 """Checkpoints: the reference saves ``BSON.@save "policy.bson" policy`` after ``cpu(p)``
 (src/experiments/atari/Dopamine_DQN_Atari.jl:123-126).  This module writes the learner's state -- online / target parameters,
 optimiser state and step, the learner's counters and hyper-parameters -- as one BSON document (bsonspec.org v1.1) and reads it
-back into a learner, bit-exactly.
+back into a learner: parameters, optimiser state, ADAM's beta^t (rebuilt by the same repeated fp64 multiplication the run
+carried) and the counter of the on-device tau stream are restored bit-exactly.
 
 Arrays are lowered the way BSON.jl lowers ``Array{Float32,N}``: ``{tag: "array", type: {tag: "datatype", params: [], name:
 ["Core", "Float32"]}, size: [dims...], data: <binary>}`` with the *Julia* dimensions and column-major bytes (= the ABI bytes), so
@@ -146,8 +147,10 @@ def _approx_doc(app):
         t = C.c_int64()
         L.check(L.lib().zoo_opt_get_step(app.opt_h, C.byref(t)))
         n_slots = 2 if o.kind == L.OPT_ADAM else 1
+        rng = C.c_uint64()
+        L.check(L.lib().zoo_opt_get_rng(app.opt_h, C.byref(rng)))
         d["optimizer"] = {"kind": "ADAM" if o.kind == L.OPT_ADAM else "RMSProp", "eta": o.eta, "a": o.a, "b": o.b, "t": int(t.value),
-                          "state": [app.opt_state(s) for s in range(n_slots)]}
+                          "rng": int(rng.value), "state": [app.opt_state(s) for s in range(n_slots)]}
     return d
 
 
@@ -186,7 +189,8 @@ def _load_approx(app, d):
             for i, p in enumerate(tensors):
                 a = _abi(p)
                 L.check(L.lib().zoo_opt_set_state(app.opt_h, slot, i, a.ctypes.data, a.size))
-        L.check(L.lib().zoo_opt_set_step(app.opt_h, C.c_int64(int(o["t"]))))
+        L.check(L.lib().zoo_opt_set_step(app.opt_h, C.c_int64(int(o["t"]))))  # also rebuilds beta^t by repeated multiplication
+        L.check(L.lib().zoo_opt_set_rng(app.opt_h, C.c_uint64(int(o.get("rng", 0)))))
 
 
 def load_policy(path, learner):

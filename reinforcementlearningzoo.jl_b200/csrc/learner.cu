@@ -461,9 +461,32 @@ zoo_status zoo_opt_set_step(zoo_opt *o, int64_t t) {
     OptScalars h{};
     ZOO_CUDA(cudaDeviceSynchronize());
     ZOO_CUDA(cudaMemcpy(&h, o->sc, sizeof(h), cudaMemcpyDeviceToHost));
-    h.b1p = std::pow(o->a, (double)(t + 1)); h.b2p = std::pow(o->b, (double)(t + 1)); h.t = (unsigned long long)t;
+    // beta^(t+1) by the same repeated fp64 multiplication the run carried (opt_tick_kernel), so that a restored ADAM state is
+    // bit-identical to the one that was saved (std::pow can differ in the last bit)
+    double b1p = o->a, b2p = o->b;
+    for (int64_t i = 0; i < t; ++i) { b1p *= o->a; b2p *= o->b; }
+    h.b1p = b1p; h.b2p = b2p; h.t = (unsigned long long)t;
     ZOO_CUDA(cudaMemcpy(o->sc, &h, sizeof(h), cudaMemcpyHostToDevice));
     o->host_t = t;
+    return ZOO_OK;
+}
+
+// counter of the on-device tau stream (IQN: one tick per update that drew its own quantiles); saved / restored by checkpoints
+zoo_status zoo_opt_get_rng(const zoo_opt *o, uint64_t *counter) {
+    ZOO_REQUIRE(o && counter, "zoo_opt_get_rng: null argument");
+    OptScalars h{};
+    ZOO_CUDA(cudaDeviceSynchronize());
+    ZOO_CUDA(cudaMemcpy(&h, o->sc, sizeof(h), cudaMemcpyDeviceToHost));
+    *counter = h.rng;
+    return ZOO_OK;
+}
+zoo_status zoo_opt_set_rng(zoo_opt *o, uint64_t counter) {
+    ZOO_REQUIRE(o, "zoo_opt_set_rng: null argument");
+    OptScalars h{};
+    ZOO_CUDA(cudaDeviceSynchronize());
+    ZOO_CUDA(cudaMemcpy(&h, o->sc, sizeof(h), cudaMemcpyDeviceToHost));
+    h.rng = counter;
+    ZOO_CUDA(cudaMemcpy(o->sc, &h, sizeof(h), cudaMemcpyHostToDevice));
     return ZOO_OK;
 }
 

@@ -79,6 +79,19 @@ class _Learner:
         override the on-device RNG (used for parity)."""
         lib = L.lib()
         b, keep = self._batch(batch, tau, tau_prime)
+        if b.on_device:
+            # the update may return before the device has read the batch (want_loss=False): keep the tensors alive until the next
+            # update or sync, and make the learner's stream wait for the stream that produced them (no host block)
+            self._keep = keep
+            try:
+                import torch
+                cur = torch.cuda.current_stream(keep[0].device)
+                if cur.cuda_stream != self.stream():
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    torch.cuda.ExternalStream(self.stream(), device=keep[0].device).wait_event(ev)
+            except ImportError:
+                pass
         per = batch.get("priority") is not None
         loss = C.c_float(0)
         prio = np.empty(b.B, np.float32) if (per and want_priorities) else None
@@ -111,6 +124,7 @@ class _Learner:
 
     def sync(self):
         L.check(L.lib().zoo_learner_sync(self.h))
+        self._keep = None
 
     def stream(self):
         s = C.c_void_p()
