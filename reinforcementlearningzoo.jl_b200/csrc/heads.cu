@@ -37,14 +37,6 @@ __device__ float block_max(float v, float *red) {
     return s;
 }
 
-__device__ __forceinline__ float sample_scale(const HeadArgs &h, int b) {
-    // dot(w, l) * 1//B with w ./= maximum(w)  (prioritized_dqn.jl:126,141) or mean (dqn.jl:137)
-    if (h.w_raw) return __fmul_rn(__fdiv_rn(h.w_raw[b], h.w_max[0]), h.inv_B);
-    return h.inv_B;
-}
-// Julia argmax/findmax order: NaN counts as the maximum, ties go to the lowest index (q8)
-__device__ __forceinline__ bool better(float v, float best) { return v > best || (isnan(v) && !isnan(best)); }
-
 // w = 1f0 ./ ((priority .+ 1f-10) .^ beta)  -- prioritized_dqn.jl:125, rainbow.jl:171, iqn.jl:197
 __global__ void __launch_bounds__(1024) per_weights_kernel(const float *__restrict__ priority, float beta, int B,
                                                            float *__restrict__ w_raw, float *__restrict__ w_max) {
@@ -66,46 +58,7 @@ __global__ void dqn_head_kernel(int kind, int double_dqn, HeadArgs h, const floa
     pdl_trigger();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= h.B) return;
-    const int A = h.A;
-    const uint8_t *mk = h.mask ? h.mask + (size_t)b * A : nullptr;
-    float q2;
-    int amax = 0;
-    if (kind == ZOO_LEARNER_BASIC_DQN) {
-        const float *qn = q_on + (size_t)(h.B + b) * A;  // Q(s') of the same network
-        float best = qn[0];
-        for (int a = 1; a < A; ++a) if (better(qn[a], best)) { best = qn[a]; amax = a; }
-        q2 = best;
-    } else if (double_dqn) {
-        const float *qn = q_on + (size_t)(h.B + b) * A;  // online Q(s') selects, target evaluates
-        float best = qn[0] + ((mk && !mk[0]) ? -INFINITY : 0.f);
-        for (int a = 1; a < A; ++a) {
-            float v = qn[a] + ((mk && !mk[a]) ? -INFINITY : 0.f);
-            if (better(v, best)) { best = v; amax = a; }
-        }
-        q2 = q_t[(size_t)b * A + amax];
-    } else {
-        const float *qn = q_t + (size_t)b * A;
-        float best = qn[0] + ((mk && !mk[0]) ? -INFINITY : 0.f);
-        for (int a = 1; a < A; ++a) {
-            float v = qn[a] + ((mk && !mk[a]) ? -INFINITY : 0.f);
-            if (better(v, best)) { best = v; amax = a; }
-        }
-        q2 = best;
-    }
-    // G = r .+ gamma^n .* (1 .- t) .* q'
-    const float disc = __fmul_rn(gamma_n, h.terminal[b] ? 0.f : 1.f);
-    const float G = __fadd_rn(h.reward[b], __fmul_rn(disc, q2));
-    const int a_b = h.action[b];
-    const float q = q_on[(size_t)b * A + a_b];
-    // huber_loss(G, q; delta = 1): strict < mask (q4)
-    const float e = __fsub_rn(G, q), ae = fabsf(e);
-    const bool quad = ae < 1.0f;
-    h.per_sample[b] = quad ? __fmul_rn(__fmul_rn(ae, ae), 0.5f) : __fsub_rn(ae, 0.5f);
-    const float dG = quad ? e : (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f));
-    const float sc = sample_scale(h, b);
-    for (int a = 0; a < A; ++a) dout[(size_t)b * A + a] = a == a_b ? -dG * sc : 0.f;
-    if (kind == ZOO_LEARNER_BASIC_DQN)  // gradient also flows through the target (q3)
-        for (int a = 0; a < A; ++a) dout[(size_t)(h.B + b) * A + a] = a == amax ? dG * disc * sc : 0.f;
+    dqn_head_sample(kind, double_dqn, h, b, q_on, q_t, gamma_n, dout);
 }
 
 // rainbow.jl:146-191 + project_distribution rainbow.jl:204-221 + logitcrossentropy (Dopamine_Rainbow_Atari.jl:54)

@@ -16,6 +16,11 @@ int dp_world(const zoo_dp *dp);
 zoo_status dp_alloc_registered(zoo_dp *dp, size_t bytes, void **ptr, void **handle);
 void dp_deregister(zoo_dp *dp, void *handle);
 
+bool dqn_tail_supported(int N, long long K, int x_bf16, int rows_fwd);
+zoo_status dqn_tail(int kind, int double_dqn, const HeadArgs &h, const void *X, int x_bf16, const float *W, const float *bias, const float *q_t, float gamma_n,
+                    float beta, int rows_fwd, int rows_bwd, long long K, int relu_prev, float *q_out, float *dq_out, void *dX, float *dW, float *db,
+                    float *db_prev, float *loss, float *prio_out, cudaStream_t st);
+
 struct OptScalars {
     double b1p, b2p;        // beta^t carried like Flux's per-array state (starts at beta)
     float c1, c2;           // 1/(1-b1p), 1/(1-b2p) for the step being applied
@@ -245,7 +250,38 @@ static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bo
         h.w_raw = L->d_wraw; h.w_max = L->d_wmax;
     }
     int bwd_rows = B, n_tau = 0;
-    if (c.kind == ZOO_LEARNER_BASIC_DQN) {
+    // DQN family at Dopamine batch sizes: head layer forward + TD head + loss + head layer backward in ONE launch (narrow.cu)
+    bool tail = false;
+    if ((c.kind == ZOO_LEARNER_BASIC_DQN || c.kind == ZOO_LEARNER_DQN || c.kind == ZOO_LEARNER_PRIORITIZED_DQN) && on->desc.kind == ZOO_NET_CHAIN &&
+        on->a.layers.size() >= 2) {
+        static const bool tail_on = [] { const char *e = getenv("ZOO_DQN_TAIL"); return !(e && e[0] == '0'); }();
+        const LayerExec &Lh = on->a.layers.back();
+        const int dbl = c.kind == ZOO_LEARNER_DQN && c.double_dqn;
+        const int rows_fwd = (c.kind == ZOO_LEARNER_BASIC_DQN || dbl) ? 2 * B : B;
+        tail = tail_on && Lh.kind == ZOO_LAYER_DENSE && Lh.out_fp32 && !Lh.relu && !(split && on->tensors[Lh.wt].offset == on->late_off) &&
+               dqn_tail_supported(c.n_actions, Lh.K, on->prec == ZOO_PREC_BF16, rows_fwd);
+        if (tail) {
+            const LayerExec &Lp = on->a.layers[on->a.layers.size() - 2];
+            bwd_rows = c.kind == ZOO_LEARNER_BASIC_DQN ? 2 * B : B;
+            if (c.kind != ZOO_LEARNER_BASIC_DQN) ZOO_TRY(target_forward(L, tg, s2_ptr, nullptr, 0, st));  // side lane, rejoined before the tail
+            on->skip_head = true;
+            zoo_status s = net_forward(on, s_ptr, L->obs_dtype, rows_fwd, nullptr, 0, st, bwd_rows);
+            if (s == ZOO_OK && c.kind != ZOO_LEARNER_BASIC_DQN) s = target_join(L, st);
+            if (s == ZOO_OK) {
+                prof_label("tail:t%d[%dx%dx%lld]", Lh.wt, rows_fwd, c.n_actions, Lh.K);
+                s = dqn_tail(c.kind, dbl, h, Lp.out, on->prec == ZOO_PREC_BF16, on->params + on->tensors[Lh.wt].offset, on->params + on->tensors[Lh.bt].offset,
+                             tg ? tg->out_final : nullptr, c.kind == ZOO_LEARNER_BASIC_DQN ? c.gamma : L->gamma_n, c.beta_priority, rows_fwd, bwd_rows, Lh.K,
+                             Lp.relu, on->out_final, on->dout_final, Lp.dout, on->grads + on->tensors[Lh.wt].offset, on->grads + on->tensors[Lh.bt].offset,
+                             on->grads + on->tensors[Lp.bt].offset, L->d_loss, L->d_prio, st);
+            }
+            if (s == ZOO_OK) s = net_backward(on, L->obs_dtype, s_ptr, bwd_rows, 0, st);
+            on->skip_head = false;
+            on->late_cb = nullptr;
+            ZOO_TRY(s);
+        }
+    }
+    if (tail) {
+    } else if (c.kind == ZOO_LEARNER_BASIC_DQN) {
         ZOO_TRY(net_forward(on, s_ptr, L->obs_dtype, 2 * B, nullptr, 0, st, 2 * B));  // Q([s; s'])
         prof_label("head"); ZOO_TRY(launch_dqn_head(c.kind, 0, h, on->out_final, nullptr, c.gamma, on->dout_final, st));
         bwd_rows = 2 * B;
@@ -286,8 +322,10 @@ static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bo
         prof_label("head"); ZOO_TRY(launch_iqn_loss(h, c.N, c.N_prime, on->out_final, L->d_target, L->d_tau, c.kappa, on->dout_final, st));
         n_tau = c.N;
     }
-    prof_label("head"); ZOO_TRY(launch_loss_reduce(h, c.beta_priority, L->d_loss, L->d_prio, st));
-    ZOO_TRY(net_backward(on, L->obs_dtype, s_ptr, bwd_rows, n_tau, st));
+    if (!tail) {
+        prof_label("head"); ZOO_TRY(launch_loss_reduce(h, c.beta_priority, L->d_loss, L->d_prio, st));
+        ZOO_TRY(net_backward(on, L->obs_dtype, s_ptr, bwd_rows, n_tau, st));
+    }
     on->late_cb = nullptr;
     const long long early_end = split ? on->late_off : on->n_flat + 64;  // gradients (+ loss, in the last bucket) per collective
     if (L->dp) ZOO_TRY(dp_allreduce_sum(L->dp, on->grads, early_end, st));

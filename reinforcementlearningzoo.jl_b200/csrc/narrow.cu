@@ -7,7 +7,7 @@
 //                       gradient in ONE pass over X (they were four launches: colsum, wgrad GEMM, dgrad GEMM, colsum)
 // Reference layers: Dense(512, n_actions) at src/experiments/atari/Dopamine_DQN_Atari.jl:34 and the IQN header
 // Dopamine_IQN_Atari.jl:40-43 (rows = batch x quantiles, 32 768 at the bench size); differentiated at dqn.jl:135, iqn.jl:203.
-#include "common.cuh"
+#include "heads.cuh"
 
 namespace zoo {
 
@@ -237,6 +237,165 @@ zoo_status narrow_backward(const void *X, int x_bf16, const float *dY, const flo
         ZOO_CUDA(launch_pdl(narrow_bwd_kernel<bf16>, grid, block, smem, st, (const bf16 *)X, dY, W, (bf16 *)dX, dW, db, db_prev, (int)M, N, (int)K, relu_prev));
     else
         ZOO_CUDA(launch_pdl(narrow_bwd_kernel<float>, grid, block, smem, st, (const float *)X, dY, W, (float *)dX, dW, db, db_prev, (int)M, N, (int)K, relu_prev));
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+
+// ---------------------------------------------------------------- fused small-batch tail of the DQN-family update
+// One CTA does everything between "fc1's activations are ready" and "fc1's output gradient is ready" for BasicDQN / DQN /
+// PrioritizedDQN at Dopamine batch sizes (rows <= TAIL_ROWS):  Q = h W2^T + b2 for the online rows ([s; s'] when the learner
+// needs Q(s') of the online net), the TD target / Huber head per sample (dqn.jl:115-142), loss = sum_b scale_b * l_b and the new
+// priorities (prioritized_dqn.jl:141-143), then the head layer's whole backward as in narrow_bwd_kernel.  It replaces four
+// dependent launches on the critical path (narrow_fwd, dqn_head, loss_reduce, narrow_bwd).
+static constexpr int TAIL_ROWS = 128;
+template <typename T>
+__global__ void __launch_bounds__(256) dqn_tail_kernel(int kind, int double_dqn, HeadArgs h, const T *__restrict__ X, const float *__restrict__ W,
+                                                       const float *__restrict__ bias, const float *__restrict__ q_t, float gamma_n, float beta,
+                                                       int rows_fwd, int rows_bwd, int K, int relu_prev, float *__restrict__ q_out, float *__restrict__ dq_out,
+                                                       T *__restrict__ dX, float *__restrict__ dW, float *__restrict__ db, float *__restrict__ db_prev,
+                                                       float *__restrict__ loss, float *__restrict__ prio_out) {
+    extern __shared__ float sm_[];
+    const int N = h.A;
+    float *Ws = sm_;                               // [N][K]  (later the dW accumulator)
+    float *dbp_s = Ws + NARROW_NMAX * K;           // [K]
+    float *q_s = dbp_s + K;                        // [TAIL_ROWS][N]
+    float *dq_s = q_s + TAIL_ROWS * NARROW_NMAX;   // [TAIL_ROWS][N]
+    float *red = dq_s + TAIL_ROWS * NARROW_NMAX;   // [32] + dbn [N]
+    float *dbn_s = red + 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_wait();
+    for (int i = threadIdx.x; i < N * K / 4; i += 256) reinterpret_cast<float4 *>(Ws)[i] = __ldg(reinterpret_cast<const float4 *>(W) + i);
+    for (int i = threadIdx.x; i < K + 32 + NARROW_NMAX; i += 256) (i < K ? dbp_s[i] : red[i - K]) = 0.f;
+    for (int i = threadIdx.x; i < TAIL_ROWS * NARROW_NMAX; i += 256) dq_s[i] = 0.f;
+    __syncthreads();
+    // ---- forward: one warp per row, lanes stride over K
+    for (int m = warp; m < rows_fwd; m += 8) {
+        float acc[NARROW_NMAX];
+#pragma unroll
+        for (int n = 0; n < NARROW_NMAX; ++n) acc[n] = 0.f;
+        for (int k = lane; k < K; k += 32) {
+            const float x = sizeof(T) == 2 ? __bfloat162float(reinterpret_cast<const bf16 *>(X)[(long long)m * K + k]) : reinterpret_cast<const float *>(X)[(long long)m * K + k];
+#pragma unroll
+            for (int n = 0; n < NARROW_NMAX; ++n)
+                if (n < N) acc[n] = fmaf(x, Ws[n * K + k], acc[n]);
+        }
+#pragma unroll
+        for (int n = 0; n < NARROW_NMAX; ++n) {
+            float v = acc[n];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == n && n < N) { v += __ldg(bias + n); q_s[m * N + n] = v; q_out[(long long)m * N + n] = v; }
+        }
+    }
+    __syncthreads();
+    // ---- head + loss (dqn_head_sample writes per_sample to global; the scale is re-read below)
+    float part = 0.f;
+    for (int b = threadIdx.x; b < h.B; b += 256) {
+        dqn_head_sample(kind, double_dqn, h, b, q_s, q_t, gamma_n, dq_s);
+        const float l = h.per_sample[b];
+        part += l * sample_scale(h, b);
+        if (prio_out) prio_out[b] = powf(__fadd_rn(l, 1e-10f), beta);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float sum = 0.f;
+        for (int i = 0; i < 8; ++i) sum += red[i];
+        loss[0] = sum;
+    }
+    for (int i = threadIdx.x; i < rows_bwd * N; i += 256) dq_out[i] = dq_s[i];
+    pdl_trigger();
+    // ---- backward of the head layer (as narrow_bwd_kernel; dY = dq_s)
+    const int TPR = K >> 3, RPP = 256 / TPR;
+    const int kq = threadIdx.x % TPR, rl = threadIdx.x / TPR;
+    float w[NARROW_NMAX][8], dw[NARROW_NMAX][8], dbp[8], dbn[NARROW_NMAX];
+#pragma unroll
+    for (int n = 0; n < NARROW_NMAX; ++n) {
+        dbn[n] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { w[n][e] = n < N ? Ws[n * K + kq * 8 + e] : 0.f; dw[n][e] = 0.f; }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dbp[e] = 0.f;
+    __syncthreads();  // every thread holds its W columns: Ws becomes the dW accumulator
+    for (int i = threadIdx.x; i < NARROW_NMAX * K; i += 256) Ws[i] = 0.f;
+    for (int m = rl; m < rows_bwd; m += RPP) {
+        float x[8], dy[NARROW_NMAX];
+        if (sizeof(T) == 2) {
+            NarrowVec<bf16>::unpack(*reinterpret_cast<const uint4 *>(reinterpret_cast<const bf16 *>(X) + (long long)m * K + kq * 8), x);
+        } else {
+            const float4 a = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(X) + (long long)m * K + kq * 8);
+            const float4 b = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(X) + (long long)m * K + kq * 8 + 4);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        }
+#pragma unroll
+        for (int n = 0; n < NARROW_NMAX; ++n) dy[n] = n < N ? dq_s[m * N + n] : 0.f;
+        float dx[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float s2 = 0.f;
+#pragma unroll
+            for (int n = 0; n < NARROW_NMAX; ++n) s2 = fmaf(dy[n], w[n][e], s2);
+            if (relu_prev && !(x[e] > 0.f)) s2 = 0.f;
+            dx[e] = s2;
+            dbp[e] += s2;
+#pragma unroll
+            for (int n = 0; n < NARROW_NMAX; ++n) dw[n][e] = fmaf(dy[n], x[e], dw[n][e]);
+        }
+        if (sizeof(T) == 2) {
+            *reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(dX) + (long long)m * K + kq * 8) = NarrowVec<bf16>::pack(dx);
+        } else {
+            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(dX) + (long long)m * K + kq * 8) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(dX) + (long long)m * K + kq * 8 + 4) = make_float4(dx[4], dx[5], dx[6], dx[7]);
+        }
+        if (kq == 0) {
+#pragma unroll
+            for (int n = 0; n < NARROW_NMAX; ++n) dbn[n] += dy[n];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < NARROW_NMAX; ++n) {
+        if (n < N) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(Ws + n * K + kq * 8 + e, dw[n][e]);
+            if (kq == 0) atomicAdd(dbn_s + n, dbn[n]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(dbp_s + kq * 8 + e, dbp[e]);
+    __syncthreads();
+    // single CTA and the gradient buffer is all-zero on entry: plain adds
+    for (int i = threadIdx.x; i < N * K; i += 256) dW[i] += Ws[i];
+    if (db_prev)
+        for (int i = threadIdx.x; i < K; i += 256) db_prev[i] += dbp_s[i];
+    if (threadIdx.x < N) db[threadIdx.x] += dbn_s[threadIdx.x];
+}
+
+bool dqn_tail_supported(int N, long long K, int x_bf16, int rows_fwd) {
+    return narrow_supported(N, K, x_bf16) && rows_fwd <= TAIL_ROWS;
+}
+
+zoo_status dqn_tail(int kind, int double_dqn, const HeadArgs &h, const void *X, int x_bf16, const float *W, const float *bias, const float *q_t, float gamma_n,
+                    float beta, int rows_fwd, int rows_bwd, long long K, int relu_prev, float *q_out, float *dq_out, void *dX, float *dW, float *db,
+                    float *db_prev, float *loss, float *prio_out, cudaStream_t st) {
+    ZOO_REQUIRE(dqn_tail_supported(h.A, K, x_bf16, rows_fwd) && rows_bwd <= rows_fwd, "dqn_tail: unsupported shape");
+    const size_t smem = (size_t)(NARROW_NMAX * K + K + 2 * TAIL_ROWS * NARROW_NMAX + 32 + NARROW_NMAX) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        const int mx = (int)((NARROW_NMAX * 2048 + 2048 + 2 * TAIL_ROWS * NARROW_NMAX + 32 + NARROW_NMAX) * sizeof(float));
+        ZOO_CUDA(cudaFuncSetAttribute(dqn_tail_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        ZOO_CUDA(cudaFuncSetAttribute(dqn_tail_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        attr = true;
+    }
+    if (x_bf16)
+        ZOO_CUDA(launch_pdl(dqn_tail_kernel<bf16>, dim3(1), dim3(256), smem, st, kind, double_dqn, h, (const bf16 *)X, W, bias, q_t, gamma_n, beta, rows_fwd, rows_bwd,
+                            (int)K, relu_prev, q_out, dq_out, (bf16 *)dX, dW, db, db_prev, loss, prio_out));
+    else
+        ZOO_CUDA(launch_pdl(dqn_tail_kernel<float>, dim3(1), dim3(256), smem, st, kind, double_dqn, h, (const float *)X, W, bias, q_t, gamma_n, beta, rows_fwd,
+                            rows_bwd, (int)K, relu_prev, q_out, dq_out, (float *)dX, dW, db, db_prev, loss, prio_out));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }

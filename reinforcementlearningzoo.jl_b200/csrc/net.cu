@@ -20,7 +20,9 @@ static bool narrow_enabled() {
 // see DESIGN.md section 4), so they are opt-in: ZOO_IMPLICIT_CONV=1.
 // forward convs with TMA-fetched im2col rows (CONV_TMA) are the default where the layer geometry allows; ZOO_TMA_CONV=0 disables
 static bool tma_dgrad_enabled() {
-    static const bool on = [] { const char *e = getenv("ZOO_TMA_DGRAD"); return e ? atoi(e) != 0 : false; }();  // opt-in: parity-green, but 31 CTAs lose to the 279-CTA GEMM + col2im at B=32
+    // data gradients of the convolutions by sub-pixel decomposition with TMA-fetched dY boxes and a TMA store into the strided
+    // class view of dX: no dcols matrix, no col2im pass.  ZOO_TMA_DGRAD=0 restores GEMM + col2im.
+    static const bool on = [] { const char *e = getenv("ZOO_TMA_DGRAD"); return !(e && e[0] == '0'); }();
     return on;
 }
 static bool tma_conv_enabled() {
@@ -511,6 +513,7 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
     const void *cur = in;
     int cur_kind = in_kind;
     for (auto &L : ch.layers) {
+        if (net->skip_head && &ch == &net->a && &L == &ch.layers.back()) break;  // the fused tail evaluates the head layer
         const long long M = rows * L.opr;
         const TensorInfo &W = net->tensors[L.wt];
         const TensorInfo &Bt = net->tensors[L.bt];
@@ -609,7 +612,9 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
 static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in_kind, long long rows, void *dx, const void *dx_mask,
                                  cudaStream_t st, int bias_done = -1) {  // bias_done: layer whose bias gradient a fused kernel already produced
     const int bf = is_bf(net);
-    for (int li = (int)ch.layers.size() - 1; li >= 0; --li) {
+    int top = (int)ch.layers.size() - 1;
+    if (net->skip_head && &ch == &net->a) { --top; bias_done = top; }  // head layer + the bias gradient below it: done by the fused tail
+    for (int li = top; li >= 0; --li) {
         LayerExec &L = ch.layers[li];
         const long long M = rows * L.opr;
         const TensorInfo &W = net->tensors[L.wt];

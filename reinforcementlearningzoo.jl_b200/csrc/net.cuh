@@ -66,6 +66,9 @@ struct zoo_net {
     float *out_final = nullptr, *dout_final = nullptr;
     // IQN extras.  iqn_fused: phi's last GEMM multiplies by psi in its epilogue and writes `merged` directly (phi's own output
     // is never materialised: its last layer's `out` aliases `merged`); the backward recovers what it needs from merged and psi
+    // fused small-batch tail (narrow.cu: dqn_tail): the learner runs the head layer itself -- forward stops before the last layer of
+    // chain a, backward starts below it (its gradients and the previous layer's bias gradient are already in place)
+    bool skip_head = false;
     bool iqn_fused = false;
     void *emb = nullptr, *merged = nullptr, *dmerged = nullptr;
     float *tau_dev = nullptr;

@@ -280,7 +280,9 @@ zoo_status zoo_sumtree_destroy(zoo_sumtree *t) {
 
 static zoo_status update_dev_impl(zoo_sumtree *t, const long long *idx_dev, const float *p_dev, long long n, int physical, cudaStream_t st = nullptr) {
     if (!st) st = t->st;
-    static const bool small_on = [] { const char *e = getenv("ZOO_SUMTREE_SMALL"); return !(e && e[0] == '0'); }();
+    // measured on B200 (scripts/probe_sumtree_small.py): this single-launch variant is SLOWER than the two sorted launches
+    // (B = 32: 59 vs 10 us), so it is opt-in (ZOO_SUMTREE_SMALL=1) until that is understood
+    static const bool small_on = [] { const char *e = getenv("ZOO_SUMTREE_SMALL"); return e && e[0] == '1'; }();
     if (small_on && n > 0 && n <= SMALL_N) {
         const int threads = (int)std::min<long long>(1024, std::max<long long>(32, ((long long)(t->depth + 1) * n + 31) / 32 * 32));
         static const int dbg = [] { const char *e = getenv("ZOO_ST_DBG"); return e ? atoi(e) : 0; }();

@@ -70,10 +70,13 @@ def test_split_k_is_consistent(zoo, engine, split):
         assert run(zoo, engine, M, N, K, 1, 1, split) <= TOL[engine]  # second launch: the workspace really was left zeroed
 
 
-@pytest.mark.parametrize("env,val", [("ZOO_IMPLICIT_CONV", "1"), ("ZOO_TMA_DGRAD", "1"), ("ZOO_PDL", "0"), ("ZOO_TMA_CONV", "0")])
+@pytest.mark.parametrize("env,val", [("ZOO_IMPLICIT_CONV", "1"), ("ZOO_TMA_DGRAD", "0"), ("ZOO_TMA_WGRAD", "0"), ("ZOO_PDL", "0"), ("ZOO_TMA_CONV", "0"),
+                                     ("ZOO_TMA_STORE", "0"), ("ZOO_DQN_TAIL", "0"), ("ZOO_NARROW", "0"), ("ZOO_IQN_FUSE", "0")])
 def test_non_default_kernel_paths_keep_parity(env, val):
-    """The gathered-A implicit conv and the TMA stride-1 data gradient are opt-in; programmatic dependent launch and the
-    TMA-im2col forward conv can be switched off.  In every setting the Atari learner parity tests (fp32 and bf16) must still pass."""
+    """Every kernel path that has a switch: the gathered-A implicit conv (opt-in), and -- switched OFF here -- the TMA data / weight
+    gradients (falls back to GEMM + col2im / im2col + GEMM), programmatic dependent launch, the TMA-im2col forward conv, the TMA-store
+    epilogue, the fused DQN tail, the narrow Q-head kernels and the fused IQN merge.  In every setting the Atari learner parity tests
+    (fp32 and bf16) must still pass."""
     e = dict(os.environ)
     e[env] = val
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_learners.py"), "-m", "gpu", "-q", "-x", "-k",
