@@ -115,6 +115,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// tcgen05.st: this warp's 32 TMEM lanes (thread = lane), 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
+        "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+        "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+// tcgen05.mma with the A operand in tensor memory (lane = row, one 32-bit column per tf32 K element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in [0,14),
 // leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version = 1 in [46,48),
 // layout type SWIZZLE_128B = 2 in [61,64).
@@ -487,6 +509,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
     const int NST = GA == 1 ? C::STAGES : P.stages;  // ring depth of this launch
+    // 3xTF32 with a K-major A tile and BN <= 64: the A operand lives in TENSOR MEMORY.  Each converter thread owns one tile row:
+    // it reads the landed fp32 row once from shared memory and writes it (the hi operand: tcgen05 ignores the low 13 mantissa
+    // bits) and lo = x - trunc(x) to 2 x 32 TMEM columns of the stage's A slot; the three products then read A from TMEM and only
+    // B from shared memory -- 80 KB instead of 128 KB of shared-memory traffic per K-block (BN = 64), which is what bounds this
+    // kernel.  TMEM: two accumulators (2 x 2 BN columns) + 64 columns per stage.
+    constexpr bool ATM = X3 && A_K && GA != 1 && BN <= 64;
+    uint32_t tmem_cols = C::TMEM_COLS;
+    if (ATM) {
+        const uint32_t need = 2u * C::ACC_COLS + 64u * (uint32_t)NST;
+        tmem_cols = 32;
+        while (tmem_cols < need) tmem_cols <<= 1;
+    }
     uint64_t *full_bar = (uint64_t *)(smem + NST * C::STAGE_BYTES);
     uint64_t *empty_bar = full_bar + C::STAGES;
     uint64_t *conv_bar = empty_bar + C::STAGES;  // X3: lo tiles written (128 converter threads arrive)
@@ -552,7 +586,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = threadIdx.x; i < NST * C::STAGE_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -681,7 +715,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         constexpr uint32_t idesc2 = make_idesc(2 * BN, !A_K, !B_K, 2u);
                         const uint64_t adl = A_K ? make_smem_desc(sa + C::LO_A_OFF + ao, 16, 1024)
                                                  : make_smem_desc(sa + C::LO_A_OFF + ao, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
-                        if (P.xmode & 2) {
+                        if (ATM) {
+                            const uint32_t ta = tmem_base + 2u * C::ACC_COLS + 64u * (uint32_t)s + 8u * (uint32_t)k;  // hi; lo 32 columns on
+                            umma_tf32_ts(td, ta, bd, idesc2, !(chain_start && k == 0));
+                            umma_tf32_ts(td, ta + 32u, bd, idesc, 1);
+                        } else if (P.xmode & 2) {
                             umma<EB>(td, ad, bd, idesc, !(chain_start && k == 0));
                         } else {
                             umma<EB>(td, ad, bd, idesc2, !(chain_start && k == 0));
@@ -782,9 +820,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // is written.  Rows past M / N are never stored, so they are skipped.
                     const uint4 *raw = reinterpret_cast<const uint4 *>(stage);
                     uint4 *lo = reinterpret_cast<uint4 *>(stage + C::RAW_BYTES);  // [B lo][A lo]
+                    if (ATM) {
+                        // A: row t of the K-major SWIZZLE_128B tile (chunk j at j ^ (t % 8)) -> TMEM lanes of this warp's quadrant
+                        {   // (every lane takes part: tcgen05.st is warp-collective; rows past the tile's last row carry stale data
+                            //  into accumulator rows that are never stored)
+                            uint32_t hi[32], lw[32];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const uint4 v = *reinterpret_cast<const uint4 *>(stage + t * 128 + ((j ^ (t & 7)) << 4));
+                                const uint4 l = tf32_lo(v);
+                                hi[4 * j] = v.x; hi[4 * j + 1] = v.y; hi[4 * j + 2] = v.z; hi[4 * j + 3] = v.w;
+                                lw[4 * j] = l.x; lw[4 * j + 1] = l.y; lw[4 * j + 2] = l.z; lw[4 * j + 3] = l.w;
+                            }
+                            const uint32_t ta = tq + 2u * C::ACC_COLS + 64u * (uint32_t)s;
+                            tmem_st32(ta, hi);
+                            tmem_st32(ta + 32u, lw);
+                        }
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        tc_fence_before();
+                    }
                     // batches of 8 x 16 B per thread: all loads first, then all stores -- raw and lo may alias as far as the
                     // compiler knows, so an element-wise loop serialises on shared-memory latency (measured 0.4 us per stage)
-                    for (int j0 = t; j0 < ((P.xmode & 1) ? 0 : conv_units); j0 += 8 * 128) {
+                    for (int j0 = t + (ATM ? a_units : 0); j0 < ((P.xmode & 1) ? 0 : conv_units); j0 += 8 * 128) {
                         uint4 v[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
@@ -1259,7 +1316,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) dbg_stamp(P, 7);
-    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
     if (threadIdx.x == 32) dbg_stamp(P, 8);
 }
 
@@ -1367,6 +1424,9 @@ static int tc_pick_stages(int BN, long long ctas, int nkb) {
     const int mx = BN == 32 ? TcCfg<EB, 32, X3, SPAN>::MAX_STAGES : (BN == 64 ? TcCfg<EB, 64, X3, SPAN>::MAX_STAGES : TcCfg<EB, 128, X3, SPAN>::MAX_STAGES);
     const int two = BN == 32 ? TcCfg<EB, 32, X3, SPAN>::TWO_CTA_STAGES : (BN == 64 ? TcCfg<EB, 64, X3, SPAN>::TWO_CTA_STAGES : TcCfg<EB, 128, X3, SPAN>::TWO_CTA_STAGES);
     int stg = ctas > g_sm_budget ? two : mx;
+    // 3xTF32, BN = 64: with the A operand in tensor memory a CTA holds 2 x 128 accumulator + 64 columns per stage = all 512
+    // columns from 4 stages on, and 384 -> 512 even with 2, so two CTAs never share an SM: always take the deep ring
+    if (X3 && BN == 64) stg = mx;
     const int force = g_tc_stages_force & 0xff;  // ZOO_TC_STAGES / zoo_test_set_tc_stages
     if (force >= 2) stg = force < mx ? force : mx;
     if (stg > nkb + 1) stg = nkb + 1 < 2 ? 2 : nkb + 1;  // no point in a ring deeper than the K loop
