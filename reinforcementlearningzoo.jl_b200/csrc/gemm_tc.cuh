@@ -825,9 +825,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         {   // (every lane takes part: tcgen05.st is warp-collective; rows past the tile's last row carry stale data
                             //  into accumulator rows that are never stored)
                             uint32_t hi[32], lw[32];
+                            const int ar = q * 32 + lane;  // a warp reaches only the TMEM lanes of its quadrant (warp % 4): row = lane id there
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const uint4 v = *reinterpret_cast<const uint4 *>(stage + t * 128 + ((j ^ (t & 7)) << 4));
+                                const uint4 v = *reinterpret_cast<const uint4 *>(stage + ar * 128 + ((j ^ (ar & 7)) << 4));
                                 const uint4 l = tf32_lo(v);
                                 hi[4 * j] = v.x; hi[4 * j + 1] = v.y; hi[4 * j + 2] = v.z; hi[4 * j + 3] = v.w;
                                 lw[4 * j] = l.x; lw[4 * j + 1] = l.y; lw[4 * j + 2] = l.z; lw[4 * j + 3] = l.w;

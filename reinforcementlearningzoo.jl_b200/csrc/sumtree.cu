@@ -195,6 +195,52 @@ sumtree_update_small_kernel(float *__restrict__ tree, long long nparents, long l
     }
 }
 
+// Dopamine-sized batches (n <= 32): ONE launch, one warp per tree level.  Lane k owns batch entry k.  Warp 0 settles the leaf
+// level: __match_any groups the lanes that hit the same leaf; within a group an entry's change is p[k] minus the p of the group's
+// previous lane (or the stored leaf value for the first), the last lane stores the leaf.  After one barrier warp l (1 .. depth)
+// owns the ancestors l levels up: the lowest lane of every group of equal ancestors adds the group's changes IN LANE ORDER =
+// batch order (a uniform 32-step shuffle loop, no shared-memory traffic), which is the reference's sequential
+// `tree[node] += change` -- bit-exact, duplicates included -- with every level and every node in parallel.
+__global__ void __launch_bounds__(1024)
+sumtree_update_warp_kernel(float *__restrict__ tree, long long nparents, long long capacity, long long first, int depth, int physical,
+                           const long long *__restrict__ idx, const float *__restrict__ p, int n) {
+    __shared__ float change_s[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool on = lane < n;
+    long long h = -1 - lane;  // inactive lanes: distinct dummies, never grouped
+    float pk = 0.f;
+    if (on) {
+        long long s = idx[lane];
+        if (!physical) { s = s + first - 1; if (s > capacity) s -= capacity; }
+        h = nparents + s;
+        pk = p[lane];
+    }
+    // every warp prefetches the node it will update (independent of the leaf phase)
+    const long long a = (on && warp >= 1 && warp <= depth) ? (h >> warp) : -1 - lane;
+    float acc = (on && warp >= 1 && warp <= depth) ? tree[a] : 0.f;
+    if (warp == 0) {
+        const float leaf = on ? tree[h] : 0.f;
+        const unsigned grp = __match_any_sync(0xffffffffu, h);
+        const unsigned below = grp & ((1u << lane) - 1u);
+        const int prev = below ? 31 - __clz(below) : -1;
+        const float pprev = __shfl_sync(0xffffffffu, pk, prev < 0 ? 0 : prev);
+        change_s[lane] = on ? __fsub_rn(pk, prev < 0 ? leaf : pprev) : 0.f;
+        if (on && (grp >> lane) == 1u) tree[h] = pk;  // highest lane of the group: the leaf ends up holding the last p
+    }
+    __syncthreads();
+    if (warp >= 1 && warp <= depth) {
+        const float ch = change_s[lane];
+        const unsigned grp = __match_any_sync(0xffffffffu, a);
+        const bool leader = on && (grp & ((1u << lane) - 1u)) == 0u;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float cj = __shfl_sync(0xffffffffu, ch, j);
+            if ((grp >> j) & 1u) acc = __fadd_rn(acc, cj);  // grp = the lanes sharing MY node; lane order = batch order
+        }
+        if (leader) tree[a] = acc;
+    }
+}
+
 // push! of ONE priority (common.jl:36): slot and value travel as kernel arguments (no staging copies, no host sync); lane l owns
 // the ancestor l levels above the leaf -- all distinct nodes, so the single `+= change` per node needs no ordering.
 __global__ void sumtree_push1_kernel(float *__restrict__ tree, long long leaf, float p, int depth) {
@@ -282,6 +328,12 @@ static zoo_status update_dev_impl(zoo_sumtree *t, const long long *idx_dev, cons
     if (!st) st = t->st;
     // measured on B200 (scripts/probe_sumtree_small.py): this single-launch variant is SLOWER than the two sorted launches
     // (B = 32: 59 vs 10 us), so it is opt-in (ZOO_SUMTREE_SMALL=1) until that is understood
+    static const bool warp_on = [] { const char *e = getenv("ZOO_SUMTREE_WARP"); return !(e && e[0] == '0'); }();
+    if (warp_on && n > 0 && n <= 32 && t->depth <= 31) {
+        sumtree_update_warp_kernel<<<1, 32 * (t->depth + 1), 0, st>>>(t->tree, t->nparents, t->capacity, t->first, t->depth, physical, idx_dev, p_dev, (int)n);
+        ZOO_LAUNCH_CHECK();
+        return ZOO_OK;
+    }
     static const bool small_on = [] { const char *e = getenv("ZOO_SUMTREE_SMALL"); return e && e[0] == '1'; }();
     if (small_on && n > 0 && n <= SMALL_N) {
         const int threads = (int)std::min<long long>(1024, std::max<long long>(32, ((long long)(t->depth + 1) * n + 31) / 32 * 32));
