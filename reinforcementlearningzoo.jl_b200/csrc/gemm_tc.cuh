@@ -25,6 +25,9 @@ namespace zoo {
 static constexpr int BM = 128;      // UMMA M (cta_group::1)
 // per stage: one 128-byte swizzle span of K per row -> BK = 128 / EB elements, 4 MMAs of K = 32 / EB each
 static constexpr int TC_THREADS = 192;
+// 3xTF32 kernels carry a second converter warpgroup (warps 6..9): the two groups split the K-blocks between them (even / odd), so
+// the conversion latency of one block (smem read, split, tcgen05.st / smem write, proxy fence, barrier) overlaps the next one's
+template <bool X3, int GA> constexpr int tc_threads() { return (X3 && GA != 1) ? 320 : TC_THREADS; }
 static constexpr int X3_CHAIN_KB = 4;         // 3xTF32: K-blocks (of 32 floats) per TMEM accumulation chain (see the kernel)
 static constexpr int TC_WS_COUNTERS = 4096;  // tail of the split-K workspace: per-tile arrival counters
 
@@ -498,7 +501,7 @@ __device__ __forceinline__ void epi_cols_store(const float *rp, int ncols, T *op
 //         row) -- so no im2col matrix exists in either direction.  A K-block's pixel rows past R x OW are never written
 //         (the ring is zeroed once at kernel start), grid.z splits the images, partial sums are red-added into the gradient.
 template <int EB, int BN, bool A_K, bool B_K, bool X3, int GA = 0, int SPAN = 128>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(tc_threads<X3, GA>(), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams P) {
     static_assert(GA == 0 || GA == 4 || A_K, "the gathered A operand is K-major");
     static_assert(GA != 4 || (!A_K && !B_K), "the weight-gradient operands are MN-major");
@@ -583,7 +586,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (GA == 4) {  // pad rows of every stage (pixel rows past R x OW, feature boxes past N, channel rows past Cout) must read as zero
-        for (int i = threadIdx.x; i < NST * C::STAGE_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < NST * C::STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -593,6 +596,62 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) dbg_stamp(P, 1);
     pdl_wait();  // everything above ran under the predecessor's tail; from here on global memory is touched
+
+    // 3xTF32 operand split of K-block i by one converter warpgroup (t = thread 0..127 of the group, q = its TMEM lane quadrant)
+    constexpr bool DG = X3 && GA != 1;  // two converter groups: even blocks -> warps 2..5, odd blocks -> warps 6..9
+    const int cv_va = vrows, cv_vb = min(BN, P.N - n0);  // valid rows of the A / B tiles
+    const int a_units = GA == 1 ? 0 : (A_K ? cv_va * 128 : ((cv_va + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
+    const int b_units = (B_K ? cv_vb * 128 : ((cv_vb + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
+    const int conv_units = a_units + b_units;
+    auto x3_convert = [&](int i, int t, int q) {
+        const int s = i % NST;
+        const uint32_t ph = (i / NST) & 1;
+        uint8_t *stage = smem + s * C::STAGE_BYTES;
+        mbar_wait(&full_bar[s], ph);
+        // tcgen05 kind::tf32 ignores the low 13 mantissa bits of an fp32 operand (measured: bit-identical results
+        // for raw and pre-truncated inputs), so the landed tile itself is the hi operand; only lo = x - trunc(x)
+        // is written.  Rows past M / N are never stored, so they are skipped.
+        const uint4 *raw = reinterpret_cast<const uint4 *>(stage);
+        uint4 *lo = reinterpret_cast<uint4 *>(stage + C::RAW_BYTES);  // [B lo][A lo]
+        if (ATM) {
+            // A: row ar of the K-major SWIZZLE_128B tile (chunk j at j ^ (ar % 8)) -> TMEM lanes of this warp's quadrant
+            // (every lane takes part: tcgen05.st is warp-collective; rows past the tile's last row carry stale data into
+            //  accumulator rows that are never stored)
+            uint32_t hi[32], lw[32];
+            const int ar = q * 32 + (threadIdx.x & 31);  // a warp reaches only the TMEM lanes of its quadrant (warp % 4): row = lane id there
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(stage + ar * 128 + ((j ^ (ar & 7)) << 4));
+                const uint4 l = tf32_lo(v);
+                hi[4 * j] = v.x; hi[4 * j + 1] = v.y; hi[4 * j + 2] = v.z; hi[4 * j + 3] = v.w;
+                lw[4 * j] = l.x; lw[4 * j + 1] = l.y; lw[4 * j + 2] = l.z; lw[4 * j + 3] = l.w;
+            }
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + 2u * C::ACC_COLS + 64u * (uint32_t)s;
+            tmem_st32(ta, hi);
+            tmem_st32(ta + 32u, lw);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+        }
+        // batches of 8 x 16 B per thread: all loads first, then all stores -- raw and lo may alias as far as the
+        // compiler knows, so an element-wise loop serialises on shared-memory latency (measured 0.4 us per stage)
+        for (int j0 = t + (ATM ? a_units : 0); j0 < ((P.xmode & 1) ? 0 : conv_units); j0 += 8 * 128) {
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + u * 128;
+                const int jj = j < a_units ? j : j - a_units + C::A_BYTES / 16;
+                if (j < conv_units) v[u] = raw[jj];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + u * 128;
+                const int jl = j < a_units ? j + C::B_BYTES / 16 : j - a_units;
+                if (j < conv_units && !(P.xmode & 8)) lo[jl] = tf32_lo(v[u]);
+            }
+        }
+        if (!(P.xmode & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
+        mbar_arrive(&conv_bar[s]);
+    };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -734,6 +793,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             dbg_stamp(P, 4);
         }
+    } else if (DG && warp >= 6) {
+        // second converter group: the odd K-blocks
+        for (int i = 1; i < nkb; i += 2) x3_convert(i, (int)threadIdx.x - 192, warp & 3);
     } else {
         // warps 2..5: TMEM lane quadrant = warp % 4, thread = accumulator row.
         const int q = warp & 3;
@@ -749,10 +811,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // into acc
             const int t = threadIdx.x - 64;  // 0..127
             int drained = 0;
-            const int va = vrows, vb = min(BN, P.N - n0);  // valid rows of the A / B tiles
-            const int a_units = GA == 1 ? 0 : (A_K ? va * 128 : ((va + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
-            const int b_units = (B_K ? vb * 128 : ((vb + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
-            const int conv_units = a_units + b_units;
             // GA: this thread owns tile row t = output pixel (forward) / input pixel (dgrad) m0 + t
             bool gvalid = false;
             int gb = 0, gy0 = 0, gx0 = 0;
@@ -814,52 +872,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 if (X3) {
-                    mbar_wait(&full_bar[s], ph);
-                    // tcgen05 kind::tf32 ignores the low 13 mantissa bits of an fp32 operand (measured: bit-identical results
-                    // for raw and pre-truncated inputs), so the landed tile itself is the hi operand; only lo = x - trunc(x)
-                    // is written.  Rows past M / N are never stored, so they are skipped.
-                    const uint4 *raw = reinterpret_cast<const uint4 *>(stage);
-                    uint4 *lo = reinterpret_cast<uint4 *>(stage + C::RAW_BYTES);  // [B lo][A lo]
-                    if (ATM) {
-                        // A: row t of the K-major SWIZZLE_128B tile (chunk j at j ^ (t % 8)) -> TMEM lanes of this warp's quadrant
-                        {   // (every lane takes part: tcgen05.st is warp-collective; rows past the tile's last row carry stale data
-                            //  into accumulator rows that are never stored)
-                            uint32_t hi[32], lw[32];
-                            const int ar = q * 32 + lane;  // a warp reaches only the TMEM lanes of its quadrant (warp % 4): row = lane id there
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const uint4 v = *reinterpret_cast<const uint4 *>(stage + ar * 128 + ((j ^ (ar & 7)) << 4));
-                                const uint4 l = tf32_lo(v);
-                                hi[4 * j] = v.x; hi[4 * j + 1] = v.y; hi[4 * j + 2] = v.z; hi[4 * j + 3] = v.w;
-                                lw[4 * j] = l.x; lw[4 * j + 1] = l.y; lw[4 * j + 2] = l.z; lw[4 * j + 3] = l.w;
-                            }
-                            const uint32_t ta = tq + 2u * C::ACC_COLS + 64u * (uint32_t)s;
-                            tmem_st32(ta, hi);
-                            tmem_st32(ta + 32u, lw);
-                        }
-                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                        tc_fence_before();
-                    }
-                    // batches of 8 x 16 B per thread: all loads first, then all stores -- raw and lo may alias as far as the
-                    // compiler knows, so an element-wise loop serialises on shared-memory latency (measured 0.4 us per stage)
-                    for (int j0 = t + (ATM ? a_units : 0); j0 < ((P.xmode & 1) ? 0 : conv_units); j0 += 8 * 128) {
-                        uint4 v[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int j = j0 + u * 128;
-                            const int jj = j < a_units ? j : j - a_units + C::A_BYTES / 16;
-                            if (j < conv_units) v[u] = raw[jj];
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int j = j0 + u * 128;
-                            const int jl = j < a_units ? j + C::B_BYTES / 16 : j - a_units;
-                            if (j < conv_units && !(P.xmode & 8)) lo[jl] = tf32_lo(v[u]);
-                        }
-                    }
+                    if (!DG || !(i & 1)) x3_convert(i, t, q);  // (the odd blocks belong to the second converter group)
+                } else {
+                    if (!(P.xmode & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
+                    mbar_arrive(&conv_bar[s]);
                 }
-                if (!(P.xmode & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
-                mbar_arrive(&conv_bar[s]);
                 // chain `drained` ended at K-block (drained+1)*CHAIN - 1; by the time two more blocks have been converted
                 // its MMAs have retired, so the wait below does not stall the conversion pipeline
                 if (X3 && drained < nchains - 1 && i + 1 >= (drained + 1) * CHAIN + 2) {
@@ -1331,7 +1348,7 @@ static zoo_status launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, grid, dim3(TC_THREADS), (size_t)C::smem_for(P.stages), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, grid, dim3(tc_threads<X3, 0>()), (size_t)C::smem_for(P.stages), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1367,7 +1384,7 @@ static zoo_status launch_conv(const CUtensorMap &tmB, const TcParams &P, dim3 gr
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, grid, dim3(TC_THREADS), (size_t)C::SMEM, st, tmB, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, grid, dim3(tc_threads<X3, 1>()), (size_t)C::SMEM, st, tmB, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1380,7 +1397,7 @@ static zoo_status launch_conv_tma(const CUtensorMap &tmA, const CUtensorMap &tmB
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(C::SMEM, TC_EPI_SMEM)));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, grid, dim3(TC_THREADS), (size_t)std::max(C::smem_for(P.stages), TC_EPI_SMEM), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, grid, dim3(tc_threads<X3, 2>()), (size_t)std::max(C::smem_for(P.stages), TC_EPI_SMEM), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1400,7 +1417,7 @@ static zoo_status launch_conv_wgrad(const CUtensorMap &tmA, const CUtensorMap &t
     if (stg < 2) stg = 2;
     P.stages = stg;
     P.xmode = 0;
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN>, grid, dim3(TC_THREADS), (size_t)std::max(C::smem_for(stg), TC_EPI_SMEM), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN>, grid, dim3(tc_threads<X3, 4>()), (size_t)std::max(C::smem_for(stg), TC_EPI_SMEM), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }

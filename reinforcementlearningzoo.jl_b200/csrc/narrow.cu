@@ -399,11 +399,11 @@ __global__ void __launch_bounds__(256) dqn_tail_kernel(int kind, int double_dqn,
 #pragma unroll
     for (int e = 0; e < 8; ++e) atomicAdd(dbp_s + kq * 8 + e, dbp[e]);
     __syncthreads();
-    // single CTA and the gradient buffer is all-zero on entry: plain adds
-    for (int i = threadIdx.x; i < N * K; i += 256) dW[i] += Ws[i];
+    // fire-and-forget reds (a read-modify-write here waits a DRAM round trip per element: 12 dependent trips per thread)
+    for (int i = threadIdx.x; i < N * K; i += 256) atomicAdd(dW + i, Ws[i]);
     if (db_prev)
-        for (int i = threadIdx.x; i < K; i += 256) db_prev[i] += dbp_s[i];
-    if (threadIdx.x < N) db[threadIdx.x] += dbn_s[threadIdx.x];
+        for (int i = threadIdx.x; i < K; i += 256) atomicAdd(db_prev + i, dbp_s[i]);
+    if (threadIdx.x < N) atomicAdd(db + threadIdx.x, dbn_s[threadIdx.x]);
 }
 
 bool dqn_tail_supported(int N, long long K, int x_bf16, int rows_fwd) {
