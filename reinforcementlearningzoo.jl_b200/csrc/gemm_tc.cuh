@@ -177,6 +177,8 @@ struct TcParams {
     // also clips rows / columns past M / N.  tmC: 2-D map over the output, box {64 columns, 32 rows}.
     int tma_store = 0;
     int span = 128;  // bytes of K per stage row (TcCfg SPAN); 64 = the SWIZZLE_64B convolution variants
+    int threads = TC_THREADS;  // 192, or 320 with the second converter group (3xTF32, grids of <= one CTA per SM)
+    int atm = 0;     // 3xTF32: keep the A operand in tensor memory (set by the launcher for grids of <= one CTA per SM)
     CUtensorMap tmC;
     // tma_store == 2 (TMA data gradient): the whole tile is staged [rows][ts_span-byte column blocks] and stored with one 4-D box
     // per column block into the class's strided view of dX; one map per residue class (grid.z), tpi_max = tiles per image of the
@@ -517,7 +519,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // bits) and lo = x - trunc(x) to 2 x 32 TMEM columns of the stage's A slot; the three products then read A from TMEM and only
     // B from shared memory -- 80 KB instead of 128 KB of shared-memory traffic per K-block (BN = 64), which is what bounds this
     // kernel.  TMEM: two accumulators (2 x 2 BN columns) + 64 columns per stage.
-    constexpr bool ATM = X3 && A_K && GA != 1 && BN <= 64;
+    // Both this and the second converter group cost occupancy (TMEM columns / 320 threads): the host asks for them (P.atm, 320
+    // threads) only for grids of at most one CTA per SM; split-K grids that rely on two CTAs per SM keep the lean form.
+    constexpr bool ATM_OK = X3 && A_K && GA != 1 && BN <= 64;
+    const bool ATM = ATM_OK && P.atm;
     uint32_t tmem_cols = C::TMEM_COLS;
     if (ATM) {
         const uint32_t need = 2u * C::ACC_COLS + 64u * (uint32_t)NST;
@@ -598,7 +603,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     pdl_wait();  // everything above ran under the predecessor's tail; from here on global memory is touched
 
     // 3xTF32 operand split of K-block i by one converter warpgroup (t = thread 0..127 of the group, q = its TMEM lane quadrant)
-    constexpr bool DG = X3 && GA != 1;  // two converter groups: even blocks -> warps 2..5, odd blocks -> warps 6..9
+    const bool DG = X3 && GA != 1 && blockDim.x == 320;  // two converter groups: even blocks -> warps 2..5, odd blocks -> warps 6..9
     const int cv_va = vrows, cv_vb = min(BN, P.N - n0);  // valid rows of the A / B tiles
     const int a_units = GA == 1 ? 0 : (A_K ? cv_va * 128 : ((cv_va + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
     const int b_units = (B_K ? cv_vb * 128 : ((cv_vb + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
@@ -1348,7 +1353,7 @@ static zoo_status launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, grid, dim3(tc_threads<X3, 0>()), (size_t)C::smem_for(P.stages), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, grid, dim3(P.threads), (size_t)C::smem_for(P.stages), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1384,7 +1389,7 @@ static zoo_status launch_conv(const CUtensorMap &tmB, const TcParams &P, dim3 gr
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, grid, dim3(tc_threads<X3, 1>()), (size_t)C::SMEM, st, tmB, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, grid, dim3(P.threads), (size_t)C::SMEM, st, tmB, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1397,7 +1402,7 @@ static zoo_status launch_conv_tma(const CUtensorMap &tmA, const CUtensorMap &tmB
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(C::SMEM, TC_EPI_SMEM)));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, grid, dim3(tc_threads<X3, 2>()), (size_t)std::max(C::smem_for(P.stages), TC_EPI_SMEM), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, grid, dim3(P.threads), (size_t)std::max(C::smem_for(P.stages), TC_EPI_SMEM), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1417,7 +1422,7 @@ static zoo_status launch_conv_wgrad(const CUtensorMap &tmA, const CUtensorMap &t
     if (stg < 2) stg = 2;
     P.stages = stg;
     P.xmode = 0;
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN>, grid, dim3(tc_threads<X3, 4>()), (size_t)std::max(C::smem_for(stg), TC_EPI_SMEM), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN>, grid, dim3(P.threads), (size_t)std::max(C::smem_for(stg), TC_EPI_SMEM), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1444,7 +1449,7 @@ static int tc_pick_stages(int BN, long long ctas, int nkb) {
     int stg = ctas > g_sm_budget ? two : mx;
     // 3xTF32, BN = 64: with the A operand in tensor memory a CTA holds 2 x 128 accumulator + 64 columns per stage = all 512
     // columns from 4 stages on, and 384 -> 512 even with 2, so two CTAs never share an SM: always take the deep ring
-    if (X3 && BN == 64) stg = mx;
+    if (X3 && BN == 64 && ctas <= g_sm_budget) stg = mx;
     const int force = g_tc_stages_force & 0xff;  // ZOO_TC_STAGES / zoo_test_set_tc_stages
     if (force >= 2) stg = force < mx ? force : mx;
     if (stg > nkb + 1) stg = nkb + 1 < 2 ? 2 : nkb + 1;  // no point in a ring deeper than the K loop
@@ -1458,6 +1463,14 @@ static zoo_status tc_launch_mode(int kind, int BN, bool ak, bool bk, const CUten
     TcParams P = P0;
     P.stages = tc_pick_stages<EB, X3>(BN, (long long)grid.x * grid.y * grid.z, P0.kb_per_split);
     P.xmode = g_tc_stages_force >> 8;
+    {
+        // 3xTF32 with at most one CTA per SM: spend the idle half of the SM on a second converter warpgroup and on TMEM for the
+        // A operand (ZOO_X3_WIDE=0 switches both off; kind 1 = the gathered-A kernel keeps its own converter scheme)
+        static const bool wide_on = [] { const char *e = getenv("ZOO_X3_WIDE"); return !(e && e[0] == '0'); }();
+        const bool wide = X3 && wide_on && kind != 1 && (long long)grid.x * grid.y * grid.z <= g_sm_budget;
+        P.threads = wide ? 320 : TC_THREADS;
+        P.atm = wide ? 1 : 0;
+    }
     if (kind == 2 && P0.span == 64) {  // bf16 TMA-im2col convolution over 64-byte runs (SWIZZLE_64B tiles)
         if constexpr (EB == 2 && !X3) {
             P.stages = tc_pick_stages<2, false, 64>(BN, (long long)grid.x * grid.y * grid.z, P0.kb_per_split);
