@@ -25,9 +25,6 @@ namespace zoo {
 static constexpr int BM = 128;      // UMMA M (cta_group::1)
 // per stage: one 128-byte swizzle span of K per row -> BK = 128 / EB elements, 4 MMAs of K = 32 / EB each
 static constexpr int TC_THREADS = 192;
-// 3xTF32 kernels carry a second converter warpgroup (warps 6..9): the two groups split the K-blocks between them (even / odd), so
-// the conversion latency of one block (smem read, split, tcgen05.st / smem write, proxy fence, barrier) overlaps the next one's
-template <bool X3, int GA> constexpr int tc_threads() { return (X3 && GA != 1) ? 320 : TC_THREADS; }
 static constexpr int X3_CHAIN_KB = 4;         // 3xTF32: K-blocks (of 32 floats) per TMEM accumulation chain (see the kernel)
 static constexpr int TC_WS_COUNTERS = 4096;  // tail of the split-K workspace: per-tile arrival counters
 
@@ -118,28 +115,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// tcgen05.st: this warp's 32 TMEM lanes (thread = lane), 32 consecutive 32-bit columns
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
-        "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
-        "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-// tcgen05.mma with the A operand in tensor memory (lane = row, one 32-bit column per tf32 K element)
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in [0,14),
 // leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version = 1 in [46,48),
 // layout type SWIZZLE_128B = 2 in [61,64).
@@ -177,8 +152,6 @@ struct TcParams {
     // also clips rows / columns past M / N.  tmC: 2-D map over the output, box {64 columns, 32 rows}.
     int tma_store = 0;
     int span = 128;  // bytes of K per stage row (TcCfg SPAN); 64 = the SWIZZLE_64B convolution variants
-    int threads = TC_THREADS;  // 192, or 320 with the second converter group (3xTF32, grids of <= one CTA per SM)
-    int atm = 0;     // 3xTF32: keep the A operand in tensor memory (set by the launcher for grids of <= one CTA per SM)
     CUtensorMap tmC;
     // tma_store == 2 (TMA data gradient): the whole tile is staged [rows][ts_span-byte column blocks] and stored with one 4-D box
     // per column block into the class's strided view of dX; one map per residue class (grid.z), tpi_max = tiles per image of the
@@ -503,7 +476,7 @@ __device__ __forceinline__ void epi_cols_store(const float *rp, int ncols, T *op
 //         row) -- so no im2col matrix exists in either direction.  A K-block's pixel rows past R x OW are never written
 //         (the ring is zeroed once at kernel start), grid.z splits the images, partial sums are red-added into the gradient.
 template <int EB, int BN, bool A_K, bool B_K, bool X3, int GA = 0, int SPAN = 128>
-__global__ void __launch_bounds__(tc_threads<X3, GA>(), 1)
+__global__ void __launch_bounds__(TC_THREADS)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams P) {
     static_assert(GA == 0 || GA == 4 || A_K, "the gathered A operand is K-major");
     static_assert(GA != 4 || (!A_K && !B_K), "the weight-gradient operands are MN-major");
@@ -514,21 +487,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
     const int NST = GA == 1 ? C::STAGES : P.stages;  // ring depth of this launch
-    // 3xTF32 with a K-major A tile and BN <= 64: the A operand lives in TENSOR MEMORY.  Each converter thread owns one tile row:
-    // it reads the landed fp32 row once from shared memory and writes it (the hi operand: tcgen05 ignores the low 13 mantissa
-    // bits) and lo = x - trunc(x) to 2 x 32 TMEM columns of the stage's A slot; the three products then read A from TMEM and only
-    // B from shared memory -- 80 KB instead of 128 KB of shared-memory traffic per K-block (BN = 64), which is what bounds this
-    // kernel.  TMEM: two accumulators (2 x 2 BN columns) + 64 columns per stage.
-    // Both this and the second converter group cost occupancy (TMEM columns / 320 threads): the host asks for them (P.atm, 320
-    // threads) only for grids of at most one CTA per SM; split-K grids that rely on two CTAs per SM keep the lean form.
-    constexpr bool ATM_OK = X3 && A_K && GA != 1 && BN <= 64;
-    const bool ATM = ATM_OK && P.atm;
-    uint32_t tmem_cols = C::TMEM_COLS;
-    if (ATM) {
-        const uint32_t need = 2u * C::ACC_COLS + 64u * (uint32_t)NST;
-        tmem_cols = 32;
-        while (tmem_cols < need) tmem_cols <<= 1;
-    }
     uint64_t *full_bar = (uint64_t *)(smem + NST * C::STAGE_BYTES);
     uint64_t *empty_bar = full_bar + C::STAGES;
     uint64_t *conv_bar = empty_bar + C::STAGES;  // X3: lo tiles written (128 converter threads arrive)
@@ -591,72 +549,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (GA == 4) {  // pad rows of every stage (pixel rows past R x OW, feature boxes past N, channel rows past Cout) must read as zero
-        for (int i = threadIdx.x; i < NST * C::STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < NST * C::STAGE_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) dbg_stamp(P, 1);
     pdl_wait();  // everything above ran under the predecessor's tail; from here on global memory is touched
-
-    // 3xTF32 operand split of K-block i by one converter warpgroup (t = thread 0..127 of the group, q = its TMEM lane quadrant)
-    const bool DG = X3 && GA != 1 && blockDim.x == 320;  // two converter groups: even blocks -> warps 2..5, odd blocks -> warps 6..9
-    const int cv_va = vrows, cv_vb = min(BN, P.N - n0);  // valid rows of the A / B tiles
-    const int a_units = GA == 1 ? 0 : (A_K ? cv_va * 128 : ((cv_va + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
-    const int b_units = (B_K ? cv_vb * 128 : ((cv_vb + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
-    const int conv_units = a_units + b_units;
-    auto x3_convert = [&](int i, int t, int q) {
-        const int s = i % NST;
-        const uint32_t ph = (i / NST) & 1;
-        uint8_t *stage = smem + s * C::STAGE_BYTES;
-        mbar_wait(&full_bar[s], ph);
-        // tcgen05 kind::tf32 ignores the low 13 mantissa bits of an fp32 operand (measured: bit-identical results
-        // for raw and pre-truncated inputs), so the landed tile itself is the hi operand; only lo = x - trunc(x)
-        // is written.  Rows past M / N are never stored, so they are skipped.
-        const uint4 *raw = reinterpret_cast<const uint4 *>(stage);
-        uint4 *lo = reinterpret_cast<uint4 *>(stage + C::RAW_BYTES);  // [B lo][A lo]
-        if (ATM) {
-            // A: row ar of the K-major SWIZZLE_128B tile (chunk j at j ^ (ar % 8)) -> TMEM lanes of this warp's quadrant
-            // (every lane takes part: tcgen05.st is warp-collective; rows past the tile's last row carry stale data into
-            //  accumulator rows that are never stored)
-            uint32_t hi[32], lw[32];
-            const int ar = q * 32 + (threadIdx.x & 31);  // a warp reaches only the TMEM lanes of its quadrant (warp % 4): row = lane id there
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(stage + ar * 128 + ((j ^ (ar & 7)) << 4));
-                const uint4 l = tf32_lo(v);
-                hi[4 * j] = v.x; hi[4 * j + 1] = v.y; hi[4 * j + 2] = v.z; hi[4 * j + 3] = v.w;
-                lw[4 * j] = l.x; lw[4 * j + 1] = l.y; lw[4 * j + 2] = l.z; lw[4 * j + 3] = l.w;
-            }
-            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + 2u * C::ACC_COLS + 64u * (uint32_t)s;
-            tmem_st32(ta, hi);
-            tmem_st32(ta + 32u, lw);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-        }
-        // batches of 8 x 16 B per thread: all loads first, then all stores -- raw and lo may alias as far as the
-        // compiler knows, so an element-wise loop serialises on shared-memory latency (measured 0.4 us per stage)
-        for (int j0 = t + (ATM ? a_units : 0); j0 < ((P.xmode & 1) ? 0 : conv_units); j0 += 8 * 128) {
-            uint4 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int j = j0 + u * 128;
-                const int jj = j < a_units ? j : j - a_units + C::A_BYTES / 16;
-                if (j < conv_units) v[u] = raw[jj];
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int j = j0 + u * 128;
-                const int jl = j < a_units ? j + C::B_BYTES / 16 : j - a_units;
-                if (j < conv_units && !(P.xmode & 8)) lo[jl] = tf32_lo(v[u]);
-            }
-        }
-        if (!(P.xmode & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
-        mbar_arrive(&conv_bar[s]);
-    };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -779,11 +681,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         constexpr uint32_t idesc2 = make_idesc(2 * BN, !A_K, !B_K, 2u);
                         const uint64_t adl = A_K ? make_smem_desc(sa + C::LO_A_OFF + ao, 16, 1024)
                                                  : make_smem_desc(sa + C::LO_A_OFF + ao, C::BOX_BYTES, C::MN_SBO, C::MN_LAYOUT);
-                        if (ATM) {
-                            const uint32_t ta = tmem_base + 2u * C::ACC_COLS + 64u * (uint32_t)s + 8u * (uint32_t)k;  // hi; lo 32 columns on
-                            umma_tf32_ts(td, ta, bd, idesc2, !(chain_start && k == 0));
-                            umma_tf32_ts(td, ta + 32u, bd, idesc, 1);
-                        } else if (P.xmode & 2) {
+                        if (P.xmode & 2) {
                             umma<EB>(td, ad, bd, idesc, !(chain_start && k == 0));
                         } else {
                             umma<EB>(td, ad, bd, idesc2, !(chain_start && k == 0));
@@ -798,9 +696,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             dbg_stamp(P, 4);
         }
-    } else if (DG && warp >= 6) {
-        // second converter group: the odd K-blocks
-        for (int i = 1; i < nkb; i += 2) x3_convert(i, (int)threadIdx.x - 192, warp & 3);
     } else {
         // warps 2..5: TMEM lane quadrant = warp % 4, thread = accumulator row.
         const int q = warp & 3;
@@ -816,6 +711,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // into acc
             const int t = threadIdx.x - 64;  // 0..127
             int drained = 0;
+            const int va = vrows, vb = min(BN, P.N - n0);  // valid rows of the A / B tiles
+            const int a_units = GA == 1 ? 0 : (A_K ? va * 128 : ((va + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
+            const int b_units = (B_K ? vb * 128 : ((vb + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
+            const int conv_units = a_units + b_units;
             // GA: this thread owns tile row t = output pixel (forward) / input pixel (dgrad) m0 + t
             bool gvalid = false;
             int gb = 0, gy0 = 0, gx0 = 0;
@@ -877,11 +776,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 if (X3) {
-                    if (!DG || !(i & 1)) x3_convert(i, t, q);  // (the odd blocks belong to the second converter group)
-                } else {
-                    if (!(P.xmode & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
-                    mbar_arrive(&conv_bar[s]);
+                    mbar_wait(&full_bar[s], ph);
+                    // tcgen05 kind::tf32 ignores the low 13 mantissa bits of an fp32 operand (measured: bit-identical results
+                    // for raw and pre-truncated inputs), so the landed tile itself is the hi operand; only lo = x - trunc(x)
+                    // is written.  Rows past M / N are never stored, so they are skipped.
+                    const uint4 *raw = reinterpret_cast<const uint4 *>(stage);
+                    uint4 *lo = reinterpret_cast<uint4 *>(stage + C::RAW_BYTES);  // [B lo][A lo]
+                    // batches of 8 x 16 B per thread: all loads first, then all stores -- raw and lo may alias as far as the
+                    // compiler knows, so an element-wise loop serialises on shared-memory latency (measured 0.4 us per stage)
+                    for (int j0 = t; j0 < ((P.xmode & 1) ? 0 : conv_units); j0 += 8 * 128) {
+                        uint4 v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int j = j0 + u * 128;
+                            const int jj = j < a_units ? j : j - a_units + C::A_BYTES / 16;
+                            if (j < conv_units) v[u] = raw[jj];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int j = j0 + u * 128;
+                            const int jl = j < a_units ? j + C::B_BYTES / 16 : j - a_units;
+                            if (j < conv_units && !(P.xmode & 8)) lo[jl] = tf32_lo(v[u]);
+                        }
+                    }
                 }
+                if (!(P.xmode & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
+                mbar_arrive(&conv_bar[s]);
                 // chain `drained` ended at K-block (drained+1)*CHAIN - 1; by the time two more blocks have been converted
                 // its MMAs have retired, so the wait below does not stall the conversion pipeline
                 if (X3 && drained < nchains - 1 && i + 1 >= (drained + 1) * CHAIN + 2) {
@@ -1339,7 +1259,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) dbg_stamp(P, 7);
-    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
     if (threadIdx.x == 32) dbg_stamp(P, 8);
 }
 
@@ -1353,7 +1273,7 @@ static zoo_status launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, grid, dim3(P.threads), (size_t)C::smem_for(P.stages), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, grid, dim3(TC_THREADS), (size_t)C::smem_for(P.stages), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1389,7 +1309,7 @@ static zoo_status launch_conv(const CUtensorMap &tmB, const TcParams &P, dim3 gr
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, grid, dim3(P.threads), (size_t)C::SMEM, st, tmB, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, grid, dim3(TC_THREADS), (size_t)C::SMEM, st, tmB, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1402,7 +1322,7 @@ static zoo_status launch_conv_tma(const CUtensorMap &tmA, const CUtensorMap &tmB
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(C::SMEM, TC_EPI_SMEM)));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, grid, dim3(P.threads), (size_t)std::max(C::smem_for(P.stages), TC_EPI_SMEM), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, grid, dim3(TC_THREADS), (size_t)std::max(C::smem_for(P.stages), TC_EPI_SMEM), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1422,7 +1342,7 @@ static zoo_status launch_conv_wgrad(const CUtensorMap &tmA, const CUtensorMap &t
     if (stg < 2) stg = 2;
     P.stages = stg;
     P.xmode = 0;
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN>, grid, dim3(P.threads), (size_t)std::max(C::smem_for(stg), TC_EPI_SMEM), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN>, grid, dim3(TC_THREADS), (size_t)std::max(C::smem_for(stg), TC_EPI_SMEM), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1447,9 +1367,6 @@ static int tc_pick_stages(int BN, long long ctas, int nkb) {
     const int mx = BN == 32 ? TcCfg<EB, 32, X3, SPAN>::MAX_STAGES : (BN == 64 ? TcCfg<EB, 64, X3, SPAN>::MAX_STAGES : TcCfg<EB, 128, X3, SPAN>::MAX_STAGES);
     const int two = BN == 32 ? TcCfg<EB, 32, X3, SPAN>::TWO_CTA_STAGES : (BN == 64 ? TcCfg<EB, 64, X3, SPAN>::TWO_CTA_STAGES : TcCfg<EB, 128, X3, SPAN>::TWO_CTA_STAGES);
     int stg = ctas > g_sm_budget ? two : mx;
-    // 3xTF32, BN = 64: with the A operand in tensor memory a CTA holds 2 x 128 accumulator + 64 columns per stage = all 512
-    // columns from 4 stages on, and 384 -> 512 even with 2, so two CTAs never share an SM: always take the deep ring
-    if (X3 && BN == 64 && ctas <= g_sm_budget) stg = mx;
     const int force = g_tc_stages_force & 0xff;  // ZOO_TC_STAGES / zoo_test_set_tc_stages
     if (force >= 2) stg = force < mx ? force : mx;
     if (stg > nkb + 1) stg = nkb + 1 < 2 ? 2 : nkb + 1;  // no point in a ring deeper than the K loop
@@ -1463,14 +1380,6 @@ static zoo_status tc_launch_mode(int kind, int BN, bool ak, bool bk, const CUten
     TcParams P = P0;
     P.stages = tc_pick_stages<EB, X3>(BN, (long long)grid.x * grid.y * grid.z, P0.kb_per_split);
     P.xmode = g_tc_stages_force >> 8;
-    {
-        // 3xTF32 with at most one CTA per SM: spend the idle half of the SM on a second converter warpgroup and on TMEM for the
-        // A operand (ZOO_X3_WIDE=0 switches both off; kind 1 = the gathered-A kernel keeps its own converter scheme)
-        static const bool wide_on = [] { const char *e = getenv("ZOO_X3_WIDE"); return !(e && e[0] == '0'); }();
-        const bool wide = X3 && wide_on && kind != 1 && (long long)grid.x * grid.y * grid.z <= g_sm_budget;
-        P.threads = wide ? 320 : TC_THREADS;
-        P.atm = wide ? 1 : 0;
-    }
     if (kind == 2 && P0.span == 64) {  // bf16 TMA-im2col convolution over 64-byte runs (SWIZZLE_64B tiles)
         if constexpr (EB == 2 && !X3) {
             P.stages = tc_pick_stages<2, false, 64>(BN, (long long)grid.x * grid.y * grid.z, P0.kb_per_split);
