@@ -254,7 +254,9 @@ static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bo
     bool tail = false;
     if ((c.kind == ZOO_LEARNER_BASIC_DQN || c.kind == ZOO_LEARNER_DQN || c.kind == ZOO_LEARNER_PRIORITIZED_DQN) && on->desc.kind == ZOO_NET_CHAIN &&
         on->a.layers.size() >= 2) {
-        static const bool tail_on = [] { const char *e = getenv("ZOO_DQN_TAIL"); return !(e && e[0] == '0'); }();
+        // opt-in (ZOO_DQN_TAIL=1): parity-green, but measured on B200 the single CTA takes ~26 us against ~18 us for the four small
+        // launches it replaces (they run on many SMs), so the update is 4 % slower with it (profiles/r02_dqn_tail_ab.txt)
+        static const bool tail_on = [] { const char *e = getenv("ZOO_DQN_TAIL"); return e && e[0] == '1'; }();
         const LayerExec &Lh = on->a.layers.back();
         const int dbl = c.kind == ZOO_LEARNER_DQN && c.double_dqn;
         const int rows_fwd = (c.kind == ZOO_LEARNER_BASIC_DQN || dbl) ? 2 * B : B;
