@@ -25,11 +25,6 @@ namespace zoo {
 static constexpr int BM = 128;      // UMMA M (cta_group::1)
 // per stage: one 128-byte swizzle span of K per row -> BK = 128 / EB elements, 4 MMAs of K = 32 / EB each
 static constexpr int TC_THREADS = 192;
-// 3xTF32 with BN = 128 (the large-batch GEMMs: 64 KB stages, one CTA per SM whatever the thread count): a second converter
-// warpgroup (warps 6..9) takes the odd K-blocks, so the split of one block (smem read, lo = x - trunc(x), smem write, proxy fence,
-// barrier) overlaps the next one's.  Smaller tiles keep 192 threads: there the extra warps cost the second CTA per SM that the
-// split-K grids rely on (measured: profiles/r02_x3_tmem_a_and_dual_converter_negative.txt).
-template <bool X3, int BN, int GA> __host__ __device__ constexpr int tc_threads() { return (X3 && BN == 128 && GA != 1) ? 320 : TC_THREADS; }
 static constexpr int X3_CHAIN_KB = 4;         // 3xTF32: K-blocks (of 32 floats) per TMEM accumulation chain (see the kernel)
 static constexpr int TC_WS_COUNTERS = 4096;  // tail of the split-K workspace: per-tile arrival counters
 
@@ -481,7 +476,7 @@ __device__ __forceinline__ void epi_cols_store(const float *rp, int ncols, T *op
 //         row) -- so no im2col matrix exists in either direction.  A K-block's pixel rows past R x OW are never written
 //         (the ring is zeroed once at kernel start), grid.z splits the images, partial sums are red-added into the gradient.
 template <int EB, int BN, bool A_K, bool B_K, bool X3, int GA = 0, int SPAN = 128>
-__global__ void __launch_bounds__(tc_threads<X3, BN, GA>(), tc_threads<X3, BN, GA>() == 320 ? 1 : 0)
+__global__ void __launch_bounds__(TC_THREADS)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams P) {
     static_assert(GA == 0 || GA == 4 || A_K, "the gathered A operand is K-major");
     static_assert(GA != 4 || (!A_K && !B_K), "the weight-gradient operands are MN-major");
@@ -492,7 +487,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
     const int NST = GA == 1 ? C::STAGES : P.stages;  // ring depth of this launch
-    constexpr bool DG = tc_threads<X3, BN, GA>() == 320;  // two converter groups (see tc_threads)
     uint64_t *full_bar = (uint64_t *)(smem + NST * C::STAGE_BYTES);
     uint64_t *empty_bar = full_bar + C::STAGES;
     uint64_t *conv_bar = empty_bar + C::STAGES;  // X3: lo tiles written (128 converter threads arrive)
@@ -555,7 +549,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (GA == 4) {  // pad rows of every stage (pixel rows past R x OW, feature boxes past N, channel rows past Cout) must read as zero
-        for (int i = threadIdx.x; i < NST * C::STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < NST * C::STAGE_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -702,37 +696,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             dbg_stamp(P, 4);
         }
-    } else if (DG && warp >= 6) {
-        // second converter group (3xTF32, BN = 128): splits the odd K-blocks exactly as warps 2..5 split the even ones
-        const int t = threadIdx.x - 192;
-        const int va = vrows, vb = min(BN, P.N - n0);
-        const int a_units = (A_K ? va * 128 : ((va + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
-        const int b_units = (B_K ? vb * 128 : ((vb + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
-        const int conv_units = a_units + b_units;
-        for (int i = 1; i < nkb; i += 2) {
-            const int s = i % NST;
-            uint8_t *stage = smem + s * C::STAGE_BYTES;
-            mbar_wait(&full_bar[s], (i / NST) & 1);
-            const uint4 *raw = reinterpret_cast<const uint4 *>(stage);
-            uint4 *lo = reinterpret_cast<uint4 *>(stage + C::RAW_BYTES);  // [B lo][A lo]
-            for (int j0 = t; j0 < conv_units; j0 += 8 * 128) {
-                uint4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int j = j0 + u * 128;
-                    const int jj = j < a_units ? j : j - a_units + C::A_BYTES / 16;
-                    if (j < conv_units) v[u] = raw[jj];
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int j = j0 + u * 128;
-                    const int jl = j < a_units ? j + C::B_BYTES / 16 : j - a_units;
-                    if (j < conv_units) lo[jl] = tf32_lo(v[u]);
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&conv_bar[s]);
-        }
     } else {
         // warps 2..5: TMEM lane quadrant = warp % 4, thread = accumulator row.
         const int q = warp & 3;
@@ -812,7 +775,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                if (X3 && !(DG && (i & 1))) {  // (with two converter groups the odd blocks belong to warps 6..9)
+                if (X3) {
                     mbar_wait(&full_bar[s], ph);
                     // tcgen05 kind::tf32 ignores the low 13 mantissa bits of an fp32 operand (measured: bit-identical results
                     // for raw and pre-truncated inputs), so the landed tile itself is the hi operand; only lo = x - trunc(x)
@@ -837,10 +800,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                if (!(DG && (i & 1))) {
-                    if (!(P.xmode & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
-                    mbar_arrive(&conv_bar[s]);
-                }
+                if (!(P.xmode & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
+                mbar_arrive(&conv_bar[s]);
                 // chain `drained` ended at K-block (drained+1)*CHAIN - 1; by the time two more blocks have been converted
                 // its MMAs have retired, so the wait below does not stall the conversion pipeline
                 if (X3 && drained < nchains - 1 && i + 1 >= (drained + 1) * CHAIN + 2) {
@@ -1312,7 +1273,7 @@ static zoo_status launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, grid, dim3(tc_threads<X3, BN, 0>()), (size_t)C::smem_for(P.stages), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, grid, dim3(TC_THREADS), (size_t)C::smem_for(P.stages), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1361,7 +1322,7 @@ static zoo_status launch_conv_tma(const CUtensorMap &tmA, const CUtensorMap &tmB
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(C::SMEM, TC_EPI_SMEM)));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, grid, dim3(tc_threads<X3, BN, 2>()), (size_t)std::max(C::smem_for(P.stages), TC_EPI_SMEM), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, grid, dim3(TC_THREADS), (size_t)std::max(C::smem_for(P.stages), TC_EPI_SMEM), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1381,7 +1342,7 @@ static zoo_status launch_conv_wgrad(const CUtensorMap &tmA, const CUtensorMap &t
     if (stg < 2) stg = 2;
     P.stages = stg;
     P.xmode = 0;
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN>, grid, dim3(tc_threads<X3, 128, 4>()), (size_t)std::max(C::smem_for(stg), TC_EPI_SMEM), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN>, grid, dim3(TC_THREADS), (size_t)std::max(C::smem_for(stg), TC_EPI_SMEM), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
