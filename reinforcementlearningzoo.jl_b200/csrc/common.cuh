@@ -170,6 +170,10 @@ zoo_status simt_gemm(const Operand &A, const Operand &B, int M, int N, int K, co
 bool tc_gemm_supported(const Operand &A, const Operand &B, int M, int N, int K);
 zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, int split_k,
                    float *ws, size_t ws_elems, cudaStream_t st);
+// persistent tcgen05 engine for the large-batch bf16 contractions (gemm_persist.cu): 128 x 256 tiles, one CTA per SM, double-buffered
+// TMEM accumulators, TMA-store epilogue
+bool tc_gemm_persist_ok(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi);
+zoo_status tc_gemm_persist(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, cudaStream_t st);
 // dispatch: tcgen05 when supported (bf16 x bf16, or fp32 x fp32 with epi.tf32_passes > 0), otherwise SIMT
 zoo_status gemm(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, int split_k, float *ws,
                 size_t ws_elems, cudaStream_t st);

@@ -214,6 +214,7 @@ zoo_status gemm(const Operand &A, const Operand &B, int M, int N, int K, const E
         t.bias_mode = epi.bias_mode == 1 ? 2 : (epi.bias_mode == 2 ? 1 : 0);
         return tc_gemm(B, A, N, M, K, t, split_k, ws, ws_elems, st);
     }
+    if (want_tc && split_k <= 0 && tc_gemm_supported(A, B, M, N, K) && tc_gemm_persist_ok(A, B, M, N, K, epi)) return tc_gemm_persist(A, B, M, N, K, epi, st);
     if (want_tc && tc_gemm_supported(A, B, M, N, K)) return tc_gemm(A, B, M, N, K, epi, split_k, ws, ws_elems, st);
     return simt_gemm(A, B, M, N, K, epi, split_k, ws, ws_elems, st);
 }
