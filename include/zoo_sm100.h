@@ -292,7 +292,8 @@ ZOO_API zoo_status zoo_prof_timeline_get(int32_t i, char *name, int32_t name_cap
 /* ------------------------------------------------------------------ test hooks ---------- */
 /* Stand-alone GEMM of the two contraction engines, for parity tests of the kernels themselves:
  * D[M][N] = sum_k A(m,k) B(n,k).  a_kmajor: A stored [M][K] (1) or [K][M] (0); same for B ([N][K] / [K][N]).
- * engine: 0 = CUDA-core fp32, 1 = tcgen05 bf16 (inputs rounded to bf16), 2 = tcgen05 tf32, 3 = tcgen05 3xTF32.  Host pointers. */
+ * engine: 0 = CUDA-core fp32, 1 = tcgen05 bf16 (inputs rounded to bf16), 2 = tcgen05 tf32, 3 = tcgen05 3xTF32,
+ * 4 = the persistent tcgen05 bf16 engine (large shapes only).  Host pointers. */
 ZOO_API zoo_status zoo_test_gemm(int32_t engine, int32_t M, int32_t N, int32_t K, const float *A, int32_t a_kmajor,
                                  const float *B, int32_t b_kmajor, float *D, int32_t split_k);
 

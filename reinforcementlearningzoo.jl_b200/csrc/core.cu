@@ -197,14 +197,19 @@ zoo_status zoo_test_gemm(int32_t engine, int32_t M, int32_t N, int32_t K, const 
     Epilogue e;
     e.out = dD; e.sm = N; e.sn = 1;
     zoo_status s;
-    if (engine == 1) {
+    if (engine == 1 || engine == 4) {
         ZOO_CUDA(cudaMalloc(&hA, na * 2));
         ZOO_CUDA(cudaMalloc(&hB, nb * 2));
         f32_to_bf16_kernel<<<cdiv(na, 256), 256, 0, st>>>(dA, hA, na);
         f32_to_bf16_kernel<<<cdiv(nb, 256), 256, 0, st>>>(dB, hB, nb);
         oa.p = hA; oa.is_bf16 = 1; ob.p = hB; ob.is_bf16 = 1;
         ZOO_REQUIRE(tc_gemm_supported(oa, ob, M, N, K), "zoo_test_gemm: shape not supported by the tcgen05 engine");
-        s = tc_gemm(oa, ob, M, N, K, e, split_k, ws, nd + 4096, st);
+        if (engine == 4) {  // the persistent engine (large-batch bf16 GEMMs)
+            ZOO_REQUIRE(tc_gemm_persist_ok(oa, ob, M, N, K, e), "zoo_test_gemm: shape not taken by the persistent engine");
+            s = tc_gemm_persist(oa, ob, M, N, K, e, st);
+        } else {
+            s = tc_gemm(oa, ob, M, N, K, e, split_k, ws, nd + 4096, st);
+        }
     } else if (engine == 2 || engine == 3) {
         e.tf32_passes = engine == 2 ? 1 : 3;
         ZOO_REQUIRE(tc_gemm_supported(oa, ob, M, N, K), "zoo_test_gemm: shape not supported by the tcgen05 engine");

@@ -29,7 +29,7 @@ def run(zoo, engine, M, N, K, ak, bk, split):
     D = np.zeros((M, N), np.float32)
     s = zoo.lib().zoo_test_gemm(engine, M, N, K, Am.ctypes.data, ak, Bm.ctypes.data, bk, D.ctypes.data, split)
     assert s == 0, zoo.lib().zoo_last_error()
-    if engine == 1:
+    if engine in (1, 4):
         ref = bf16_round(A).astype(np.float64) @ bf16_round(B).astype(np.float64).T
     else:
         ref = A.astype(np.float64) @ B.astype(np.float64).T
@@ -54,6 +54,18 @@ def test_engines_all_majors(zoo, engine, M, N, K):
             assert err <= TOL[engine], (engine, M, N, K, ak, bk, err)
 
 
+@pytest.mark.parametrize("M,N,K", [(16384, 1024, 128), (16400, 1000, 192), (512, 7744, 4096), (20000, 264, 64)])
+def test_persistent_engine_all_majors(zoo, M, N, K):
+    """gemm_persist.cu (128 x 256 tiles, one CTA per SM, double-buffered TMEM accumulators, TMA-store epilogue) against the float64
+    product of the bf16-rounded inputs: every operand major, ragged M / N / K tails, the long-K few-tiles case."""
+    for ak in (1, 0):
+        for bk in (1, 0):
+            if ((M if not ak else K) % 8) or ((N if not bk else K) % 8):
+                continue
+            err = run(zoo, 4, M, N, K, ak, bk, 0)
+            assert err <= TOL[1], (M, N, K, ak, bk, err)
+
+
 @pytest.mark.parametrize("M,N", [(1024, 6), (1025, 6), (2048, 6), (4096, 13), (2048, 8), (2048, 16)])
 def test_narrow_heads_many_rows(zoo, M, N):
     # fc2 of an IQN batch (batch x quantiles rows, n_actions columns): above 1024 rows the CUDA-core engine switches to its
@@ -71,7 +83,7 @@ def test_split_k_is_consistent(zoo, engine, split):
 
 
 @pytest.mark.parametrize("env,val", [("ZOO_IMPLICIT_CONV", "1"), ("ZOO_TMA_DGRAD", "0"), ("ZOO_TMA_WGRAD", "0"), ("ZOO_PDL", "0"), ("ZOO_TMA_CONV", "0"),
-                                     ("ZOO_TMA_STORE", "0"), ("ZOO_DQN_TAIL", "1"), ("ZOO_NARROW", "0"), ("ZOO_IQN_FUSE", "0")])
+                                     ("ZOO_TMA_STORE", "0"), ("ZOO_PERSIST_GEMM", "0"), ("ZOO_DQN_TAIL", "1"), ("ZOO_NARROW", "0"), ("ZOO_IQN_FUSE", "0")])
 def test_non_default_kernel_paths_keep_parity(env, val):
     """Every kernel path that has a switch: the gathered-A implicit conv (opt-in), and -- switched OFF here -- the TMA data / weight
     gradients (falls back to GEMM + col2im / im2col + GEMM), programmatic dependent launch, the TMA-im2col forward conv, the TMA-store
