@@ -69,35 +69,44 @@ __global__ void __launch_bounds__(256) narrow_fwd_kernel(const T *__restrict__ X
         }
     float bn = lane < N ? __ldg(bias + lane) : 0.f;
     pdl_trigger();
-    for (int m = blockIdx.x * 8 + (threadIdx.x >> 5); m < M; m += gridDim.x * 8) {
-        float acc[NARROW_NMAX];
+    // ROWS rows in flight per warp: a streaming kernel with 8 resident warps per SM needs several independent 16-byte loads per
+    // lane to cover the DRAM latency (one row at a time ran at 0.87 TB/s, profiles/r02_ncu_full_iqn_b512_bf16.txt)
+    constexpr int ROWS = CPL >= 4 ? 1 : 4;  // (CPL = 4: the weights alone fill the register file)
+    for (int mb = (blockIdx.x * 8 + (threadIdx.x >> 5)) * ROWS; mb < M; mb += gridDim.x * 8 * ROWS) {
+        typename NV::raw r[ROWS][CPL];
 #pragma unroll
-        for (int n = 0; n < NARROW_NMAX; ++n) acc[n] = 0.f;
-        const typename NV::raw *row = reinterpret_cast<const typename NV::raw *>(X + (long long)m * K);
-        typename NV::raw r[CPL];
+        for (int u = 0; u < ROWS; ++u)
 #pragma unroll
-        for (int c = 0; c < CPL; ++c)
-            if (lane + 32 * c < nchunks) r[c] = row[lane + 32 * c];
+            for (int c = 0; c < CPL; ++c)
+                if (mb + u < M && lane + 32 * c < nchunks) r[u][c] = reinterpret_cast<const typename NV::raw *>(X + (long long)(mb + u) * K)[lane + 32 * c];
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            if (lane + 32 * c < nchunks) {
-                float x[V];
-                NV::unpack(r[c], x);
+        for (int u = 0; u < ROWS; ++u) {
+            const int m = mb + u;
+            if (m >= M) break;
+            float acc[NARROW_NMAX];
 #pragma unroll
-                for (int n = 0; n < NARROW_NMAX; ++n)
+            for (int n = 0; n < NARROW_NMAX; ++n) acc[n] = 0.f;
 #pragma unroll
-                    for (int e = 0; e < V; ++e) acc[n] = fmaf(x[e], w[n][c * V + e], acc[n]);
+            for (int c = 0; c < CPL; ++c) {
+                if (lane + 32 * c < nchunks) {
+                    float x[V];
+                    NV::unpack(r[u][c], x);
+#pragma unroll
+                    for (int n = 0; n < NARROW_NMAX; ++n)
+#pragma unroll
+                        for (int e = 0; e < V; ++e) acc[n] = fmaf(x[e], w[n][c * V + e], acc[n]);
+                }
             }
-        }
-        float mine = 0.f;
+            float mine = 0.f;
 #pragma unroll
-        for (int n = 0; n < NARROW_NMAX; ++n) {
-            float v = acc[n];
+            for (int n = 0; n < NARROW_NMAX; ++n) {
+                float v = acc[n];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == n) mine = v;
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == n) mine = v;
+            }
+            if (lane < N) out[(long long)m * N + lane] = mine + bn;
         }
-        if (lane < N) out[(long long)m * N + lane] = mine + bn;
     }
 }
 
@@ -133,20 +142,32 @@ __global__ void __launch_bounds__(256) narrow_bwd_kernel(const T *__restrict__ X
 #pragma unroll
     for (int e = 0; e < 8; ++e) dbp[e] = 0.f;
     pdl_trigger();
-    for (long long m = (long long)blockIdx.x * RPP + rl; m < M; m += (long long)gridDim.x * RPP) {
-        float x[8], dy[NARROW_NMAX];
-        if (sizeof(T) == 2) {
-            float t8[8];
-            NarrowVec<bf16>::unpack(*reinterpret_cast<const uint4 *>(reinterpret_cast<const bf16 *>(X) + m * K + kq * 8), t8);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = t8[e];
-        } else {
-            const float4 a = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(X) + m * K + kq * 8);
-            const float4 b = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(X) + m * K + kq * 8 + 4);
-            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    // the next row's input and output gradient are fetched before this row is computed (one row per thread group at a time left
+    // the kernel latency-bound: 0.52 TB/s at 32 768 rows)
+    uint4 nx0 = make_uint4(0u, 0u, 0u, 0u), nx1 = nx0;
+    float ndy[NARROW_NMAX];
+    auto fetch = [&](long long m) {
+        if (sizeof(T) == 2) nx0 = *reinterpret_cast<const uint4 *>(reinterpret_cast<const bf16 *>(X) + m * K + kq * 8);
+        else {
+            nx0 = *reinterpret_cast<const uint4 *>(reinterpret_cast<const float *>(X) + m * K + kq * 8);
+            nx1 = *reinterpret_cast<const uint4 *>(reinterpret_cast<const float *>(X) + m * K + kq * 8 + 4);
         }
 #pragma unroll
-        for (int n = 0; n < NARROW_NMAX; ++n) dy[n] = n < N ? __ldg(dY + m * N + n) : 0.f;
+        for (int n = 0; n < NARROW_NMAX; ++n) ndy[n] = n < N ? __ldg(dY + m * N + n) : 0.f;
+    };
+    const long long mstep = (long long)gridDim.x * RPP;
+    if ((long long)blockIdx.x * RPP + rl < M) fetch((long long)blockIdx.x * RPP + rl);
+    for (long long m = (long long)blockIdx.x * RPP + rl; m < M; m += mstep) {
+        float x[8], dy[NARROW_NMAX];
+        if (sizeof(T) == 2) {
+            NarrowVec<bf16>::unpack(nx0, x);
+        } else {
+            x[0] = __uint_as_float(nx0.x); x[1] = __uint_as_float(nx0.y); x[2] = __uint_as_float(nx0.z); x[3] = __uint_as_float(nx0.w);
+            x[4] = __uint_as_float(nx1.x); x[5] = __uint_as_float(nx1.y); x[6] = __uint_as_float(nx1.z); x[7] = __uint_as_float(nx1.w);
+        }
+#pragma unroll
+        for (int n = 0; n < NARROW_NMAX; ++n) dy[n] = ndy[n];
+        if (m + mstep < M) fetch(m + mstep);
         float dx[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -200,7 +221,7 @@ zoo_status narrow_forward(const void *X, int x_bf16, const float *W, const float
     ZOO_REQUIRE(narrow_supported(N, K, x_bf16) && M > 0 && M < (1ll << 31), "narrow_forward: unsupported shape (N=%d K=%lld)", N, K);
     const int v = x_bf16 ? 8 : 4;
     const int cpl = cdiv(K / v, 32);
-    const dim3 grid((unsigned)std::min<long long>(cdiv(M, 8), 148 * 2)), block(256);
+    const dim3 grid((unsigned)std::min<long long>(cdiv(M, 8 * (cpl <= 2 ? 4 : 1)), 148 * 2)), block(256);
     const size_t smem = (size_t)N * K * sizeof(float);
     static bool attr = false;
     if (!attr) {
