@@ -23,9 +23,9 @@ static constexpr int PST = 3;                 // ring depth
 static constexpr int P_A_BYTES = BM * 128;    // 16 KB
 static constexpr int P_B_BYTES = PBN * 128;   // 32 KB
 static constexpr int P_STAGE = P_A_BYTES + P_B_BYTES;
-static constexpr int P_EPI_OFF = PST * P_STAGE;             // epilogue staging: 4 warps x 2 x 4 KB
-static constexpr int P_BIAS_OFF = P_EPI_OFF + 4 * 8192;      // bias [256] floats, then rowmul [4][256] floats
-static constexpr int P_BAR_OFF = P_BIAS_OFF + 5 * PBN * 4;
+static constexpr int P_EPI_OFF = PST * P_STAGE;             // epilogue staging: 4 warps x 16 KB (a warp's whole 32 x 256 slab: 4 blocks of 32 rows x 128 B)
+static constexpr int P_BIAS_OFF = P_EPI_OFF + 4 * 16384;     // per warp: bias [256] + rowmul [256] floats
+static constexpr int P_BAR_OFF = P_BIAS_OFF + 4 * 2 * PBN * 4;
 static constexpr int P_SMEM = P_BAR_OFF + 256;
 
 struct PersistParams {
@@ -122,94 +122,117 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const void *const maskp = e.mask;
         const long long msm = e.mask_sm;
         const bool rmul = e.rowmul != nullptr;
-        float *const bias_s = reinterpret_cast<float *>(smem + P_BIAS_OFF);
-        float *const rm_s = bias_s + PBN + q * PBN;
-        const uint32_t sbase = smem_u32(smem) + P_EPI_OFF + q * 8192;
-        const int tt = threadIdx.x - 64;
+        // everything below is private to the warp (its own bias / multiplier copy, its own staging slab): no CTA-level barrier in
+        // the tile loop.  Per tile: the bias / multiplier loads are issued BEFORE the wait for the accumulator, the warp's 32 x 256
+        // slab is converted into four SWIZZLE_128B blocks, ONE proxy fence, then one TMA store per block (fp32 output: two rounds of
+        // four 32-column blocks); the stores of tile t are only waited for when tile t + 1 is about to overwrite the slab.
+        float *const bias_s = reinterpret_cast<float *>(smem + P_BIAS_OFF) + q * 2 * PBN;
+        float *const rm_s = bias_s + PBN;
+        const uint32_t sbase = smem_u32(smem) + P_EPI_OFF + q * 16384;
         const int cpg = out_bf16 ? 64 : 32;  // columns per 128-byte staging row
-        int t = 0, issued = 0, buf = 0;
+        int t = 0;
+        bool pending = false;
         for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++t) {
             const int ab = t & 1;
             const int m0 = (tile / P.ntn) * BM, n0 = (tile % P.ntn) * PBN;
             const int row0 = m0 + q * 32;
-            // stage bias / row multiplier of this tile (the previous tile's readers are past the barrier below)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int j = tt; j < PBN; j += 128) bias_s[j] = (bias_mode == 1 && n0 + j < Nn) ? __ldg(e.bias + n0 + j) : 0.f;
-            for (int j = lane; j < PBN; j += 32)
-                rm_s[j] = (rmul && n0 + j < Nn) ? ldg_elem(e.rowmul, out_bf16, (long long)(row0 / e.rowmul_div) * e.rowmul_ld + n0 + j) : 1.f;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            float bv[PBN / 32], rv[PBN / 32];
+#pragma unroll
+            for (int j = 0; j < PBN / 32; ++j) {
+                const int n = n0 + lane + 32 * j;
+                bv[j] = (bias_mode == 1 && n < Nn) ? __ldg(e.bias + n) : 0.f;
+                rv[j] = (rmul && n < Nn) ? ldg_elem(e.rowmul, out_bf16, (long long)(row0 / e.rowmul_div) * e.rowmul_ld + n) : 1.f;
+            }
             mbar_wait(&acc_full[ab], (t >> 1) & 1);
             tc_fence_after();
+            if (pending) {  // the previous tile's stores have read the slab
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                pending = false;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < PBN / 32; ++j) { bias_s[lane + 32 * j] = bv[j]; rm_s[lane + 32 * j] = rv[j]; }
+            __syncwarp();
             const bool rowok = row0 + lane < P.M;
+            const int ncols = min(PBN, Nn - n0);
 #pragma unroll 1
-            for (int c = 0; c < PBN; c += cpg) {
-                if (n0 + c >= Nn) break;
-                if (issued >= 2) {
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            for (int half = 0; half < (out_bf16 ? 1 : 2); ++half) {  // fp32: 128 columns (4 blocks of 32) per round
+                if (half * 128 >= ncols) break;
+                if (half == 1) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     __syncwarp();
                 }
-                const uint32_t sb = sbase + buf * 4096 + lane * 128;
 #pragma unroll 1
-                for (int h = 0; h < cpg / 32; ++h) {
-                    uint32_t r[32];
-                    tmem_ld32(tq + (uint32_t)(ab * PBN + c + 32 * h), r);
-                    const int nb = n0 + c + 32 * h;
-                    uint4 mk[4];
-                    if (maskp) {  // relu' source: bf16 [M][msm], same rows / columns as the output
-                        const bf16 *mp = (const bf16 *)maskp + (long long)(row0 + lane) * msm + nb;
-                        if (rowok && nb + 32 <= Nn) {
+                for (int blk = 0; blk < 4; ++blk) {
+                    const int c = half * 128 + blk * cpg;
+                    if (c >= ncols) break;
+                    const uint32_t sb = sbase + blk * 4096 + lane * 128;
+#pragma unroll 1
+                    for (int h = 0; h < cpg / 32; ++h) {
+                        uint32_t r[32];
+                        tmem_ld32(tq + (uint32_t)(ab * PBN + c + 32 * h), r);
+                        const int nb = n0 + c + 32 * h;
+                        uint4 mk[4];
+                        if (maskp) {  // relu' source: bf16 [M][msm], same rows / columns as the output
+                            const bf16 *mp = (const bf16 *)maskp + (long long)(row0 + lane) * msm + nb;
+                            if (rowok && nb + 32 <= Nn) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) mk[j] = __ldg(reinterpret_cast<const uint4 *>(mp) + j);
-                        } else {
+                                for (int j = 0; j < 4; ++j) mk[j] = __ldg(reinterpret_cast<const uint4 *>(mp) + j);
+                            } else {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint32_t w[4];
+                                for (int j = 0; j < 4; ++j) {
+                                    uint32_t w[4];
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const int col = j * 8 + 2 * i;
-                                    const uint32_t lo = (rowok && nb + col < Nn) ? (uint32_t)__bfloat16_as_ushort(__ldg(mp + col)) : 0u;
-                                    const uint32_t hi = (rowok && nb + col + 1 < Nn) ? (uint32_t)__bfloat16_as_ushort(__ldg(mp + col + 1)) : 0u;
-                                    w[i] = lo | (hi << 16);
+                                    for (int i = 0; i < 4; ++i) {
+                                        const int col = j * 8 + 2 * i;
+                                        const uint32_t lo = (rowok && nb + col < Nn) ? (uint32_t)__bfloat16_as_ushort(__ldg(mp + col)) : 0u;
+                                        const uint32_t hi = (rowok && nb + col + 1 < Nn) ? (uint32_t)__bfloat16_as_ushort(__ldg(mp + col + 1)) : 0u;
+                                        w[i] = lo | (hi << 16);
+                                    }
+                                    mk[j] = make_uint4(w[0], w[1], w[2], w[3]);
                                 }
-                                mk[j] = make_uint4(w[0], w[1], w[2], w[3]);
                             }
                         }
-                    }
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        const uint32_t mw[4] = {mk[j8].x, mk[j8].y, mk[j8].z, mk[j8].w};
-                        float x[8];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int col = c + 32 * h + j8 * 8 + 2 * i;
-                            float x0 = __uint_as_float(r[j8 * 8 + 2 * i]) + bias_s[col], x1 = __uint_as_float(r[j8 * 8 + 2 * i + 1]) + bias_s[col + 1];
-                            const float r0f = fmaxf(x0, 0.f), r1f = fmaxf(x1, 0.f);
-                            x0 = relu ? r0f : x0;
-                            x1 = relu ? r1f : x1;
-                            if (maskp) {
-                                x0 = __uint_as_float(mw[i] << 16) > 0.f ? x0 : 0.f;
-                                x1 = __uint_as_float(mw[i] & 0xffff0000u) > 0.f ? x1 : 0.f;
-                            }
-                            x[2 * i] = x0 * rm_s[col];
-                            x[2 * i + 1] = x1 * rm_s[col + 1];
-                        }
-                        if (out_bf16) {  // 8 values = one 16-byte chunk; chunk index within the 128-byte row = h * 4 + j8
-                            uint32_t pk[4];
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            const uint32_t mw[4] = {mk[j8].x, mk[j8].y, mk[j8].z, mk[j8].w};
+                            const int col0 = c + 32 * h + j8 * 8;
+                            const float4 b0 = *reinterpret_cast<const float4 *>(bias_s + col0), b1 = *reinterpret_cast<const float4 *>(bias_s + col0 + 4);
+                            const float4 m0v = *reinterpret_cast<const float4 *>(rm_s + col0), m1v = *reinterpret_cast<const float4 *>(rm_s + col0 + 4);
+                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                            const float mm[8] = {m0v.x, m0v.y, m0v.z, m0v.w, m1v.x, m1v.y, m1v.z, m1v.w};
+                            float x[8];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
-                                pk[i] = *reinterpret_cast<const uint32_t *>(&hh);
+                                float x0 = __uint_as_float(r[j8 * 8 + 2 * i]) + bb[2 * i], x1 = __uint_as_float(r[j8 * 8 + 2 * i + 1]) + bb[2 * i + 1];
+                                const float r0f = fmaxf(x0, 0.f), r1f = fmaxf(x1, 0.f);
+                                x0 = relu ? r0f : x0;
+                                x1 = relu ? r1f : x1;
+                                if (maskp) {
+                                    x0 = __uint_as_float(mw[i] << 16) > 0.f ? x0 : 0.f;
+                                    x1 = __uint_as_float(mw[i] & 0xffff0000u) > 0.f ? x1 : 0.f;
+                                }
+                                x[2 * i] = x0 * mm[2 * i];
+                                x[2 * i + 1] = x1 * mm[2 * i + 1];
                             }
-                            const int jc = h * 4 + j8;
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + ((uint32_t)(jc ^ (lane & 7)) << 4)), "r"(pk[0]), "r"(pk[1]),
-                                         "r"(pk[2]), "r"(pk[3]) : "memory");
-                        } else {         // fp32: 8 values = two chunks; 32 columns fill the 128-byte row (h == 0)
+                            if (out_bf16) {  // 8 values = one 16-byte chunk; chunk index within the 128-byte row = h * 4 + j8
+                                uint32_t pk[4];
 #pragma unroll
-                            for (int hc = 0; hc < 2; ++hc) {
-                                const int jc = j8 * 2 + hc;
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + ((uint32_t)(jc ^ (lane & 7)) << 4)),
-                                             "r"(__float_as_uint(x[4 * hc])), "r"(__float_as_uint(x[4 * hc + 1])), "r"(__float_as_uint(x[4 * hc + 2])),
-                                             "r"(__float_as_uint(x[4 * hc + 3])) : "memory");
+                                for (int i = 0; i < 4; ++i) {
+                                    const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+                                    pk[i] = *reinterpret_cast<const uint32_t *>(&hh);
+                                }
+                                const int jc = h * 4 + j8;
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + ((uint32_t)(jc ^ (lane & 7)) << 4)), "r"(pk[0]), "r"(pk[1]),
+                                             "r"(pk[2]), "r"(pk[3]) : "memory");
+                            } else {         // fp32: 8 values = two chunks; 32 columns fill the 128-byte row (h == 0)
+#pragma unroll
+                                for (int hc = 0; hc < 2; ++hc) {
+                                    const int jc = j8 * 2 + hc;
+                                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + ((uint32_t)(jc ^ (lane & 7)) << 4)),
+                                                 "r"(__float_as_uint(x[4 * hc])), "r"(__float_as_uint(x[4 * hc + 1])), "r"(__float_as_uint(x[4 * hc + 2])),
+                                                 "r"(__float_as_uint(x[4 * hc + 3])) : "memory");
+                                }
                             }
                         }
                     }
@@ -217,13 +240,16 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&P.tmC),
-                                 "r"(sbase + buf * 4096), "r"(n0 + c), "r"(row0)
-                                 : "memory");
+                    for (int blk = 0; blk < 4; ++blk) {
+                        const int c = half * 128 + blk * cpg;
+                        if (c >= ncols) break;
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&P.tmC),
+                                     "r"(sbase + blk * 4096), "r"(n0 + c), "r"(row0)
+                                     : "memory");
+                    }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                ++issued;
-                buf ^= 1;
+                pending = true;
             }
             // every TMEM read of this tile is done (tcgen05.ld waits inside tmem_ld32): hand the accumulator back
             tc_fence_before();
@@ -243,13 +269,18 @@ static bool persist_enabled() {
     return on;
 }
 
+static int persist_min_k() {
+    static const int k = [] { const char *e = getenv("ZOO_PERSIST_MIN_K"); return e ? atoi(e) : 256; }();
+    return k;
+}
+
 // host: the shapes this engine takes (everything else stays with tc_gemm)
 bool tc_gemm_persist_ok(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi) {
     if (!persist_enabled() || !A.is_bf16 || !B.is_bf16) return false;
     const long long tiles = (long long)cdiv(M, BM) * cdiv(N, PBN);
     // enough work to keep every SM busy without a K split -- and a main loop long enough to hide the epilogue of the previous tile
     // behind it (measured: the K = 64 phi GEMM, one K-block per tile, runs 428 us here against 237 us on the one-tile-per-CTA engine)
-    if (N < 256 || K < 256 || tiles < 100 || (tiles < 2 * g_sm_budget && K < 4096)) return false;
+    if (N < 256 || K < persist_min_k() || tiles < 100 || (tiles < 2 * g_sm_budget && K < 4096)) return false;
     if (epi.accumulate == 1 || epi.bias_mode == 2 || epi.sn != 1 || !epi.out || ((uintptr_t)epi.out & 15)) return false;
     const int esz = epi.out_bf16 ? 2 : 4;
     if ((epi.sm * esz) % 16) return false;

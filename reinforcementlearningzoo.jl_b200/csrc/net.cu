@@ -287,19 +287,23 @@ __global__ void iqn_merge_bwd_vec_kernel(const T *__restrict__ dm, const T *__re
 //   relu(phi)  = merged / psi wherever psi > 0, and where psi == 0 relu'(psi) = 0 kills d psi anyway.
 // so  dphi = dm .* psi .* [merged > 0],   dpsi[b] = [psi > 0] / psi .* sum_n dm .* merged,   dbias_phi += sum over rows of dphi
 // (the bias gradient of phi's last layer is folded in: it was a separate column-sum pass over the 0.5 GB dphi tensor).
-// One CTA per sample: its 256 threads sweep the feature axis, so every quantile row is read and written in 4 KB contiguous pieces
-// (32 x 8 threads over 8 samples moved 512-byte granules and reached 56 % of the HBM peak, profiles/r02_ncu_full_iqn_b512_bf16.txt);
-// the bias sums go out as one red per (sample, feature).
+// CTA = 32 feature vectors (x) x 8 samples (y): one thread per (feature vector, sample) walks the N quantile rows; the bias sums
+// of the 8 samples are combined in shared memory, so the CTA issues one atomic per feature.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) iqn_merge_bwd_fused_kernel(const T *__restrict__ dm, const T *__restrict__ feat, const T *__restrict__ merged,
                                                                   T *__restrict__ dea, T *__restrict__ dfeat, float *__restrict__ dbias, int B, int F, int N) {
+    __shared__ float red[8][32 * VEC + 1];
     const int fv = F / VEC;
-    const int b = blockIdx.x;
-    for (int f = blockIdx.y * 256 + threadIdx.x; f < fv; f += gridDim.y * 256) {  // (small batches split the feature axis over gridDim.y)
-        const VecT<T, VEC> ftv = *reinterpret_cast<const VecT<T, VEC> *>(feat + (long long)b * F + (long long)f * VEC);
-        float ft[VEC], acc[VEC], bsum[VEC];
+    const int f = blockIdx.x * 32 + threadIdx.x;
+    const int b = blockIdx.y * 8 + threadIdx.y;
+    float bsum[VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) { ft[i] = to_f(ftv.v[i]); acc[i] = 0.f; bsum[i] = 0.f; }
+    for (int i = 0; i < VEC; ++i) bsum[i] = 0.f;
+    if (f < fv && b < B) {
+        const VecT<T, VEC> ftv = *reinterpret_cast<const VecT<T, VEC> *>(feat + (long long)b * F + (long long)f * VEC);
+        float ft[VEC], acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { ft[i] = to_f(ftv.v[i]); acc[i] = 0.f; }
 #pragma unroll 4
         for (int n = 0; n < N; ++n) {
             const long long o = ((long long)b * N + n) * F + (long long)f * VEC;
@@ -320,8 +324,18 @@ __global__ void __launch_bounds__(256) iqn_merge_bwd_fused_kernel(const T *__res
 #pragma unroll
         for (int i = 0; i < VEC; ++i) of.v[i] = from_f<T>(ft[i] > 0.f ? acc[i] / ft[i] : 0.f);
         *reinterpret_cast<VecT<T, VEC> *>(dfeat + (long long)b * F + (long long)f * VEC) = of;
+    }
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) atomicAdd(dbias + (long long)f * VEC + i, bsum[i]);
+    for (int i = 0; i < VEC; ++i) red[threadIdx.y][threadIdx.x * VEC + i] = bsum[i];
+    __syncthreads();
+    for (int j = threadIdx.y * 32 + threadIdx.x; j < 32 * VEC; j += 256) {
+        const int fcol = blockIdx.x * 32 * VEC + j;
+        if (fcol < F) {
+            float s = 0.f;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) s += red[y][j];
+            atomicAdd(dbias + fcol, s);
+        }
     }
 }
 
@@ -813,7 +827,8 @@ static zoo_status net_backward_impl(zoo_net *net, int obs_dtype, const void *obs
     prof_label("iqn_merge_bwd[%lldx%d]", (long long)rows * n_tau, F);
     if (net->iqn_fused) {
         float *dbias = net->grads + net->tensors[Pphi.bt].offset;
-#define MBWD(T, V) iqn_merge_bwd_fused_kernel<T, V><<<dim3(rows, std::max(1, std::min(cdiv(F / V, 256), 296 / rows))), dim3(256), 0, st>>>((const T *)net->dmerged, (const T *)Ppsi.out, (const T *)net->merged, (T *)Pphi.dout, (T *)Ppsi.dout, dbias, rows, F, n_tau)
+        const dim3 blk(32, 8);
+#define MBWD(T, V) iqn_merge_bwd_fused_kernel<T, V><<<dim3(cdiv(F / V, 32), cdiv(rows, 8)), blk, 0, st>>>((const T *)net->dmerged, (const T *)Ppsi.out, (const T *)net->merged, (T *)Pphi.dout, (T *)Ppsi.dout, dbias, rows, F, n_tau)
         if (bf && F % 8 == 0) MBWD(bf16, 8);
         else if (!bf && F % 4 == 0) MBWD(float, 4);
         else if (bf) MBWD(bf16, 1);
