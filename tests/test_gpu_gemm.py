@@ -66,6 +66,19 @@ def test_persistent_engine_all_majors(zoo, M, N, K):
             assert err <= TOL[1], (M, N, K, ak, bk, err)
 
 
+@pytest.mark.parametrize("env,val", [("ZOO_PAIR_GEMM", "0"), ("ZOO_PAIR_MIN_K", "64")])
+def test_persistent_engine_pair_modes(env, val):
+    """The persistent engine picks CTA pairs (cta_group::2, 256 x 256 tiles, each CTA stages half of B) for K >= 1024 and one CTA per
+    128 x 256 tile below that.  Both forced everywhere: the stand-alone GEMM cases above, and the IQN 512 x 64 bf16 update against the
+    twin (rowmul / relu'-mask epilogues of the phi forward and the fc1 data gradient on the pair kernel)."""
+    e = dict(os.environ)
+    e[env] = val
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_gemm.py"), os.path.join(ROOT, "tests", "test_gpu_full_size.py"),
+                        "-m", "gpu", "-q", "-x", "-k", "persistent_engine_all_majors or (pinned and iqn_atari_b512 and bf16)"],
+                       env=e, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("M,N", [(1024, 6), (1025, 6), (2048, 6), (4096, 13), (2048, 8), (2048, 16)])
 def test_narrow_heads_many_rows(zoo, M, N):
     # fc2 of an IQN batch (batch x quantiles rows, n_actions columns): above 1024 rows the CUDA-core engine switches to its
