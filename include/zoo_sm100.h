@@ -181,6 +181,13 @@ ZOO_API zoo_status zoo_learner_destroy(zoo_learner *lrn);
 /* update!(learner, batch): loss_out -> learner.loss (NULL => fully asynchronous enqueue, no sync);
  * new_priority_out: [B] floats (batch_losses .+ 1f-10).^beta, or NULL. */
 ZOO_API zoo_status zoo_learner_update(zoo_learner *lrn, const zoo_batch *batch, float *loss_out, float *new_priority_out);
+/* update! without waiting for the result (the reference's update! is just as asynchronous under CUDA.jl: dqn.jl:138-140 only stores
+ * the loss): submit enqueues the update and a device->host copy of its loss (and, if want_priorities, of its new priorities) into
+ * library-owned pinned memory; collect waits for the OLDEST submitted update and hands its results out.  At most 4 updates may be
+ * in flight.  Host batches (on_device = 0) are copied on a second stream into one of two staging slots, so the H2D copy of update
+ * i + 1 overlaps the kernels of update i; the arrays a batch points to must stay valid until the matching collect returns. */
+ZOO_API zoo_status zoo_learner_submit(zoo_learner *lrn, const zoo_batch *batch, int32_t want_priorities);
+ZOO_API zoo_status zoo_learner_collect(zoo_learner *lrn, float *loss_out, float *new_priority_out);
 /* The two halves of update!, for parity tests and external all-reduce:
  * compute_grads = everything up to and including Zygote.gradient; apply = update!(Q, gs). */
 ZOO_API zoo_status zoo_learner_compute_grads(zoo_learner *lrn, const zoo_batch *batch, float *loss_out, float *new_priority_out);

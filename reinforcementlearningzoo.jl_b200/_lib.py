@@ -79,6 +79,8 @@ SIGNATURES = {
     "zoo_learner_destroy": [V],
     "zoo_learner_update": [V, C.POINTER(Batch), V, V],
     "zoo_learner_compute_grads": [V, C.POINTER(Batch), V, V],
+    "zoo_learner_submit": [V, C.POINTER(Batch), C.c_int32],
+    "zoo_learner_collect": [V, V, V],
     "zoo_learner_apply": [V],
     "zoo_learner_get_grad": [V, I32, V, I64],
     "zoo_learner_grad_buffer": [V, PV, C.POINTER(I64)],

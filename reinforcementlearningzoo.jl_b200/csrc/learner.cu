@@ -162,6 +162,20 @@ struct zoo_learner {
     int warm = 0;
     bool target_forked = false;
     void *nccl_reg = nullptr;  // ncclCommRegister handle of the gradient buffer (data-parallel learners)
+    // pipelined host batches (zoo_learner_submit / zoo_learner_collect): the H2D copies of update i + 1 run on a copy stream into
+    // one of two staging slots while update i computes; one staging launch moves a slot into d_obs / d_pack on the learner's stream
+    struct HostSlot {
+        uint8_t *d_obs = nullptr, *d_pack = nullptr, *h_pack = nullptr;
+        cudaEvent_t ev_copied = nullptr, ev_consumed = nullptr;
+        bool used = false;
+    } slot[2];
+    int slot_next = 0;
+    cudaStream_t st_copy = nullptr;
+    static constexpr int PIPE = 4;     // submitted-but-not-collected updates
+    float *h_res[PIPE] = {};           // pinned: loss, then B priorities
+    cudaEvent_t ev_res[PIPE] = {};
+    bool res_prio[PIPE] = {};
+    int res_head = 0, res_count = 0;
 };
 
 static zoo_status opt_tick(zoo_opt *o, cudaStream_t st) {
@@ -344,7 +358,25 @@ static zoo_status late_bucket(void *ctx_, cudaStream_t st) {
     return ZOO_OK;
 }
 
-static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b) {
+static zoo_status pipe_alloc(zoo_learner *L) {
+    if (L->st_copy) return ZOO_OK;
+    ZOO_CUDA(cudaStreamCreateWithFlags(&L->st_copy, cudaStreamNonBlocking));
+    const size_t obs_cap = (size_t)2 * L->B * obs_elems(L->online) * sizeof(float);
+    for (auto &sl : L->slot) {
+        ZOO_CUDA(cudaMalloc(&sl.d_obs, obs_cap));
+        ZOO_CUDA(cudaMalloc(&sl.d_pack, L->pack_bytes));
+        ZOO_CUDA(cudaHostAlloc(&sl.h_pack, L->pack_bytes, cudaHostAllocDefault));
+        ZOO_CUDA(cudaEventCreateWithFlags(&sl.ev_copied, cudaEventDisableTiming));
+        ZOO_CUDA(cudaEventCreateWithFlags(&sl.ev_consumed, cudaEventDisableTiming));
+    }
+    for (int i = 0; i < zoo_learner::PIPE; ++i) {
+        ZOO_CUDA(cudaHostAlloc(&L->h_res[i], (size_t)(1 + L->B) * sizeof(float), cudaHostAllocDefault));
+        ZOO_CUDA(cudaEventCreateWithFlags(&L->ev_res[i], cudaEventDisableTiming));
+    }
+    return ZOO_OK;
+}
+
+static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b, bool pipelined = false) {
     const zoo_learner_cfg &c = L->cfg;
     cudaStream_t st = L->st;
     const int B = L->B;
@@ -355,6 +387,43 @@ static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b) {
     L->obs_dtype = b->obs_dtype;
     const size_t obs_bytes = (size_t)B * obs_elems(L->online) * (b->obs_dtype == ZOO_OBS_U8 ? 1 : 4);
     if (c.kind == ZOO_LEARNER_IQN) ZOO_REQUIRE((b->tau != nullptr) == (b->tau_prime != nullptr), "update: pass both tau and tau_prime or neither");
+    zoo_batch via;  // pipelined host batch: what the staging launch below reads (the slot's device copies)
+    if (pipelined && !b->on_device && obs_bytes % 16 == 0) {
+        ZOO_TRY(pipe_alloc(L));
+        auto &sl = L->slot[L->slot_next];
+        L->slot_next ^= 1;
+        if (sl.used) ZOO_CUDA(cudaEventSynchronize(sl.ev_consumed));  // the staging launch of two submits ago has read the slot
+        uint8_t *h = sl.h_pack;
+        memcpy(h + L->off_action, b->action, (size_t)B * sizeof(int));
+        memcpy(h + L->off_reward, b->reward, (size_t)B * sizeof(float));
+        memcpy(h + L->off_terminal, b->terminal, (size_t)B);
+        if (b->priority) memcpy(h + L->off_priority, b->priority, (size_t)B * sizeof(float));
+        if (b->next_mask) memcpy(h + L->off_mask, b->next_mask, (size_t)B * c.n_actions);
+        const bool has_tau = (c.kind == ZOO_LEARNER_IQN || c.kind == ZOO_LEARNER_REM_DQN) && b->tau;
+        if (c.kind == ZOO_LEARNER_IQN && b->tau) {
+            memcpy(h + L->off_tau, b->tau, (size_t)B * c.N * sizeof(float));
+            memcpy(h + L->off_taup, b->tau_prime, (size_t)B * c.N_prime * sizeof(float));
+        }
+        if (c.kind == ZOO_LEARNER_REM_DQN && b->tau) memcpy(h + L->off_tau, b->tau, (size_t)c.N * sizeof(float));
+        const size_t used = has_tau ? L->pack_bytes : (L->off_tau ? L->off_tau : L->pack_bytes);
+        ZOO_CUDA(cudaMemcpyAsync(sl.d_obs, b->state, obs_bytes, cudaMemcpyHostToDevice, L->st_copy));
+        ZOO_CUDA(cudaMemcpyAsync(sl.d_obs + obs_bytes, b->next_state, obs_bytes, cudaMemcpyHostToDevice, L->st_copy));
+        ZOO_CUDA(cudaMemcpyAsync(sl.d_pack, h, used, cudaMemcpyHostToDevice, L->st_copy));
+        ZOO_CUDA(cudaEventRecord(sl.ev_copied, L->st_copy));
+        ZOO_CUDA(cudaStreamWaitEvent(st, sl.ev_copied, 0));
+        via = *b;
+        via.on_device = 1;
+        via.state = sl.d_obs; via.next_state = sl.d_obs + obs_bytes;
+        via.action = (const int32_t *)(sl.d_pack + L->off_action); via.reward = (const float *)(sl.d_pack + L->off_reward);
+        via.terminal = sl.d_pack + L->off_terminal;
+        via.priority = b->priority ? (const float *)(sl.d_pack + L->off_priority) : nullptr;
+        via.next_mask = b->next_mask ? sl.d_pack + L->off_mask : nullptr;
+        via.tau = has_tau ? (const float *)(sl.d_pack + L->off_tau) : nullptr;
+        via.tau_prime = (c.kind == ZOO_LEARNER_IQN && b->tau) ? (const float *)(sl.d_pack + L->off_taup) : nullptr;
+        sl.used = true;
+        b = &via;
+    }
+    zoo_learner::HostSlot *const consumed = (b == &via) ? &L->slot[L->slot_next ^ 1] : nullptr;
     if (b->on_device && obs_bytes % 16 == 0 && ((uintptr_t)b->state & 15) == 0 && ((uintptr_t)b->next_state & 15) == 0) {
         StageArgs a{};
         a.s = (const uint4 *)b->state; a.s2 = (const uint4 *)b->next_state; a.obs = (uint4 *)L->d_obs; a.obs16 = (long long)(obs_bytes / 16);
@@ -367,6 +436,7 @@ static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b) {
         long long n = std::max<long long>(a.obs16, (long long)B * std::max(std::max(c.n_actions, c.N), std::max(c.N_prime, 1)));
         stage_batch_kernel<<<cdiv(n, 256), 256, 0, st>>>(a);
         ZOO_LAUNCH_CHECK();
+        if (consumed) ZOO_CUDA(cudaEventRecord(consumed->ev_consumed, st));
         return ZOO_OK;
     }
     if (!b->on_device) {
@@ -407,9 +477,9 @@ static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b) {
     return ZOO_OK;
 }
 
-static zoo_status run_update(zoo_learner *L, const zoo_batch *b, float *loss_out, float *prio_out, bool full) {
+static zoo_status run_update(zoo_learner *L, const zoo_batch *b, float *loss_out, float *prio_out, bool full, bool pipelined = false) {
     ZOO_REQUIRE(L, "update: null learner");
-    ZOO_TRY(stage_batch(L, b));
+    ZOO_TRY(stage_batch(L, b, pipelined));
     // the gradient buffer must be zero on entry; the optimiser kernels leave it so, anything else (creation, a
     // compute_grads without apply, a set of optimiser state) marks it dirty and costs one memset here, outside the graph
     if (L->online->grads_dirty) {
@@ -630,6 +700,21 @@ zoo_status zoo_learner_destroy(zoo_learner *L) {
     if (L->nccl_reg) dp_deregister(L->dp, L->nccl_reg);
     if (L->h_pack) cudaFreeHost(L->h_pack);
     if (L->ev_pack) cudaEventDestroy(L->ev_pack);
+    if (L->st_copy) {
+        cudaStreamSynchronize(L->st_copy);
+        for (auto &sl : L->slot) {
+            if (sl.d_obs) cudaFree(sl.d_obs);
+            if (sl.d_pack) cudaFree(sl.d_pack);
+            if (sl.h_pack) cudaFreeHost(sl.h_pack);
+            if (sl.ev_copied) cudaEventDestroy(sl.ev_copied);
+            if (sl.ev_consumed) cudaEventDestroy(sl.ev_consumed);
+        }
+        for (int i = 0; i < zoo_learner::PIPE; ++i) {
+            if (L->h_res[i]) cudaFreeHost(L->h_res[i]);
+            if (L->ev_res[i]) cudaEventDestroy(L->ev_res[i]);
+        }
+        cudaStreamDestroy(L->st_copy);
+    }
     void *ptrs[] = {L->d_obs, L->d_pack, L->d_support,
                     L->d_target, L->d_tdist, L->d_per, L->d_prio, L->d_wraw, L->d_wmax};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -639,6 +724,36 @@ zoo_status zoo_learner_destroy(zoo_learner *L) {
 }
 
 zoo_status zoo_learner_update(zoo_learner *L, const zoo_batch *b, float *loss_out, float *prio_out) { return run_update(L, b, loss_out, prio_out, true); }
+
+// update! without waiting for its result: the loss (and the new priorities) of this update are fetched by a later
+// zoo_learner_collect, in submission order.  Host batches are copied on a second stream into one of two staging slots, so the
+// H2D copy of update i + 1 overlaps the kernels of update i; the caller's arrays must stay valid until the matching collect.
+zoo_status zoo_learner_submit(zoo_learner *L, const zoo_batch *b, int32_t want_priorities) {
+    ZOO_REQUIRE(L && b, "zoo_learner_submit: null argument");
+    ZOO_REQUIRE(L->res_count < zoo_learner::PIPE, "zoo_learner_submit: %d updates are already in flight, collect one first", zoo_learner::PIPE);
+    ZOO_TRY(run_update(L, b, nullptr, nullptr, true, true));
+    ZOO_TRY(pipe_alloc(L));
+    const int r = (L->res_head + L->res_count) % zoo_learner::PIPE;
+    ZOO_CUDA(cudaMemcpyAsync(L->h_res[r], L->d_loss, sizeof(float), cudaMemcpyDeviceToHost, L->st));
+    if (want_priorities) ZOO_CUDA(cudaMemcpyAsync(L->h_res[r] + 1, L->d_prio, L->B * sizeof(float), cudaMemcpyDeviceToHost, L->st));
+    ZOO_CUDA(cudaEventRecord(L->ev_res[r], L->st));
+    L->res_prio[r] = want_priorities != 0;
+    L->res_count += 1;
+    return ZOO_OK;
+}
+
+zoo_status zoo_learner_collect(zoo_learner *L, float *loss_out, float *prio_out) {
+    ZOO_REQUIRE(L, "zoo_learner_collect: null learner");
+    ZOO_REQUIRE(L->res_count > 0, "zoo_learner_collect: nothing was submitted");
+    const int r = L->res_head;
+    ZOO_REQUIRE(!prio_out || L->res_prio[r], "zoo_learner_collect: this update was submitted without want_priorities");
+    ZOO_CUDA(cudaEventSynchronize(L->ev_res[r]));
+    if (loss_out) *loss_out = L->h_res[r][0];
+    if (prio_out) memcpy(prio_out, L->h_res[r] + 1, L->B * sizeof(float));
+    L->res_head = (r + 1) % zoo_learner::PIPE;
+    L->res_count -= 1;
+    return ZOO_OK;
+}
 zoo_status zoo_learner_compute_grads(zoo_learner *L, const zoo_batch *b, float *loss_out, float *prio_out) { return run_update(L, b, loss_out, prio_out, false); }
 
 zoo_status zoo_learner_apply(zoo_learner *L) {

@@ -101,6 +101,25 @@ class _Learner:
             self.loss = np.float32(loss.value)
         return prio
 
+    def submit(self, batch, tau=None, tau_prime=None, want_priorities=False):
+        """``update!`` without waiting for its loss: the result is fetched by a later :meth:`collect` (first in, first out; at most
+        four updates in flight).  Host batches travel on a copy stream into one of two staging slots, so the H2D copy of the next
+        batch overlaps this update's kernels (``zoo_learner_submit``).  The batch's arrays are kept alive until the collect."""
+        b, keep = self._batch(batch, tau, tau_prime)
+        if not hasattr(self, "_inflight"):
+            self._inflight = []
+        L.check(L.lib().zoo_learner_submit(self.h, C.byref(b), int(bool(want_priorities))))
+        self._inflight.append((keep, bool(want_priorities), b.B))
+
+    def collect(self):
+        """Result of the oldest submitted update: sets ``self.loss``; returns the new priorities if they were asked for."""
+        keep, want_prio, B = self._inflight.pop(0)
+        loss = C.c_float(0)
+        prio = np.empty(B, np.float32) if want_prio else None
+        L.check(L.lib().zoo_learner_collect(self.h, C.byref(loss), L.ptr(prio)))
+        self.loss = np.float32(loss.value)
+        return prio
+
     def compute_grads(self, batch, tau=None, tau_prime=None):
         """The gradient half of update! (parity hook): returns (loss, grads list, priorities|None)."""
         prio = self.update(batch, tau, tau_prime, apply=False)

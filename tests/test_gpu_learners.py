@@ -300,3 +300,50 @@ def test_update_equals_grads_then_apply_and_graph_replay(zoo):
             for a, r in zip(app.params(), ref[1]):
                 # split-K atomics reorder fp32 sums between runs: compare steps loosely, parameters tightly
                 assert nrel(a, r) <= 1e-3
+
+
+@pytest.mark.parametrize("kind", ["dqn", "per_dqn"])
+def test_submit_collect_pipeline_matches_blocking_updates(zoo, kind):
+    """zoo_learner_submit / zoo_learner_collect (loss fetched one or two updates later, host batches staged on a copy stream into
+    two alternating slots) gives the losses, priorities and parameters of the same sequence of blocking zoo_learner_update calls."""
+    B = 8
+    net = O.chain_net(O.nature_cnn(6))
+    p, tp = O.init_params(net, 1, 0.05), O.init_params(net, 2, 0.05)
+    per = kind == "per_dqn"
+    batches = [atari_batch(40 + i, B) for i in range(7)]
+    if per:
+        for i, b in enumerate(batches):
+            b["priority"] = np.random.default_rng(i).random(B).astype(np.float32) + 0.1
+    out = {}
+    for mode in ("blocking", "pipelined"):
+        app = make_approx(zoo, net, p, zoo.RMSProp(0.00025, 0.95), max_batch=B, precision="fp32_simt")
+        tapp = make_approx(zoo, net, tp, max_batch=B, precision="fp32_simt")
+        lrn = (zoo.PrioritizedDQNLearner if per else zoo.DQNLearner)(app, tapp, batch_size=B)
+        app.set_params(p)
+        lrn.use_graph(True)
+        losses, prios = [], []
+        if mode == "blocking":
+            for b in batches:
+                pr = lrn.update(b)
+                losses.append(float(lrn.loss)); prios.append(pr)
+        else:
+            depth = 0
+            for b in batches:
+                lrn.submit(b, want_priorities=per)
+                depth += 1
+                if depth == 3:  # two further updates are already enqueued when this one is read
+                    prios.append(lrn.collect()); losses.append(float(lrn.loss)); depth -= 1
+            while depth:
+                prios.append(lrn.collect()); losses.append(float(lrn.loss)); depth -= 1
+            with pytest.raises(Exception):
+                lrn.collect()  # nothing in flight
+        out[mode] = (losses, prios, app.params())
+    for a, r in zip(out["pipelined"][0], out["blocking"][0]):
+        assert abs(a - r) <= 1e-5 * max(1.0, abs(r)), (out["pipelined"][0], out["blocking"][0])
+    if per:
+        for a, r in zip(out["pipelined"][1], out["blocking"][1]):
+            assert nrel(a, r) <= 1e-5
+    # parameters after 7 RMSProp steps: the first steps are sign-like (an element with |g| ~ 1e-8 moves by eta either way), and
+    # split-K atomics reorder fp32 sums between runs -- the per-step losses above are the tight check, this one is loose
+    for a, r in zip(out["pipelined"][2], out["blocking"][2]):
+        assert nrel(a, r) <= 2e-3, nrel(a, r)
