@@ -305,7 +305,9 @@ def test_update_equals_grads_then_apply_and_graph_replay(zoo):
 @pytest.mark.parametrize("kind", ["dqn", "per_dqn"])
 def test_submit_collect_pipeline_matches_blocking_updates(zoo, kind):
     """zoo_learner_submit / zoo_learner_collect (loss fetched one or two updates later, host batches staged on a copy stream into
-    two alternating slots) gives the losses, priorities and parameters of the same sequence of blocking zoo_learner_update calls."""
+    two alternating slots) gives the losses, priorities and parameters of the same sequence of blocking zoo_learner_update calls.
+    The yardstick is a second blocking run: split-K atomics reorder fp32 sums between runs and RMSProp's first steps are sign-like
+    (an element with |g| ~ 1e-8 moves by eta either way), so two identical runs already differ."""
     B = 8
     net = O.chain_net(O.nature_cnn(6))
     p, tp = O.init_params(net, 1, 0.05), O.init_params(net, 2, 0.05)
@@ -315,14 +317,14 @@ def test_submit_collect_pipeline_matches_blocking_updates(zoo, kind):
         for i, b in enumerate(batches):
             b["priority"] = np.random.default_rng(i).random(B).astype(np.float32) + 0.1
     out = {}
-    for mode in ("blocking", "pipelined"):
+    for mode in ("blocking", "blocking2", "pipelined"):
         app = make_approx(zoo, net, p, zoo.RMSProp(0.00025, 0.95), max_batch=B, precision="fp32_simt")
         tapp = make_approx(zoo, net, tp, max_batch=B, precision="fp32_simt")
         lrn = (zoo.PrioritizedDQNLearner if per else zoo.DQNLearner)(app, tapp, batch_size=B)
         app.set_params(p)
         lrn.use_graph(True)
         losses, prios = [], []
-        if mode == "blocking":
+        if mode != "pipelined":
             for b in batches:
                 pr = lrn.update(b)
                 losses.append(float(lrn.loss)); prios.append(pr)
@@ -338,12 +340,14 @@ def test_submit_collect_pipeline_matches_blocking_updates(zoo, kind):
             with pytest.raises(Exception):
                 lrn.collect()  # nothing in flight
         out[mode] = (losses, prios, app.params())
-    for a, r in zip(out["pipelined"][0], out["blocking"][0]):
-        assert abs(a - r) <= 1e-5 * max(1.0, abs(r)), (out["pipelined"][0], out["blocking"][0])
+    ref, again, pipe = out["blocking"], out["blocking2"], out["pipelined"]
+    for a, r, r2 in zip(pipe[0], ref[0], again[0]):
+        assert abs(a - r) <= max(1e-5 * max(1.0, abs(r)), 4 * abs(r2 - r)), (pipe[0], ref[0], again[0])
+    assert abs(pipe[0][0] - ref[0][0]) <= 1e-6 * max(1.0, abs(ref[0][0]))  # first update: same parameters, same batch
     if per:
-        for a, r in zip(out["pipelined"][1], out["blocking"][1]):
-            assert nrel(a, r) <= 1e-5
-    # parameters after 7 RMSProp steps: the first steps are sign-like (an element with |g| ~ 1e-8 moves by eta either way), and
-    # split-K atomics reorder fp32 sums between runs -- the per-step losses above are the tight check, this one is loose
-    for a, r in zip(out["pipelined"][2], out["blocking"][2]):
-        assert nrel(a, r) <= 2e-3, nrel(a, r)
+        for a, r, r2 in zip(pipe[1], ref[1], again[1]):
+            assert nrel(a, r) <= max(1e-5, 4 * nrel(r2, r)), (nrel(a, r), nrel(r2, r))
+    # parameters: loose by nature (elements whose gradient is rounding noise take a +-eta step of random sign in the first updates;
+    # the losses above, which depend on every earlier update, are the tight check)
+    for a, r, r2 in zip(pipe[2], ref[2], again[2]):
+        assert nrel(a, r) <= max(2e-2, 4 * nrel(r2, r)), (nrel(a, r), nrel(r2, r))
