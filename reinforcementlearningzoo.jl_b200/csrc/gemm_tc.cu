@@ -107,8 +107,14 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
     // one M tile (skinny batch x wide layer): many narrow N tiles first, so fewer K splits have to be summed
     if (M <= BM && N >= 256) BN = 32;
     if (eb == 2 && BN == 32 && !B.kmajor) BN = 64;
-    dim3 grid(cdiv(M, BM), cdiv(N, BN), 1);
     const int total_kb = cdiv(K, bk);
+    // fp32-grade, shortish K, many tiles (IQN phi forward: K = 64, 15 616 tiles; fc1 data gradient: K = 512): a 128-wide tile takes all
+    // 512 TMEM columns and 128 KB of shared memory, i.e. one CTA per SM with nothing to overlap its epilogue; 64-wide tiles fit two
+    // per SM.  IQN 512 x 64 fp32: phi forward 1103 -> 780 us, fc1 dgrad 2770 -> 2408 us; no gain at K = 7744 (the main loop is
+    // shared-memory-bandwidth bound there either way).  ZOO_X3_NARROW = longest K, in K-blocks of 32, that takes the narrow tile.
+    static const int x3_narrow = [] { const char *e = getenv("ZOO_X3_NARROW"); return e ? atoi(e) : 16; }();
+    if (x3 && BN == 128 && total_kb <= x3_narrow && (long long)cdiv(M, BM) * cdiv(N, 128) > 4LL * g_sm_budget) BN = 64;
+    dim3 grid(cdiv(M, BM), cdiv(N, BN), 1);
     const long long tiles = (long long)grid.x * grid.y;
     const long long cap_ctas = g_sm_budget * ((x3 && BN >= 128) ? 1 : 2);  // resident CTAs (TcCfg::TWO_CTA_STAGES)
     if (split_k <= 0) {
@@ -151,6 +157,14 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
             ((uintptr_t)pe.out & 15) == 0 && rm_ok && mask_ok) {
             ZOO_TRY(make_map(&P.tmC, pe.out, 2, N, M, pe.sm, 64, 32, false));
             P.tma_store = 1;
+        }
+        // fp32-grade (3xTF32) kernels with a plain fp32 row-major output: same idea, 32-column boxes (tma_store == 3).  The phi forward
+        // of IQN at 512 x 64 rows (1 GB of fp32 output, K = 64) spent most of its 1.19 ms in the slab + per-row stores.
+        const bool mask32_ok = !pe.mask || (!pe.mask_bf16 && pe.mask_sn == 1 && (pe.mask_sm & 3) == 0 && ((uintptr_t)pe.mask & 15) == 0);
+        if (ts_on && x3 && BN >= 64 && split_k == 1 && !pe.out_bf16 && !pe.accumulate && pe.bias_mode != 2 && pe.sn == 1 && (pe.sm & 3) == 0 &&
+            ((uintptr_t)pe.out & 15) == 0 && rm_ok && mask32_ok && (long long)M * N >= (1 << 22)) {
+            ZOO_TRY(make_map(&P.tmC, pe.out, 4, N, M, pe.sm, 32, 32, false));
+            P.tma_store = 3;
         }
     }
     CUtensorMap tmA, tmB;

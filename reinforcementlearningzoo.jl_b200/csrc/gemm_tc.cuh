@@ -875,6 +875,79 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // chain and parks the whole 32 x BN slab of this warp in shared memory (row stride BN + 1: conflict-free both ways)
         constexpr int XLD = BN + 1;
         float *const xst = reinterpret_cast<float *>(smem) + q * 32 * XLD;
+        if (X3 && GA == 0 && BN >= 64 && P.tma_store == 3) {
+            // fp32-grade TMA-store epilogue: lane = tile row already holds 32 consecutive columns after tcgen05.ld, so the chain sums,
+            // bias / relu / relu' mask / row multiplier are applied in registers and the row's 128 bytes go to a SWIZZLE_128B staging
+            // block as eight 16-byte pieces (piece j of row r at j ^ (r % 8)); one bulk store per 32 x 32 chunk, two blocks per warp
+            float *const bias_s = reinterpret_cast<float *>(smem + 32768);
+            float *const rm_s = bias_s + 128 + q * 128;
+            {
+                const int t = threadIdx.x - 64;
+                if (t < BN) bias_s[t] = (bias_mode == 1 && n0 + t < Nn) ? __ldg(e.bias + n0 + t) : 0.f;
+                for (int j = lane; j < BN; j += 32) rm_s[j] = (rmul && n0 + j < Nn) ? ldg_elem(rmp, 0, (long long)(min(row0, P.M - 1) / rm_div) * rm_ld + n0 + j) : 1.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const uint32_t sbase = smem_u32(smem) + q * 8192;
+            const bool rowok = lane < rows;
+            int issued = 0;
+#pragma unroll
+            for (int c = 0; c < BN; c += 32) {
+                if (n0 + c < Nn) {
+                    if (issued >= 2) {  // the block about to be overwritten has been read by its bulk store
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        __syncwarp();
+                    }
+                    unsigned mbits = 0xffffffffu;
+                    if (maskp) {  // relu' source: fp32 [M][msm]; one bit per column of this lane's row
+                        mbits = 0u;
+                        const float *mp = (const float *)maskp + (long long)(row0 + lane) * msm + n0 + c;
+                        if (rowok && n0 + c + 32 <= Nn) {
+                            float4 mv[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) mv[j] = __ldg(reinterpret_cast<const float4 *>(mp) + j);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mbits |= ((mv[j].x > 0.f ? 1u : 0u) | (mv[j].y > 0.f ? 2u : 0u) | (mv[j].z > 0.f ? 4u : 0u) | (mv[j].w > 0.f ? 8u : 0u)) << (4 * j);
+                        } else {
+#pragma unroll 1
+                            for (int j = 0; j < 32; ++j)
+                                if (rowok && n0 + c + j < Nn && __ldg(mp + j) > 0.f) mbits |= 1u << j;
+                        }
+                    }
+                    uint32_t r[32], r2[32];
+                    tmem_ld32(tq + (uint32_t)(lb * C::ACC_COLS + c), r);
+                    tmem_ld32(tq + (uint32_t)(lb * C::ACC_COLS + BN + c), r2);
+                    const uint32_t sb = sbase + (issued & 1) * 4096 + lane * 128;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float x[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int j = j4 * 4 + i;
+                            float v = __fadd_rn(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])), acc[X3 ? c + j : 0]) + bias_s[c + j];
+                            const float vr = fmaxf(v, 0.f);
+                            v = relu ? vr : v;
+                            v = ((mbits >> j) & 1u) ? v : 0.f;
+                            x[i] = v * rm_s[c + j];
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + ((uint32_t)(j4 ^ (lane & 7)) << 4)), "r"(__float_as_uint(x[0])),
+                                     "r"(__float_as_uint(x[1])), "r"(__float_as_uint(x[2])), "r"(__float_as_uint(x[3]))
+                                     : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&P.tmC),
+                                     "r"(sbase + (issued & 1) * 4096), "r"(n0 + c), "r"(row0)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++issued;
+                }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __syncwarp();
+        } else {
         if (X3) {
 #pragma unroll
             for (int c = 0; c < BN; c += 32) {
@@ -1254,6 +1327,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         refill = true;
         }
         }
+        }  // tma_store != 3
     }
     if (threadIdx.x == 64) dbg_stamp(P, 6);
     tc_fence_before();
@@ -1367,6 +1441,10 @@ static int tc_pick_stages(int BN, long long ctas, int nkb) {
     const int mx = BN == 32 ? TcCfg<EB, 32, X3, SPAN>::MAX_STAGES : (BN == 64 ? TcCfg<EB, 64, X3, SPAN>::MAX_STAGES : TcCfg<EB, 128, X3, SPAN>::MAX_STAGES);
     const int two = BN == 32 ? TcCfg<EB, 32, X3, SPAN>::TWO_CTA_STAGES : (BN == 64 ? TcCfg<EB, 64, X3, SPAN>::TWO_CTA_STAGES : TcCfg<EB, 128, X3, SPAN>::TWO_CTA_STAGES);
     int stg = ctas > g_sm_budget ? two : mx;
+    // bf16 grids of many waves (the large-batch convolutions): a two-deep ring lets three or four CTAs share an SM and overlap
+    // their prologues / epilogues -- Rainbow B = 1024 conv2 / conv3 forward 39 -> 30 us each, step 1187 -> 1100 us; IQN 512 x 64
+    // 2434 -> 2388 us.  (The fp32-grade kernels lose with it: their converter warps need the deeper ring.)
+    if (EB == 2 && !X3 && ctas > 4LL * g_sm_budget) stg = 2;
     const int force = g_tc_stages_force & 0xff;  // ZOO_TC_STAGES / zoo_test_set_tc_stages
     if (force >= 2) stg = force < mx ? force : mx;
     if (stg > nkb + 1) stg = nkb + 1 < 2 ? 2 : nkb + 1;  // no point in a ring deeper than the K loop
