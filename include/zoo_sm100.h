@@ -316,6 +316,13 @@ ZOO_API zoo_status zoo_test_gemm_bench(int32_t engine, int32_t M, int32_t N, int
 ZOO_API zoo_status zoo_test_gemm_trace(int32_t engine, int32_t M, int32_t N, int32_t K, int32_t a_kmajor, int32_t b_kmajor,
                                        int32_t split_k, uint64_t *stamps9);
 
+/* Per-launch phase trace of the tcgen05 engine: begin(cap) arms it; every engine launch from then on (also those captured into a
+ * CUDA graph, on every replay) stamps CTA (0,0,0)'s phases into its own 16-slot record; stop() returns the number of records and
+ * stops handing out new ones; get(i) reads record i (name = kind[MxNxK]<grid>, stamps = ns of %globaltimer, see core.cu). */
+ZOO_API zoo_status zoo_test_trace_begin(int32_t cap);
+ZOO_API zoo_status zoo_test_trace_stop(int32_t *n);
+ZOO_API zoo_status zoo_test_trace_get(int32_t i, char *name, int32_t name_cap, uint64_t *stamps16);
+
 /* Parity hook (tests/test_gpu_full_size.py): raw bytes of the output buffer of parameter layer `layer` of chain `chain`
  * (0 = Chain / psi / base, 1 = phi / val, 2 = header / adv) as the last forward left it: post-activation values, internal
  * layout [rows][out_h][out_w][out_c] in the net's activation type.  *is_bf16 tells the element type (the network's output

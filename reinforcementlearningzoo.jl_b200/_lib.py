@@ -126,6 +126,9 @@ SIGNATURES = {
     "zoo_prof_get": [I32, C.c_char_p, I32, C.POINTER(F32)],
     "zoo_test_gemm": [I32, I32, I32, I32, V, I32, V, I32, V, I32],
     "zoo_test_gemm_trace": [I32, I32, I32, I32, I32, I32, I32, V],
+    "zoo_test_trace_begin": [I32],
+    "zoo_test_trace_stop": [C.POINTER(I32)],
+    "zoo_test_trace_get": [I32, C.c_char_p, I32, V],
     "zoo_test_set_tc_stages": [I32],
     "zoo_test_gemm_bench": [I32, I32, I32, I32, I32, I32, I32, I32, I32, C.POINTER(F32)],
     "zoo_test_net_activation": [V, I32, I32, I64, V, I64, C.POINTER(I32)],

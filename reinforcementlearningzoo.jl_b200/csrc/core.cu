@@ -75,6 +75,9 @@ __global__ void prof_delay_kernel(unsigned long long ns) {
 
 // No CPU fallback and no other architecture: everything here is sm_100a SASS.
 extern unsigned long long *g_tc_dbg;
+extern unsigned long long *g_tc_trace;
+extern int g_tc_trace_cap, g_tc_trace_n;
+extern std::vector<std::string> g_tc_trace_names;
 
 zoo_status require_sm100() {
     static int cached = -1;
@@ -243,6 +246,32 @@ zoo_status zoo_test_gemm_trace(int32_t engine, int32_t M, int32_t N, int32_t K, 
     ZOO_CUDA(cudaMemcpy(stamps9, d, 16 * 8, cudaMemcpyDeviceToHost));
     cudaFree(d);
     return s;
+}
+
+// Per-launch phase trace of the tcgen05 engine (see gemm_tc.cu): begin(cap) arms it, every engine launch from then on -- also
+// the ones captured into a CUDA graph -- stamps CTA (0,0,0)'s phases into its own slot; get(i) reads slot i back.
+zoo_status zoo_test_trace_begin(int32_t cap) {
+    ZOO_REQUIRE(cap > 0 && cap <= 4096, "zoo_test_trace_begin: bad capacity");
+    if (g_tc_trace) cudaFree(g_tc_trace);
+    g_tc_trace = nullptr;
+    unsigned long long *d;
+    ZOO_CUDA(cudaMalloc(&d, (size_t)cap * 16 * 8));
+    ZOO_CUDA(cudaMemset(d, 0, (size_t)cap * 16 * 8));
+    g_tc_trace_names.clear();
+    g_tc_trace_cap = cap; g_tc_trace_n = 0; g_tc_trace = d;
+    return ZOO_OK;
+}
+zoo_status zoo_test_trace_stop(int32_t *n) {  // disarms; the slots stay readable (and graph replays keep stamping them)
+    ZOO_REQUIRE(n, "zoo_test_trace_stop: null argument");
+    *n = g_tc_trace_n;
+    g_tc_trace_cap = g_tc_trace_n;
+    return ZOO_OK;
+}
+zoo_status zoo_test_trace_get(int32_t i, char *name, int32_t name_cap, uint64_t *stamps16) {
+    ZOO_REQUIRE(g_tc_trace && name && stamps16 && i >= 0 && i < g_tc_trace_n && name_cap > 0, "zoo_test_trace_get: bad index");
+    snprintf(name, name_cap, "%s", g_tc_trace_names[i].c_str());
+    ZOO_CUDA(cudaMemcpy(stamps16, g_tc_trace + 16 * i, 16 * 8, cudaMemcpyDeviceToHost));
+    return ZOO_OK;
 }
 
 // Forces the tcgen05 GEMM's smem ring depth (0 = per-launch choice); a tuning / test hook.

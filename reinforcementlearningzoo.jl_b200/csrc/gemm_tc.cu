@@ -9,6 +9,20 @@ namespace zoo {
 
 unsigned long long *g_tc_dbg = nullptr;  // set by zoo_test_gemm_trace
 
+// Per-launch phase trace (zoo_test_trace_*): while armed, launch i of the engine gets its own 16-stamp slot, so an update that is
+// captured into a CUDA graph while armed keeps writing CTA (0,0,0)'s phase stamps on every replay -- the graph's real timeline.
+unsigned long long *g_tc_trace = nullptr;
+int g_tc_trace_cap = 0, g_tc_trace_n = 0;
+std::vector<std::string> g_tc_trace_names;
+static unsigned long long *trace_slot(const char *kind, int M, int N, int K, dim3 grid) {
+    if (!g_tc_trace) return g_tc_dbg;
+    if (g_tc_trace_n >= g_tc_trace_cap) return nullptr;
+    char buf[96];
+    snprintf(buf, sizeof(buf), "%s[%dx%dx%d]<%u,%u,%u>", kind, M, N, K, grid.x, grid.y, grid.z);
+    g_tc_trace_names.push_back(buf);
+    return g_tc_trace + 16 * (g_tc_trace_n++);
+}
+
 static zoo_status tc_launch(int eb, bool x3, int kind, int BN, bool ak, bool bk, const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P,
                             dim3 grid, cudaStream_t st) {
     if (eb == 2) return tc_launch_bf16(kind, BN, ak, bk, tmA, tmB, P, grid, st);
@@ -173,6 +187,7 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
     if (B.kmajor) ZOO_TRY(make_map(&tmB, B.p, eb, K, N, B.ld, bk, BN, false));
     else ZOO_TRY(make_map(&tmB, B.p, eb, N, K, B.ld, mn_box, bk, true));
 
+    P.dbg = trace_slot("gemm", M, N, K, grid);
     ZOO_TRY(tc_launch(eb, x3, 0, BN, A.kmajor, B.kmajor, tmA, tmB, P, grid, st));
     return ZOO_OK;
 }
@@ -257,6 +272,7 @@ static zoo_status tc_conv_tma(ConvGeom g, const Operand &Wop, int images, int N,
         ZOO_TRY(make_map4(&tmA, g.x, eb, dims, str, box, es, span));
     }
     ZOO_TRY(make_map(&tmB, Wop.p, eb, K, N, Wop.ld, bk, BN, false, span));
+    P.dbg = trace_slot("conv", P.M, N, K, grid);
     return tc_launch(eb, x3, 2, BN, true, true, tmA, tmB, P, grid, st);
 }
 
@@ -348,6 +364,7 @@ zoo_status tc_conv_wgrad(ConvGeom g, const void *dy, int is_bf16, int images, co
                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_err("tc_conv_wgrad: cuTensorMapEncodeTiled(4D) failed (%d)", (int)r); return ZOO_CUDA_ERROR; }
     }
+    P.dbg = trace_slot("cwgrad", P.M, N, total_kb, grid);
     return tc_launch(eb, x3, 4, BN, false, false, tmA, tmB, P, grid, st);
 }
 
@@ -396,6 +413,7 @@ zoo_status tc_conv_gemm(const ConvGeom &g, const Operand &Wop, int M, int N, int
         const cuuint32_t es[4] = {1, 1, 1, 1};
         ZOO_TRY(make_map4(&tmA, g.x, eb, dims, str, box, es));
         ZOO_TRY(make_map(&tmB, Wop.p, eb, Wop.ld, g.Cout, Wop.ld, mn_box, bk, true));  // W as [Cout][ks*ks*C]: boxes at tap offsets
+        P.dbg = trace_slot("cdgrad", M, N, K, grid);
         return tc_launch(eb, x3, 3, BN, true, false, tmA, tmB, P, grid, st);
     }
     const int eb = Wop.is_bf16 ? 2 : 4;

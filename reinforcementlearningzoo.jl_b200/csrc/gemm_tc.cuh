@@ -948,7 +948,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             __syncwarp();
         } else {
-        if (X3) {
+        if (X3 && !(GA == 2 && P.tma_store == 2)) {  // (the whole-tile TMA store path reads TMEM itself)
 #pragma unroll
             for (int c = 0; c < BN; c += 32) {
                 uint32_t r[32], r2[32];
@@ -996,6 +996,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(rr[j]);
                     }
+                    if (c == 0 && threadIdx.x == 64) dbg_stamp(P, 12);
                     if (bias_mode == 1) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) x[j] += (n0 + c + j < Nn) ? __ldg(e.bias + n0 + c + j) : 0.f;
@@ -1009,10 +1010,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int j = 0; j < 32; ++j) x[j] = 0.f;
                         } else if (mask_bf16) {
+                            uint4 mk4[4];
 #pragma unroll
                             for (int j4 = 0; j4 < 4; ++j4) {
-                                uint4 mk = make_uint4(0u, 0u, 0u, 0u);
-                                if (c + j4 * 8 + 8 <= vN) mk = __ldg(reinterpret_cast<const uint4 *>(mrow + (c + j4 * 8) * 2));
+                                mk4[j4] = make_uint4(0u, 0u, 0u, 0u);
+                                if (c + j4 * 8 + 8 <= vN) mk4[j4] = __ldg(reinterpret_cast<const uint4 *>(mrow + (c + j4 * 8) * 2));
+                            }
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const uint4 mk = mk4[j4];
                                 const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
@@ -1021,10 +1027,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 }
                             }
                         } else {
+                            float4 mk8[8];
 #pragma unroll
                             for (int j4 = 0; j4 < 8; ++j4) {
-                                float4 mk = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (c + j4 * 4 + 4 <= vN) mk = __ldg(reinterpret_cast<const float4 *>(mrow + (c + j4 * 4) * 4));
+                                mk8[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (c + j4 * 4 + 4 <= vN) mk8[j4] = __ldg(reinterpret_cast<const float4 *>(mrow + (c + j4 * 4) * 4));
+                            }
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 mk = mk8[j4];
                                 if (!(mk.x > 0.f)) x[j4 * 4] = 0.f;
                                 if (!(mk.y > 0.f)) x[j4 * 4 + 1] = 0.f;
                                 if (!(mk.z > 0.f)) x[j4 * 4 + 2] = 0.f;
@@ -1032,6 +1043,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                     }
+                    if (c == 0 && threadIdx.x == 64) dbg_stamp(P, 13);
                     if (out_bf16) {
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
@@ -1056,15 +1068,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
+            if (threadIdx.x == 64) dbg_stamp(P, 9);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (threadIdx.x == 64) {
+                dbg_stamp(P, 10);
                 const int nbox = (vN * esz + span - 1) / span;
                 for (int bx = 0; bx < nbox; ++bx)
                     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&P.tmC4[blockIdx.z]),
                                  "r"(stg0 + (uint32_t)(bx * BM * span)), "r"(n0 + bx * (span / esz)), "r"(0), "r"(coy0), "r"(cimg)
                                  : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                dbg_stamp(P, 11);
                 asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             }
         } else
@@ -1245,10 +1260,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const bool mine = trans ? lane < rows : n < Nn;
                 const long long mbase = trans ? (long long)(row0 + lane) * msm + (long long)(n0 + c) * msn : (long long)row0 * msm + (long long)n * msn;
                 const long long mstep = trans ? msn : msm;
+                // (one load per register: written as "load, then test" per element type, the compiler funnels all 32 loads through
+                // one destination register and they serialise on L2 latency -- measured 6.8 us for this block on fc1's data gradient)
+                if (mask_bf16) {
+                    unsigned short mv[32];
+                    const unsigned short *mp16 = (const unsigned short *)mq + mbase;
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (mine && i < cnt) mbits |= (ldg_elem(mq, mask_bf16, mbase + i * mstep) > 0.f ? 1u : 0u) << i;
+                    for (int i = 0; i < 32; ++i) mv[i] = (mine && i < cnt) ? __ldg(mp16 + i * mstep) : (unsigned short)0x8000u;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mbits |= (__uint_as_float((unsigned)mv[i] << 16) > 0.f ? 1u : 0u) << i;
+                } else {
+                    float mv[32];
+                    const float *mp32 = (const float *)mq + mbase;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mv[i] = (mine && i < cnt) ? __ldg(mp32 + i * mstep) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mbits |= (mv[i] > 0.f ? 1u : 0u) << i;
+                }
             }
+            if (c == 0 && threadIdx.x == 64 && !refill) dbg_stamp(P, 15);
             const bool narrow = sm < (1 << 24) && sn < (1 << 24) && Nn < (1 << 24);  // 32-bit strides inside a chunk
             const bool hasmask = maskp != nullptr;
             if (trans && direct && narrow && bias_mode != 1) {
