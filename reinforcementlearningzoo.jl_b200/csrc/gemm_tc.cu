@@ -130,7 +130,12 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
     if (x3 && BN == 128 && total_kb <= x3_narrow && (long long)cdiv(M, BM) * cdiv(N, 128) > 4LL * g_sm_budget) BN = 64;
     dim3 grid(cdiv(M, BM), cdiv(N, BN), 1);
     const long long tiles = (long long)grid.x * grid.y;
-    const long long cap_ctas = g_sm_budget * ((x3 && BN >= 128) ? 1 : 2);  // resident CTAs (TcCfg::TWO_CTA_STAGES)
+    static const int split_cap_pct = [] { const char *e = getenv("ZOO_SPLIT_CAP_PCT"); return e ? atoi(e) : 25; }();
+    // (a quarter of the resident-CTA capacity: the update runs three lanes of kernels at once and every fp32-grade CTA owns an SM for
+    // its whole life, so SM-time, not the latency of a kernel alone on the GPU, is what the step pays for -- fc1 forward of both nets
+    // at 49 splits = 392 one-per-SM CTAs in 2.6 waves; at 18 splits both fit in one.  Measured on the B = 32 update: 100 % 0.2571 ms,
+    // 50 % 0.2590, 25 % 0.2542)
+    const long long cap_ctas = g_sm_budget * ((x3 && BN >= 128) ? 1 : 2) * split_cap_pct / 100;  // resident CTAs (TcCfg::TWO_CTA_STAGES)
     if (split_k <= 0) {
         // split only when the output grid leaves most SMs idle AND one CTA would walk a long K: each split costs
         // atomics on the whole tile, so keep >= 4 K-blocks per CTA and stay within one resident wave
@@ -326,7 +331,8 @@ zoo_status tc_conv_wgrad(ConvGeom g, const void *dy, int is_bf16, int images, co
     const int N = g.ks * g.ks * g.C, BN = 128;
     const int total_kb = images * g.tpi;
     const int ntiles = cdiv(N, BN);
-    const long long cap = g_sm_budget * (x3 ? 1 : 2);
+    static const int wgrad_cap_pct = [] { const char *e = getenv("ZOO_WGRAD_CAP_PCT"); return e ? atoi(e) : 50; }();  // (see tc_gemm's split cap)
+    const long long cap = g_sm_budget * (x3 ? 1 : 2) * wgrad_cap_pct / 100;
     int split = (int)std::max<long long>(1, std::min<long long>(total_kb, cap / ntiles));
     const int kbps = cdiv(total_kb, split);
     split = cdiv(total_kb, kbps);

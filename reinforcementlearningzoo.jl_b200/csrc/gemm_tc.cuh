@@ -392,6 +392,30 @@ __device__ __forceinline__ void epi_rows_red(const float *cp, int rows, float *o
         }
     }
 }
+// the same with 16-byte reds (red.global.add.v4.f32): eight lanes cover the 32 columns of a row, the warp four rows per instruction --
+// a quarter of the red instructions.  The per-SM atomic issue rate, not L2, bounds these epilogues: the weight-gradient and split-K
+// CTAs spent 5 - 6 us issuing 8 192 scalar reds each.  cp = the chunk's element (0, 0); op = its output element (0, 0), 16-byte aligned.
+template <int LD>
+__device__ __forceinline__ void epi_rows_red_v4(const float *cp, int rows, float *op, int stride, int lane) {
+    op = in_reg(op); stride = in_reg(stride);
+    const int rr = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll 1
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+        float v[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[u][e] = cp[(r0 + 4 * u + rr) * LD + c4 + e];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int r = r0 + 4 * u + rr;
+            if (r < rows)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + (long long)r * stride + c4), "f"(v[u][0]), "f"(v[u][1]), "f"(v[u][2]),
+                             "f"(v[u][3])
+                             : "memory");
+        }
+    }
+}
 // packed bf16 rows: lane = column pair, staging row stride 66 floats; mask (relu') rows are bf16x2 as well
 template <bool MASK>
 __device__ __forceinline__ void epi_rows_store_bf16x2(const float *cp, int rows, __nv_bfloat162 *op, int stride2, float b0, float b1, int relu,
@@ -700,6 +724,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // warps 2..5: TMEM lane quadrant = warp % 4, thread = accumulator row.
         const int q = warp & 3;
         const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (P.epi.mask && GA != 4) {
+            // The relu' mask of the epilogue is an activation tensor the forward pass wrote ~100 us earlier; by now the optimiser's
+            // and the weight gradients' streams have pushed it out of L2, and the epilogue's loads paid a DRAM round trip under load
+            // (measured 2.5 - 3 us per 128-byte line of a row).  Each thread asks L2 for its share of the tile's mask now.
+            const int t = threadIdx.x - 64;
+            const int mesz = P.epi.mask_bf16 ? 2 : 4;
+            const uint8_t *mbase = (const uint8_t *)P.epi.mask;
+            if (GA == 2 && P.tma_store == 2) {
+                if (t < vrows) {
+                    const int ry = t / cols_c, rx = t - ry * cols_c;
+                    const int y = (coy0 + ry) * P.conv.s + cls_py, xx = rx * P.conv.s + cls_px;
+                    if (y < P.conv.H && xx < P.conv.W) {
+                        const uint8_t *row = mbase + ((((long long)cimg * P.conv.H + y) * P.conv.W + xx) * P.epi.mask_sm + n0) * mesz;
+                        const int bytes = min(BN, P.N - n0) * mesz;
+                        for (int b = 0; b < bytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
+                    }
+                }
+            } else if (GA == 0) {
+                if (P.epi.mask_sn == 1) {  // rows of the mask run along n
+                    if (t < vrows) {
+                        const uint8_t *row = mbase + ((long long)(m0 + t) * P.epi.mask_sm + n0) * mesz;
+                        const int bytes = min(BN, P.N - n0) * mesz;
+                        for (int b = 0; b < bytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
+                    }
+                } else if (P.epi.mask_sm == 1) {  // swap-AB outputs: the mask runs along m
+                    const int segs = (BM * mesz) / 128;  // 128-byte pieces per column of the tile
+                    for (int j = t; j < BN * segs; j += 128) {
+                        const int n = n0 + j / segs, mm = m0 + (j % segs) * (128 / mesz);
+                        if (n < P.N && mm < P.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(mbase + ((long long)n * P.epi.mask_sn + mm) * mesz));
+                    }
+                }
+            }
+        }
         float acc[X3 ? BN : 1];  // running fp32 sum of the drained chains (3xTF32 only)
         if (X3) {
 #pragma unroll
@@ -1297,6 +1354,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         else epi_cols_store<float, false>(rp, ncols, (float *)e.out + o0, (int)sn, bm, relu, mbits);
                     }
                 }
+            } else if (!direct && narrow && n0 + c + 32 <= Nn && (red_ws ? ((Nn & 3) == 0 && ((uintptr_t)ws & 15) == 0)
+                                                                         : (sn == 1 && (sm & 3) == 0 && ((uintptr_t)e.out & 15) == 0)) && ((n0 + c) & 3) == 0) {
+                // split-K partial sums into the workspace / wgrad-style accumulation into the output, four columns per red
+                float *bp = red_ws ? ws + (long long)row0 * Nn + n0 + c : (float *)e.out + (long long)row0 * sm + n0 + c;
+                epi_rows_red_v4<LDC>(chunk, rows, bp, red_ws ? Nn : (int)sm, lane);
             } else if (n < Nn) {
                 if (!direct && narrow) {
                     // split-K partial sums into the workspace, or wgrad-style accumulation into the output

@@ -31,50 +31,49 @@ __device__ __forceinline__ float sample_scale(const HeadArgs &h, int b) {
 __device__ __forceinline__ bool better(float v, float best) { return v > best || (isnan(v) && !isnan(best)); }
 
 // One sample of the DQN-family head (dqn.jl:115-142, prioritized_dqn.jl:129-146, basic_dqn.jl:78-87): TD target, Huber loss,
-// d loss / d Q.  q_on: [rows][A] online output ([s; s'] for basic / double), q_t: [B][A] target output on s' (null for basic).
-// Shared by dqn_head_kernel and the fused small-batch tail (narrow.cu); q_on / dout may live in shared memory there.
-__device__ __forceinline__ void dqn_head_sample(int kind, int double_dqn, const HeadArgs &h, int b, const float *q_on, const float *q_t, float gamma_n,
-                                                float *dout) {
+// d loss / d Q, on explicit rows: q_s = online Q(s_b), q_n = online Q(s'_b) (basic / double, else unused), q_tr = target Q(s'_b)
+// (null for basic); dout_s / dout_n = the gradient rows of Q(s_b) / Q(s'_b) (dout_n: basic only).
+__device__ __forceinline__ void dqn_head_rows(int kind, int double_dqn, const HeadArgs &h, int b, const float *q_s, const float *q_n, const float *q_tr,
+                                              float gamma_n, float *dout_s, float *dout_n) {
     const int A = h.A;
     const uint8_t *mk = h.mask ? h.mask + (size_t)b * A : nullptr;
     float q2;
     int amax = 0;
     if (kind == ZOO_LEARNER_BASIC_DQN) {
-        const float *qn = q_on + (size_t)(h.B + b) * A;  // Q(s') of the same network
-        float best = qn[0];
-        for (int a = 1; a < A; ++a) if (better(qn[a], best)) { best = qn[a]; amax = a; }
+        float best = q_n[0];  // Q(s') of the same network
+        for (int a = 1; a < A; ++a) if (better(q_n[a], best)) { best = q_n[a]; amax = a; }
         q2 = best;
-    } else if (double_dqn) {
-        const float *qn = q_on + (size_t)(h.B + b) * A;  // online Q(s') selects, target evaluates
-        float best = qn[0] + ((mk && !mk[0]) ? -INFINITY : 0.f);
-        for (int a = 1; a < A; ++a) {
-            float v = qn[a] + ((mk && !mk[a]) ? -INFINITY : 0.f);
-            if (better(v, best)) { best = v; amax = a; }
-        }
-        q2 = q_t[(size_t)b * A + amax];
     } else {
-        const float *qn = q_t + (size_t)b * A;
+        const float *qn = double_dqn ? q_n : q_tr;  // double: online Q(s') selects, target evaluates
         float best = qn[0] + ((mk && !mk[0]) ? -INFINITY : 0.f);
         for (int a = 1; a < A; ++a) {
             float v = qn[a] + ((mk && !mk[a]) ? -INFINITY : 0.f);
             if (better(v, best)) { best = v; amax = a; }
         }
-        q2 = best;
+        q2 = double_dqn ? q_tr[amax] : best;
     }
     // G = r .+ gamma^n .* (1 .- t) .* q'
     const float disc = __fmul_rn(gamma_n, h.terminal[b] ? 0.f : 1.f);
     const float G = __fadd_rn(h.reward[b], __fmul_rn(disc, q2));
     const int a_b = h.action[b];
-    const float q = q_on[(size_t)b * A + a_b];
+    const float q = q_s[a_b];
     // huber_loss(G, q; delta = 1): strict < mask (q4)
     const float e = __fsub_rn(G, q), ae = fabsf(e);
     const bool quad = ae < 1.0f;
     h.per_sample[b] = quad ? __fmul_rn(__fmul_rn(ae, ae), 0.5f) : __fsub_rn(ae, 0.5f);
     const float dG = quad ? e : (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f));
     const float sc = sample_scale(h, b);
-    for (int a = 0; a < A; ++a) dout[(size_t)b * A + a] = a == a_b ? -dG * sc : 0.f;
+    for (int a = 0; a < A; ++a) dout_s[a] = a == a_b ? -dG * sc : 0.f;
     if (kind == ZOO_LEARNER_BASIC_DQN)  // gradient also flows through the target (q3)
-        for (int a = 0; a < A; ++a) dout[(size_t)(h.B + b) * A + a] = a == amax ? dG * disc * sc : 0.f;
+        for (int a = 0; a < A; ++a) dout_n[a] = a == amax ? dG * disc * sc : 0.f;
+}
+// The same on whole matrices: q_on [rows][A] online output ([s; s'] for basic / double), q_t [B][A] target output on s' (null for
+// basic), dout shaped like q_on.  Shared by dqn_head_kernel and the fused small-batch tails (narrow.cu).
+__device__ __forceinline__ void dqn_head_sample(int kind, int double_dqn, const HeadArgs &h, int b, const float *q_on, const float *q_t, float gamma_n,
+                                                float *dout) {
+    const size_t A = h.A;
+    dqn_head_rows(kind, double_dqn, h, b, q_on + (size_t)b * A, q_on + (size_t)(h.B + b) * A, q_t ? q_t + (size_t)b * A : nullptr, gamma_n,
+                  dout + (size_t)b * A, dout + (size_t)(h.B + b) * A);
 }
 #endif
 

@@ -17,6 +17,10 @@ zoo_status dp_alloc_registered(zoo_dp *dp, size_t bytes, void **ptr, void **hand
 void dp_deregister(zoo_dp *dp, void *handle);
 
 bool dqn_tail_supported(int N, long long K, int x_bf16, int rows_fwd);
+bool dqn_tail_multi_supported(int N, long long K, int x_bf16, int B);
+zoo_status dqn_tail_multi(int kind, int double_dqn, const HeadArgs &h, const void *X, int x_bf16, const float *W, const float *bias, const float *q_t,
+                          float gamma_n, float beta, int two_rows, int bwd_next, long long K, int relu_prev, float *q_out, float *dq_out, void *dX,
+                          float *dW, float *db, float *db_prev, float *loss, float *prio_out, float *part, unsigned *ticket, cudaStream_t st);
 zoo_status dqn_tail(int kind, int double_dqn, const HeadArgs &h, const void *X, int x_bf16, const float *W, const float *bias, const float *q_t, float gamma_n,
                     float beta, int rows_fwd, int rows_bwd, long long K, int relu_prev, float *q_out, float *dq_out, void *dX, float *dW, float *db,
                     float *db_prev, float *loss, float *prio_out, cudaStream_t st);
@@ -145,6 +149,7 @@ struct zoo_learner {
     uint8_t *d_mask = nullptr; float *d_tau = nullptr, *d_taup = nullptr;
     float *d_support = nullptr, *d_target = nullptr, *d_tdist = nullptr;
     float *d_per = nullptr, *d_prio = nullptr, *d_wraw = nullptr, *d_wmax = nullptr;
+    float *d_tail_part = nullptr;  // multi-CTA DQN tail: 64 partial losses + the arrival ticket
     // the small per-sample vectors above live in one device block mirrored by a pinned host block: one H2D per update
     uint8_t *d_pack = nullptr, *h_pack = nullptr;
     size_t pack_bytes = 0;
@@ -268,14 +273,17 @@ static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bo
     bool tail = false;
     if ((c.kind == ZOO_LEARNER_BASIC_DQN || c.kind == ZOO_LEARNER_DQN || c.kind == ZOO_LEARNER_PRIORITIZED_DQN) && on->desc.kind == ZOO_NET_CHAIN &&
         on->a.layers.size() >= 2) {
-        // opt-in (ZOO_DQN_TAIL=1): parity-green, but measured on B200 the single CTA takes ~26 us against ~18 us for the four small
-        // launches it replaces (they run on many SMs), so the update is 4 % slower with it (profiles/r02_dqn_tail_ab.txt)
-        static const bool tail_on = [] { const char *e = getenv("ZOO_DQN_TAIL"); return e && e[0] == '1'; }();
+        // ZOO_DQN_TAIL: 0 (default) = four launches (narrow_fwd, dqn_head, loss_reduce, narrow_bwd); 2 = the multi-CTA tail (each CTA owns
+        // 2048 / K samples; 20 us eager against 37 us for the four, but the graph-replayed update does not get faster: 0.2538 vs
+        // 0.2508 ms, the four small kernels leave more SMs to the lanes running beside them); 1 = the single-CTA tail (~26 us).
+        // All three are parity-tested (tests/test_gpu_gemm.py::test_non_default_kernel_paths_keep_parity).
+        static const int tail_mode = [] { const char *e = getenv("ZOO_DQN_TAIL"); return e ? atoi(e) : 0; }();
         const LayerExec &Lh = on->a.layers.back();
         const int dbl = c.kind == ZOO_LEARNER_DQN && c.double_dqn;
         const int rows_fwd = (c.kind == ZOO_LEARNER_BASIC_DQN || dbl) ? 2 * B : B;
-        tail = tail_on && Lh.kind == ZOO_LAYER_DENSE && Lh.out_fp32 && !Lh.relu && !(split && on->tensors[Lh.wt].offset == on->late_off) &&
-               dqn_tail_supported(c.n_actions, Lh.K, on->prec == ZOO_PREC_BF16, rows_fwd);
+        const bool tail_ok = Lh.kind == ZOO_LAYER_DENSE && Lh.out_fp32 && !Lh.relu && !(split && on->tensors[Lh.wt].offset == on->late_off);
+        const bool multi = tail_mode == 2 && tail_ok && dqn_tail_multi_supported(c.n_actions, Lh.K, on->prec == ZOO_PREC_BF16, B);
+        tail = multi || (tail_mode == 1 && tail_ok && dqn_tail_supported(c.n_actions, Lh.K, on->prec == ZOO_PREC_BF16, rows_fwd));
         if (tail) {
             const LayerExec &Lp = on->a.layers[on->a.layers.size() - 2];
             bwd_rows = c.kind == ZOO_LEARNER_BASIC_DQN ? 2 * B : B;
@@ -285,6 +293,14 @@ static zoo_status enqueue_grads(zoo_learner *L, bool has_prio, bool has_mask, bo
             if (s == ZOO_OK && c.kind != ZOO_LEARNER_BASIC_DQN) s = target_join(L, st);
             if (s == ZOO_OK) {
                 prof_label("tail:t%d[%dx%dx%lld]", Lh.wt, rows_fwd, c.n_actions, Lh.K);
+                if (multi)
+                    s = dqn_tail_multi(c.kind, dbl, h, Lp.out, on->prec == ZOO_PREC_BF16, on->params + on->tensors[Lh.wt].offset,
+                                       on->params + on->tensors[Lh.bt].offset, tg ? tg->out_final : nullptr,
+                                       c.kind == ZOO_LEARNER_BASIC_DQN ? c.gamma : L->gamma_n, c.beta_priority, rows_fwd == 2 * B,
+                                       c.kind == ZOO_LEARNER_BASIC_DQN, Lh.K, Lp.relu, on->out_final, on->dout_final, Lp.dout,
+                                       on->grads + on->tensors[Lh.wt].offset, on->grads + on->tensors[Lh.bt].offset, on->grads + on->tensors[Lp.bt].offset,
+                                       L->d_loss, L->d_prio, L->d_tail_part, (unsigned *)(L->d_tail_part + 64), st);
+                else
                 s = dqn_tail(c.kind, dbl, h, Lp.out, on->prec == ZOO_PREC_BF16, on->params + on->tensors[Lh.wt].offset, on->params + on->tensors[Lh.bt].offset,
                              tg ? tg->out_final : nullptr, c.kind == ZOO_LEARNER_BASIC_DQN ? c.gamma : L->gamma_n, c.beta_priority, rows_fwd, bwd_rows, Lh.K,
                              Lp.relu, on->out_final, on->dout_final, Lp.dout, on->grads + on->tensors[Lh.wt].offset, on->grads + on->tensors[Lh.bt].offset,
@@ -626,7 +642,14 @@ zoo_status zoo_learner_create(const zoo_learner_cfg *cfg, zoo_net *online, zoo_n
     L->cfg = *cfg; L->cfg.support = nullptr;
     L->online = online; L->target = target; L->opt = opt; L->dp = dp; L->B = cfg->batch_size;
     L->gamma_n = (float)std::pow((double)cfg->gamma, (double)cfg->update_horizon);  // gamma^n, gamma::Float32 (dqn.jl:133)
-    ZOO_CUDA(cudaStreamCreateWithFlags(&L->st, cudaStreamNonBlocking));
+    {
+        // the learner's stream carries the update's critical path (online forward -> head -> data-gradient chain); the nets' side /
+        // comm lanes (target forward, weight gradients, late bucket) fill the SMs it leaves free.  ZOO_LANE_PRIO=0: all lanes equal.
+        static const bool prio = [] { const char *e = getenv("ZOO_LANE_PRIO"); return !(e && e[0] == '0'); }();
+        int lo = 0, hi = 0;
+        ZOO_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        ZOO_CUDA(cudaStreamCreateWithPriority(&L->st, cudaStreamNonBlocking, prio ? hi : 0));
+    }
     const int B = L->B, A = cfg->n_actions;
     if (dp && dp_world(dp) > 1 && !online->grads_nccl) {
         // data parallel: move the flat gradient buffer into NCCL-allocated, communicator-registered memory (zero-copy all-reduce)
@@ -680,6 +703,8 @@ zoo_status zoo_learner_create(const zoo_learner_cfg *cfg, zoo_net *online, zoo_n
     ZOO_CUDA(cudaMalloc(&L->d_prio, B * sizeof(float)));
     ZOO_CUDA(cudaMalloc(&L->d_wraw, B * sizeof(float)));
     ZOO_CUDA(cudaMalloc(&L->d_wmax, sizeof(float)));
+    ZOO_CUDA(cudaMalloc(&L->d_tail_part, 65 * sizeof(float)));
+    ZOO_CUDA(cudaMemset(L->d_tail_part, 0, 65 * sizeof(float)));
     if (cfg->kind == ZOO_LEARNER_RAINBOW) {
         ZOO_CUDA(cudaMalloc(&L->d_support, cfg->n_atoms * sizeof(float)));
         ZOO_CUDA(cudaMemcpy(L->d_support, cfg->support, cfg->n_atoms * sizeof(float), cudaMemcpyHostToDevice));
@@ -716,7 +741,7 @@ zoo_status zoo_learner_destroy(zoo_learner *L) {
         cudaStreamDestroy(L->st_copy);
     }
     void *ptrs[] = {L->d_obs, L->d_pack, L->d_support,
-                    L->d_target, L->d_tdist, L->d_per, L->d_prio, L->d_wraw, L->d_wmax};
+                    L->d_target, L->d_tdist, L->d_per, L->d_prio, L->d_wraw, L->d_wmax, L->d_tail_part};
     for (void *p : ptrs) if (p) cudaFree(p);
     cudaStreamDestroy(L->st);
     delete L;

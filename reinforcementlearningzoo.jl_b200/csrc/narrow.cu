@@ -427,6 +427,229 @@ __global__ void __launch_bounds__(256) dqn_tail_kernel(int kind, int double_dqn,
     if (threadIdx.x < N) atomicAdd(db + threadIdx.x, dbn_s[threadIdx.x]);
 }
 
+// The same tail spread over the batch: CTA c owns the RPP = 2048 / K samples [c RPP, (c + 1) RPP) -- 4 at K = 512, so a batch of 32
+// runs on 8 SMs -- and does for them what the single-CTA kernel does for the whole batch.  Every dependent global round trip
+// happens once per CTA instead of once per group of rows: the head layer's input rows are read once (forward) and kept in shared
+// memory for the backward.  The loss is summed in a fixed order by the last CTA to arrive (per-CTA partials + a ticket), so it is
+// bit-reproducible.  It replaces narrow_fwd + dqn_head + loss_reduce + narrow_bwd (27 - 34 us of the B = 32 critical path).
+template <typename T>
+__global__ void __launch_bounds__(256) dqn_tail_multi_kernel(int kind, int double_dqn, HeadArgs h, const T *__restrict__ X, const float *__restrict__ W,
+                                                             const float *__restrict__ bias, const float *__restrict__ q_t, float gamma_n, float beta,
+                                                             int two_rows, int bwd_next, int K, int relu_prev, float *__restrict__ q_out,
+                                                             float *__restrict__ dq_out, T *__restrict__ dX, float *__restrict__ dW, float *__restrict__ db,
+                                                             float *__restrict__ db_prev, float *__restrict__ loss, float *__restrict__ prio_out,
+                                                             float *__restrict__ part, unsigned *__restrict__ ticket) {
+    extern __shared__ float sm_[];
+    const int N = h.A, B = h.B;
+    const int TPR = K >> 3, RPP = 256 / TPR;           // threads per row, samples per CTA
+    float *Ws = sm_;                                   // [N][K]  (later the dW accumulator)
+    float *dbp_s = Ws + NARROW_NMAX * K;               // [K]
+    T *Xs = reinterpret_cast<T *>(dbp_s + K);          // [2 RPP][K]: rows of s, then rows of s'  (RPP K = 2048 elements)
+    float *q_s = dbp_s + K + 2 * 2048;                 // [2 RPP][N]
+    float *dq_s = q_s + 64 * NARROW_NMAX;              // [2 RPP][N]
+    float *dbn_s = dq_s + 64 * NARROW_NMAX;            // [N]
+    float *ls_s = dbn_s + NARROW_NMAX;                 // [RPP] scaled per-sample losses
+    float *qt_s = ls_s + 32;                           // [RPP][N] target Q(s') of this CTA's samples
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b0 = blockIdx.x * RPP;
+    const int nloc = min(RPP, B - b0);                 // samples of this CTA
+    const int nrows = two_rows ? 2 * RPP : RPP;
+    pdl_wait();
+    for (int i = threadIdx.x; i < N * K / 4; i += 256) reinterpret_cast<float4 *>(Ws)[i] = __ldg(reinterpret_cast<const float4 *>(W) + i);
+    for (int i = threadIdx.x; i < K + NARROW_NMAX; i += 256) (i < K ? dbp_s[i] : dbn_s[i - K]) = 0.f;
+    for (int i = threadIdx.x; i < 64 * NARROW_NMAX; i += 256) dq_s[i] = 0.f;
+    if (q_t && threadIdx.x < nloc * N) qt_s[threadIdx.x] = __ldg(q_t + (size_t)b0 * N + threadIdx.x);
+    // ---- this CTA's input rows: global -> registers -> shared (all loads of a thread in flight together)
+    {
+        constexpr int V = NarrowVec<T>::V;
+        const int cpr = K / V;  // 16-byte chunks per row
+        typename NarrowVec<T>::raw r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = threadIdx.x + 256 * u;
+            const int ri = j / cpr, ch = j - ri * cpr;
+            if (ri < nrows) {
+                const int loc = ri < RPP ? ri : ri - RPP;
+                const long long m = ri < RPP ? b0 + loc : (long long)B + b0 + loc;
+                r[u] = loc < nloc ? reinterpret_cast<const typename NarrowVec<T>::raw *>(X + m * K)[ch] : typename NarrowVec<T>::raw{};
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = threadIdx.x + 256 * u;
+            if (j / cpr < nrows) reinterpret_cast<typename NarrowVec<T>::raw *>(Xs)[j] = r[u];
+        }
+    }
+    __syncthreads();
+    // ---- forward: one warp per row
+    {
+        using NV = NarrowVec<T>;
+        constexpr int V = NV::V;
+        const int nchunks = K / V;
+        for (int ri = warp; ri < nrows; ri += 8) {
+            const int loc = ri < RPP ? ri : ri - RPP;
+            if (loc >= nloc) continue;
+            float acc[NARROW_NMAX];
+#pragma unroll
+            for (int n = 0; n < NARROW_NMAX; ++n) acc[n] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (lane + 32 * c < nchunks) {
+                    float x[V];
+                    NV::unpack(reinterpret_cast<const typename NV::raw *>(Xs + (size_t)ri * K)[lane + 32 * c], x);
+                    const int k0 = (lane + 32 * c) * V;
+#pragma unroll
+                    for (int n = 0; n < NARROW_NMAX; ++n) {
+                        if (n < N) {
+#pragma unroll
+                            for (int e4 = 0; e4 < V; e4 += 4) {
+                                const float4 wv = *reinterpret_cast<const float4 *>(Ws + n * K + k0 + e4);
+                                acc[n] = fmaf(x[e4], wv.x, acc[n]); acc[n] = fmaf(x[e4 + 1], wv.y, acc[n]);
+                                acc[n] = fmaf(x[e4 + 2], wv.z, acc[n]); acc[n] = fmaf(x[e4 + 3], wv.w, acc[n]);
+                            }
+                        }
+                    }
+                }
+            }
+            const long long m = ri < RPP ? b0 + loc : (long long)B + b0 + loc;
+#pragma unroll
+            for (int n = 0; n < NARROW_NMAX; ++n) {
+                float v = acc[n];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == n && n < N) { v += __ldg(bias + n); q_s[ri * N + n] = v; q_out[m * N + n] = v; }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- head of this CTA's samples; the partial loss goes to part[c], the last CTA to arrive sums the partials in order
+    if (threadIdx.x < nloc) {
+        const int loc = threadIdx.x, b = b0 + loc;
+        dqn_head_rows(kind, double_dqn, h, b, q_s + loc * N, q_s + (RPP + loc) * N, q_t ? qt_s + loc * N : nullptr, gamma_n, dq_s + loc * N,
+                      dq_s + (RPP + loc) * N);
+        const float l = h.per_sample[b];
+        ls_s[loc] = l * sample_scale(h, b);
+        if (prio_out) prio_out[b] = powf(__fadd_rn(l, 1e-10f), beta);
+        for (int n = 0; n < N; ++n) {
+            dq_out[(size_t)b * N + n] = dq_s[loc * N + n];
+            if (bwd_next) dq_out[(size_t)(B + b) * N + n] = dq_s[(RPP + loc) * N + n];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float sum = 0.f;
+        for (int i = 0; i < nloc; ++i) sum += ls_s[i];
+        part[blockIdx.x] = sum;
+        __threadfence();
+        const unsigned old = atomicAdd(ticket, 1u);
+        if (old == gridDim.x - 1) {
+            __threadfence();
+            float tot = 0.f;
+            for (unsigned c = 0; c < gridDim.x; ++c) tot += __ldcg(part + c);
+            loss[0] = tot;
+            *ticket = 0u;
+        }
+    }
+    pdl_trigger();
+    // ---- backward of the head layer (as narrow_bwd_kernel; rows from shared memory, dY = dq_s)
+    const int kq = threadIdx.x % TPR, rl = threadIdx.x / TPR;
+    float w[NARROW_NMAX][8], dw[NARROW_NMAX][8], dbp[8], dbn[NARROW_NMAX];
+#pragma unroll
+    for (int n = 0; n < NARROW_NMAX; ++n) {
+        dbn[n] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { w[n][e] = n < N ? Ws[n * K + kq * 8 + e] : 0.f; dw[n][e] = 0.f; }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dbp[e] = 0.f;
+    __syncthreads();  // every thread holds its W columns: Ws becomes the dW accumulator
+    for (int i = threadIdx.x; i < NARROW_NMAX * K; i += 256) Ws[i] = 0.f;
+    for (int pass = 0; pass < (bwd_next ? 2 : 1); ++pass) {
+        if (rl >= nloc) break;
+        const int ri = pass * RPP + rl;
+        const long long m = pass ? (long long)B + b0 + rl : b0 + rl;
+        float x[8], dy[NARROW_NMAX];
+        if (sizeof(T) == 2) {
+            NarrowVec<bf16>::unpack(*reinterpret_cast<const uint4 *>(reinterpret_cast<const bf16 *>(Xs) + (size_t)ri * K + kq * 8), x);
+        } else {
+            const float4 a = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(Xs) + (size_t)ri * K + kq * 8);
+            const float4 b = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(Xs) + (size_t)ri * K + kq * 8 + 4);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        }
+#pragma unroll
+        for (int n = 0; n < NARROW_NMAX; ++n) dy[n] = n < N ? dq_s[ri * N + n] : 0.f;
+        float dx[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float s2 = 0.f;
+#pragma unroll
+            for (int n = 0; n < NARROW_NMAX; ++n) s2 = fmaf(dy[n], w[n][e], s2);
+            if (relu_prev && !(x[e] > 0.f)) s2 = 0.f;
+            dx[e] = s2;
+            dbp[e] += s2;
+#pragma unroll
+            for (int n = 0; n < NARROW_NMAX; ++n) dw[n][e] = fmaf(dy[n], x[e], dw[n][e]);
+        }
+        if (sizeof(T) == 2) {
+            *reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(dX) + m * K + kq * 8) = NarrowVec<bf16>::pack(dx);
+        } else {
+            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(dX) + m * K + kq * 8) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(dX) + m * K + kq * 8 + 4) = make_float4(dx[4], dx[5], dx[6], dx[7]);
+        }
+        if (kq == 0) {
+#pragma unroll
+            for (int n = 0; n < NARROW_NMAX; ++n) dbn[n] += dy[n];
+        }
+    }
+    __syncthreads();
+    if (rl < nloc) {
+#pragma unroll
+        for (int n = 0; n < NARROW_NMAX; ++n) {
+            if (n < N) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) atomicAdd(Ws + n * K + kq * 8 + e, dw[n][e]);
+                if (kq == 0) atomicAdd(dbn_s + n, dbn[n]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(dbp_s + kq * 8 + e, dbp[e]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N * K; i += 256) atomicAdd(dW + i, Ws[i]);
+    if (db_prev)
+        for (int i = threadIdx.x; i < K; i += 256) atomicAdd(db_prev + i, dbp_s[i]);
+    if (threadIdx.x < N) atomicAdd(db + threadIdx.x, dbn_s[threadIdx.x]);
+}
+
+bool dqn_tail_multi_supported(int N, long long K, int x_bf16, int B) {
+    // RPP <= 32 samples per CTA (K >= 64), at most 64 CTAs (the partial-loss scratch)
+    return narrow_supported(N, K, x_bf16) && K >= 64 && cdiv(B, 2048 / (int)K) <= 64;
+}
+
+// part: >= 64 floats of scratch, ticket: one zero-initialised counter (left zero)
+zoo_status dqn_tail_multi(int kind, int double_dqn, const HeadArgs &h, const void *X, int x_bf16, const float *W, const float *bias, const float *q_t,
+                          float gamma_n, float beta, int two_rows, int bwd_next, long long K, int relu_prev, float *q_out, float *dq_out, void *dX,
+                          float *dW, float *db, float *db_prev, float *loss, float *prio_out, float *part, unsigned *ticket, cudaStream_t st) {
+    ZOO_REQUIRE(dqn_tail_multi_supported(h.A, K, x_bf16, h.B) && (!bwd_next || two_rows), "dqn_tail_multi: unsupported shape");
+    const size_t smem = (size_t)(NARROW_NMAX * K + K + 2 * 2048 + 2 * 64 * NARROW_NMAX + NARROW_NMAX + 32 + 32 * NARROW_NMAX) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        const int mx = (int)((NARROW_NMAX * 2048 + 2048 + 2 * 2048 + 2 * 64 * NARROW_NMAX + NARROW_NMAX + 32 + 32 * NARROW_NMAX) * sizeof(float));
+        ZOO_CUDA(cudaFuncSetAttribute(dqn_tail_multi_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        ZOO_CUDA(cudaFuncSetAttribute(dqn_tail_multi_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        attr = true;
+    }
+    const dim3 grid(cdiv(h.B, 2048 / (int)K));
+    if (x_bf16)
+        ZOO_CUDA(launch_pdl(dqn_tail_multi_kernel<bf16>, grid, dim3(256), smem, st, kind, double_dqn, h, (const bf16 *)X, W, bias, q_t, gamma_n, beta, two_rows,
+                            bwd_next, (int)K, relu_prev, q_out, dq_out, (bf16 *)dX, dW, db, db_prev, loss, prio_out, part, ticket));
+    else
+        ZOO_CUDA(launch_pdl(dqn_tail_multi_kernel<float>, grid, dim3(256), smem, st, kind, double_dqn, h, (const float *)X, W, bias, q_t, gamma_n, beta, two_rows,
+                            bwd_next, (int)K, relu_prev, q_out, dq_out, (float *)dX, dW, db, db_prev, loss, prio_out, part, ticket));
+    ZOO_LAUNCH_CHECK();
+    return ZOO_OK;
+}
+
 bool dqn_tail_supported(int N, long long K, int x_bf16, int rows_fwd) {
     return narrow_supported(N, K, x_bf16) && rows_fwd <= TAIL_ROWS;
 }

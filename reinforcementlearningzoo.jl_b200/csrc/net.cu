@@ -669,7 +669,10 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
         }
         // bias grad + wgrad only need this layer's dout, which is complete on `st` here: they go to the side lane and
         // overlap the dgrad chain (the critical path) that continues on `st`
-        const bool par = net->side && !g_prof_on;
+        // (the bottom layer has no data gradient: its bias / weight gradient ARE the rest of the critical path and stay on `st`
+        // instead of queueing behind the previous layer's weight gradient on the side lane)
+        static const bool last_on_main = [] { const char *e = getenv("ZOO_LAST_WGRAD_MAIN"); return !(e && e[0] == '0'); }();
+        const bool par = net->side && !g_prof_on && !(last_on_main && li == 0 && !dx && &ch == &net->a && ch.layers.size() > 1);
         cudaStream_t sw = par ? net->side : st;
         float *wsw = par ? net->ws_side : net->ws;
         const size_t wsw_elems = par ? net->ws_side_elems : net->ws_elems;

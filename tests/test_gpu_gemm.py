@@ -96,11 +96,12 @@ def test_split_k_is_consistent(zoo, engine, split):
 
 
 @pytest.mark.parametrize("env,val", [("ZOO_IMPLICIT_CONV", "1"), ("ZOO_TMA_DGRAD", "0"), ("ZOO_TMA_WGRAD", "0"), ("ZOO_PDL", "0"), ("ZOO_TMA_CONV", "0"),
-                                     ("ZOO_TMA_STORE", "0"), ("ZOO_PERSIST_GEMM", "0"), ("ZOO_DQN_TAIL", "1"), ("ZOO_NARROW", "0"), ("ZOO_IQN_FUSE", "0")])
+                                     ("ZOO_TMA_STORE", "0"), ("ZOO_PERSIST_GEMM", "0"), ("ZOO_DQN_TAIL", "1"), ("ZOO_DQN_TAIL", "2"), ("ZOO_NARROW", "0"), ("ZOO_IQN_FUSE", "0")])
 def test_non_default_kernel_paths_keep_parity(env, val):
     """Every kernel path that has a switch: the gathered-A implicit conv (opt-in), and -- switched OFF here -- the TMA data / weight
     gradients (falls back to GEMM + col2im / im2col + GEMM), programmatic dependent launch, the TMA-im2col forward conv, the TMA-store
-    epilogue, the narrow Q-head kernels and the fused IQN merge; the fused DQN tail (opt-in) is switched ON.  In every setting the Atari learner parity tests
+    epilogue, the narrow Q-head kernels and the fused IQN merge; the DQN tail runs as the single-CTA kernel ("1") and as the
+    multi-CTA kernel ("2") instead of the default four launches.  In every setting the Atari learner parity tests
     (fp32 and bf16) must still pass."""
     e = dict(os.environ)
     e[env] = val
