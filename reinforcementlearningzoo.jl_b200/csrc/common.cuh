@@ -65,6 +65,9 @@ zoo_status require_sm100();
 // SMs the GEMM split-K heuristics may plan for: 148, or fewer while a data-parallel communicator is alive (the NCCL kernel
 // of the overlapped late bucket holds SMs; a 148-CTA one-CTA-per-SM GEMM would then fall into a second wave)
 extern int g_sm_budget;
+// set around launches that run beside the critical path (the target net's forward on the side lane): the engine then sizes its
+// ring so that two CTAs share an SM, leaving SMs to the lane that matters instead of owning 128 of them for the kernel's whole life
+extern thread_local int g_tc_shallow;
 extern int g_tc_stages_force;  // 0 = per-launch choice (tc_pick_stages); >= 2 forces the ring depth (tuning hook)
 
 // Programmatic dependent launch: a kernel launched through launch_pdl may become resident while its stream predecessor is

@@ -8,6 +8,7 @@
 namespace zoo {
 
 unsigned long long *g_tc_dbg = nullptr;  // set by zoo_test_gemm_trace
+thread_local int g_tc_shallow = 0;
 
 // Per-launch phase trace (zoo_test_trace_*): while armed, launch i of the engine gets its own 16-stamp slot, so an update that is
 // captured into a CUDA graph while armed keeps writing CTA (0,0,0)'s phase stamps on every replay -- the graph's real timeline.
@@ -127,7 +128,8 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
     // per SM.  IQN 512 x 64 fp32: phi forward 1103 -> 780 us, fc1 dgrad 2770 -> 2408 us; no gain at K = 7744 (the main loop is
     // shared-memory-bandwidth bound there either way).  ZOO_X3_NARROW = longest K, in K-blocks of 32, that takes the narrow tile.
     static const int x3_narrow = [] { const char *e = getenv("ZOO_X3_NARROW"); return e ? atoi(e) : 16; }();
-    if (x3 && BN == 128 && total_kb <= x3_narrow && (long long)cdiv(M, BM) * cdiv(N, 128) > 4LL * g_sm_budget) BN = 64;
+    static const int x3_narrow_q = [] { const char *e = getenv("ZOO_X3_NARROW_TILES_Q"); return e ? atoi(e) : 4; }();  // quarters of the SM count
+    if (x3 && BN == 128 && total_kb <= x3_narrow && 4LL * cdiv(M, BM) * cdiv(N, 128) > (long long)x3_narrow_q * g_sm_budget) BN = 64;
     dim3 grid(cdiv(M, BM), cdiv(N, BN), 1);
     const long long tiles = (long long)grid.x * grid.y;
     static const int split_cap_pct = [] { const char *e = getenv("ZOO_SPLIT_CAP_PCT"); return e ? atoi(e) : 25; }();
@@ -179,9 +181,10 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
         }
         // fp32-grade (3xTF32) kernels with a plain fp32 row-major output: same idea, 32-column boxes (tma_store == 3).  The phi forward
         // of IQN at 512 x 64 rows (1 GB of fp32 output, K = 64) spent most of its 1.19 ms in the slab + per-row stores.
+        static const long long x3_ts_min = [] { const char *e = getenv("ZOO_X3_TS_MIN"); return e ? atoll(e) : (1ll << 21); }();
         const bool mask32_ok = !pe.mask || (!pe.mask_bf16 && pe.mask_sn == 1 && (pe.mask_sm & 3) == 0 && ((uintptr_t)pe.mask & 15) == 0);
         if (ts_on && x3 && BN >= 64 && split_k == 1 && !pe.out_bf16 && !pe.accumulate && pe.bias_mode != 2 && pe.sn == 1 && (pe.sm & 3) == 0 &&
-            ((uintptr_t)pe.out & 15) == 0 && rm_ok && mask32_ok && (long long)M * N >= (1 << 22)) {
+            ((uintptr_t)pe.out & 15) == 0 && rm_ok && mask32_ok && (long long)M * N >= x3_ts_min) {
             ZOO_TRY(make_map(&P.tmC, pe.out, 4, N, M, pe.sm, 32, 32, false));
             P.tma_store = 3;
         }

@@ -900,9 +900,96 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // the chunk through shared memory (the pipeline stages are idle once the last chain has been committed) and then
         // walks the rows with lane = column, so every global access below is one coalesced 128-byte row segment.
         const int lastc = nchains - 1, lb = lastc & 1;
+        // Whole-tile TMA store (data gradient): relu' of this thread's pixel as one bit per output column, fetched and packed NOW,
+        // while the last chain's MMAs are still retiring -- inside the epilogue the loads cost a 2.5 us round trip per 32 columns
+        // on the update's critical path (the epilogue warps run alone on their schedulers: nothing hides a dependent load).
+        unsigned dmb[BN / 32];
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) dmb[i] = 0xffffffffu;
+        if (GA == 2 && P.tma_store == 2 && P.epi.mask && !(P.xmode & 16)) {
+            const int r = q * 32 + lane;
+            const int vN = min(BN, P.N - n0);
+            const uint8_t *mrow = nullptr;
+            if (r < vrows) {
+                const int ry = r / cols_c, rx = r - ry * cols_c;
+                const int y = (coy0 + ry) * P.conv.s + cls_py, xx = rx * P.conv.s + cls_px;
+                if (y < P.conv.H && xx < P.conv.W)
+                    mrow = (const uint8_t *)P.epi.mask + ((((long long)cimg * P.conv.H + y) * P.conv.W + xx) * P.epi.mask_sm + n0) * (P.epi.mask_bf16 ? 2 : 4);
+            }
+#pragma unroll
+            for (int i = 0; i < BN / 32; ++i) {
+                const int c = i * 32;
+                unsigned bits = 0u;
+                if (mrow && c < vN) {
+                    if (P.epi.mask_bf16) {
+                        uint4 mk4[4];
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            mk4[j4] = make_uint4(0u, 0u, 0u, 0u);
+                            if (c + j4 * 8 + 8 <= vN) mk4[j4] = __ldg(reinterpret_cast<const uint4 *>(mrow + (c + j4 * 8) * 2));
+                        }
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const uint32_t mw[4] = {mk4[j4].x, mk4[j4].y, mk4[j4].z, mk4[j4].w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                bits |= (__uint_as_float(mw[k] << 16) > 0.f ? 1u : 0u) << (j4 * 8 + 2 * k);
+                                bits |= (__uint_as_float(mw[k] & 0xffff0000u) > 0.f ? 1u : 0u) << (j4 * 8 + 2 * k + 1);
+                            }
+                        }
+                    } else {
+                        float4 mk8[8];
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            mk8[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (c + j4 * 4 + 4 <= vN) mk8[j4] = __ldg(reinterpret_cast<const float4 *>(mrow + (c + j4 * 4) * 4));
+                        }
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            bits |= ((mk8[j4].x > 0.f ? 1u : 0u) | (mk8[j4].y > 0.f ? 2u : 0u) | (mk8[j4].z > 0.f ? 4u : 0u) | (mk8[j4].w > 0.f ? 8u : 0u)) << (4 * j4);
+                    }
+                }
+                dmb[i] = bits;
+            }
+        }
+        // the row-walker epilogues (plain GEMMs: fc1's data gradient) take their relu' bits the same way
+        const bool pre_mask = GA == 0 && P.epi.mask && !P.ws && !P.epi.accumulate && P.tma_store == 0 &&
+                              (!P.epi.rowmul || ((P.epi.rowmul_div & 31) == 0 && P.epi.sn == 1));
+        if (pre_mask) {
+            const bool ptrans = !P.epi.rowmul && P.epi.sm == 1 && P.epi.sn != 1;
+            const int prow0 = m0 + q * 32, prows = max(0, min(32, vrows - q * 32));
+            const long long pmsm = P.epi.mask_sm, pmsn = P.epi.mask_sn;
+#pragma unroll
+            for (int i = 0; i < BN / 32; ++i) {
+                const int c = i * 32, n = n0 + c + lane;
+                unsigned bits = 0u;
+                if (n0 + c < P.N) {
+                    const int cnt = ptrans ? min(32, P.N - (n0 + c)) : prows;
+                    const bool mine = ptrans ? lane < prows : n < P.N;
+                    const long long mbase = ptrans ? (long long)(prow0 + lane) * pmsm + (long long)(n0 + c) * pmsn : (long long)prow0 * pmsm + (long long)n * pmsn;
+                    const long long mstep = ptrans ? pmsn : pmsm;
+                    if (P.epi.mask_bf16) {
+                        unsigned short mv[32];
+                        const unsigned short *mp16 = (const unsigned short *)P.epi.mask + mbase;
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) mv[k] = (mine && k < cnt) ? __ldg(mp16 + k * mstep) : (unsigned short)0x8000u;
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) bits |= (__uint_as_float((unsigned)mv[k] << 16) > 0.f ? 1u : 0u) << k;
+                    } else {
+                        float mv[32];
+                        const float *mp32 = (const float *)P.epi.mask + mbase;
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) mv[k] = (mine && k < cnt) ? __ldg(mp32 + k * mstep) : 0.f;
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) bits |= (mv[k] > 0.f ? 1u : 0u) << k;
+                    }
+                }
+                dmb[i] = bits;
+            }
+        }
         mbar_wait(&acc_full[lb], (lastc >> 1) & 1);
         tc_fence_after();
-        pdl_trigger();  // main loop done: the next kernel may become resident and run its prologue under this epilogue
+        if (!(P.xmode & 32)) pdl_trigger();  // main loop done: the next kernel may become resident and run its prologue under this epilogue
         if (threadIdx.x == 64) dbg_stamp(P, 5);
         float(*stg)[33] = reinterpret_cast<float(*)[33]>(smem) + q * 32;  // 32 x 33 floats per warp, in pipeline stage 0
         const int row0 = m0 + q * 32;
@@ -1031,13 +1118,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int r = q * 32 + lane;
             const uint32_t swz = span == 128 ? (uint32_t)(r & 7) : (span == 64 ? (uint32_t)((r >> 1) & 3) : 0u);
             const uint32_t stg0 = smem_u32(smem);
-            const uint8_t *mrow = nullptr;
-            if (maskp && r < vrows) {
-                const int ry = r / cols_c, rx = r - ry * cols_c;
-                const int y = (coy0 + ry) * P.conv.s + cls_py, xx = rx * P.conv.s + cls_px;
-                if (y < P.conv.H && xx < P.conv.W)
-                    mrow = (const uint8_t *)maskp + ((((long long)cimg * P.conv.H + y) * P.conv.W + xx) * msm + n0) * (mask_bf16 ? 2 : 4);
-            }
 #pragma unroll
             for (int c = 0; c < BN; c += 32) {
                 if (c < vN) {
@@ -1053,7 +1133,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(rr[j]);
                     }
-                    if (c == 0 && threadIdx.x == 64) dbg_stamp(P, 12);
+                    if (threadIdx.x == 64) dbg_stamp(P, c == 0 ? 12 : 14);
                     if (bias_mode == 1) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) x[j] += (n0 + c + j < Nn) ? __ldg(e.bias + n0 + c + j) : 0.f;
@@ -1063,44 +1143,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
                     }
                     if (maskp) {
-                        if (!mrow) {
+                        const unsigned mb = dmb[c / 32];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) x[j] = 0.f;
-                        } else if (mask_bf16) {
-                            uint4 mk4[4];
-#pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) {
-                                mk4[j4] = make_uint4(0u, 0u, 0u, 0u);
-                                if (c + j4 * 8 + 8 <= vN) mk4[j4] = __ldg(reinterpret_cast<const uint4 *>(mrow + (c + j4 * 8) * 2));
-                            }
-#pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) {
-                                const uint4 mk = mk4[j4];
-                                const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    if (!(__uint_as_float(mw[i] << 16) > 0.f)) x[j4 * 8 + 2 * i] = 0.f;
-                                    if (!(__uint_as_float(mw[i] & 0xffff0000u) > 0.f)) x[j4 * 8 + 2 * i + 1] = 0.f;
-                                }
-                            }
-                        } else {
-                            float4 mk8[8];
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {
-                                mk8[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (c + j4 * 4 + 4 <= vN) mk8[j4] = __ldg(reinterpret_cast<const float4 *>(mrow + (c + j4 * 4) * 4));
-                            }
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {
-                                const float4 mk = mk8[j4];
-                                if (!(mk.x > 0.f)) x[j4 * 4] = 0.f;
-                                if (!(mk.y > 0.f)) x[j4 * 4 + 1] = 0.f;
-                                if (!(mk.z > 0.f)) x[j4 * 4 + 2] = 0.f;
-                                if (!(mk.w > 0.f)) x[j4 * 4 + 3] = 0.f;
-                            }
-                        }
+                        for (int j = 0; j < 32; ++j) x[j] = ((mb >> j) & 1u) ? x[j] : 0.f;
                     }
-                    if (c == 0 && threadIdx.x == 64) dbg_stamp(P, 13);
+                    if (threadIdx.x == 64) dbg_stamp(P, c == 0 ? 13 : 15);
                     if (out_bf16) {
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
@@ -1311,7 +1358,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             unsigned mbits = 0xffffffffu;
             const void *mq = maskp;
             asm volatile("" : "+l"(mq));  // keeps the mask loads below inside this loop body
-            if (mq && direct && simple) {
+            if (pre_mask) {  // (selected by compares: a dynamic index would send the bits through local memory)
+                mbits = dmb[0];
+                if (BN > 32 && c == 32) mbits = dmb[BN > 32 ? 1 : 0];
+                if (BN > 64 && c == 64) mbits = dmb[BN > 64 ? 2 : 0];
+                if (BN > 96 && c == 96) mbits = dmb[BN > 96 ? 3 : 0];
+            } else if (mq && direct && simple) {
                 mbits = 0u;
                 const int cnt = trans ? min(32, Nn - (n0 + c)) : rows;
                 const bool mine = trans ? lane < rows : n < Nn;
@@ -1422,6 +1474,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }  // tma_store != 3
     }
     if (threadIdx.x == 64) dbg_stamp(P, 6);
+    if (P.xmode & 32) pdl_trigger();  // (experiment: dependents become resident only when this CTA is about to leave)
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) dbg_stamp(P, 7);
@@ -1532,7 +1585,7 @@ template <int EB, bool X3, int SPAN = 128>
 static int tc_pick_stages(int BN, long long ctas, int nkb) {
     const int mx = BN == 32 ? TcCfg<EB, 32, X3, SPAN>::MAX_STAGES : (BN == 64 ? TcCfg<EB, 64, X3, SPAN>::MAX_STAGES : TcCfg<EB, 128, X3, SPAN>::MAX_STAGES);
     const int two = BN == 32 ? TcCfg<EB, 32, X3, SPAN>::TWO_CTA_STAGES : (BN == 64 ? TcCfg<EB, 64, X3, SPAN>::TWO_CTA_STAGES : TcCfg<EB, 128, X3, SPAN>::TWO_CTA_STAGES);
-    int stg = ctas > g_sm_budget ? two : mx;
+    int stg = (ctas > g_sm_budget || g_tc_shallow) ? two : mx;
     // bf16 grids of many waves (the large-batch convolutions): a two-deep ring lets three or four CTAs share an SM and overlap
     // their prologues / epilogues -- Rainbow B = 1024 conv2 / conv3 forward 39 -> 30 us each, step 1187 -> 1100 us; IQN 512 x 64
     // 2434 -> 2388 us.  (The fp32-grade kernels lose with it: their converter warps need the deeper ring.)

@@ -42,6 +42,18 @@ template <> struct NarrowVec<bf16> {
     }
 };
 
+// 16-byte red (four consecutive floats): the per-SM atomic issue rate bounds these flushes, so a quarter of the instructions
+__device__ __forceinline__ void red_add_v4(float *p, const float *v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+__device__ __forceinline__ void flush_reds(float *dst, const float *src_s, int n, bool vec) {
+    if (vec) {
+        for (int i = threadIdx.x * 4; i < n; i += 1024) red_add_v4(dst + i, src_s + i);
+    } else {
+        for (int i = threadIdx.x; i < n; i += 256) atomicAdd(dst + i, src_s[i]);
+    }
+}
+
 // one warp per row (grid-stride); lane owns the 16-byte chunks lane, lane + 32, ... of the row; W lives in registers
 template <typename T, int CPL>
 __global__ void __launch_bounds__(256) narrow_fwd_kernel(const T *__restrict__ X, const float *__restrict__ W, const float *__restrict__ bias,
@@ -203,9 +215,8 @@ __global__ void __launch_bounds__(256) narrow_bwd_kernel(const T *__restrict__ X
 #pragma unroll
     for (int e = 0; e < 8; ++e) atomicAdd(dbp_s + kq * 8 + e, dbp[e]);
     __syncthreads();
-    for (int i = threadIdx.x; i < N * K; i += 256) atomicAdd(dW + i, dWs[i]);
-    if (db_prev)
-        for (int i = threadIdx.x; i < K; i += 256) atomicAdd(db_prev + i, dbp_s[i]);
+    flush_reds(dW, dWs, N * K, ((uintptr_t)dW & 15) == 0);
+    if (db_prev) flush_reds(db_prev, dbp_s, K, ((uintptr_t)db_prev & 15) == 0);
     if (threadIdx.x < N) atomicAdd(db + threadIdx.x, dbn_s[threadIdx.x]);
 }
 
@@ -421,9 +432,8 @@ __global__ void __launch_bounds__(256) dqn_tail_kernel(int kind, int double_dqn,
     for (int e = 0; e < 8; ++e) atomicAdd(dbp_s + kq * 8 + e, dbp[e]);
     __syncthreads();
     // fire-and-forget reds (a read-modify-write here waits a DRAM round trip per element: 12 dependent trips per thread)
-    for (int i = threadIdx.x; i < N * K; i += 256) atomicAdd(dW + i, Ws[i]);
-    if (db_prev)
-        for (int i = threadIdx.x; i < K; i += 256) atomicAdd(db_prev + i, dbp_s[i]);
+    flush_reds(dW, Ws, N * K, ((uintptr_t)dW & 15) == 0);
+    if (db_prev) flush_reds(db_prev, dbp_s, K, ((uintptr_t)db_prev & 15) == 0);
     if (threadIdx.x < N) atomicAdd(db + threadIdx.x, dbn_s[threadIdx.x]);
 }
 
@@ -615,9 +625,8 @@ __global__ void __launch_bounds__(256) dqn_tail_multi_kernel(int kind, int doubl
         for (int e = 0; e < 8; ++e) atomicAdd(dbp_s + kq * 8 + e, dbp[e]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < N * K; i += 256) atomicAdd(dW + i, Ws[i]);
-    if (db_prev)
-        for (int i = threadIdx.x; i < K; i += 256) atomicAdd(db_prev + i, dbp_s[i]);
+    flush_reds(dW, Ws, N * K, ((uintptr_t)dW & 15) == 0);
+    if (db_prev) flush_reds(db_prev, dbp_s, K, ((uintptr_t)db_prev & 15) == 0);
     if (threadIdx.x < N) atomicAdd(db + threadIdx.x, dbn_s[threadIdx.x]);
 }
 
