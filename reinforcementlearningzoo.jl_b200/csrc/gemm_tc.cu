@@ -137,12 +137,15 @@ zoo_status tc_gemm(const Operand &A, const Operand &B, int M, int N, int K, cons
     // its whole life, so SM-time, not the latency of a kernel alone on the GPU, is what the step pays for -- fc1 forward of both nets
     // at 49 splits = 392 one-per-SM CTAs in 2.6 waves; at 18 splits both fit in one.  Measured on the B = 32 update: 100 % 0.2571 ms,
     // 50 % 0.2590, 25 % 0.2542)
-    const long long cap_ctas = g_sm_budget * ((x3 && BN >= 128) ? 1 : 2) * split_cap_pct / 100;  // resident CTAs (TcCfg::TWO_CTA_STAGES)
+    long long cap_ctas = g_sm_budget * ((x3 && BN >= 128) ? 1 : 2);  // resident CTAs (TcCfg::TWO_CTA_STAGES)
     if (split_k <= 0) {
         // split only when the output grid leaves most SMs idle AND one CTA would walk a long K: each split costs
         // atomics on the whole tile, so keep >= 4 K-blocks per CTA and stay within one resident wave
         split_k = 1;
-        if (tiles * 2 <= cap_ctas && total_kb >= 32) split_k = (int)std::min<long long>(total_kb / 4, cap_ctas / tiles);
+        // (the reduced cap is for the skinny outputs of the Dopamine batch sizes -- a handful of tiles, K in the thousands; outputs
+        // with more tiles keep the full cap: IQN B = 32 fc1, 64 tiles, still splits 4 ways)
+        const long long split_ctas = tiles <= 8 ? cap_ctas * split_cap_pct / 100 : cap_ctas;
+        if (tiles * 2 <= cap_ctas && total_kb >= 32) split_k = (int)std::min<long long>(total_kb / 4, std::max<long long>(1, split_ctas / tiles));
         else if (x3 && tiles * 2 <= cap_ctas && total_kb >= 16 && midk_split_enabled(epi, BN)) {
             // 3xTF32 K-blocks cost ~0.85 us each, a split ~7 us (BN = 32) to ~10 us (BN = 64) of reds + finish: measured
             // (scripts/sweep_split.py) it pays for 61 x BN32 tiles at 4 splits and for 31 x BN64 tiles at 6+, not for 61 x BN64 at 4
@@ -335,7 +338,7 @@ zoo_status tc_conv_wgrad(ConvGeom g, const void *dy, int is_bf16, int images, co
     const int total_kb = images * g.tpi;
     const int ntiles = cdiv(N, BN);
     static const int wgrad_cap_pct = [] { const char *e = getenv("ZOO_WGRAD_CAP_PCT"); return e ? atoi(e) : 50; }();  // (see tc_gemm's split cap)
-    const long long cap = g_sm_budget * (x3 ? 1 : 2) * wgrad_cap_pct / 100;
+    const long long cap = g_sm_budget * (x3 ? 1 : 2) * (images <= 128 ? wgrad_cap_pct : 100) / 100;  // (large batches keep the full cap)
     int split = (int)std::max<long long>(1, std::min<long long>(total_kb, cap / ntiles));
     const int kbps = cdiv(total_kb, split);
     split = cdiv(total_kb, kbps);
