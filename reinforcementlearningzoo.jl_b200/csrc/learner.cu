@@ -109,10 +109,65 @@ struct StageArgs {
     int *d_action; float *d_reward; uint8_t *d_terminal; float *d_priority; uint8_t *d_mask; float *d_tau, *d_taup;
     int B, A;
     long long n_tau, n_taup;  // element counts of tau / tau_prime (IQN: B*N, B*N'; REM-DQN: E convex weights, 0)
+    // optional: the zero-padded NHWC copy of the 4-channel frame stacks that the first convolution reads (what obs_to_nhwc4_x4_kernel
+    // in net.cu would produce as the first launch of each net's forward), written here for the rows each net is about to consume:
+    // rows [0, on_rows) of [state; next_state] for the online net, next_state for the target net.  quads = 4-pixel groups of all 2 B rows.
+    void *nhwc_on, *nhwc_tg;
+    long long quads;
+    int on_rows, H, W, pad, scale255, in_f32, out_bf16;
 };
+template <typename Tin, typename Tout>
+__device__ __forceinline__ void stage_nhwc_quad(const StageArgs &a, long long i) {
+    const int HW = a.H * a.W;
+    const long long pix = i * 4;
+    const long long b = pix / HW, p = pix - b * HW;  // b: row of [state; next_state]
+    const bool to_on = b < a.on_rows, to_tg = a.nhwc_tg && b >= a.B;
+    if (!to_on && !to_tg) return;
+    const Tin *src = (b < a.B ? reinterpret_cast<const Tin *>(a.s) + b * 4 * HW : reinterpret_cast<const Tin *>(a.s2) + (b - a.B) * 4 * HW) + p;
+    Tin in[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (sizeof(Tin) == 1) {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(src + (long long)c * HW));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<uint8_t *>(in[c])[j] = (uint8_t)(w >> (8 * j));
+        } else {
+            const float4 w = __ldg(reinterpret_cast<const float4 *>(src + (long long)c * HW));
+            float *f = reinterpret_cast<float *>(in[c]);
+            f[0] = w.x; f[1] = w.y; f[2] = w.z; f[3] = w.w;
+        }
+    }
+    const int y = (int)(p / a.W), xx = (int)(p - (long long)y * a.W);
+    const long long PH = a.H + 2 * a.pad, PW = a.W + 2 * a.pad;
+    Tout o[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v = (float)in[c][j];
+            if (a.scale255) v = __fdiv_rn(v, 255.f);
+            if (sizeof(Tout) == 2) reinterpret_cast<bf16 *>(o[j])[c] = __float2bfloat16_rn(v);
+            else reinterpret_cast<float *>(o[j])[c] = v;
+        }
+    typedef typename std::conditional<sizeof(Tout) == 2, uint2, uint4>::type Vec;  // one pixel = 4 channels
+    if (to_on) {
+        Tout *dst = reinterpret_cast<Tout *>(a.nhwc_on) + ((b * PH + y + a.pad) * PW + xx + a.pad) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<Vec *>(dst + j * 4) = *reinterpret_cast<const Vec *>(o[j]);
+    }
+    if (to_tg) {
+        Tout *dst = reinterpret_cast<Tout *>(a.nhwc_tg) + (((b - a.B) * PH + y + a.pad) * PW + xx + a.pad) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<Vec *>(dst + j * 4) = *reinterpret_cast<const Vec *>(o[j]);
+    }
+}
 __global__ void stage_batch_kernel(StageArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.obs16) { a.obs[i] = __ldg(a.s + i); a.obs[a.obs16 + i] = __ldg(a.s2 + i); }
+    if (a.nhwc_on && i < a.quads) {
+        if (a.in_f32) { if (a.out_bf16) stage_nhwc_quad<float, bf16>(a, i); else stage_nhwc_quad<float, float>(a, i); }
+        else { if (a.out_bf16) stage_nhwc_quad<uint8_t, bf16>(a, i); else stage_nhwc_quad<uint8_t, float>(a, i); }
+    }
     if (i < a.B) {
         a.d_action[i] = a.action[i]; a.d_reward[i] = a.reward[i]; a.d_terminal[i] = a.terminal[i];
         if (a.priority) a.d_priority[i] = a.priority[i];
@@ -455,11 +510,33 @@ static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b, bool pipelined
         a.d_action = L->d_action; a.d_reward = L->d_reward; a.d_terminal = L->d_terminal; a.d_priority = L->d_priority; a.d_mask = L->d_mask;
         a.d_tau = L->d_tau; a.d_taup = L->d_taup; a.B = B; a.A = c.n_actions;
         long long n = std::max<long long>(a.obs16, (long long)B * std::max(std::max(c.n_actions, c.N), std::max(c.N_prime, 1)));
+        // the first convolution's padded NHWC input, written by this launch instead of by the first launch of each net's forward
+        // (one launch less at the head of the update's critical path, and next_state is repacked once for both nets)
+        a.nhwc_on = nullptr; a.nhwc_tg = nullptr; a.quads = 0;
+        zoo_net *on = L->online, *tg = L->target;
+        on->prestaged_src = nullptr; on->prestaged_rows = 0;
+        if (tg) { tg->prestaged_src = nullptr; tg->prestaged_rows = 0; }
+        static const bool prestage = [] { const char *e = getenv("ZOO_PRESTAGE"); return !(e && e[0] == '0'); }();
+        if (prestage && on->obs_nhwc && on->desc.in_c == 4 && on->desc.in_w % 4 == 0 && !on->a.layers.empty() && on->a.layers[0].first_raw &&
+            (!tg || (tg->obs_nhwc && tg->prec == on->prec))) {
+            const zoo::LayerExec &L0 = on->a.layers[0];
+            const bool dbl = (c.kind == ZOO_LEARNER_DQN && c.double_dqn) || c.kind == ZOO_LEARNER_BASIC_DQN;
+            a.on_rows = (int)std::min<long long>(dbl ? 2 * B : B, on->a.rows_cap);
+            a.H = on->desc.in_h; a.W = on->desc.in_w; a.pad = (L0.ih - on->desc.in_h) / 2; a.scale255 = L0.scale255;
+            a.in_f32 = b->obs_dtype == ZOO_OBS_F32; a.out_bf16 = on->prec == ZOO_PREC_BF16;
+            a.nhwc_on = on->obs_nhwc_buf; a.nhwc_tg = tg ? tg->obs_nhwc_buf : nullptr;
+            a.quads = (long long)2 * B * a.H * a.W / 4;
+            on->prestaged_src = L->d_obs; on->prestaged_rows = a.on_rows;
+            if (tg) { tg->prestaged_src = (const uint8_t *)L->d_obs + obs_bytes; tg->prestaged_rows = B; }
+            n = std::max(n, a.quads);
+        }
         stage_batch_kernel<<<cdiv(n, 256), 256, 0, st>>>(a);
         ZOO_LAUNCH_CHECK();
         if (consumed) ZOO_CUDA(cudaEventRecord(consumed->ev_consumed, st));
         return ZOO_OK;
     }
+    L->online->prestaged_src = nullptr; L->online->prestaged_rows = 0;
+    if (L->target) { L->target->prestaged_src = nullptr; L->target->prestaged_rows = 0; }
     if (!b->on_device) {
         // host batch: the two frame blocks go straight from the caller's arrays; the small vectors are packed into the pinned
         // mirror of d_pack and cross PCIe in one copy (seven tiny copies cost ~5 us of launch latency each)
@@ -509,7 +586,8 @@ static zoo_status run_update(zoo_learner *L, const zoo_batch *b, float *loss_out
     }
     if (!full) L->online->grads_dirty = true;
     const bool has_prio = b->priority != nullptr, has_mask = b->next_mask != nullptr, has_tau = b->tau != nullptr;
-    const int key = (has_prio ? 1 : 0) | (has_mask ? 2 : 0) | (has_tau ? 4 : 0) | (L->obs_dtype << 3) | (full ? 16 : 0);
+    const int key = (has_prio ? 1 : 0) | (has_mask ? 2 : 0) | (has_tau ? 4 : 0) | (L->obs_dtype << 3) | (full ? 16 : 0) |
+                    (L->online->prestaged_src ? 64 : 0);  // (the captured forward skips or keeps its own repack launch accordingly)
     g_launches = 0;
     if (L->use_graph && L->warm) {
         if (!L->gexec || L->graph_key != key) {

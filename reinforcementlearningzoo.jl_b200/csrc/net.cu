@@ -559,6 +559,10 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
             if (cur_kind == 2) { set_err("conv: first layer expects a raw observation"); return ZOO_BAD_ARG; }
             const int oh_ = net->desc.in_h, ow_ = net->desc.in_w, op_ = (L.ih - oh_) / 2;  // L.ih / L.iw describe the padded copy
             const long long pixels = rows * oh_ * ow_;
+            if (net->prestaged_src == cur && rows <= net->prestaged_rows) {  // the staging launch already wrote the padded NHWC copy
+                cur = net->obs_nhwc_buf;
+                cur_kind = 2;
+            } else {
             prof_label("obs2nhwc[%lld]", pixels);
             const bool x4 = (ow_ % 4) == 0 && ((uintptr_t)cur % (cur_kind == 0 ? 4 : 16)) == 0;
 #define OBS2NHWC(Tin, Tout)                                                                                                                        \
@@ -572,6 +576,7 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
             ZOO_LAUNCH_CHECK();
             cur = net->obs_nhwc_buf;
             cur_kind = 2;
+            }
         }
         const bool raw_conv = L.kind == ZOO_LAYER_CONV && L.first_raw && !net->obs_nhwc;
         if (L.kind == ZOO_LAYER_CONV) {

@@ -79,6 +79,10 @@ struct zoo_net {
     void *obs = nullptr;  // staged observation for zoo_net_forward
     bool obs_nhwc = false;        // first conv reads an fp32 NHWC copy of the observation (fp32-storage nets, 4 channels)
     void *obs_nhwc_buf = nullptr;
+    // set by the learner's staging launch when it has already written the padded NHWC copy of `prestaged_rows` observation rows
+    // starting at `prestaged_src` into obs_nhwc_buf (learner.cu stage_batch_kernel): the forward then skips its own repack launch
+    const void *prestaged_src = nullptr;
+    long long prestaged_rows = 0;
     float *stage = nullptr; size_t stage_elems = 0;  // param up/download staging
     cudaStream_t st = nullptr;
     // stream contract: learner updates run on the learner's stream and may return before they finish (loss_out == NULL); every
