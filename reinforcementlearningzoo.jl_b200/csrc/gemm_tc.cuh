@@ -25,6 +25,22 @@ namespace zoo {
 static constexpr int BM = 128;      // UMMA M (cta_group::1)
 // per stage: one 128-byte swizzle span of K per row -> BK = 128 / EB elements, 4 MMAs of K = 32 / EB each
 static constexpr int TC_THREADS = 192;
+// Epilogue / converter warps.  Four (one per TMEM lane quadrant) everywhere, EIGHT for the fp32-grade kernels with tiles of 64
+// columns or more: two warps per quadrant, each owning half of the tile's columns.  One warp alone on its scheduler issues at
+// ~0.2 IPC through the converter and the epilogues (load -> wait -> dependent math -> store); a second one doubles that, halves the
+// register-resident chain sums per thread (no more spills) and -- at the Dopamine batch sizes, where every CTA owns its SM for its
+// whole life and the update is bound by SM residency -- shortens the part of a CTA's life that is not its main loop.
+template <int BN, bool X3, int GA>
+struct TcWarps {
+    // (convolution kernels only: forward / data gradient GA = 2, weight gradient GA = 4.  They own their SM anyway -- 190 KB of ring --
+    // so 320 threads x up to 204 registers cost nothing; the plain-GEMM instantiations keep four warps and 168 registers, because
+    // the 64-wide ones run two CTAs per SM where that pays (fc1's weight gradient).)
+    static constexpr int EW = (X3 && BN >= 64 && (GA == 2 || GA == 4)) ? 8 : 4;
+    static constexpr int MIN_CTAS = EW == 8 ? 1 : 0;
+    static constexpr int NT = EW * 32;          // converter / epilogue threads
+    static constexpr int THREADS = 64 + NT;     // + TMA producer warp + MMA warp
+    static constexpr int HC = BN / (EW / 4);    // tile columns per epilogue warp
+};
 static constexpr int X3_CHAIN_KB = 4;         // 3xTF32: K-blocks (of 32 floats) per TMEM accumulation chain (see the kernel)
 static constexpr int TC_WS_COUNTERS = 4096;  // tail of the split-K workspace: per-tile arrival counters
 
@@ -500,12 +516,14 @@ __device__ __forceinline__ void epi_cols_store(const float *rp, int ncols, T *op
 //         row) -- so no im2col matrix exists in either direction.  A K-block's pixel rows past R x OW are never written
 //         (the ring is zeroed once at kernel start), grid.z splits the images, partial sums are red-added into the gradient.
 template <int EB, int BN, bool A_K, bool B_K, bool X3, int GA = 0, int SPAN = 128>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__((TcWarps<BN, X3, GA>::THREADS), (TcWarps<BN, X3, GA>::MIN_CTAS))
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams P) {
     static_assert(GA == 0 || GA == 4 || A_K, "the gathered A operand is K-major");
     static_assert(GA != 4 || (!A_K && !B_K), "the weight-gradient operands are MN-major");
     static_assert(SPAN == 128 || (SPAN == 64 && EB == 2 && !X3 && ((GA == 2 && A_K && B_K) || GA == 4)), "64-byte spans: bf16 TMA-im2col convolutions only");
     using C = TcCfg<EB, BN, X3, SPAN, GA == 4>;
+    using TW = TcWarps<BN, X3, GA>;
+    constexpr int NT = TW::NT, HC = TW::HC;
     // SWIZZLE_128B tiles need 1024-byte alignment; declaring it on the array (instead of rounding the pointer up) keeps
     // the shared address space visible to the compiler, so the epilogue staging below compiles to LDS/STS
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -564,16 +582,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < NST; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
-            mbar_init(&conv_bar[s], 128);
+            mbar_init(&conv_bar[s], NT);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 128);
+            mbar_init(&acc_empty[b], NT);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (GA == 4) {  // pad rows of every stage (pixel rows past R x OW, feature boxes past N, channel rows past Cout) must read as zero
-        for (int i = threadIdx.x; i < NST * C::STAGE_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < NST * C::STAGE_BYTES / 16; i += TW::THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -721,8 +739,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             dbg_stamp(P, 4);
         }
     } else {
-        // warps 2..5: TMEM lane quadrant = warp % 4, thread = accumulator row.
+        // warps 2..5 (2..9): TMEM lane quadrant = warp % 4, thread = accumulator row; with eight warps, column half = (warp - 2) / 4.
         const int q = warp & 3;
+        const int c0 = TW::EW == 8 ? ((warp - 2) >> 2) * HC : 0;  // first tile column of this warp
         const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
         if (P.epi.mask && GA != 4) {
             // The relu' mask of the epilogue is an activation tensor the forward pass wrote ~100 us earlier; by now the optimiser's
@@ -750,23 +769,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 } else if (P.epi.mask_sm == 1) {  // swap-AB outputs: the mask runs along m
                     const int segs = (BM * mesz) / 128;  // 128-byte pieces per column of the tile
-                    for (int j = t; j < BN * segs; j += 128) {
+                    for (int j = t; j < BN * segs; j += NT) {
                         const int n = n0 + j / segs, mm = m0 + (j % segs) * (128 / mesz);
                         if (n < P.N && mm < P.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(mbase + ((long long)n * P.epi.mask_sn + mm) * mesz));
                     }
                 }
             }
         }
-        float acc[X3 ? BN : 1];  // running fp32 sum of the drained chains (3xTF32 only)
+        float acc[X3 ? HC : 1];  // running fp32 sum of the drained chains (3xTF32 only): this warp's columns [c0, c0 + HC)
         if (X3) {
 #pragma unroll
-            for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+            for (int j = 0; j < HC; ++j) acc[j] = 0.f;
         }
         if (X3 || GA == 1) {
             // per K-block: (GA) gather this thread's A row into the stage -- hi and, for 3xTF32, lo -- and (3xTF32) split the
             // TMA-landed fp32 tiles into hi (the tile itself) and lo; one chain behind the MMA warp, fold finished chains
             // into acc
-            const int t = threadIdx.x - 64;  // 0..127
+            const int t = threadIdx.x - 64;  // 0..NT-1
             int drained = 0;
             const int va = vrows, vb = min(BN, P.N - n0);  // valid rows of the A / B tiles
             const int a_units = GA == 1 ? 0 : (A_K ? va * 128 : ((va + C::MN_BOX - 1) / C::MN_BOX) * C::BOX_BYTES) / 16;
@@ -841,17 +860,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint4 *lo = reinterpret_cast<uint4 *>(stage + C::RAW_BYTES);  // [B lo][A lo]
                     // batches of 8 x 16 B per thread: all loads first, then all stores -- raw and lo may alias as far as the
                     // compiler knows, so an element-wise loop serialises on shared-memory latency (measured 0.4 us per stage)
-                    for (int j0 = t; j0 < ((P.xmode & 1) ? 0 : conv_units); j0 += 8 * 128) {
+                    for (int j0 = t; j0 < ((P.xmode & 1) ? 0 : conv_units); j0 += 8 * NT) {
                         uint4 v[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const int j = j0 + u * 128;
+                            const int j = j0 + u * NT;
                             const int jj = j < a_units ? j : j - a_units + C::A_BYTES / 16;
                             if (j < conv_units) v[u] = raw[jj];
                         }
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const int j = j0 + u * 128;
+                            const int j = j0 + u * NT;
                             const int jl = j < a_units ? j + C::B_BYTES / 16 : j - a_units;
                             if (j < conv_units && !(P.xmode & 8)) lo[jl] = tf32_lo(v[u]);
                         }
@@ -866,13 +885,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&acc_full[cb], (drained >> 1) & 1);
                     tc_fence_after();
 #pragma unroll
-                    for (int c = 0; c < BN; c += 32) {
+                    for (int cc = 0; cc < HC; cc += 32) {
+                        const int c = c0 + cc;
                         uint32_t r[32], r2[32];
                         tmem_ld32(tq + (uint32_t)(cb * C::ACC_COLS + c), r);
                         tmem_ld32(tq + (uint32_t)(cb * C::ACC_COLS + BN + c), r2);
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            acc[X3 ? c + j : 0] = __fadd_rn(acc[X3 ? c + j : 0], __fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
+                            acc[X3 ? cc + j : 0] = __fadd_rn(acc[X3 ? cc + j : 0], __fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
                     }
                     tc_fence_before();
                     mbar_arrive(&acc_empty[cb]);
@@ -884,13 +904,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&acc_full[cb], (drained >> 1) & 1);
                 tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < BN; c += 32) {
+                for (int cc = 0; cc < HC; cc += 32) {
+                    const int c = c0 + cc;
                     uint32_t r[32], r2[32];
                     tmem_ld32(tq + (uint32_t)(cb * C::ACC_COLS + c), r);
                     tmem_ld32(tq + (uint32_t)(cb * C::ACC_COLS + BN + c), r2);
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        acc[X3 ? c + j : 0] = __fadd_rn(acc[X3 ? c + j : 0], __fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
+                        acc[X3 ? cc + j : 0] = __fadd_rn(acc[X3 ? cc + j : 0], __fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[cb]);
@@ -903,9 +924,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // Whole-tile TMA store (data gradient): relu' of this thread's pixel as one bit per output column, fetched and packed NOW,
         // while the last chain's MMAs are still retiring -- inside the epilogue the loads cost a 2.5 us round trip per 32 columns
         // on the update's critical path (the epilogue warps run alone on their schedulers: nothing hides a dependent load).
-        unsigned dmb[BN / 32];
+        unsigned dmb[HC / 32];  // bits of this warp's chunks: dmb[i] <-> columns [c0 + 32 i, c0 + 32 i + 32)
 #pragma unroll
-        for (int i = 0; i < BN / 32; ++i) dmb[i] = 0xffffffffu;
+        for (int i = 0; i < HC / 32; ++i) dmb[i] = 0xffffffffu;
         if (GA == 2 && P.tma_store == 2 && P.epi.mask && !(P.xmode & 16)) {
             const int r = q * 32 + lane;
             const int vN = min(BN, P.N - n0);
@@ -917,8 +938,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mrow = (const uint8_t *)P.epi.mask + ((((long long)cimg * P.conv.H + y) * P.conv.W + xx) * P.epi.mask_sm + n0) * (P.epi.mask_bf16 ? 2 : 4);
             }
 #pragma unroll
-            for (int i = 0; i < BN / 32; ++i) {
-                const int c = i * 32;
+            for (int i = 0; i < HC / 32; ++i) {
+                const int c = c0 + i * 32;
                 unsigned bits = 0u;
                 if (mrow && c < vN) {
                     if (P.epi.mask_bf16) {
@@ -960,8 +981,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int prow0 = m0 + q * 32, prows = max(0, min(32, vrows - q * 32));
             const long long pmsm = P.epi.mask_sm, pmsn = P.epi.mask_sn;
 #pragma unroll
-            for (int i = 0; i < BN / 32; ++i) {
-                const int c = i * 32, n = n0 + c + lane;
+            for (int i = 0; i < HC / 32; ++i) {
+                const int c = c0 + i * 32, n = n0 + c + lane;
                 unsigned bits = 0u;
                 if (n0 + c < P.N) {
                     const int cnt = ptrans ? min(32, P.N - (n0 + c)) : prows;
@@ -1023,19 +1044,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // fp32-grade TMA-store epilogue: lane = tile row already holds 32 consecutive columns after tcgen05.ld, so the chain sums,
             // bias / relu / relu' mask / row multiplier are applied in registers and the row's 128 bytes go to a SWIZZLE_128B staging
             // block as eight 16-byte pieces (piece j of row r at j ^ (r % 8)); one bulk store per 32 x 32 chunk, two blocks per warp
-            float *const bias_s = reinterpret_cast<float *>(smem + 32768);
-            float *const rm_s = bias_s + 128 + q * 128;
+            // (staging: 8 KB per warp = two 32 x 128-byte blocks; bias / multiplier copies behind the last warp's)
+            float *const bias_s = reinterpret_cast<float *>(smem + TW::EW * 8192);
+            float *const rm_s = bias_s + 128 + q * 128;  // per quadrant: the two warps of a quadrant write the same values
             {
                 const int t = threadIdx.x - 64;
                 if (t < BN) bias_s[t] = (bias_mode == 1 && n0 + t < Nn) ? __ldg(e.bias + n0 + t) : 0.f;
                 for (int j = lane; j < BN; j += 32) rm_s[j] = (rmul && n0 + j < Nn) ? ldg_elem(rmp, 0, (long long)(min(row0, P.M - 1) / rm_div) * rm_ld + n0 + j) : 1.f;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const uint32_t sbase = smem_u32(smem) + q * 8192;
+            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+            const uint32_t sbase = smem_u32(smem) + (uint32_t)((c0 / HC) * 4 + q) * 8192;
             const bool rowok = lane < rows;
             int issued = 0;
 #pragma unroll
-            for (int c = 0; c < BN; c += 32) {
+            for (int cc = 0; cc < HC; cc += 32) {
+                const int c = c0 + cc;
                 if (n0 + c < Nn) {
                     if (issued >= 2) {  // the block about to be overwritten has been read by its bulk store
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -1068,7 +1091,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int j = j4 * 4 + i;
-                            float v = __fadd_rn(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])), acc[X3 ? c + j : 0]) + bias_s[c + j];
+                            float v = __fadd_rn(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])), acc[X3 ? cc + j : 0]) + bias_s[c + j];
                             const float vr = fmaxf(v, 0.f);
                             v = relu ? vr : v;
                             v = ((mbits >> j) & 1u) ? v : 0.f;
@@ -1094,13 +1117,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
         if (X3 && !(GA == 2 && P.tma_store == 2)) {  // (the whole-tile TMA store path reads TMEM itself)
 #pragma unroll
-            for (int c = 0; c < BN; c += 32) {
+            for (int cc = 0; cc < HC; cc += 32) {
+                const int c = c0 + cc;
                 uint32_t r[32], r2[32];
                 tmem_ld32(tq + (uint32_t)(lb * C::ACC_COLS + c), r);
                 tmem_ld32(tq + (uint32_t)(lb * C::ACC_COLS + BN + c), r2);
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    xst[lane * XLD + c + j] = __fadd_rn(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])), acc[X3 ? c + j : 0]);
+                    xst[lane * XLD + c + j] = __fadd_rn(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])), acc[X3 ? cc + j : 0]);
             }
             __syncwarp();
             if (threadIdx.x == 64) dbg_stamp(P, 9);
@@ -1119,7 +1143,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t swz = span == 128 ? (uint32_t)(r & 7) : (span == 64 ? (uint32_t)((r >> 1) & 3) : 0u);
             const uint32_t stg0 = smem_u32(smem);
 #pragma unroll
-            for (int c = 0; c < BN; c += 32) {
+            for (int cc = 0; cc < HC; cc += 32) {
+                const int c = c0 + cc;
                 if (c < vN) {
                     uint32_t rr[32];
                     float x[32];
@@ -1128,12 +1153,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         uint32_t r2[32];
                         tmem_ld32(tq + (uint32_t)(lb * C::ACC_COLS + BN + c), r2);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) x[j] = __fadd_rn(__fadd_rn(__uint_as_float(rr[j]), __uint_as_float(r2[j])), acc[X3 ? c + j : 0]);
+                        for (int j = 0; j < 32; ++j) x[j] = __fadd_rn(__fadd_rn(__uint_as_float(rr[j]), __uint_as_float(r2[j])), acc[X3 ? cc + j : 0]);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(rr[j]);
                     }
-                    if (threadIdx.x == 64) dbg_stamp(P, c == 0 ? 12 : 14);
+                    if (threadIdx.x == 64) dbg_stamp(P, cc == 0 ? 12 : 14);
                     if (bias_mode == 1) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) x[j] += (n0 + c + j < Nn) ? __ldg(e.bias + n0 + c + j) : 0.f;
@@ -1143,11 +1168,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
                     }
                     if (maskp) {
-                        const unsigned mb = dmb[c / 32];
+                        const unsigned mb = dmb[cc / 32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) x[j] = ((mb >> j) & 1u) ? x[j] : 0.f;
                     }
-                    if (threadIdx.x == 64) dbg_stamp(P, c == 0 ? 13 : 15);
+                    if (threadIdx.x == 64) dbg_stamp(P, cc == 0 ? 13 : 15);
                     if (out_bf16) {
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
@@ -1174,7 +1199,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (threadIdx.x == 64) dbg_stamp(P, 9);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
             if (threadIdx.x == 64) {
                 dbg_stamp(P, 10);
                 const int nbox = (vN * esz + span - 1) / span;
@@ -1315,7 +1340,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = c0; c < c0 + HC; c += 32) {
             if (n0 + c >= Nn) break;  // the whole chunk lies past N (uniform)
             constexpr int LDC = X3 ? XLD : 33;
             float *const cbuf = X3 ? xst + c : &stg[0][0];  // element (r, j) of the chunk at cbuf[r * LDC + j]
@@ -1360,9 +1385,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("" : "+l"(mq));  // keeps the mask loads below inside this loop body
             if (pre_mask) {  // (selected by compares: a dynamic index would send the bits through local memory)
                 mbits = dmb[0];
-                if (BN > 32 && c == 32) mbits = dmb[BN > 32 ? 1 : 0];
-                if (BN > 64 && c == 64) mbits = dmb[BN > 64 ? 2 : 0];
-                if (BN > 96 && c == 96) mbits = dmb[BN > 96 ? 3 : 0];
+                if (HC > 32 && c - c0 == 32) mbits = dmb[HC > 32 ? 1 : 0];
+                if (HC > 64 && c - c0 == 64) mbits = dmb[HC > 64 ? 2 : 0];
+                if (HC > 96 && c - c0 == 96) mbits = dmb[HC > 96 ? 3 : 0];
             } else if (mq && direct && simple) {
                 mbits = 0u;
                 const int cnt = trans ? min(32, Nn - (n0 + c)) : rows;
@@ -1455,7 +1480,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (!red_ws) break;
         __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
         unsigned *ctr = P.ctr + blockIdx.y * gridDim.x + blockIdx.x;
         if (threadIdx.x == 64) {
             __threadfence();  // cumulative: the other 127 threads' reds, observed through the barrier, are ordered before the ticket
@@ -1464,7 +1489,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (last) *ctr = 0u;
             *tmem_slot = last ? 1u : 0u;  // tmem_slot is dead after tmem_base was read
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
         if (!*tmem_slot) break;
         __threadfence();
         red_ws = false;
@@ -1492,7 +1517,7 @@ static zoo_status launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, grid, dim3(TC_THREADS), (size_t)C::smem_for(P.stages), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, A_K, B_K, X3, 0>, grid, dim3(TcWarps<BN, X3, 0>::THREADS), (size_t)C::smem_for(P.stages), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1528,7 +1553,7 @@ static zoo_status launch_conv(const CUtensorMap &tmB, const TcParams &P, dim3 gr
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, grid, dim3(TC_THREADS), (size_t)C::SMEM, st, tmB, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 1>, grid, dim3(TcWarps<BN, X3, 1>::THREADS), (size_t)C::SMEM, st, tmB, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1541,7 +1566,7 @@ static zoo_status launch_conv_tma(const CUtensorMap &tmA, const CUtensorMap &tmB
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(C::SMEM, TC_EPI_SMEM)));
         attr_set = true;
     }
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, grid, dim3(TC_THREADS), (size_t)std::max(C::smem_for(P.stages), TC_EPI_SMEM), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, grid, dim3(TcWarps<BN, X3, 2>::THREADS), (size_t)std::max(C::smem_for(P.stages), TC_EPI_SMEM), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
@@ -1561,7 +1586,7 @@ static zoo_status launch_conv_wgrad(const CUtensorMap &tmA, const CUtensorMap &t
     if (stg < 2) stg = 2;
     P.stages = stg;
     P.xmode = 0;
-    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN>, grid, dim3(TC_THREADS), (size_t)std::max(C::smem_for(stg), TC_EPI_SMEM), st, tmA, tmB, P));
+    ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN>, grid, dim3(TcWarps<128, X3, 4>::THREADS), (size_t)std::max(C::smem_for(stg), TC_EPI_SMEM), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;
 }
