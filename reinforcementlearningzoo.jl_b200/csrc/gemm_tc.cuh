@@ -30,12 +30,14 @@ static constexpr int TC_THREADS = 192;
 // ~0.2 IPC through the converter and the epilogues (load -> wait -> dependent math -> store); a second one doubles that, halves the
 // register-resident chain sums per thread (no more spills) and -- at the Dopamine batch sizes, where every CTA owns its SM for its
 // whole life and the update is bound by SM residency -- shortens the part of a CTA's life that is not its main loop.
-template <int BN, bool X3, int GA>
+template <int BN, bool X3, int GA, bool WIDE = false>
 struct TcWarps {
     // (convolution kernels only: forward / data gradient GA = 2, weight gradient GA = 4.  They own their SM anyway -- 190 KB of ring --
     // so 320 threads x up to 204 registers cost nothing; the plain-GEMM instantiations keep four warps and 168 registers, because
     // the 64-wide ones run two CTAs per SM where that pays (fc1's weight gradient).)
-    static constexpr int EW = (X3 && BN >= 64 && (GA == 2 || GA == 4)) ? 8 : 4;
+    // WIDE is chosen per launch: grids of at most one CTA per SM (the Dopamine batch sizes).  Many-wave grids keep four warps and
+    // 168 registers so that two CTAs still share an SM (Rainbow B = 1024 fp32-grade: 2.46 ms with four warps, 2.71 ms with eight).
+    static constexpr int EW = (WIDE && X3 && BN >= 64 && (GA == 2 || GA == 4)) ? 8 : 4;
     static constexpr int MIN_CTAS = EW == 8 ? 1 : 0;
     static constexpr int NT = EW * 32;          // converter / epilogue threads
     static constexpr int THREADS = 64 + NT;     // + TMA producer warp + MMA warp
@@ -515,14 +517,14 @@ __device__ __forceinline__ void epi_cols_store(const float *rp, int ncols, T *op
 //         {Cout, pixels, images}, the activations through the same 4-D strided boxes as the forward conv (one per tap / kernel
 //         row) -- so no im2col matrix exists in either direction.  A K-block's pixel rows past R x OW are never written
 //         (the ring is zeroed once at kernel start), grid.z splits the images, partial sums are red-added into the gradient.
-template <int EB, int BN, bool A_K, bool B_K, bool X3, int GA = 0, int SPAN = 128>
-__global__ void __launch_bounds__((TcWarps<BN, X3, GA>::THREADS), (TcWarps<BN, X3, GA>::MIN_CTAS))
+template <int EB, int BN, bool A_K, bool B_K, bool X3, int GA = 0, int SPAN = 128, bool WIDE = false>
+__global__ void __launch_bounds__((TcWarps<BN, X3, GA, WIDE>::THREADS), (TcWarps<BN, X3, GA, WIDE>::MIN_CTAS))
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams P) {
     static_assert(GA == 0 || GA == 4 || A_K, "the gathered A operand is K-major");
     static_assert(GA != 4 || (!A_K && !B_K), "the weight-gradient operands are MN-major");
     static_assert(SPAN == 128 || (SPAN == 64 && EB == 2 && !X3 && ((GA == 2 && A_K && B_K) || GA == 4)), "64-byte spans: bf16 TMA-im2col convolutions only");
     using C = TcCfg<EB, BN, X3, SPAN, GA == 4>;
-    using TW = TcWarps<BN, X3, GA>;
+    using TW = TcWarps<BN, X3, GA, WIDE>;
     constexpr int NT = TW::NT, HC = TW::HC;
     // SWIZZLE_128B tiles need 1024-byte alignment; declaring it on the array (instead of rounding the pointer up) keeps
     // the shared address space visible to the compiler, so the epilogue staging below compiles to LDS/STS
@@ -1508,6 +1510,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------- launch templates ---------
+static inline bool tc_wide_enabled() {  // ZOO_TC_WIDE=0: four epilogue / converter warps everywhere (A/B)
+    static const bool on = [] { const char *e = getenv("ZOO_TC_WIDE"); return !(e && e[0] == '0'); }();
+    return on;
+}
 static constexpr int TC_EPI_SMEM = 40 * 1024;  // the epilogue stages through the (idle) pipeline stages: never launch with less
 template <int EB, int BN, bool A_K, bool B_K, bool X3>
 static zoo_status launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &P, dim3 grid, cudaStream_t st) {
@@ -1564,7 +1570,17 @@ static zoo_status launch_conv_tma(const CUtensorMap &tmA, const CUtensorMap &tmB
     static bool attr_set = false;
     if (!attr_set) {
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(C::SMEM, TC_EPI_SMEM)));
+        if constexpr (X3 && BN >= 64)
+            ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(C::SMEM, TC_EPI_SMEM)));
         attr_set = true;
+    }
+    if constexpr (X3 && BN >= 64) {
+        if ((long long)grid.x * grid.y * grid.z <= g_sm_budget && tc_wide_enabled()) {  // one CTA per SM anyway: eight epilogue / converter warps
+            ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN, true>, grid, dim3(TcWarps<BN, X3, 2, true>::THREADS),
+                                (size_t)std::max(C::smem_for(P.stages), TC_EPI_SMEM), st, tmA, tmB, P));
+            ZOO_LAUNCH_CHECK();
+            return ZOO_OK;
+        }
     }
     ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, BN, true, B_K, X3, 2, SPAN>, grid, dim3(TcWarps<BN, X3, 2>::THREADS), (size_t)std::max(C::smem_for(P.stages), TC_EPI_SMEM), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
@@ -1577,6 +1593,7 @@ static zoo_status launch_conv_wgrad(const CUtensorMap &tmA, const CUtensorMap &t
     static bool attr_set = false;
     if (!attr_set) {
         ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        if constexpr (X3) ZOO_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
     TcParams P = P0;
@@ -1586,6 +1603,14 @@ static zoo_status launch_conv_wgrad(const CUtensorMap &tmA, const CUtensorMap &t
     if (stg < 2) stg = 2;
     P.stages = stg;
     P.xmode = 0;
+    if constexpr (X3) {
+        if (ctas <= g_sm_budget && tc_wide_enabled()) {
+            ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN, true>, grid, dim3(TcWarps<128, X3, 4, true>::THREADS),
+                                (size_t)std::max(C::smem_for(stg), TC_EPI_SMEM), st, tmA, tmB, P));
+            ZOO_LAUNCH_CHECK();
+            return ZOO_OK;
+        }
+    }
     ZOO_CUDA(launch_pdl(tc_gemm_kernel<EB, 128, false, false, X3, 4, SPAN>, grid, dim3(TcWarps<128, X3, 4>::THREADS), (size_t)std::max(C::smem_for(stg), TC_EPI_SMEM), st, tmA, tmB, P));
     ZOO_LAUNCH_CHECK();
     return ZOO_OK;

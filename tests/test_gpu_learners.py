@@ -341,12 +341,15 @@ def test_submit_collect_pipeline_matches_blocking_updates(zoo, kind):
                 lrn.collect()  # nothing in flight
         out[mode] = (losses, prios, app.params())
     ref, again, pipe = out["blocking"], out["blocking2"], out["pipelined"]
+    # (two runs of the SAME mode land in one of a few discrete outcomes -- an atomics order flips a rounding-level gradient's sign under
+    # RMSProp -- 3.7e-5 apart in the later losses, 1.6e-5 in the priorities: the floor below covers that, a wrong batch or stale
+    # parameters would be off by O(1))
     for a, r, r2 in zip(pipe[0], ref[0], again[0]):
-        assert abs(a - r) <= max(1e-5 * max(1.0, abs(r)), 4 * abs(r2 - r)), (pipe[0], ref[0], again[0])
+        assert abs(a - r) <= max(1e-4 * max(1.0, abs(r)), 4 * abs(r2 - r)), (pipe[0], ref[0], again[0])
     assert abs(pipe[0][0] - ref[0][0]) <= 1e-6 * max(1.0, abs(ref[0][0]))  # first update: same parameters, same batch
     if per:
         for a, r, r2 in zip(pipe[1], ref[1], again[1]):
-            assert nrel(a, r) <= max(1e-5, 4 * nrel(r2, r)), (nrel(a, r), nrel(r2, r))
+            assert nrel(a, r) <= max(1e-4, 4 * nrel(r2, r)), (nrel(a, r), nrel(r2, r))
     # parameters: loose by nature (elements whose gradient is rounding noise take a +-eta step of random sign in the first updates;
     # the losses above, which depend on every earlier update, are the tight check)
     for a, r, r2 in zip(pipe[2], ref[2], again[2]):
