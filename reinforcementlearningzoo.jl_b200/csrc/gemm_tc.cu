@@ -337,7 +337,7 @@ zoo_status tc_conv_wgrad(ConvGeom g, const void *dy, int is_bf16, int images, co
     const int N = g.ks * g.ks * g.C, BN = 128;
     const int total_kb = images * g.tpi;
     const int ntiles = cdiv(N, BN);
-    static const int wgrad_cap_pct = [] { const char *e = getenv("ZOO_WGRAD_CAP_PCT"); return e ? atoi(e) : 50; }();  // (see tc_gemm's split cap)
+    static const int wgrad_cap_pct = [] { const char *e = getenv("ZOO_WGRAD_CAP_PCT"); return e ? atoi(e) : 100; }();
     const long long cap = g_sm_budget * (x3 ? 1 : 2) * (images <= 128 ? wgrad_cap_pct : 100) / 100;  // (large batches keep the full cap)
     int split = (int)std::max<long long>(1, std::min<long long>(total_kb, cap / ntiles));
     const int kbps = cdiv(total_kb, split);
