@@ -126,6 +126,7 @@ struct Epilogue {
     const void *rowmul = nullptr;  // multiply by rowmul[(m / rowmul_div)][n] (IQN Hadamard merge), same dtype as out
     int rowmul_div = 1;
     long long rowmul_ld = 0;
+    int rowmul_nonneg = 0;  // the multiplier is a relu output (>= 0): relu(x) * rm may be evaluated as relu(x * rm)
     int accumulate = 0;  // 1: atomically add into fp32 out (out must be fp32; bias/relu/mask not allowed);
                          // 2: out is pre-zeroed fp32: plain store when the GEMM is not K-split, atomic add when it is
     int tf32_passes = 0; // fp32 operands on tcgen05: 0 = never (CUDA cores), 1 = plain tf32, 3 = 3xTF32 (fp32-grade)

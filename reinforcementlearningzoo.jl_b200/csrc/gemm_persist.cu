@@ -158,6 +158,32 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const uint4 (
     }
 }
 
+// The same chunk for the bf16 outputs without a relu' mask (phi forward with the IQN merge, fc1 forward, fc1 data gradient), on
+// packed fp32 pairs: y = fma(acc, rm, bias rm) as one FFMA2 per two columns, relu folded into the bf16x2 conversion -- one
+// instruction per column instead of ten (ncu: these epilogues were issue-bound, 40 % of the issue slots with 8 warps).  With
+// rm = 1 (no multiplier) this is bit-identical to (acc + bias); with the IQN multiplier it needs rm >= 0 (relu(x) rm = relu(x rm)),
+// which the caller asserts through Epilogue::rowmul_nonneg.
+template <bool RELU>
+__device__ __forceinline__ void epi_chunk_fma(const uint32_t (&r)[32], const float *brm_c, const float *rm_c, uint32_t sb, int h, int lane) {
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+        const float4 b0 = *reinterpret_cast<const float4 *>(brm_c + j8 * 8), b1 = *reinterpret_cast<const float4 *>(brm_c + j8 * 8 + 4);
+        const float4 m0v = *reinterpret_cast<const float4 *>(rm_c + j8 * 8), m1v = *reinterpret_cast<const float4 *>(rm_c + j8 * 8 + 4);
+        const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+        const float2 mm[4] = {make_float2(m0v.x, m0v.y), make_float2(m0v.z, m0v.w), make_float2(m1v.x, m1v.y), make_float2(m1v.z, m1v.w)};
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 y = __ffma2_rn(make_float2(__uint_as_float(r[j8 * 8 + 2 * i]), __uint_as_float(r[j8 * 8 + 2 * i + 1])), mm[i], bb[i]);
+            if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(y.y), "f"(y.x));
+            else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(y.y), "f"(y.x));
+        }
+        const int jc = h * 4 + j8;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + ((uint32_t)(jc ^ (lane & 7)) << 4)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                     "r"(pk[3]) : "memory");
+    }
+}
+
 template <bool A_K, bool B_K, int CG>
 __global__ void __launch_bounds__(P_THREADS, 1)
 tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ PersistParams P) {
@@ -268,6 +294,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const void *const maskp = e.mask;
         const long long msm = e.mask_sm;
         const bool rmul = e.rowmul != nullptr;
+        const bool fma_path = out_bf16 && !maskp && (!rmul || e.rowmul_nonneg) && !(P.ablate & 4);
         // everything below is private to the warp (its own bias / multiplier copy, its own staging slab): no CTA-level barrier in
         // the tile loop.  Per tile the warp converts its 32 rows x 128 columns into two SWIZZLE_128B blocks (fp32 output: two rounds
         // of two 32-column blocks), ONE proxy fence per round, then one TMA store per block; the stores of tile t are only waited
@@ -276,7 +303,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         float *const rm_s = bias_s + PHALF;
         const uint32_t sbase = smem_u32(smem) + P_EPI_OFF + ew * 8192;
         int t = 0;
-        bool pending = false;
+        int nblk = 0;  // staging blocks this warp has handed to the TMA unit so far (buffer = nblk & 1)
         // bias / multiplier of a tile are fetched one tile ahead (raw bits; converted when they are copied to shared memory), and
         // the relu' source of a 32-column chunk one chunk ahead, so that no global-load latency sits in the per-tile critical path
         // (ncu source page of the K = 64 phi GEMM: 41 % of all samples were on those loads before)
@@ -328,35 +355,39 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             if (maskp && ncols > 0) fetch_mask(0, mk);
             mbar_wait(&acc_full[ab], (t >> 1) & 1);
             tc_fence_after();
-            if (pending) {  // the previous tile's stores have read the slab
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                pending = false;
-            }
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < PHALF / 32; ++j) {
-                bias_s[lane + 32 * j] = bv[j];
-                rm_s[lane + 32 * j] = __uint_as_float(rraw[j] << 16);
+                const float rmf = __uint_as_float(rraw[j] << 16);
+                bias_s[lane + 32 * j] = fma_path ? bv[j] * rmf : bv[j];  // fma path: y = acc rm + (bias rm)
+                rm_s[lane + 32 * j] = rmf;
             }
             __syncwarp();
             if (tile + tile_step < P.ntiles) fetch_cols(tile + tile_step);
             const int nchunk = (ncols + 31) >> 5;            // 32-column chunks of this warp's half
-            const int cpr = out_bf16 ? 4 : 2;                // chunks per store round (2 staging blocks of 128-byte rows)
             const uint32_t tcol = tq + (uint32_t)(ab * PBN + hh * PHALF);
+            // A staging block = 32 rows x 128 bytes (bf16: two 32-column chunks, fp32: one).  Each finished block is fenced, stored and
+            // committed as its own bulk group, alternating between the warp's two 4 KB buffers; a buffer is only waited for (its store of
+            // two blocks ago has READ it) when it is about to be overwritten, so a store has a whole block's conversion time to drain.
+            // (Ablation, phi forward K = 64: with the stores waited for at the top of every tile they cost 33 us of 170, the fc1 data
+            // gradient 56 us of 237 -- profiles/r02_persist_epilogue_ablation.txt.)
             auto process = [&](const uint32_t (&rc)[32], int ch) {
                 const int c = ch * 32;
-                const int cr = ch % cpr;                     // chunk within the round
-                if (ch && cr == 0) {                         // fp32 second round: the first round's stores have read the slab
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                const int h = out_bf16 ? (ch & 1) : 0;       // chunk within its block
+                if (h == 0) {
+                    if (nblk >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     __syncwarp();
                 }
-                const int blk = out_bf16 ? cr >> 1 : cr, h = out_bf16 ? cr & 1 : 0;
-                const uint32_t sb = sbase + blk * 4096 + lane * 128;
+                const uint32_t bufa = sbase + (uint32_t)(nblk & 1) * 4096;
+                const uint32_t sb = bufa + lane * 128;
                 uint4 mkc[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) mkc[j] = mk[j];
                 if (maskp && ch + 1 < nchunk) fetch_mask(c + 32, mk);
                 if (P.ablate & 2) {
+                } else if (fma_path) {
+                    if (relu) epi_chunk_fma<true>(rc, bias_s + c, rm_s + c, sb, h, lane);
+                    else epi_chunk_fma<false>(rc, bias_s + c, rm_s + c, sb, h, lane);
                 } else if (out_bf16) {
                     if (maskp) epi_chunk<true, true>(rc, mkc, bias_s + c, rm_s + c, relu, sb, h, lane);
                     else epi_chunk<true, false>(rc, mkc, bias_s + c, rm_s + c, relu, sb, h, lane);
@@ -364,22 +395,17 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     if (maskp) epi_chunk<false, true>(rc, mkc, bias_s + c, rm_s + c, relu, sb, h, lane);
                     else epi_chunk<false, false>(rc, mkc, bias_s + c, rm_s + c, relu, sb, h, lane);
                 }
-                if (cr == cpr - 1 || ch == nchunk - 1) {     // a round is staged: one proxy fence, one TMA store per block
+                if (!out_bf16 || h == 1 || ch == nchunk - 1) {  // the block is staged: one proxy fence, one TMA store
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
-                        const int cpg = out_bf16 ? 64 : 32;  // columns per 128-byte staging row
-                        const int cbase = (ch - cr) * 32;
-                        for (int b2 = 0; b2 < 2; ++b2) {
-                            const int cc = cbase + b2 * cpg;
-                            if (cc >= ncols || (P.ablate & 1)) break;
-                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&P.tmC),
-                                         "r"(sbase + b2 * 4096), "r"(n0 + cc), "r"(row0)
+                        if (!(P.ablate & 1))
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&P.tmC), "r"(bufa),
+                                         "r"(n0 + (ch - h) * 32), "r"(row0)
                                          : "memory");
-                        }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    pending = true;
+                    ++nblk;
                 }
             };
             // two register sets: the tcgen05.ld of chunk ch + 1 is in flight while chunk ch is converted

@@ -116,39 +116,56 @@ struct StageArgs {
     long long quads;
     int on_rows, H, W, pad, scale255, in_f32, out_bf16;
 };
+// exact IEEE RN(v / 255) for the 256 values a uint8 frame can hold: q0 = RN(v r), rem = v - 255 q0 (exact), q = RN(q0 + rem r) with
+// r = RN(1 / 255) -- three instructions instead of the ~25 of the IEEE divide's general path.  tests/test_host_logic.py checks all
+// 256 values against exact rational arithmetic; the staging launch was issue-bound on the divides (ncu: 76 % issue slots busy).
+__device__ __forceinline__ float div255_u8(float x) {
+    constexpr float r = 1.0f / 255.0f;
+    const float q0 = __fmul_rn(x, r);
+    const float rem = __fmaf_rn(-q0, 255.f, x);
+    return __fmaf_rn(rem, r, q0);
+}
 template <typename Tin, typename Tout>
 __device__ __forceinline__ void stage_nhwc_quad(const StageArgs &a, long long i) {
-    const int HW = a.H * a.W;
-    const long long pix = i * 4;
-    const long long b = pix / HW, p = pix - b * HW;  // b: row of [state; next_state]
-    const bool to_on = b < a.on_rows, to_tg = a.nhwc_tg && b >= a.B;
+    const unsigned HW = (unsigned)(a.H * a.W), W = (unsigned)a.W;
+    const unsigned qpi = HW >> 2;                    // quads per image (the host checks W % 4 == 0 and quads < 2^31)
+    const unsigned b = (unsigned)i / qpi;            // b: row of [state; next_state]
+    const unsigned p = ((unsigned)i - b * qpi) << 2;
+    const bool to_on = (int)b < a.on_rows, to_tg = a.nhwc_tg && (int)b >= a.B;
     if (!to_on && !to_tg) return;
-    const Tin *src = (b < a.B ? reinterpret_cast<const Tin *>(a.s) + b * 4 * HW : reinterpret_cast<const Tin *>(a.s2) + (b - a.B) * 4 * HW) + p;
-    Tin in[4][4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        if (sizeof(Tin) == 1) {
-            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(src + (long long)c * HW));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) reinterpret_cast<uint8_t *>(in[c])[j] = (uint8_t)(w >> (8 * j));
-        } else {
-            const float4 w = __ldg(reinterpret_cast<const float4 *>(src + (long long)c * HW));
-            float *f = reinterpret_cast<float *>(in[c]);
-            f[0] = w.x; f[1] = w.y; f[2] = w.z; f[3] = w.w;
-        }
-    }
-    const int y = (int)(p / a.W), xx = (int)(p - (long long)y * a.W);
-    const long long PH = a.H + 2 * a.pad, PW = a.W + 2 * a.pad;
+    const Tin *src = ((int)b < a.B ? reinterpret_cast<const Tin *>(a.s) + (size_t)b * 4 * HW : reinterpret_cast<const Tin *>(a.s2) + (size_t)(b - a.B) * 4 * HW) + p;
+    const unsigned y = p / W, xx = p - y * W;
+    const size_t PH = a.H + 2 * a.pad, PW = a.W + 2 * a.pad;
     Tout o[4][4];
+    if (sizeof(Tin) == 1) {
+        uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+        for (int c = 0; c < 4; ++c) w[c] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)c * HW));
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float v = (float)((w[c] >> (8 * j)) & 0xffu);
+                if (a.scale255) v = div255_u8(v);
+                if (sizeof(Tout) == 2) reinterpret_cast<bf16 *>(o[j])[c] = __float2bfloat16_rn(v);
+                else reinterpret_cast<float *>(o[j])[c] = v;
+            }
+    } else {
+        float4 w[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) w[c] = __ldg(reinterpret_cast<const float4 *>(src + (size_t)c * HW));
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            float v = (float)in[c][j];
-            if (a.scale255) v = __fdiv_rn(v, 255.f);
-            if (sizeof(Tout) == 2) reinterpret_cast<bf16 *>(o[j])[c] = __float2bfloat16_rn(v);
-            else reinterpret_cast<float *>(o[j])[c] = v;
+            const float f[4] = {w[c].x, w[c].y, w[c].z, w[c].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v = f[j];
+                if (a.scale255) v = __fdiv_rn(v, 255.f);
+                if (sizeof(Tout) == 2) reinterpret_cast<bf16 *>(o[j])[c] = __float2bfloat16_rn(v);
+                else reinterpret_cast<float *>(o[j])[c] = v;
+            }
         }
+    }
     typedef typename std::conditional<sizeof(Tout) == 2, uint2, uint4>::type Vec;  // one pixel = 4 channels
     if (to_on) {
         Tout *dst = reinterpret_cast<Tout *>(a.nhwc_on) + ((b * PH + y + a.pad) * PW + xx + a.pad) * 4;
@@ -517,7 +534,7 @@ static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b, bool pipelined
         on->prestaged_src = nullptr; on->prestaged_rows = 0;
         if (tg) { tg->prestaged_src = nullptr; tg->prestaged_rows = 0; }
         static const bool prestage = [] { const char *e = getenv("ZOO_PRESTAGE"); return !(e && e[0] == '0'); }();
-        if (prestage && on->obs_nhwc && on->desc.in_c == 4 && on->desc.in_w % 4 == 0 && !on->a.layers.empty() && on->a.layers[0].first_raw &&
+        if (prestage && on->obs_nhwc && on->desc.in_c == 4 && on->desc.in_w % 4 == 0 && (long long)2 * B * on->desc.in_h * on->desc.in_w < (1ll << 32) && !on->a.layers.empty() && on->a.layers[0].first_raw &&
             (!tg || (tg->obs_nhwc && tg->prec == on->prec))) {
             const zoo::LayerExec &L0 = on->a.layers[0];
             const bool dbl = (c.kind == ZOO_LEARNER_DQN && c.double_dqn) || c.kind == ZOO_LEARNER_BASIC_DQN;
@@ -525,7 +542,7 @@ static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b, bool pipelined
             a.H = on->desc.in_h; a.W = on->desc.in_w; a.pad = (L0.ih - on->desc.in_h) / 2; a.scale255 = L0.scale255;
             a.in_f32 = b->obs_dtype == ZOO_OBS_F32; a.out_bf16 = on->prec == ZOO_PREC_BF16;
             a.nhwc_on = on->obs_nhwc_buf; a.nhwc_tg = tg ? tg->obs_nhwc_buf : nullptr;
-            a.quads = (long long)2 * B * a.H * a.W / 4;
+            a.quads = (long long)2 * B * a.H * a.W / 4;  // < 2^31: the kernel indexes quads with 32-bit arithmetic
             on->prestaged_src = L->d_obs; on->prestaged_rows = a.on_rows;
             if (tg) { tg->prestaged_src = (const uint8_t *)L->d_obs + obs_bytes; tg->prestaged_rows = B; }
             n = std::max(n, a.quads);

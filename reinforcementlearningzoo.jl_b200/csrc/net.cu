@@ -321,8 +321,8 @@ __global__ void iqn_merge_bwd_vec_kernel(const T *__restrict__ dm, const T *__re
 // (the bias gradient of phi's last layer is folded in: it was a separate column-sum pass over the 0.5 GB dphi tensor).
 // CTA = 32 feature vectors (x) x 8 samples (y): one thread per (feature vector, sample) walks the N quantile rows; the bias sums
 // of the 8 samples are combined in shared memory, so the CTA issues one atomic per feature.
-template <typename T, int VEC>
-__global__ void __launch_bounds__(256) iqn_merge_bwd_fused_kernel(const T *__restrict__ dm, const T *__restrict__ feat, const T *__restrict__ merged,
+template <typename T, int VEC, int G, int MINB>
+__global__ void __launch_bounds__(256, MINB) iqn_merge_bwd_fused_kernel(const T *__restrict__ dm, const T *__restrict__ feat, const T *__restrict__ merged,
                                                                   T *__restrict__ dea, T *__restrict__ dfeat, float *__restrict__ dbias, int B, int F, int N) {
     __shared__ float red[8][32 * VEC + 1];
     const int fv = F / VEC;
@@ -336,11 +336,8 @@ __global__ void __launch_bounds__(256) iqn_merge_bwd_fused_kernel(const T *__res
         float ft[VEC], acc[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) { ft[i] = to_f(ftv.v[i]); acc[i] = 0.f; }
-#pragma unroll 4
-        for (int n = 0; n < N; ++n) {
-            const long long o = ((long long)b * N + n) * F + (long long)f * VEC;
-            const VecT<T, VEC> d = *reinterpret_cast<const VecT<T, VEC> *>(dm + o);
-            const VecT<T, VEC> m = *reinterpret_cast<const VecT<T, VEC> *>(merged + o);
+        const long long o0 = (long long)b * N * F + (long long)f * VEC;
+        auto one = [&](const VecT<T, VEC> &d, const VecT<T, VEC> &m, long long o) {
             VecT<T, VEC> out;
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
@@ -351,6 +348,36 @@ __global__ void __launch_bounds__(256) iqn_merge_bwd_fused_kernel(const T *__res
                 acc[i] = fmaf(dd, mm, acc[i]);
             }
             *reinterpret_cast<VecT<T, VEC> *>(dea + o) = out;
+        };
+        if (G > 0 && (N % (2 * (G > 0 ? G : 1))) == 0) {
+            // software pipeline over groups of 4 quantile rows: the 8 loads of group g + 1 are issued before group g is reduced and
+            // stored, so the thread always has a group in flight (the plain unrolled loop drained its loads before every compute phase:
+            // 80 % of its stall samples were long-scoreboard, 4.67 TB/s)
+            constexpr int GG = G > 0 ? G : 1;
+            VecT<T, VEC> d0[GG], m0[GG], d1[GG], m1[GG];
+            auto ldg = [&](VecT<T, VEC> (&d)[GG], VecT<T, VEC> (&m)[GG], int n) {
+#pragma unroll
+                for (int u = 0; u < GG; ++u) {
+                    d[u] = *reinterpret_cast<const VecT<T, VEC> *>(dm + o0 + (long long)(n + u) * F);
+                    m[u] = *reinterpret_cast<const VecT<T, VEC> *>(merged + o0 + (long long)(n + u) * F);
+                }
+            };
+            ldg(d0, m0, 0);
+#pragma unroll 1
+            for (int n = 0; n < N; n += 2 * GG) {
+                ldg(d1, m1, n + GG);
+#pragma unroll
+                for (int u = 0; u < GG; ++u) one(d0[u], m0[u], o0 + (long long)(n + u) * F);
+                if (n + 2 * GG < N) ldg(d0, m0, n + 2 * GG);
+#pragma unroll
+                for (int u = 0; u < GG; ++u) one(d1[u], m1[u], o0 + (long long)(n + GG + u) * F);
+            }
+        } else {
+#pragma unroll 4
+            for (int n = 0; n < N; ++n) {
+                const long long o = o0 + (long long)n * F;
+                one(*reinterpret_cast<const VecT<T, VEC> *>(dm + o), *reinterpret_cast<const VecT<T, VEC> *>(merged + o), o);
+            }
         }
         VecT<T, VEC> of;
 #pragma unroll
@@ -554,7 +581,7 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
         Epilogue e;
         e.out = L.out; e.out_bf16 = L.out_fp32 ? 0 : bf; e.sm = L.cout; e.sn = 1;
         e.bias = net->params + Bt.offset; e.bias_mode = 1; e.relu = L.relu; e.tf32_passes = net->tf32_passes;
-        if (L.rowmul) { e.rowmul = L.rowmul; e.rowmul_div = L.rowmul_div; e.rowmul_ld = L.rowmul_ld; }
+        if (L.rowmul) { e.rowmul = L.rowmul; e.rowmul_div = L.rowmul_div; e.rowmul_ld = L.rowmul_ld; e.rowmul_nonneg = L.rowmul_nonneg; }
         if (L.kind == ZOO_LAYER_CONV && L.first_raw && net->obs_nhwc) {
             if (cur_kind == 2) { set_err("conv: first layer expects a raw observation"); return ZOO_BAD_ARG; }
             const int oh_ = net->desc.in_h, ow_ = net->desc.in_w, op_ = (L.ih - oh_) / 2;  // L.ih / L.iw describe the padded copy
@@ -818,7 +845,7 @@ zoo_status net_forward(zoo_net *net, const void *obs, int obs_dtype, int rows, c
     ZOO_LAUNCH_CHECK();
     if (net->iqn_fused) {  // phi's last GEMM writes merged = psi[b] .* relu(W cos + b) from its epilogue (iqn.jl:27-30)
         LayerExec &Lp = net->b.layers.back();
-        Lp.rowmul = net->a.out(); Lp.rowmul_div = n_tau; Lp.rowmul_ld = F;
+        Lp.rowmul = net->a.out(); Lp.rowmul_div = n_tau; Lp.rowmul_ld = F; Lp.rowmul_nonneg = net->a.layers.back().relu ? 1 : 0;
         ZOO_TRY(chain_forward(net, net->b, net->emb, 2, R, st));
         return chain_forward(net, net->c, net->merged, 2, R, st);
     }
@@ -877,11 +904,14 @@ static zoo_status net_backward_impl(zoo_net *net, int obs_dtype, const void *obs
     if (net->iqn_fused) {
         float *dbias = net->grads + net->tensors[Pphi.bt].offset;
         const dim3 blk(32, 8);
-#define MBWD(T, V) iqn_merge_bwd_fused_kernel<T, V><<<dim3(cdiv(F / V, 32), cdiv(rows, 8)), blk, 0, st>>>((const T *)net->dmerged, (const T *)Ppsi.out, (const T *)net->merged, (T *)Pphi.dout, (T *)Ppsi.dout, dbias, rows, F, n_tau)
-        if (bf && F % 8 == 0) MBWD(bf16, 8);
-        else if (!bf && F % 4 == 0) MBWD(float, 4);
-        else if (bf) MBWD(bf16, 1);
-        else MBWD(float, 1);
+        // ZOO_MERGE_BWD_VAR: 0 = the plain unrolled loop (round-2 first half), 1 = pipelined groups of 2 rows at 2 CTAs / SM (default: 258 us = 5.9 TB/s against 335-359 us for 0),
+        // 2 = groups of 4 rows at 2 CTAs / SM (279 us, spills), 3 = groups of 2 rows at 3 CTAs / SM (314 us, spills)
+        static const int var = [] { const char *e = getenv("ZOO_MERGE_BWD_VAR"); return e ? atoi(e) : 1; }();
+#define MBWD(T, V, G, MB) iqn_merge_bwd_fused_kernel<T, V, G, MB><<<dim3(cdiv(F / V, 32), cdiv(rows, 8)), blk, 0, st>>>((const T *)net->dmerged, (const T *)Ppsi.out, (const T *)net->merged, (T *)Pphi.dout, (T *)Ppsi.dout, dbias, rows, F, n_tau)
+        if (bf && F % 8 == 0) { if (var == 0) MBWD(bf16, 8, 0, 3); else if (var == 1) MBWD(bf16, 8, 2, 2); else if (var == 3) MBWD(bf16, 8, 2, 3); else MBWD(bf16, 8, 4, 2); }
+        else if (!bf && F % 4 == 0) { if (var == 0) MBWD(float, 4, 0, 3); else MBWD(float, 4, 4, 2); }
+        else if (bf) MBWD(bf16, 1, 0, 3);
+        else MBWD(float, 1, 0, 3);
 #undef MBWD
         ZOO_LAUNCH_CHECK();
         ZOO_TRY(chain_backward(net, net->b, net->emb, 2, R, nullptr, nullptr, st, (int)net->b.layers.size() - 1));

@@ -34,6 +34,7 @@ struct LayerExec {
     void *cols = nullptr, *out = nullptr, *dout = nullptr, *dcols = nullptr;
     // fused IQN merge (set per forward call on phi's last layer): out = relu(.) .* rowmul[row / rowmul_div]  -- iqn.jl:28-30
     const void *rowmul = nullptr; int rowmul_div = 1; long long rowmul_ld = 0;
+    int rowmul_nonneg = 0;  // psi ends in a relu (the Nature-CNN trunk does): the multiplier is >= 0
 };
 
 struct Chain {

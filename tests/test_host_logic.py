@@ -129,3 +129,40 @@ def test_data_parallel_gradients_equal_single_process_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert out.get() <= 1e-5
+
+
+def test_staging_division_by_255_is_exact_for_every_uint8():
+    """learner.cu:div255_u8 replaces the IEEE divide of `x ./ 255` (Dopamine_DQN_Atari.jl:28) by q0 = RN(v r), rem = v - 255 q0,
+    q = RN(q0 + rem r), r = RN(1/255).  Checked here in exact rational arithmetic for all 256 frame values: the sequence returns the
+    correctly rounded fp32 quotient (a plain multiply by r does not)."""
+    from fractions import Fraction
+
+    def rn32(fr):  # exact round-to-nearest-even of a non-negative rational to fp32 (normal range)
+        if fr == 0:
+            return Fraction(0)
+        e = fr.numerator.bit_length() - fr.denominator.bit_length()
+        while Fraction(2) ** e > fr:
+            e -= 1
+        while Fraction(2) ** (e + 1) <= fr:
+            e += 1
+        ulp = Fraction(2) ** (e - 23)
+        m = fr / ulp
+        fl = m.numerator // m.denominator
+        rem = m - fl
+        if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and fl % 2 == 1):
+            fl += 1
+        return fl * ulp
+
+    r = rn32(Fraction(1, 255))
+    assert float(r) == float(np.float32(1.0) / np.float32(255.0))
+    plain_multiply_wrong = 0
+    for v in range(256):
+        exact = rn32(Fraction(v, 255))
+        assert float(exact) == float(np.float32(v) / np.float32(255.0))
+        q0 = rn32(v * r)
+        rem = Fraction(v) - q0 * 255  # representable: the fma computes it without rounding
+        assert rem == 0 or abs(rem) == rn32(abs(rem))
+        q = rn32(q0 + rem * r) if q0 + rem * r >= 0 else None
+        assert q == exact, v
+        plain_multiply_wrong += q0 != exact
+    assert plain_multiply_wrong > 0
