@@ -496,7 +496,7 @@ static bool pair_enabled() {
 }
 
 static int pair_min_k() {
-    static const int k = [] { const char *e = getenv("ZOO_PAIR_MIN_K"); return e ? atoi(e) : 1024; }();
+    static const int k = [] { const char *e = getenv("ZOO_PAIR_MIN_K"); return e ? atoi(e) : 512; }();
     return k;
 }
 
@@ -538,7 +538,8 @@ static zoo_status launch_persist_cg(bool ak, bool bk, const CUtensorMap &tmA, co
 zoo_status tc_gemm_persist(const Operand &A, const Operand &B, int M, int N, int K, const Epilogue &epi, cudaStream_t st) {
     ZOO_REQUIRE(tc_gemm_persist_ok(A, B, M, N, K, epi), "tc_gemm_persist: unsupported shape");
     // pairs pay where the main loop is long (operand traffic through L2 is the bound: fc1 forward 215 vs 255 us, weight gradient
-    // 209 vs 254 us); short-K, store-bound shapes are faster one CTA per tile (phi forward K = 64: 190 vs 219 us)
+    // 209 vs 254 us, fc1 data gradient K = 512: 225 vs 231 us); short-K, store-bound shapes are faster one CTA per tile (phi forward
+    // K = 64: 150 vs 180 us)
     const int cg = (pair_enabled() && M > BM && g_sm_budget >= 2 && K >= pair_min_k()) ? 2 : 1;
     PersistParams P;
     static const int ablate = [] { const char *e = getenv("ZOO_PERSIST_ABLATE"); return e ? atoi(e) : 0; }();

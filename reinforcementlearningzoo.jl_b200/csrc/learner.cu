@@ -125,65 +125,81 @@ __device__ __forceinline__ float div255_u8(float x) {
     const float rem = __fmaf_rn(-q0, 255.f, x);
     return __fmaf_rn(rem, r, q0);
 }
-template <typename Tin, typename Tout>
-__device__ __forceinline__ void stage_nhwc_quad(const StageArgs &a, long long i) {
+// One quad = 4 horizontally adjacent pixels x 4 channels of one observation row of [state; next_state]: four 4-byte (uint8) or 16-byte
+// (fp32) loads, one 4-pixel run of the padded NHWC copy out (for the online net, the target net, or both).
+template <typename Tin>
+struct StageQuad {
+    typedef typename std::conditional<sizeof(Tin) == 1, uint32_t, float4>::type Word;
+    Word w[4];
+    unsigned b, y, xx;
+    bool to_on, to_tg;
+};
+template <typename Tin>
+__device__ __forceinline__ void stage_quad_load(const StageArgs &a, long long i, StageQuad<Tin> &q) {
     const unsigned HW = (unsigned)(a.H * a.W), W = (unsigned)a.W;
     const unsigned qpi = HW >> 2;                    // quads per image (the host checks W % 4 == 0 and quads < 2^31)
-    const unsigned b = (unsigned)i / qpi;            // b: row of [state; next_state]
-    const unsigned p = ((unsigned)i - b * qpi) << 2;
-    const bool to_on = (int)b < a.on_rows, to_tg = a.nhwc_tg && (int)b >= a.B;
-    if (!to_on && !to_tg) return;
-    const Tin *src = ((int)b < a.B ? reinterpret_cast<const Tin *>(a.s) + (size_t)b * 4 * HW : reinterpret_cast<const Tin *>(a.s2) + (size_t)(b - a.B) * 4 * HW) + p;
-    const unsigned y = p / W, xx = p - y * W;
+    q.to_on = false; q.to_tg = false;
+    if (i >= a.quads) return;
+    q.b = (unsigned)i / qpi;                         // row of [state; next_state]
+    const unsigned p = ((unsigned)i - q.b * qpi) << 2;
+    q.to_on = (int)q.b < a.on_rows; q.to_tg = a.nhwc_tg && (int)q.b >= a.B;
+    if (!q.to_on && !q.to_tg) return;
+    const Tin *src = ((int)q.b < a.B ? reinterpret_cast<const Tin *>(a.s) + (size_t)q.b * 4 * HW : reinterpret_cast<const Tin *>(a.s2) + (size_t)(q.b - a.B) * 4 * HW) + p;
+    q.y = p / W; q.xx = p - q.y * W;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) q.w[c] = __ldg(reinterpret_cast<const typename StageQuad<Tin>::Word *>(src + (size_t)c * HW));
+}
+template <typename Tin, typename Tout>
+__device__ __forceinline__ void stage_quad_store(const StageArgs &a, const StageQuad<Tin> &q) {
+    if (!q.to_on && !q.to_tg) return;
     const size_t PH = a.H + 2 * a.pad, PW = a.W + 2 * a.pad;
     Tout o[4][4];
-    if (sizeof(Tin) == 1) {
-        uint32_t w[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) w[c] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)c * HW));
+    for (int c = 0; c < 4; ++c) {
+        float f[4];
+        if constexpr (sizeof(Tin) == 1) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 4; ++j) f[j] = (float)((q.w[c] >> (8 * j)) & 0xffu);
+        } else {
+            f[0] = q.w[c].x; f[1] = q.w[c].y; f[2] = q.w[c].z; f[3] = q.w[c].w;
+        }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float v = (float)((w[c] >> (8 * j)) & 0xffu);
-                if (a.scale255) v = div255_u8(v);
-                if (sizeof(Tout) == 2) reinterpret_cast<bf16 *>(o[j])[c] = __float2bfloat16_rn(v);
-                else reinterpret_cast<float *>(o[j])[c] = v;
-            }
-    } else {
-        float4 w[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) w[c] = __ldg(reinterpret_cast<const float4 *>(src + (size_t)c * HW));
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float f[4] = {w[c].x, w[c].y, w[c].z, w[c].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float v = f[j];
-                if (a.scale255) v = __fdiv_rn(v, 255.f);
-                if (sizeof(Tout) == 2) reinterpret_cast<bf16 *>(o[j])[c] = __float2bfloat16_rn(v);
-                else reinterpret_cast<float *>(o[j])[c] = v;
-            }
+        for (int j = 0; j < 4; ++j) {
+            float v = f[j];
+            if (a.scale255) v = sizeof(Tin) == 1 ? div255_u8(v) : __fdiv_rn(v, 255.f);
+            if (sizeof(Tout) == 2) reinterpret_cast<bf16 *>(o[j])[c] = __float2bfloat16_rn(v);
+            else reinterpret_cast<float *>(o[j])[c] = v;
         }
     }
     typedef typename std::conditional<sizeof(Tout) == 2, uint2, uint4>::type Vec;  // one pixel = 4 channels
-    if (to_on) {
-        Tout *dst = reinterpret_cast<Tout *>(a.nhwc_on) + ((b * PH + y + a.pad) * PW + xx + a.pad) * 4;
+    if (q.to_on) {
+        Tout *dst = reinterpret_cast<Tout *>(a.nhwc_on) + ((q.b * PH + q.y + a.pad) * PW + q.xx + a.pad) * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j) *reinterpret_cast<Vec *>(dst + j * 4) = *reinterpret_cast<const Vec *>(o[j]);
     }
-    if (to_tg) {
-        Tout *dst = reinterpret_cast<Tout *>(a.nhwc_tg) + (((b - a.B) * PH + y + a.pad) * PW + xx + a.pad) * 4;
+    if (q.to_tg) {
+        Tout *dst = reinterpret_cast<Tout *>(a.nhwc_tg) + (((q.b - a.B) * PH + q.y + a.pad) * PW + q.xx + a.pad) * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j) *reinterpret_cast<Vec *>(dst + j * 4) = *reinterpret_cast<const Vec *>(o[j]);
     }
 }
+// two quads per thread (i and i + half), both loaded before either is converted: eight independent loads in flight per thread
+template <typename Tin, typename Tout>
+__device__ __forceinline__ void stage_nhwc_pair(const StageArgs &a, long long i) {
+    const long long half = (a.quads + 1) >> 1;
+    if (i >= half) return;
+    StageQuad<Tin> q0, q1;
+    stage_quad_load<Tin>(a, i, q0);
+    stage_quad_load<Tin>(a, i + half, q1);
+    stage_quad_store<Tin, Tout>(a, q0);
+    stage_quad_store<Tin, Tout>(a, q1);
+}
 __global__ void stage_batch_kernel(StageArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.obs16) { a.obs[i] = __ldg(a.s + i); a.obs[a.obs16 + i] = __ldg(a.s2 + i); }
-    if (a.nhwc_on && i < a.quads) {
-        if (a.in_f32) { if (a.out_bf16) stage_nhwc_quad<float, bf16>(a, i); else stage_nhwc_quad<float, float>(a, i); }
-        else { if (a.out_bf16) stage_nhwc_quad<uint8_t, bf16>(a, i); else stage_nhwc_quad<uint8_t, float>(a, i); }
+    if (a.nhwc_on) {
+        if (a.in_f32) { if (a.out_bf16) stage_nhwc_pair<float, bf16>(a, i); else stage_nhwc_pair<float, float>(a, i); }
+        else { if (a.out_bf16) stage_nhwc_pair<uint8_t, bf16>(a, i); else stage_nhwc_pair<uint8_t, float>(a, i); }
     }
     if (i < a.B) {
         a.d_action[i] = a.action[i]; a.d_reward[i] = a.reward[i]; a.d_terminal[i] = a.terminal[i];
@@ -545,7 +561,15 @@ static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b, bool pipelined
             a.quads = (long long)2 * B * a.H * a.W / 4;  // < 2^31: the kernel indexes quads with 32-bit arithmetic
             on->prestaged_src = L->d_obs; on->prestaged_rows = a.on_rows;
             if (tg) { tg->prestaged_src = (const uint8_t *)L->d_obs + obs_bytes; tg->prestaged_rows = B; }
-            n = std::max(n, a.quads);
+            // Both nets now read the padded NHWC copy only (the first layer is a convolution; its weight gradient reads the same copy), so
+            // the raw [state; next_state] block is not duplicated into d_obs any more -- d_obs stays the identity of the staged batch
+            // (prestaged_src).  ZOO_STAGE_RAW=1 keeps the copy (A/B; Rainbow B = 1024: 116 MB of traffic per update).
+            static const bool keep_raw = [] { const char *e = getenv("ZOO_STAGE_RAW"); return e && e[0] == '1'; }();
+            if (!keep_raw && a.on_rows >= (dbl ? 2 * B : B)) {
+                a.obs16 = 0;
+                n = (long long)B * std::max(std::max(c.n_actions, c.N), std::max(c.N_prime, 1));
+            }
+            n = std::max(n, (a.quads + 1) / 2);  // two quads per thread
         }
         stage_batch_kernel<<<cdiv(n, 256), 256, 0, st>>>(a);
         ZOO_LAUNCH_CHECK();

@@ -66,7 +66,9 @@ __global__ void __launch_bounds__(256) narrow_fwd_kernel(const T *__restrict__ X
     const int nchunks = K / V;
     for (int i = threadIdx.x; i < N * K / 4; i += 256) reinterpret_cast<float4 *>(w_s)[i] = __ldg(reinterpret_cast<const float4 *>(W) + i);
     __syncthreads();
-    float w[NARROW_NMAX][CPL * V];
+    // weights as packed pairs: the dot products run on FFMA2 (two k per instruction) -- this kernel was issue-bound, not
+    // memory-bound (ncu: 42 % of the issue slots at 12 % occupancy, 1.3 TB/s)
+    float2 w[NARROW_NMAX][CPL * V / 2];
 #pragma unroll
     for (int n = 0; n < NARROW_NMAX; ++n)
 #pragma unroll
@@ -76,10 +78,12 @@ __global__ void __launch_bounds__(256) narrow_fwd_kernel(const T *__restrict__ X
             for (int e4 = 0; e4 < V; e4 += 4) {
                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (n < N && ch < nchunks) t = *reinterpret_cast<const float4 *>(w_s + n * K + ch * V + e4);
-                w[n][c * V + e4] = t.x; w[n][c * V + e4 + 1] = t.y; w[n][c * V + e4 + 2] = t.z; w[n][c * V + e4 + 3] = t.w;
+                w[n][(c * V + e4) / 2] = make_float2(t.x, t.y); w[n][(c * V + e4) / 2 + 1] = make_float2(t.z, t.w);
             }
         }
-    float bn = lane < N ? __ldg(bias + lane) : 0.f;
+    // after the butterfly below, lane l holds the row's output n = 4 b4 + 2 b3 + b2 (bits of l); lanes with l % 4 == 0 store it
+    const int n_mine = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    const float bn = n_mine < N ? __ldg(bias + n_mine) : 0.f;
     pdl_trigger();
     // ROWS rows in flight per warp: a streaming kernel with 8 resident warps per SM needs several independent 16-byte loads per
     // lane to cover the DRAM latency (one row at a time ran at 0.87 TB/s, profiles/r02_ncu_full_iqn_b512_bf16.txt)
@@ -95,9 +99,9 @@ __global__ void __launch_bounds__(256) narrow_fwd_kernel(const T *__restrict__ X
         for (int u = 0; u < ROWS; ++u) {
             const int m = mb + u;
             if (m >= M) break;
-            float acc[NARROW_NMAX];
+            float2 acc[NARROW_NMAX];
 #pragma unroll
-            for (int n = 0; n < NARROW_NMAX; ++n) acc[n] = 0.f;
+            for (int n = 0; n < NARROW_NMAX; ++n) acc[n] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
                 if (lane + 32 * c < nchunks) {
@@ -106,18 +110,30 @@ __global__ void __launch_bounds__(256) narrow_fwd_kernel(const T *__restrict__ X
 #pragma unroll
                     for (int n = 0; n < NARROW_NMAX; ++n)
 #pragma unroll
-                        for (int e = 0; e < V; ++e) acc[n] = fmaf(x[e], w[n][c * V + e], acc[n]);
+                        for (int e = 0; e < V; e += 2) acc[n] = __ffma2_rn(make_float2(x[e], x[e + 1]), w[n][(c * V + e) / 2], acc[n]);
                 }
             }
-            float mine = 0.f;
+            // eight sums over 32 lanes in 9 shuffles: each exchange halves the values a lane still carries (16: n < 4 stay in the lanes
+            // with bit 4 clear, n >= 4 in the others; 8 and 4 likewise), the last two steps are a plain butterfly on the one left
+            float t4[4], t2[2];
+            {
+                const bool hi = lane & 16;
 #pragma unroll
-            for (int n = 0; n < NARROW_NMAX; ++n) {
-                float v = acc[n];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == n) mine = v;
+                for (int i = 0; i < 4; ++i) {
+                    const float a0 = acc[i].x + acc[i].y, a1 = acc[i + 4].x + acc[i + 4].y;
+                    t4[i] = (hi ? a1 : a0) + __shfl_xor_sync(0xffffffffu, hi ? a0 : a1, 16);
+                }
             }
-            if (lane < N) out[(long long)m * N + lane] = mine + bn;
+            {
+                const bool hi = lane & 8;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) t2[i] = (hi ? t4[i + 2] : t4[i]) + __shfl_xor_sync(0xffffffffu, hi ? t4[i] : t4[i + 2], 8);
+            }
+            const bool hi4 = lane & 4;
+            float v = (hi4 ? t2[1] : t2[0]) + __shfl_xor_sync(0xffffffffu, hi4 ? t2[0] : t2[1], 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            if ((lane & 3) == 0 && n_mine < N) out[(long long)m * N + n_mine] = v + bn;
         }
     }
 }
@@ -136,7 +152,8 @@ __global__ void __launch_bounds__(256) narrow_bwd_kernel(const T *__restrict__ X
     // W is staged through the (not yet used) dW accumulator with coalesced 16-byte loads, then each thread keeps its 8 columns
     for (int i = threadIdx.x; i < N * K / 4; i += 256) reinterpret_cast<float4 *>(dWs)[i] = __ldg(reinterpret_cast<const float4 *>(W) + i);
     __syncthreads();
-    float w[NARROW_NMAX][8], dw[NARROW_NMAX][8], dbp[8], dbn[NARROW_NMAX];
+    float2 w[NARROW_NMAX][4], dw[NARROW_NMAX][4];  // packed pairs of this thread's 8 columns: the row loop runs on FFMA2
+    float dbp[8], dbn[NARROW_NMAX];
 #pragma unroll
     for (int n = 0; n < NARROW_NMAX; ++n) {
         dbn[n] = 0.f;
@@ -145,9 +162,9 @@ __global__ void __launch_bounds__(256) narrow_bwd_kernel(const T *__restrict__ X
             a = *reinterpret_cast<const float4 *>(dWs + n * K + kq * 8);
             b = *reinterpret_cast<const float4 *>(dWs + n * K + kq * 8 + 4);
         }
-        w[n][0] = a.x; w[n][1] = a.y; w[n][2] = a.z; w[n][3] = a.w; w[n][4] = b.x; w[n][5] = b.y; w[n][6] = b.z; w[n][7] = b.w;
+        w[n][0] = make_float2(a.x, a.y); w[n][1] = make_float2(a.z, a.w); w[n][2] = make_float2(b.x, b.y); w[n][3] = make_float2(b.z, b.w);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) dw[n][e] = 0.f;
+        for (int e = 0; e < 4; ++e) dw[n][e] = make_float2(0.f, 0.f);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < NARROW_NMAX * K + K + NARROW_NMAX; i += 256) acc_s[i] = 0.f;
@@ -182,15 +199,16 @@ __global__ void __launch_bounds__(256) narrow_bwd_kernel(const T *__restrict__ X
         if (m + mstep < M) fetch(m + mstep);
         float dx[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float s = 0.f;
+        for (int e = 0; e < 4; ++e) {  // same per-element order of operations as the scalar loop: bit-identical results
+            float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int n = 0; n < NARROW_NMAX; ++n) s = fmaf(dy[n], w[n][e], s);
-            if (relu_prev && !(x[e] > 0.f)) s = 0.f;
-            dx[e] = s;
-            dbp[e] += s;
+            for (int n = 0; n < NARROW_NMAX; ++n) s = __ffma2_rn(make_float2(dy[n], dy[n]), w[n][e], s);
+            if (relu_prev && !(x[2 * e] > 0.f)) s.x = 0.f;
+            if (relu_prev && !(x[2 * e + 1] > 0.f)) s.y = 0.f;
+            dx[2 * e] = s.x; dx[2 * e + 1] = s.y;
+            dbp[2 * e] += s.x; dbp[2 * e + 1] += s.y;
 #pragma unroll
-            for (int n = 0; n < NARROW_NMAX; ++n) dw[n][e] = fmaf(dy[n], x[e], dw[n][e]);
+            for (int n = 0; n < NARROW_NMAX; ++n) dw[n][e] = __ffma2_rn(make_float2(dy[n], dy[n]), make_float2(x[2 * e], x[2 * e + 1]), dw[n][e]);
         }
         if (sizeof(T) == 2) {
             *reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(dX) + m * K + kq * 8) = NarrowVec<bf16>::pack(dx);
@@ -208,7 +226,7 @@ __global__ void __launch_bounds__(256) narrow_bwd_kernel(const T *__restrict__ X
     for (int n = 0; n < NARROW_NMAX; ++n) {
         if (n < N) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(dWs + n * K + kq * 8 + e, dw[n][e]);
+            for (int e = 0; e < 8; ++e) atomicAdd(dWs + n * K + kq * 8 + e, (e & 1) ? dw[n][e >> 1].y : dw[n][e >> 1].x);
             if (kq == 0) atomicAdd(dbn_s + n, dbn[n]);
         }
     }
