@@ -518,7 +518,13 @@ __device__ __forceinline__ void epi_cols_store(const float *rp, int ncols, T *op
 //         row) -- so no im2col matrix exists in either direction.  A K-block's pixel rows past R x OW are never written
 //         (the ring is zeroed once at kernel start), grid.z splits the images, partial sums are red-added into the gradient.
 template <int EB, int BN, bool A_K, bool B_K, bool X3, int GA = 0, int SPAN = 128, bool WIDE = false>
-__global__ void __launch_bounds__((TcWarps<BN, X3, GA, WIDE>::THREADS), (TcWarps<BN, X3, GA, WIDE>::MIN_CTAS))
+#ifndef ZOO_BF16_CONV_MIN_CTAS
+#define ZOO_BF16_CONV_MIN_CTAS 5  // measured (Rainbow B = 1024 bf16): 0 -> 0.811 ms, 3 -> 0.770, 4 -> 0.707, 5 -> 0.684 ms per update (conv1 forward 108 -> 61 us)
+#endif
+// bf16 TMA-im2col convolutions with narrow tiles (BN <= 64) are many-wave, fixed-cost-bound grids at the large batch sizes
+// (Rainbow B = 1024 conv1: 4 096 tiles of ~4 us of prologue / epilogue around a 0.5 us main loop): what helps is more resident CTAs
+// per SM, which the 168 registers of the unconstrained build cap at two.
+__global__ void __launch_bounds__((TcWarps<BN, X3, GA, WIDE>::THREADS), ((EB == 2 && !X3 && BN <= 64 && GA == 2) ? ZOO_BF16_CONV_MIN_CTAS : TcWarps<BN, X3, GA, WIDE>::MIN_CTAS))
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams P) {
     static_assert(GA == 0 || GA == 4 || A_K, "the gathered A operand is K-major");
     static_assert(GA != 4 || (!A_K && !B_K), "the weight-gradient operands are MN-major");
