@@ -352,5 +352,12 @@ def test_submit_collect_pipeline_matches_blocking_updates(zoo, kind):
             assert nrel(a, r) <= max(1e-4, 4 * nrel(r2, r)), (nrel(a, r), nrel(r2, r))
     # parameters: loose by nature (elements whose gradient is rounding noise take a +-eta step of random sign in the first updates;
     # the losses above, which depend on every earlier update, are the tight check)
+    # A sign flip moves an element by up to eta / sqrt(1 - rho) per update whatever its gradient's size, so the norm of the difference
+    # says little; what separates "same computation, different atomics order" (measured: ~2 % of fc1's elements -- the overlapped copies
+    # change the timing of the red-adds) from "a wrong batch or stale parameters" (every element with a gradient moves differently)
+    # is HOW MANY elements differ.
+    def moved(a, r):
+        return float(np.mean(np.abs(a - r) > 1e-5 + 1e-4 * np.abs(r)))
     for a, r, r2 in zip(pipe[2], ref[2], again[2]):
-        assert nrel(a, r) <= max(2e-2, 4 * nrel(r2, r)), (nrel(a, r), nrel(r2, r))
+        assert moved(a, r) <= max(0.1, 4 * moved(r2, r)), (moved(a, r), moved(r2, r), nrel(a, r), nrel(r2, r))
+        assert nrel(a, r) <= max(0.1, 4 * nrel(r2, r)), (nrel(a, r), nrel(r2, r))
