@@ -114,7 +114,7 @@ struct StageArgs {
     // rows [0, on_rows) of [state; next_state] for the online net, next_state for the target net.  quads = 4-pixel groups of all 2 B rows.
     void *nhwc_on, *nhwc_tg;
     long long quads;
-    int on_rows, H, W, pad, scale255, in_f32, out_bf16, oct;
+    int on_rows, H, W, pad, scale255, in_f32, out_bf16;
 };
 // exact IEEE RN(v / 255) for the 256 values a uint8 frame can hold: q0 = RN(v r), rem = v - 255 q0 (exact), q = RN(q0 + rem r) with
 // r = RN(1 / 255) -- three instructions instead of the ~25 of the IEEE divide's general path.  tests/test_host_logic.py checks all
@@ -153,7 +153,7 @@ template <typename Tin, typename Tout>
 __device__ __forceinline__ void stage_quad_store(const StageArgs &a, const StageQuad<Tin> &q) {
     if (!q.to_on && !q.to_tg) return;
     const size_t PH = a.H + 2 * a.pad, PW = a.W + 2 * a.pad;
-    Tout o[4][4];
+    __align__(16) Tout o[4][4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         float f[4];
@@ -172,16 +172,17 @@ __device__ __forceinline__ void stage_quad_store(const StageArgs &a, const Stage
         }
     }
     typedef typename std::conditional<sizeof(Tout) == 2, uint2, uint4>::type Vec;  // one pixel = 4 channels
-    if (q.to_on) {
-        Tout *dst = reinterpret_cast<Tout *>(a.nhwc_on) + ((q.b * PH + q.y + a.pad) * PW + q.xx + a.pad) * 4;
+    auto put = [&](Tout *dst) {
+        if (sizeof(Tout) == 2 && ((uintptr_t)dst & 15) == 0) {  // bf16: the quad is 32 bytes -- two 16-byte stores when the run is aligned
+            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(o[0]);
+            *reinterpret_cast<uint4 *>(dst + 8) = *reinterpret_cast<const uint4 *>(o[2]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) *reinterpret_cast<Vec *>(dst + j * 4) = *reinterpret_cast<const Vec *>(o[j]);
-    }
-    if (q.to_tg) {
-        Tout *dst = reinterpret_cast<Tout *>(a.nhwc_tg) + (((q.b - a.B) * PH + q.y + a.pad) * PW + q.xx + a.pad) * 4;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) *reinterpret_cast<Vec *>(dst + j * 4) = *reinterpret_cast<const Vec *>(o[j]);
-    }
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<Vec *>(dst + j * 4) = *reinterpret_cast<const Vec *>(o[j]);
+        }
+    };
+    if (q.to_on) put(reinterpret_cast<Tout *>(a.nhwc_on) + ((q.b * PH + q.y + a.pad) * PW + q.xx + a.pad) * 4);
+    if (q.to_tg) put(reinterpret_cast<Tout *>(a.nhwc_tg) + (((q.b - a.B) * PH + q.y + a.pad) * PW + q.xx + a.pad) * 4);
 }
 // two quads per thread (i and i + half), both loaded before either is converted: eight independent loads in flight per thread
 template <typename Tin, typename Tout>
@@ -194,52 +195,14 @@ __device__ __forceinline__ void stage_nhwc_pair(const StageArgs &a, long long i)
     stage_quad_store<Tin, Tout>(a, q0);
     stage_quad_store<Tin, Tout>(a, q1);
 }
-// uint8 frames whose H x W is a multiple of 8: the unit is an octet (8 consecutive pixels = two quads of the same image), one 8-byte
-// load per channel, two octets per thread -> 64 bytes in flight per thread.  (ncu, Rainbow B = 1024: with 4-byte loads the launch
-// was latency-bound at 2.2 TB/s -- 40 % long-scoreboard stalls, 32 bytes in flight per thread.)
-template <typename Tout>
-__device__ __forceinline__ void stage_nhwc_octs(const StageArgs &a, long long i) {
-    const long long octs = a.quads >> 1, half = (octs + 1) >> 1;
-    if (i >= half) return;
-    const unsigned HW = (unsigned)(a.H * a.W), W = (unsigned)a.W, opi = HW >> 3;
-    uint2 w[2][4];
-    unsigned bb[2], pp[2];
-    bool on[2], tg[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const long long idx = i + u * half;
-        on[u] = false; tg[u] = false; bb[u] = 0; pp[u] = 0;
-        if (idx < octs) {
-            bb[u] = (unsigned)idx / opi;
-            pp[u] = ((unsigned)idx - bb[u] * opi) << 3;
-            on[u] = (int)bb[u] < a.on_rows; tg[u] = a.nhwc_tg && (int)bb[u] >= a.B;
-            if (on[u] || tg[u]) {
-                const uint8_t *src = ((int)bb[u] < a.B ? reinterpret_cast<const uint8_t *>(a.s) + (size_t)bb[u] * 4 * HW
-                                                       : reinterpret_cast<const uint8_t *>(a.s2) + (size_t)(bb[u] - a.B) * 4 * HW) + pp[u];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) w[u][c] = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)c * HW));
-            }
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            StageQuad<uint8_t> q;
-            q.b = bb[u]; q.to_on = on[u]; q.to_tg = tg[u];
-            const unsigned pix = pp[u] + 4 * h;
-            q.y = pix / W; q.xx = pix - q.y * W;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) q.w[c] = h ? w[u][c].y : w[u][c].x;
-            stage_quad_store<uint8_t, Tout>(a, q);
-        }
-}
-__global__ void stage_batch_kernel(StageArgs a) {
+#ifndef ZOO_STAGE_MINB
+#define ZOO_STAGE_MINB 4
+#endif
+__global__ void __launch_bounds__(256, ZOO_STAGE_MINB) stage_batch_kernel(StageArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.obs16) { a.obs[i] = __ldg(a.s + i); a.obs[a.obs16 + i] = __ldg(a.s2 + i); }
     if (a.nhwc_on) {
         if (a.in_f32) { if (a.out_bf16) stage_nhwc_pair<float, bf16>(a, i); else stage_nhwc_pair<float, float>(a, i); }
-        else if (a.oct) { if (a.out_bf16) stage_nhwc_octs<bf16>(a, i); else stage_nhwc_octs<float>(a, i); }
         else { if (a.out_bf16) stage_nhwc_pair<uint8_t, bf16>(a, i); else stage_nhwc_pair<uint8_t, float>(a, i); }
     }
     if (i < a.B) {
@@ -610,8 +573,8 @@ static zoo_status stage_batch(zoo_learner *L, const zoo_batch *b, bool pipelined
                 a.obs16 = 0;
                 n = (long long)B * std::max(std::max(c.n_actions, c.N), std::max(c.N_prime, 1));
             }
-            a.oct = (!a.in_f32 && (a.H * a.W) % 8 == 0 && ((uintptr_t)b->state & 7) == 0 && ((uintptr_t)b->next_state & 7) == 0) ? 1 : 0;
-            n = std::max(n, a.oct ? (a.quads / 2 + 1) / 2 : (a.quads + 1) / 2);  // two octets / two quads per thread
+            // (8-byte loads -- 8 pixels per thread and channel -- were measured slower: 80 vs 64 us at B = 1024, the 64-byte store stride costs more than the loads gain)
+            n = std::max(n, (a.quads + 1) / 2);  // two quads per thread
         }
         stage_batch_kernel<<<cdiv(n, 256), 256, 0, st>>>(a);
         ZOO_LAUNCH_CHECK();
