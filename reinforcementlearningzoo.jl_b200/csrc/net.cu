@@ -417,6 +417,27 @@ __global__ void iqn_merge_bwd_kernel(const T *__restrict__ dm, const T *__restri
     dfeat[idx] = from_f<T>((!psi_relu || ft > 0.f) ? acc : 0.f);
 }
 
+// bf16 nets whose output layer is wide (Rainbow: Dense(512 => n_actions * n_atoms) = 306 columns): the head kernels leave d(loss)/d(logits)
+// in fp32 [rows][N] -- an odd row pitch that TMA cannot address and an operand type the bf16 engine does not take, so both gradient
+// GEMMs of that layer used to fall back to the CUDA-core engine (67 us of a 0.68 ms update at B = 1024).  One pass writes the bf16 copy
+// with rows padded to a multiple of 8 columns (zeros), which both GEMMs read by TMA.
+__global__ void head_dy_to_bf16_kernel(const float *__restrict__ dy, bf16 *__restrict__ out, long long rows, int N, int Np) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 8-column group
+    const int gpr = Np >> 3;
+    if (i >= rows * gpr) return;
+    const long long m = i / gpr;
+    const int c0 = (int)(i - m * gpr) << 3;
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + 2 * k;
+        const float a = c < N ? dy[m * N + c] : 0.f, b = c + 1 < N ? dy[m * N + c + 1] : 0.f;
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        w[k] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    *reinterpret_cast<uint4 *>(out + m * Np + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // DuelingNetwork: q = val .+ adv .- mean(adv, dims=1)  -- common.jl:51-56
 __global__ void dueling_combine_kernel(const float *__restrict__ val, const float *__restrict__ adv, float *__restrict__ q, int B, int A) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -676,6 +697,11 @@ static zoo_status chain_forward(zoo_net *net, Chain &ch, const void *in, int in_
     return ZOO_OK;
 }
 
+static bool head_bf16_enabled() {  // ZOO_HEAD_BF16=0: the wide output layer's gradients on the CUDA-core engine again (A/B, parity tests)
+    static const bool on = [] { const char *e = getenv("ZOO_HEAD_BF16"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 // Each layer's dout must already hold d(loss)/d(out) with the layer's own relu' applied.
 // dx (optional): gradient w.r.t. the chain input, internal T [rows][in_feat]; dx_mask: relu' source for it.
 static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in_kind, long long rows, void *dx, const void *dx_mask,
@@ -688,7 +714,9 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
         const long long M = rows * L.opr;
         const TensorInfo &W = net->tensors[L.wt];
         const TensorInfo &Bt = net->tensors[L.bt];
-        const int dy_bf = L.out_fp32 ? 0 : bf;
+        int dy_bf = L.out_fp32 ? 0 : bf;
+        const void *dy_p = L.dout;   // what the two gradient GEMMs read (the bias gradient always sums L.dout itself)
+        long long dy_ld = L.cout;
         if (li > 0 && L.kind == ZOO_LAYER_DENSE && L.out_fp32 && !L.relu && narrow_enabled() && narrow_supported(L.cout, L.K, bf) &&
             !(net->late_cb && W.offset == net->late_off)) {
             // the Q head: data, weight and bias gradient plus the previous layer's bias gradient in one pass over its input
@@ -698,6 +726,13 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
                                     net->grads + net->tensors[P.bt].offset, M, L.cout, L.K, P.relu, st));
             bias_done = li - 1;
             continue;
+        }
+        if (bf && L.out_fp32 && L.kind == ZOO_LAYER_DENSE && L.dcols && head_bf16_enabled()) {
+            const int Np = (L.cout + 7) & ~7;
+            prof_label("dy2bf16:t%d[%lldx%d]", L.wt, M, L.cout);
+            head_dy_to_bf16_kernel<<<cdiv(M * (Np >> 3), 256), 256, 0, st>>>((const float *)L.dout, (bf16 *)L.dcols, M, L.cout, Np);
+            ZOO_LAUNCH_CHECK();
+            dy_p = L.dcols; dy_ld = Np; dy_bf = 1;
         }
         // bias grad + wgrad only need this layer's dout, which is complete on `st` here: they go to the side lane and
         // overlap the dgrad chain (the critical path) that continues on `st`
@@ -715,7 +750,7 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
         if (bias_aside) ZOO_TRY(net_side_fork(net, st));
         if (bias_done != li) {
             prof_label("bgrad:t%d", L.bt);
-            ZOO_TRY(launch_colsum(L.dout, dy_bf, M, L.cout, net->grads + Bt.offset, bias_aside ? net->side : sw));
+            ZOO_TRY(launch_colsum(L.dout, L.out_fp32 ? 0 : bf, M, L.cout, net->grads + Bt.offset, bias_aside ? net->side : sw));
         }
         // wgrad: dW[cout][K] += dY^T X   (both operands MN-major: stored [rows][features])
         ConvGeom gw;
@@ -731,7 +766,7 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
             if (L.kind == ZOO_LAYER_CONV) X = Operand{L.cols, bf, L.K, 0};
             else if (li == 0) X = Operand{in, in_kind == 2 ? bf : 0, L.K, 0};
             else X = Operand{ch.layers[li - 1].out, bf, L.K, 0};
-            Operand dYt{L.dout, dy_bf, L.cout, 0};
+            Operand dYt{dy_p, dy_bf, dy_ld, 0};
             Epilogue ew;
             ew.out = net->grads + W.offset; ew.sm = L.K; ew.sn = 1; ew.tf32_passes = net->tf32_passes;
             ew.accumulate = 2;  // grads are zeroed per update: plain store, or atomic add when the GEMM is K-split
@@ -740,7 +775,7 @@ static zoo_status chain_backward(zoo_net *net, Chain &ch, const void *in, int in
         const bool late_here = net->late_cb && W.offset == net->late_off;
         // dgrad
         if (li == 0 && !dx) { if (late_here) ZOO_TRY(net_late_bucket(net, st, sw, par)); continue; }
-        Operand dY{L.dout, dy_bf, L.cout, 1};
+        Operand dY{dy_p, dy_bf, dy_ld, 1};
         prof_label("dgrad:t%d[%lldx%lldx%d]", L.wt, M, L.K, L.cout);
         Operand Wn = weight_operand(net, W, dY, (int)M, (int)L.K, L.cout, L.K, 0);
         Epilogue ed;
@@ -1018,6 +1053,8 @@ static zoo_status alloc_chain_bwd(zoo_net *net, Chain &ch, float *final_dout) {
         if (L.out_fp32 && final_dout) L.dout = final_dout;
         else ZOO_CUDA(cudaMalloc(&L.dout, (size_t)M * L.cout * (L.out_fp32 ? 4 : net->esz)));
         if (L.kind == ZOO_LAYER_CONV && i > 0) ZOO_CUDA(cudaMalloc(&L.dcols, (size_t)M * L.K * net->esz));
+        // wide fp32 output layer of a bf16 net: the bf16, row-padded copy of its incoming gradient (head_dy_to_bf16_kernel)
+        if (L.kind == ZOO_LAYER_DENSE && L.out_fp32 && is_bf(net) && L.cout > 8) ZOO_CUDA(cudaMalloc(&L.dcols, (size_t)M * ((L.cout + 7) & ~7) * sizeof(bf16)));
     }
     return ZOO_OK;
 }
