@@ -19,8 +19,13 @@
 namespace zoo {
 
 static constexpr int PBN = 256;               // tile columns = UMMA N
-static constexpr int PHALF = PBN / 2;         // columns per epilogue warp
-static constexpr int P_THREADS = 320;         // TMA producer, MMA issuer, 8 epilogue warps
+// EW epilogue warps (8 or 16): TMEM lane quadrant = warp % 4, column slice = (warp - 2) / 4 of EW / 4 slices of 256 / (EW / 4) columns
+template <int EW> struct PersistWarps {
+    static constexpr int THREADS = 64 + EW * 32;  // + TMA producer, MMA issuer
+    static constexpr int PCOLS = PBN / (EW / 4);  // columns per epilogue warp (128 / 64)
+    static constexpr int SLAB = 65536 / EW;       // staging bytes per warp: two 4 KB blocks (8 warps) or one (16 warps)
+    static constexpr int NBUF = SLAB / 4096;
+};
 static constexpr int P_A_BYTES = BM * 128;    // 16 KB
 static constexpr int P_RING = 3 * (P_A_BYTES + PBN * 128);  // 144 KB of operand ring: 3 x 48 KB stages (one CTA per tile) or 4 x 32 KB (CTA pair)
 static constexpr int P_EPI_OFF = P_RING;                    // epilogue staging: 4 warps x 16 KB (a warp's whole 32 x 256 slab: 4 blocks of 32 rows x 128 B)
@@ -184,8 +189,8 @@ __device__ __forceinline__ void epi_chunk_fma(const uint32_t (&r)[32], const flo
     }
 }
 
-template <bool A_K, bool B_K, int CG>
-__global__ void __launch_bounds__(P_THREADS, 1)
+template <bool A_K, bool B_K, int CG, int EW = 8>
+__global__ void __launch_bounds__(PersistWarps<EW>::THREADS, 1)
 tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ PersistParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
@@ -207,7 +212,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < PST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 256 * CG); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EW * 32 * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -288,20 +293,22 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         // in profiles/r02_ncu_persist_epilogue.txt)
         const int q = warp & 3, hh = (warp - 2) >> 2;
         const int ew = hh * 4 + q;  // private slab / bias copy of this warp
+        constexpr int PHALF = PersistWarps<EW>::PCOLS, NBUF = PersistWarps<EW>::NBUF;
+        constexpr bool LEAN = EW == 16;  // sixteen warps have 96 registers each: only the packed bf16 path without a relu' mask is compiled in
         const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
         const Epilogue e = P.epi;
         const int Nn = P.N, out_bf16 = e.out_bf16, relu = e.relu, bias_mode = e.bias_mode;
-        const void *const maskp = e.mask;
+        const void *const maskp = LEAN ? nullptr : e.mask;
         const long long msm = e.mask_sm;
         const bool rmul = e.rowmul != nullptr;
-        const bool fma_path = out_bf16 && !maskp && (!rmul || e.rowmul_nonneg) && !(P.ablate & 4);
+        const bool fma_path = LEAN || (out_bf16 && !maskp && (!rmul || e.rowmul_nonneg) && !(P.ablate & 4));
         // everything below is private to the warp (its own bias / multiplier copy, its own staging slab): no CTA-level barrier in
         // the tile loop.  Per tile the warp converts its 32 rows x 128 columns into two SWIZZLE_128B blocks (fp32 output: two rounds
         // of two 32-column blocks), ONE proxy fence per round, then one TMA store per block; the stores of tile t are only waited
         // for when tile t + 1 is about to overwrite the slab.
         float *const bias_s = reinterpret_cast<float *>(smem + P_BIAS_OFF) + ew * 2 * PHALF;
         float *const rm_s = bias_s + PHALF;
-        const uint32_t sbase = smem_u32(smem) + P_EPI_OFF + ew * 8192;
+        const uint32_t sbase = smem_u32(smem) + P_EPI_OFF + ew * PersistWarps<EW>::SLAB;
         int t = 0;
         int nblk = 0;  // staging blocks this warp has handed to the TMA unit so far (buffer = nblk & 1)
         // bias / multiplier of a tile are fetched one tile ahead (raw bits; converted when they are copied to shared memory), and
@@ -352,7 +359,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 }
             };
             uint4 mk[4] = {};
-            if (maskp && ncols > 0) fetch_mask(0, mk);
+            if (!LEAN && maskp && ncols > 0) fetch_mask(0, mk);
             mbar_wait(&acc_full[ab], (t >> 1) & 1);
             tc_fence_after();
             __syncwarp();
@@ -375,19 +382,23 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 const int c = ch * 32;
                 const int h = out_bf16 ? (ch & 1) : 0;       // chunk within its block
                 if (h == 0) {
-                    if (nblk >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    if (nblk >= NBUF && lane == 0) {
+                        if (NBUF == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
                     __syncwarp();
                 }
-                const uint32_t bufa = sbase + (uint32_t)(nblk & 1) * 4096;
+                const uint32_t bufa = sbase + (uint32_t)(nblk & (NBUF - 1)) * 4096;
                 const uint32_t sb = bufa + lane * 128;
                 uint4 mkc[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) mkc[j] = mk[j];
-                if (maskp && ch + 1 < nchunk) fetch_mask(c + 32, mk);
+                if (!LEAN && maskp && ch + 1 < nchunk) fetch_mask(c + 32, mk);
                 if (P.ablate & 2) {
                 } else if (fma_path) {
                     if (relu) epi_chunk_fma<true>(rc, bias_s + c, rm_s + c, sb, h, lane);
                     else epi_chunk_fma<false>(rc, bias_s + c, rm_s + c, sb, h, lane);
+                } else if (LEAN) {
                 } else if (out_bf16) {
                     if (maskp) epi_chunk<true, true>(rc, mkc, bias_s + c, rm_s + c, relu, sb, h, lane);
                     else epi_chunk<true, false>(rc, mkc, bias_s + c, rm_s + c, relu, sb, h, lane);
@@ -500,10 +511,11 @@ static int pair_min_k() {
     return k;
 }
 
-template <bool A_K, bool B_K, int CG>
+template <bool A_K, bool B_K, int CG, int EW = 8>
 static zoo_status launch_persist(const CUtensorMap &tmA, const CUtensorMap &tmB, const PersistParams &P, int grid, cudaStream_t st) {
     static bool attr = false;
-    auto kern = tc_gemm_persist_kernel<A_K, B_K, CG>;
+    auto kern = tc_gemm_persist_kernel<A_K, B_K, CG, EW>;
+    constexpr int P_THREADS = PersistWarps<EW>::THREADS;
     if (!attr) {
         ZOO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
         attr = true;
@@ -528,7 +540,9 @@ static zoo_status launch_persist(const CUtensorMap &tmA, const CUtensorMap &tmB,
 }
 
 template <int CG>
-static zoo_status launch_persist_cg(bool ak, bool bk, const CUtensorMap &tmA, const CUtensorMap &tmB, const PersistParams &P, int grid, cudaStream_t st) {
+static zoo_status launch_persist_cg(bool ak, bool bk, const CUtensorMap &tmA, const CUtensorMap &tmB, const PersistParams &P, int grid, cudaStream_t st, int ew = 8) {
+    if (CG == 1 && ew == 16 && ak && bk) return launch_persist<true, true, 1, 16>(tmA, tmB, P, grid, st);
+    if (CG == 2 && ew == 16 && ak && !bk) return launch_persist<true, false, 2, 16>(tmA, tmB, P, grid, st);
     if (ak && bk) return launch_persist<true, true, CG>(tmA, tmB, P, grid, st);
     if (ak && !bk) return launch_persist<true, false, CG>(tmA, tmB, P, grid, st);
     if (!ak && bk) return launch_persist<false, true, CG>(tmA, tmB, P, grid, st);
@@ -554,12 +568,21 @@ zoo_status tc_gemm_persist(const Operand &A, const Operand &B, int M, int N, int
     else ZOO_TRY(pmap(&tmB, B.p, bf, 2, N, K, B.ld, 64, 64));
     if (epi.out_bf16) ZOO_TRY(pmap(&P.tmC, epi.out, bf, 2, N, M, epi.sm, 64, 32));
     else ZOO_TRY(pmap(&P.tmC, epi.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, N, M, epi.sm, 32, 32));
+    static const int ew_pref = [] { const char *e = getenv("ZOO_PERSIST_EW"); return e ? atoi(e) : 16; }();
+    const bool lean_ok = ew_pref >= 16 && epi.out_bf16 && !epi.mask && (!epi.rowmul || epi.rowmul_nonneg) && !(ablate & 4);
     if (cg == 2) {
         const int grid = 2 * (int)std::min<long long>(P.ntiles, g_sm_budget / 2);
-        return launch_persist_cg<2>(A.kmajor, B.kmajor, tmA, tmB, P, grid, st);
+        // (the fc1 data gradient, K = 512: eight K-blocks per 256 x 256 tile -- its epilogue is as long as its main loop)
+        // sixteen warps measured SLOWER here (239 vs 225 us): the pair's main loop already competes with the epilogue for shared-memory
+        // bandwidth; ZOO_PERSIST_EW=32 forces them for the A/B
+        const int ew2 = (ew_pref == 32 && lean_ok && K <= 512 && A.kmajor && !B.kmajor) ? 16 : 8;
+        return launch_persist_cg<2>(A.kmajor, B.kmajor, tmA, tmB, P, grid, st, ew2);
     }
     const int grid = (int)std::min<long long>(P.ntiles, g_sm_budget);
-    return launch_persist_cg<1>(A.kmajor, B.kmajor, tmA, tmB, P, grid, st);
+    // short-K, all-epilogue shapes (the IQN phi forward: K = 64, 0.5 GB of bf16 output): sixteen epilogue warps, four per scheduler, so
+    // that one warp's tcgen05.ld / convert / fence / bulk-store chain overlaps three others' (ZOO_PERSIST_EW=8: the eight-warp kernel)
+    const int ew = (lean_ok && K <= 256 && A.kmajor && B.kmajor) ? 16 : 8;
+    return launch_persist_cg<1>(A.kmajor, B.kmajor, tmA, tmB, P, grid, st, ew);
 }
 
 }  // namespace zoo
