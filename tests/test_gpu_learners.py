@@ -348,8 +348,12 @@ def test_submit_collect_pipeline_matches_blocking_updates(zoo, kind):
         assert abs(a - r) <= max(1e-4 * max(1.0, abs(r)), 4 * abs(r2 - r)), (pipe[0], ref[0], again[0])
     assert abs(pipe[0][0] - ref[0][0]) <= 1e-6 * max(1.0, abs(ref[0][0]))  # first update: same parameters, same batch
     if per:
+        # first update: same parameters, same batch -> the same priorities to rounding.  Later updates inherit the sign-like RMSProp steps
+        # of rounding-noise gradients (see the parameter check below): per-sample losses, hence priorities, drift at the 1e-3 level between
+        # the two modes although the mean loss stays within 1e-4; a wrong batch or stale parameters would be off by O(1).
+        assert nrel(pipe[1][0], ref[1][0]) <= 1e-5, nrel(pipe[1][0], ref[1][0])
         for a, r, r2 in zip(pipe[1], ref[1], again[1]):
-            assert nrel(a, r) <= max(1e-4, 4 * nrel(r2, r)), (nrel(a, r), nrel(r2, r))
+            assert nrel(a, r) <= max(2e-2, 4 * nrel(r2, r)), (nrel(a, r), nrel(r2, r))
     # parameters: loose by nature (elements whose gradient is rounding noise take a +-eta step of random sign in the first updates;
     # the losses above, which depend on every earlier update, are the tight check)
     # A sign flip moves an element by up to eta / sqrt(1 - rho) per update whatever its gradient's size, so the norm of the difference
