@@ -96,7 +96,7 @@ def test_split_k_is_consistent(zoo, engine, split):
 
 
 @pytest.mark.parametrize("env,val", [("ZOO_IMPLICIT_CONV", "1"), ("ZOO_TMA_DGRAD", "0"), ("ZOO_TMA_WGRAD", "0"), ("ZOO_PDL", "0"), ("ZOO_TMA_CONV", "0"),
-                                     ("ZOO_TMA_STORE", "0"), ("ZOO_PERSIST_GEMM", "0"), ("ZOO_DQN_TAIL", "1"), ("ZOO_DQN_TAIL", "2"), ("ZOO_NARROW", "0"), ("ZOO_IQN_FUSE", "0"), ("ZOO_TC_WIDE", "0"), ("ZOO_PRESTAGE", "0"), ("ZOO_HEAD_BF16", "0"), ("ZOO_STAGE_RAW", "1"), ("ZOO_MERGE_BWD_VAR", "0"), ("ZOO_LOSS_ASIDE", "1")])
+                                     ("ZOO_TMA_STORE", "0"), ("ZOO_PERSIST_GEMM", "0"), ("ZOO_DQN_TAIL", "1"), ("ZOO_DQN_TAIL", "2"), ("ZOO_NARROW", "0"), ("ZOO_IQN_FUSE", "0"), ("ZOO_TC_WIDE", "0"), ("ZOO_PRESTAGE", "0"), ("ZOO_HEAD_BF16", "0"), ("ZOO_STAGE_RAW", "1"), ("ZOO_MERGE_BWD_VAR", "0")])
 def test_non_default_kernel_paths_keep_parity(env, val):
     """Every kernel path that has a switch: the gathered-A implicit conv (opt-in), and -- switched OFF here -- the TMA data / weight
     gradients (falls back to GEMM + col2im / im2col + GEMM), programmatic dependent launch, the TMA-im2col forward conv, the TMA-store
