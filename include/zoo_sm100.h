@@ -117,7 +117,10 @@ ZOO_API zoo_status zoo_net_out_dim(const zoo_net *net, int32_t *n_out);
 enum { ZOO_OPT_RMSPROP = 0, /* Flux RMSProp(eta, rho)   Dopamine_DQN_Atari.jl:42            */
        ZOO_OPT_ADAM = 1 };  /* Flux ADAM(eta, (b1,b2))  Dopamine_Rainbow_Atari.jl:41, Dopamine_IQN_Atari.jl:51 */
 /* update!(app, gs) -- call sites dqn.jl:144, rainbow.jl:193, iqn.jl:234, basic_dqn.jl:89.
- * RMSProp: a = rho, b ignored.  ADAM: a = beta1, b = beta2.  eps is Flux's constant 1e-8. */
+ * RMSProp: a = rho, b ignored.  ADAM: a = beta1, b = beta2.  eps is Flux's constant 1e-8.
+ * Arithmetic: the kernels evaluate the update in fp32 with scalars (1 - rho, beta^t corrections) derived in fp64 on the host; Flux
+ * evaluates the broadcast with Float64 scalars and rounds once per element.  The difference is far below the 1e-4 parity gate
+ * (tests/test_witnesses.py holds both against torch.optim over 10 steps). */
 ZOO_API zoo_status zoo_opt_create(zoo_net *net, int32_t kind, double eta, double a, double b, double eps, zoo_opt **out);
 ZOO_API zoo_status zoo_opt_destroy(zoo_opt *opt);
 /* checkpointing (BSON policy save, Dopamine_DQN_Atari.jl:123-126): slot 0 = acc | m, slot 1 = v.
@@ -140,6 +143,10 @@ enum { ZOO_LEARNER_BASIC_DQN = 0,       /* basic_dqn.jl:69-90        */
        ZOO_LEARNER_REM_DQN = 6 };       /* rem_dqn.jl:100-145: cfg.N = ensemble_num; batch.tau = the E convex weights (required);
                                            net outputs n_actions*ensemble_num */
 
+/* The reference's learners take a pluggable `loss_func` (dqn.jl:137, prioritized_dqn.jl:140, rainbow.jl:180).  This library
+ * implements the ones the reference's experiment files pass: Flux huber_loss (delta = 1; `agg = identity` for the PER learners,
+ * Dopamine_DQN_Atari.jl:51) for the DQN family, logitcrossentropy(...; agg = identity) for Rainbow (Dopamine_Rainbow_Atari.jl:54),
+ * the quantile Huber loss with `kappa` for IQN / QR-DQN.  Any other loss_func is out of scope and has no entry point. */
 typedef struct {
     int32_t kind;            /* ZOO_LEARNER_* */
     int32_t batch_size;      /* sampler.batch_size */
